@@ -1,0 +1,198 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE ONLY -- see oracle/msl_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (manhattanslam_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    """Compile oracle/libmsl_oracle.so with the committed Makefile (gcc only, no GPU needed)."""
+    so = os.path.join(_HERE, "libmsl_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libmsl_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+SURFEL_DTYPE = np.dtype([("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                         ("size", "<f4"), ("color", "<f4"), ("r", "<i4"), ("g", "<i4"), ("b", "<i4"),
+                         ("weight", "<f4"), ("updateTimes", "<i4"), ("lastUpdate", "<i4")])
+
+SEED_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"),
+                       ("normX", "<f4"), ("normY", "<f4"), ("normZ", "<f4"),
+                       ("posX", "<f4"), ("posY", "<f4"), ("posZ", "<f4"),
+                       ("viewCos", "<f4"), ("meanDepth", "<f4"), ("meanIntensity", "<f4"),
+                       ("r", "<i4"), ("g", "<i4"), ("b", "<i4"),
+                       ("fused", "<i4"), ("stable", "<i4"), ("use", "<i4")])
+
+BLOCK_DTYPE = np.dtype([("center", "<f8", 3), ("normal", "<f8", 3), ("mse", "<f8"), ("curvature", "<f8"),
+                        ("N", "<i4"), ("nouse", "<i4")])
+
+GEOM_DTYPE = np.dtype([("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4"),
+                       ("mnMinX", "<f4"), ("mnMinY", "<f4"), ("mnMaxX", "<f4"), ("mnMaxY", "<f4"),
+                       ("gridWInv", "<f4"), ("gridHInv", "<f4"), ("mb", "<f4"), ("mbf", "<f4"),
+                       ("nlevels", "<i4"), ("scaleFactors", "<f4", 16)])
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_orb_create.restype = C.c_void_p
+        L.orc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_orb_destroy.argtypes = [C.c_void_p]
+        L.orc_orb_levels.argtypes = [C.c_void_p]
+        L.orc_orb_scale_factors.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.orc_orb_features_per_level.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_orb_umax.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int]
+        L.orc_orb_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_orb_level_image.restype = C.c_void_p
+        L.orc_orb_level_image.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_level_blurred.restype = C.c_void_p
+        L.orc_orb_level_blurred.argtypes = [C.c_void_p, C.c_int]
+        L.orc_orb_level_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_orb_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int]
+        L.orc_gaussian_blur_7x7_s2_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_9_16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_score_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_cv_round_f.argtypes = [C.c_float]
+        for name, setup in _LATE.items():
+            if hasattr(L, name):
+                setup(getattr(L, name))
+        _LIB = L
+    return _LIB
+
+
+_LATE = {}
+
+
+def _late(name):
+    def deco(fn):
+        _LATE[name] = fn
+        return fn
+    return deco
+
+
+# ------------------------------------------------------------------------ ORB
+
+class OrbOracle:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:42-104) on the CPU oracle."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self.L = lib()
+        self.h = self.L.orc_orb_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        if not self.h:
+            raise ValueError("bad ORB parameters")
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_orb_destroy(self.h)
+            self.h = None
+
+    def scale_factors(self):
+        out = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        self.L.orc_orb_scale_factors(self.h, *[_p(o) for o in out])
+        return out
+
+    def features_per_level(self):
+        n = np.zeros(self.nlevels, np.int32)
+        self.L.orc_orb_features_per_level(self.h, _p(n))
+        return n
+
+    def umax(self):
+        u = np.zeros(16, np.int32)
+        self.L.orc_orb_umax(self.h, _p(u))
+        return u
+
+    def __call__(self, gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        h, w = gray.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_orb_extract(self.h, _p(gray), w, h, gray.strides[0], _p(kps), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError("oracle keypoint capacity exceeded")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_image(self, level, blurred=False):
+        w, h = C.c_int(), C.c_int()
+        self.L.orc_orb_level_size(self.h, level, C.byref(w), C.byref(h))
+        ptr = (self.L.orc_orb_level_blurred if blurred else self.L.orc_orb_level_image)(self.h, level)
+        if not ptr:
+            return None
+        buf = (C.c_uint8 * (w.value * h.value)).from_address(ptr)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+
+    def level_candidates(self, level):
+        n = self.L.orc_orb_level_candidates(self.h, level, None, 0)
+        out = np.zeros((n, 3), np.int32)
+        self.L.orc_orb_level_candidates(self.h, level, _p(out), n)
+        return out
+
+    def level_keypoints(self, level):
+        n = self.L.orc_orb_level_keypoints(self.h, level, None, 0)
+        out = np.zeros(n, KP_DTYPE)
+        self.L.orc_orb_level_keypoints(self.h, level, _p(out), n)
+        return out
+
+
+def resize_linear_u8(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def gaussian_blur_7x7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().orc_gaussian_blur_7x7_s2_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_9_16(img, threshold, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.zeros((cap, 3), np.int32)
+    n = lib().orc_fast_9_16(_p(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_score_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_fast_score_map(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))

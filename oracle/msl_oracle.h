@@ -1,0 +1,203 @@
+/*
+ * msl_oracle.h -- CPU oracle for the ManhattanSLAM RGB-D front-end hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a dependency-free restatement of the
+ * reference's CPU algorithm (razayunus/ManhattanSLAM) used as the parity
+ * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs.  Nothing in the product path (manhattanslam_b200/,
+ * include/) may include, link or call it.
+ *
+ * Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
+ * section 4) and cannot be compiled here (needs OpenCV/Eigen C++ headers), so
+ * the third-party primitives restated here (cv::FAST, cv::resize INTER_LINEAR
+ * 8U, cv::GaussianBlur 7x7 8U, cv::fastAtan2) are pinned bit-exactly against
+ * Python cv2 4.13.0 in tests/test_oracle_primitives.py and through committed
+ * fixtures in tests/golden/.  Everything above the primitives (octree cull,
+ * superpixels, surfel fusion, peac block statistics, grid search) follows the
+ * reference source line by line; those stages are "parity unpinned" by any
+ * reference-side test because none exists.
+ *
+ * All functions are plain C ABI so that Python ctypes can drive them.
+ */
+#ifndef MSL_ORACLE_H
+#define MSL_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ ORB --- */
+
+typedef struct {
+    float x, y;      /* cv::KeyPoint::pt (level-0 coordinates after O8 scaling) */
+    float size;      /* (int)(31 * scaleFactor[level])                          */
+    float angle;     /* degrees, cv::fastAtan2                                  */
+    float response;  /* FAST corner score                                       */
+    int32_t octave;  /* pyramid level                                           */
+    int32_t class_id;/* always -1                                               */
+} orc_keypoint;      /* 28 bytes */
+
+typedef struct orc_orb orc_orb;
+
+/* ORBextractor::ORBextractor, src/ORBextractor.cc:412-468 */
+orc_orb *orc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+void orc_orb_destroy(orc_orb *);
+/* getters: vectors of length nlevels (ORBextractor.h:58-82) */
+int orc_orb_levels(const orc_orb *);
+void orc_orb_scale_factors(const orc_orb *, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2);
+void orc_orb_features_per_level(const orc_orb *, int32_t *n);
+void orc_orb_umax(const orc_orb *, int32_t *umax16);
+
+/* ORBextractor::operator(), src/ORBextractor.cc:813-870.  Returns the number of
+ * keypoints (<= cap) or -1 if cap is too small.  desc is n x 32 bytes. */
+int orc_orb_extract(orc_orb *, const uint8_t *gray, int w, int h, int stride,
+                    orc_keypoint *kps, uint8_t *desc, int cap);
+
+/* Stage dumps of the LAST orc_orb_extract call (for stage-level parity). */
+int orc_orb_level_size(const orc_orb *, int level, int *w, int *h);
+const uint8_t *orc_orb_level_image(const orc_orb *, int level);          /* w*h, dense */
+const uint8_t *orc_orb_level_blurred(const orc_orb *, int level);        /* w*h, dense */
+/* candidates fed to DistributeOctTree (x,y relative to minBorder, response) */
+int orc_orb_level_candidates(const orc_orb *, int level, int32_t *xyr, int cap);
+/* keypoints per level after the octree (level coordinates, before O8 scaling) */
+int orc_orb_level_keypoints(const orc_orb *, int level, orc_keypoint *kps, int cap);
+
+/* Primitives (pinned against cv2 4.13). */
+void orc_resize_linear_u8(const uint8_t *src, int sw, int sh, int sstride,
+                          uint8_t *dst, int dw, int dh, int dstride);
+void orc_gaussian_blur_7x7_s2_u8(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride);
+/* cv::FAST(img, kps, threshold, nonmaxSuppression=true, TYPE_9_16): out = (x,y,score) triples */
+int orc_fast_9_16(const uint8_t *img, int w, int h, int stride, int threshold, int nms,
+                  int32_t *xyr, int cap);
+/* threshold-free score map: S_max(p) (0..255); FAST score = S_max-1; corner at t <=> S_max > t */
+void orc_fast_score_map(const uint8_t *img, int w, int h, int stride, uint8_t *smax, int ostride);
+float orc_fast_atan2(float y, float x);
+int orc_cv_round_f(float v);
+
+/* -------------------------------------------------------------- matcher --- */
+
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:835-849 */
+int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
+
+typedef struct {
+    float fx, fy, cx, cy;
+    float mnMinX, mnMinY, mnMaxX, mnMaxY;
+    float gridWInv, gridHInv; /* mfGridElementWidthInv / HeightInv */
+    float mb, mbf;
+    int32_t nlevels;
+    float scaleFactors[16];
+} orc_frame_geom;
+
+/* Frame::AssignFeaturesToGrid + GetFeaturesInArea, src/Frame.cc:155-168,332-381,418-427.
+ * Returns the number of indices written (candidate order of the reference). */
+int orc_features_in_area(const orc_frame_geom *g, const float *kp_xy, const int32_t *kp_octave, int n,
+                         float x, float y, float r, int minLevel, int maxLevel, int32_t *out, int cap);
+
+/* ORBmatcher::SearchByProjection(Frame&Cur, const Frame&Last, th), src/ORBmatcher.cc:548-678.
+ * Last-frame side: per keypoint i: has_mp[i], outlier[i], world position, MapPoint descriptor,
+ * octave and (undistorted) angle.  Cur side: undistorted keypoints, uRight, descriptors and
+ * cur_occupied[i] = (mvpMapPoints[i] && Observations()>0) on entry.  last_mp_obs[i] =
+ * (pMP->Observations() > 0) decides whether a slot assigned during this call blocks later queries.
+ * Output: cur_match[i2] = index of the Last keypoint whose MapPoint was assigned to slot i2
+ * (-1 none; slots that were occupied on entry keep -2).  Returns nmatches. */
+int orc_search_by_projection_frame(const orc_frame_geom *g, const float Tcw_cur[16], const float Tcw_last[16],
+                                   float th, int check_orientation,
+                                   int n_last, const uint8_t *last_has_mp, const uint8_t *last_outlier,
+                                   const uint8_t *last_mp_obs, const float *last_mp_world,
+                                   const uint8_t *last_mp_desc, const int32_t *last_octave, const float *last_angle,
+                                   int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle,
+                                   const float *cur_uright, const uint8_t *cur_desc, const uint8_t *cur_occupied,
+                                   int32_t *cur_match);
+
+/* ORBmatcher::SearchByProjection(Frame&F, const vector<MapPoint*>&, th), src/ORBmatcher.cc:40-117.
+ * Per map point: track_in_view && !bad flag, mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos,
+ * descriptor, mp_obs = Observations()>0.  Output cur_match as above.  Returns nmatches. */
+int orc_search_by_projection_points(const orc_frame_geom *g, float th, float nnratio,
+                                    int n_mp, const uint8_t *mp_valid, const uint8_t *mp_obs,
+                                    const float *mp_proj_xyr, const int32_t *mp_level, const float *mp_viewcos,
+                                    const uint8_t *mp_desc,
+                                    int n_cur, const float *cur_xy, const int32_t *cur_octave,
+                                    const float *cur_uright, const uint8_t *cur_desc, const uint8_t *cur_occupied,
+                                    int32_t *cur_match);
+
+/* ---------------------------------------------------- plane pre-stage --- */
+
+typedef struct {
+    double center[3];
+    double normal[3];
+    double mse;
+    double curvature;
+    int32_t N;
+    int32_t nouse;
+} orc_block_stat;
+
+/* PlaneDetection::readDepthImage (src/PlaneExtractor.cpp:44-76) -> cloud (h2*w2*3 doubles),
+ * PlaneSeg ctor + Stats::compute per 10x10 block (AHCPlaneSeg.hpp:235-312,148-181),
+ * initGraph seed test and edges (AHCPlaneFitter.hpp:756-928).
+ * seed[b] = 1 if block b becomes a graph node; edges[b] bit0=left,1=right,2=up,3=down. */
+void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px,
+                        float fx, float fy, float cx, float cy, float depthMapFactor,
+                        double *cloud_xyz, orc_block_stat *blocks, uint8_t *seed, uint8_t *edges);
+/* symmetric 3x3 eigen-decomposition used above (ascending eigenvalues, columns of V) */
+void orc_eig33sym(const double K[9], double s[3], double V[9]);
+
+/* -------------------------------------------------------------- surfels --- */
+
+typedef struct {
+    float px, py, pz;
+    float nx, ny, nz;
+    float size;
+    float color;
+    int32_t r, g, b;
+    float weight;
+    int32_t updateTimes;
+    int32_t lastUpdate;
+} orc_surfel; /* include/Surfel.h:28-37, 56 bytes */
+
+typedef struct {
+    float x, y;
+    float size;
+    float normX, normY, normZ;
+    float posX, posY, posZ;
+    float viewCos;
+    float meanDepth;
+    float meanIntensity;
+    int32_t r, g, b;
+    int32_t fused, stable, use;
+} orc_seed; /* SuperpixelSeed, include/SurfelFusion.h:46-58 (bools widened to int32) */
+
+typedef struct orc_surfel_fusion orc_surfel_fusion;
+
+/* SurfelFusion::SurfelFusion, src/SurfelFusion.cpp:29-38 */
+orc_surfel_fusion *orc_surfel_create(int w, int h, float fx, float fy, float cx, float cy,
+                                     float fuseFar, float fuseNear);
+void orc_surfel_destroy(orc_surfel_fusion *);
+
+/* SurfelFusion::fuseInitializeMap, src/SurfelFusion.cpp:40-73.  local is updated in place,
+ * new_surfels receives up to cap_new entries; returns the number of new surfels.
+ * threads: 1 = sequential slices 0..9 (the deterministic oracle order); >1 uses std::thread
+ * over the same slices for the fuse scan only (result is slice-independent, see S8). */
+int orc_surfel_fuse(orc_surfel_fusion *, int referenceFrameIndex,
+                    const uint8_t *gray, int gray_stride, const float *depth, const int32_t *membership,
+                    const float Twc[16], orc_surfel *local, int64_t n_local,
+                    orc_surfel *new_surfels, int cap_new, int threads);
+
+/* Stage dumps of the last call. */
+const int32_t *orc_surfel_index(const orc_surfel_fusion *);         /* w*h */
+const orc_seed *orc_surfel_seeds(const orc_surfel_fusion *);        /* (w/8)*(h/8) */
+const float *orc_surfel_normmap(const orc_surfel_fusion *);         /* w*h*3 */
+/* snapshot of seeds/index after updateSeeds of iteration it (0..2) */
+const orc_seed *orc_surfel_seeds_iter(const orc_surfel_fusion *, int it);
+const int32_t *orc_surfel_index_iter(const orc_surfel_fusion *, int it);
+
+/* SurfelMapping::fuseMap tail, src/SurfelMapping.cpp:366-391: refill deleted slots from the back of
+ * the deleted list with new surfels, append the rest, swap-remove remaining deleted slots.
+ * local must have room for n_local + n_new.  Returns the new local size. */
+int64_t orc_surfel_compact(orc_surfel *local, int64_t n_local, const orc_surfel *new_surfels, int n_new);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
