@@ -1,0 +1,256 @@
+/*
+ * msl_frontend.h -- C ABI of the B200-native RGB-D front-end for ManhattanSLAM.
+ *
+ * This is the drop-in boundary: a thin extern "C" shim (plain pointers and sizes, no C++/torch
+ * types) over hand-written sm_100a CUDA kernels.  The reference-side adapters in adapters/ implement
+ * the reference's C++ class surfaces on top of it so Tracking.cc / Frame.cc / SurfelMapping.cpp
+ * compile unchanged.  Citations are into razayunus/ManhattanSLAM.
+ *
+ * Conventions
+ *   - every function returns MSL_OK (0) or a negative msl_status; msl_last_error() gives the text of
+ *     the last failure on the calling thread;
+ *   - handles are opaque, own one CUDA stream plus all device scratch, and -- like the reference
+ *     objects they replace (one ORBextractor per Tracking thread, one SurfelFusion per SurfelMapping
+ *     thread) -- are NOT thread-safe;
+ *   - "host" entry points take caller-allocated host buffers and include the H2D/D2H copies;
+ *     "_dev" entry points take device pointers, enqueue on the handle's stream and do not
+ *     synchronise (call msl_*_sync);
+ *   - there is no CPU fallback: without a CUDA device every create call fails with MSL_ERR_CUDA.
+ */
+#ifndef MSL_FRONTEND_H
+#define MSL_FRONTEND_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MSL_OK = 0,
+    MSL_ERR_INVALID = -1,   /* bad argument */
+    MSL_ERR_CUDA = -2,      /* CUDA runtime failure (no device, OOM, launch error) */
+    MSL_ERR_CAPACITY = -3,  /* a device-side capacity was exceeded (candidates, nodes, new surfels) */
+    MSL_ERR_STATE = -4      /* call order violated (e.g. fuse before upload_map) */
+} msl_status;
+
+const char *msl_last_error(void);
+const char *msl_version(void);
+/* number of CUDA kernels this library has launched since load (all handles, all threads) */
+uint64_t msl_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ ORB
+ * Replaces ORB_SLAM2::ORBextractor (include/ORBextractor.h:42-104, src/ORBextractor.cc:412-893). */
+
+typedef struct {
+    float x, y;       /* cv::KeyPoint::pt   (src/ORBextractor.cc:788-797, scaled at :861-866) */
+    float size;       /* cv::KeyPoint::size = (int)(31*scaleFactor[octave])                    */
+    float angle;      /* IC_Angle, degrees  (:75-99)                                           */
+    float response;   /* FAST score                                                            */
+    int32_t octave;
+    int32_t class_id; /* -1 */
+} msl_keypoint;       /* 28 bytes, field order of cv::KeyPoint */
+
+typedef struct {
+    int32_t nfeatures;   /* ORBextractor.nFeatures  (Example/TUM1.yaml:42) */
+    float scale_factor;  /* ORBextractor.scaleFactor */
+    int32_t nlevels;     /* ORBextractor.nLevels (<= 16) */
+    int32_t ini_th_fast; /* ORBextractor.iniThFAST */
+    int32_t min_th_fast; /* ORBextractor.minThFAST */
+} msl_orb_params;
+
+typedef struct msl_orb msl_orb;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:412-468).  The handle is sized for frames of
+ * exactly w x h and up to max_batch frames per call. */
+int msl_orb_create(const msl_orb_params *params, int w, int h, int max_batch, int device, msl_orb **out);
+void msl_orb_destroy(msl_orb *);
+
+/* Getters of include/ORBextractor.h:58-82; arrays of nlevels floats (any may be NULL). */
+int msl_orb_levels(const msl_orb *);
+int msl_orb_scale_factors(const msl_orb *, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2);
+/* rows of kps/desc reserved per frame by msl_orb_extract (>= nfeatures + 3*nlevels) */
+int msl_orb_capacity(const msl_orb *);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:813-870) on `batch` independent gray frames.
+ *   gray   : batch images, image b at gray + b*frame_stride, rows `stride` bytes apart (CV_8UC1)
+ *   kps    : batch x capacity msl_keypoint          desc : batch x capacity x 32 bytes
+ *   counts : batch int32 (keypoints found per frame)
+ * Keypoint order = reference order (levels ascending, octree list order inside a level). */
+int msl_orb_extract(msl_orb *, const uint8_t *gray, int stride, size_t frame_stride, int batch,
+                    msl_keypoint *kps, uint8_t *desc, int32_t *counts);
+/* Same with device pointers; asynchronous on the handle's stream. */
+int msl_orb_extract_dev(msl_orb *, const uint8_t *d_gray, int stride, size_t frame_stride, int batch,
+                        msl_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts);
+int msl_orb_sync(msl_orb *);
+void *msl_orb_stream(msl_orb *); /* cudaStream_t */
+
+/* Stage read-back of the last extract call (parity tests): level image / blurred level image of
+ * frame `frame` (dense w*h bytes), FAST candidates fed to the octree (x,y relative to minBorder, score). */
+int msl_orb_debug_level_size(const msl_orb *, int level, int *w, int *h);
+int msl_orb_debug_level(msl_orb *, int frame, int level, int blurred, uint8_t *out);
+int msl_orb_debug_candidates(msl_orb *, int frame, int level, int32_t *xyr, int cap, int *n);
+
+/* -------------------------------------------------------------------------------------- matcher
+ * Replaces ORBmatcher::DescriptorDistance and the window searches of ORBmatcher::SearchByProjection
+ * (src/ORBmatcher.cc:40-117, 548-678, 835-849) including Frame::GetFeaturesInArea semantics
+ * (src/Frame.cc:155-168, 332-381, 418-427). */
+
+typedef struct {
+    float fx, fy, cx, cy;                 /* Frame::fx.. */
+    float mnMinX, mnMinY, mnMaxX, mnMaxY; /* Frame::mnMinX.. (src/Frame.cc:466-493) */
+    float gridWInv, gridHInv;             /* Frame::mfGridElementWidthInv / HeightInv (:137-138) */
+    float mb, mbf;                        /* Frame::mb, Frame::mbf */
+    int32_t nlevels;
+    float scaleFactors[16];               /* Frame::mvScaleFactors */
+} msl_frame_geom;
+
+typedef struct msl_matcher msl_matcher;
+
+int msl_matcher_create(int max_queries, int max_train, int max_batch, int device, msl_matcher **out);
+void msl_matcher_destroy(msl_matcher *);
+
+/* All-pairs Hamming distance of 256-bit descriptors: dist[b][i][j] = popcount(q[b][i] ^ t[b][j]),
+ * batch pairs; q: batch x nq x 32, t: batch x nt x 32, dist: batch x nq x nt uint16. */
+int msl_hamming_all_pairs(msl_matcher *, const uint8_t *q, int nq, const uint8_t *t, int nt, int batch,
+                          uint16_t *dist);
+/* Brute-force best/second-best per query row (ties: lowest train index). */
+int msl_hamming_best2(msl_matcher *, const uint8_t *q, int nq, const uint8_t *t, int nt, int batch,
+                      int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
+int msl_hamming_best2_dev(msl_matcher *, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int batch,
+                          int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist);
+
+/* ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th) (src/ORBmatcher.cc:548-678).
+ * The adapter flattens the Frame/MapPoint graph into arrays:
+ *   Last side, per keypoint i < n_last: last_has_mp (mvpMapPoints[i]!=NULL), last_outlier (mvbOutlier),
+ *     last_mp_obs (pMP->Observations()>0), last_mp_world (GetWorldPos, xyz), last_mp_desc (GetDescriptor,
+ *     32 B), last_octave (mvKeys[i].octave), last_angle (mvKeysUn[i].angle);
+ *   Cur side, per keypoint j < n_cur: cur_xy (mvKeysUn pt), cur_octave, cur_angle, cur_uright (mvuRight),
+ *     cur_desc (mDescriptors), cur_occupied (mvpMapPoints[j] && Observations()>0 on entry).
+ * Output: cur_match[j] = index i of the Last keypoint whose MapPoint now sits in slot j, -1 if none,
+ * -2 if the slot was occupied on entry; *nmatches = return value of the reference method (after the
+ * rotation-histogram pruning when check_orientation != 0). */
+int msl_search_by_projection_frame(msl_matcher *, const msl_frame_geom *geom, const float Tcw_cur[16],
+                                   const float Tcw_last[16], float th, int check_orientation, int n_last,
+                                   const uint8_t *last_has_mp, const uint8_t *last_outlier,
+                                   const uint8_t *last_mp_obs, const float *last_mp_world,
+                                   const uint8_t *last_mp_desc, const int32_t *last_octave,
+                                   const float *last_angle, int n_cur, const float *cur_xy,
+                                   const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
+                                   const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match,
+                                   int32_t *nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &, th) (src/ORBmatcher.cc:40-117).
+ * Per map point k: mp_valid (mbTrackInView && !isBad()), mp_obs (Observations()>0), mp_proj_xyr
+ * (mTrackProjX, mTrackProjY, mTrackProjXR), mp_level (mnTrackScaleLevel), mp_viewcos (mTrackViewCos),
+ * mp_desc.  nnratio = ORBmatcher::mfNNratio.  cur_match[j] = k as above. */
+int msl_search_by_projection_points(msl_matcher *, const msl_frame_geom *geom, float th, float nnratio,
+                                    int n_mp, const uint8_t *mp_valid, const uint8_t *mp_obs,
+                                    const float *mp_proj_xyr, const int32_t *mp_level, const float *mp_viewcos,
+                                    const uint8_t *mp_desc, int n_cur, const float *cur_xy,
+                                    const int32_t *cur_octave, const float *cur_uright, const uint8_t *cur_desc,
+                                    const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches);
+
+/* ----------------------------------------------------------------------------- plane pre-stage
+ * Replaces PlaneDetection::readDepthImage (src/PlaneExtractor.cpp:44-76) and the peac pre-stage:
+ * PlaneSeg ctor + Stats::compute per 10x10 block (include/peac/AHCPlaneSeg.hpp:148-181, 235-312)
+ * and the node/edge initialisation of PlaneFitter::initGraph (include/peac/AHCPlaneFitter.hpp:756-928). */
+
+typedef struct {
+    double center[3];
+    double normal[3];
+    double mse;
+    double curvature;
+    int32_t N;     /* member points (0 if rejected) */
+    int32_t nouse; /* 1 = rejected by missing data / depth discontinuity */
+} msl_block_stat;  /* 72 bytes */
+
+typedef struct msl_plane msl_plane;
+
+int msl_plane_create(int w, int h, int max_batch, int device, msl_plane **out);
+void msl_plane_destroy(msl_plane *);
+/* depth: batch CV_16U images (row stride in pixels = dstride_px, image b at depth + b*frame_stride_px).
+ * K = {fx, fy, cx, cy}.  Outputs per frame (any may be NULL): cloud_xyz (h2*w2*3 doubles, h2=ceil(h/2)),
+ * blocks ((h2/10)*(w2/10) msl_block_stat), seed (1 = graph node), edges (bit0 left,1 right,2 up,3 down). */
+int msl_plane_prestage(msl_plane *, const uint16_t *depth, int dstride_px, size_t frame_stride_px, int batch,
+                       const float K[4], float depth_map_factor, double *cloud_xyz, msl_block_stat *blocks,
+                       uint8_t *seed, uint8_t *edges);
+int msl_plane_prestage_dev(msl_plane *, const uint16_t *d_depth, int dstride_px, size_t frame_stride_px,
+                           int batch, const float K[4], float depth_map_factor, double *d_cloud_xyz,
+                           msl_block_stat *d_blocks, uint8_t *d_seed, uint8_t *d_edges);
+int msl_plane_sync(msl_plane *);
+void *msl_plane_stream(msl_plane *);
+
+/* ------------------------------------------------------------------------------------- surfels
+ * Replaces SurfelFusion (include/SurfelFusion.h:44-139, src/SurfelFusion.cpp) and the compaction
+ * tail of SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391). */
+
+typedef struct {
+    float px, py, pz;
+    float nx, ny, nz;
+    float size;
+    float color;
+    int32_t r, g, b;
+    float weight;
+    int32_t updateTimes;
+    int32_t lastUpdate;
+} msl_surfel; /* include/Surfel.h:28-37, 56 bytes */
+
+typedef struct {
+    float x, y;
+    float size;
+    float normX, normY, normZ;
+    float posX, posY, posZ;
+    float viewCos;
+    float meanDepth;
+    float meanIntensity;
+    int32_t r, g, b;
+    int32_t fused, stable, use;
+} msl_seed; /* SurfelFusion::SuperpixelSeed (include/SurfelFusion.h:46-58), bools widened */
+
+typedef struct msl_surfel_fusion msl_surfel_fusion;
+
+/* SurfelFusion::SurfelFusion (src/SurfelFusion.cpp:29-38); max_surfels = capacity of the
+ * device-resident local map (Map::mvLocalSurfels). */
+int msl_surfel_create(int w, int h, float fx, float fy, float cx, float cy, float fuse_far, float fuse_near,
+                      int64_t max_surfels, int device, msl_surfel_fusion **out);
+void msl_surfel_destroy(msl_surfel_fusion *);
+
+/* Explicit sync points for the device-resident map (the host mutates mvLocalSurfels between
+ * keyframes in SurfelMapping::moveAddSurfels, src/SurfelMapping.cpp:194-304). */
+int msl_surfel_upload_map(msl_surfel_fusion *, const msl_surfel *local, int64_t n);
+int msl_surfel_download_map(msl_surfel_fusion *, msl_surfel *local, int64_t cap, int64_t *n);
+int64_t msl_surfel_map_size(const msl_surfel_fusion *);
+
+/* SurfelFusion::fuseInitializeMap (src/SurfelFusion.cpp:40-73) on the device-resident map.
+ *   gray (CV_8UC1, row stride gray_stride), depth (CV_32F metres, dense w*h), membership (CV_32SC1,
+ *   ceil(h/2) x ceil(w/2), -1 = no plane), Twc (row-major 4x4 camera->world).
+ *   new_surfels (cap_new entries, may be NULL) receives SurfelFusion's newSurfels in seed order.
+ *   compact != 0 additionally applies the fuseMap tail (src/SurfelMapping.cpp:366-391) on the device.
+ *   stats (may be NULL): {n_new, n_updated, n_deleted, map_size_after}. */
+int msl_surfel_fuse(msl_surfel_fusion *, int reference_frame_index, const uint8_t *gray, int gray_stride,
+                    const float *depth, const int32_t *membership, const float Twc[16], msl_surfel *new_surfels,
+                    int cap_new, int compact, int64_t stats[4]);
+/* Device-pointer variant (inputs already resident); asynchronous, stats are device-resident until
+ * msl_surfel_read_stats. */
+int msl_surfel_fuse_dev(msl_surfel_fusion *, int reference_frame_index, const uint8_t *d_gray, int gray_stride,
+                        const float *d_depth, const int32_t *d_membership, const float Twc[16], int compact);
+int msl_surfel_read_stats(msl_surfel_fusion *, int64_t stats[4]);
+int msl_surfel_read_new(msl_surfel_fusion *, msl_surfel *new_surfels, int cap_new, int *n_new);
+int msl_surfel_sync(msl_surfel_fusion *);
+void *msl_surfel_stream(msl_surfel_fusion *);
+
+/* Batched superpixel generation only (generateSuperPixels, src/SurfelFusion.cpp:805-816) for `batch`
+ * independent frames: seeds (batch x (w/8)*(h/8) msl_seed), index (batch x w*h int32, may be NULL). */
+int msl_surfel_superpixels(msl_surfel_fusion *, const uint8_t *gray, int gray_stride, const float *depth,
+                           const int32_t *membership, int batch, msl_seed *seeds, int32_t *index);
+
+/* Stage read-back of the last fuse call. */
+int msl_surfel_debug_seeds(msl_surfel_fusion *, msl_seed *seeds);
+int msl_surfel_debug_index(msl_surfel_fusion *, int32_t *index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSL_FRONTEND_H */

@@ -1,0 +1,1075 @@
+// orb.cu -- B200-native ORB extraction (replaces src/ORBextractor.cc of razayunus/ManhattanSLAM).
+//
+// Batched over independent frames; every stage is a hand-written sm_100a kernel:
+//   k_resize      O1  8U bilinear pyramid level l from level l-1 (OpenCV fixed-point arithmetic)
+//   k_fast_cells  O2  one CTA per 30-px FAST cell: ROI tile -> shared memory, threshold-free FAST-9-16
+//                     score, in-cell 3x3 NMS, ini/min threshold fallback, ordered warp-ballot compaction
+//   k_octree      O3  one CTA per (frame, level): DistributeOctTree reformulated as rounds of parallel
+//                     quad splits with prefix sums (list order, largest-first expansion and the
+//                     creation-order tie-break reproduced exactly) + best-response pick
+//   k_blur        O6  7x7 sigma-2 fixed-point Gaussian (8.8 taps), separable, shared-memory tiles
+//   k_describe    O5+O7+O8  one warp per keypoint: IC-angle (integer moments + fastAtan2 polynomial),
+//                     steered 256-bit BRIEF on the blurred level, output scaling
+// All integer stages are bit-exact with the CPU oracle; float math avoids FMA contraction (-fmad=false).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "msl_common.cuh"
+
+namespace msl {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+}  // namespace msl
+
+using namespace msl;
+
+namespace {
+
+constexpr int EDGE_THRESHOLD = 19;  // src/ORBextractor.cc:72
+constexpr int PATCH_SIZE = 31;
+constexpr int HALF_PATCH = 15;
+constexpr int MIN_BORDER = EDGE_THRESHOLD - 3;  // 16
+constexpr int MAX_LEVELS = 16;
+constexpr int CELL_TILE = 68;  // max ROI edge (wCell < 60, +6 ring, rounded)
+constexpr int CAND_CAP = 16384;  // FAST candidates per (frame, level) fed to the octree
+
+struct LevelInfo {
+    int w, h, pitch;     // level image size and row pitch (bytes)
+    int offset;          // byte offset inside the per-frame pyramid block
+    int cellBase, nCells;
+    int nFeatures;       // mnFeaturesPerLevel
+    int nIni;            // DistributeOctTree root count
+    float hX;
+    int width, height;   // maxBorder - minBorder
+    int tabOff;          // offset (in shorts) of the resize tables of this level
+    float scale;         // mvScaleFactor[level]
+    int kpBase, kpCap;   // slot range of this level in the per-frame level-keypoint array
+    int scaledPatch;     // (int)(31 * mvScaleFactor)
+};
+
+struct Cell {
+    short x0, y0, x1, y1;  // ROI [x0,x1) x [y0,y1) in level coordinates (includes the 3-px FAST ring)
+};
+
+struct LevelKp {
+    short x, y;      // level coordinates
+    short score;     // FAST response
+    short level;
+};
+
+struct DevPattern {
+    int8_t v[1024];
+};
+__constant__ DevPattern c_pattern = {{
+#include "rbrief_pattern_31.inc"
+}};
+__constant__ int c_umax[16];
+
+inline int cv_round_f(float v) { return (int)nearbyintf(v); }
+inline int cv_floor_d(double v) {
+    int i = (int)v;
+    return i - (i > v);
+}
+inline int cv_ceil_d(double v) {
+    int i = (int)v;
+    return i + (i < v);
+}
+inline short sat_short(float v) {
+    int iv = cv_round_f(v);
+    return (short)(iv < -32768 ? -32768 : iv > 32767 ? 32767 : iv);
+}
+
+// Level 0 = the input frame (src/ORBextractor.cc:886-891), re-pitched into the pyramid block.
+__global__ void __launch_bounds__(256) k_load_level0(const uint8_t *__restrict__ src, int stride, size_t frameStride,
+                                                     uint8_t *__restrict__ pyr, int pitch, size_t pyrStride, int w,
+                                                     int h, int vec) {
+    const int y = blockIdx.y, b = blockIdx.z;
+    const uint8_t *s = src + b * frameStride + (size_t)y * stride;
+    uint8_t *d = pyr + b * pyrStride + (size_t)y * pitch;
+    if (vec) {
+        const int x = (blockIdx.x * 256 + threadIdx.x) * 16;
+        if (x < w) *(uint4 *)(d + x) = *(const uint4 *)(s + x);
+    } else {
+        for (int x = blockIdx.x * 256 * 16 + threadIdx.x; x < min(w, (int)(blockIdx.x + 1) * 256 * 16); x += 256) d[x] = s[x];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ O1
+// cv::resize INTER_LINEAR 8UC1: D = ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2 with
+// H = S[sx]*a0 + S[sx+1]*a1 (11-bit coefficients).  Tables are built on the host exactly as OpenCV does.
+__global__ void __launch_bounds__(256) k_resize(const LevelInfo *__restrict__ lv, int level, uint8_t *pyr,
+                                                size_t frameStride, const short *__restrict__ tab) {
+    const LevelInfo L = lv[level], P = lv[level - 1];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= L.w || y >= L.h) return;
+    const short *t = tab + L.tabOff;
+    const int sx = t[x], a0 = t[L.w + x], a1 = t[2 * L.w + x];
+    const short *ty = t + 3 * L.w;
+    const int sy = ty[y], b0 = ty[L.h + y], b1 = ty[2 * L.h + y];
+    const int sx1 = min(sx + 1, P.w - 1);
+    const int sy0 = min(max(sy, 0), P.h - 1), sy1 = min(max(sy + 1, 0), P.h - 1);
+    const uint8_t *src = pyr + blockIdx.z * frameStride + P.offset;
+    const uint8_t *r0 = src + (size_t)sy0 * P.pitch, *r1 = src + (size_t)sy1 * P.pitch;
+    const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+    const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    pyr[blockIdx.z * frameStride + L.offset + (size_t)y * L.pitch + x] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------ O2
+// Threshold-free FAST-9-16 score: S_max = max over the 16 nine-pixel arcs, both polarities, of the
+// minimum signed difference; cv::FAST's response is S_max-1 and "corner at t" <=> S_max > t.
+__device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch) {
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * pitch];
+    d[1] = v - c[3 * pitch + 1];
+    d[2] = v - c[2 * pitch + 2];
+    d[3] = v - c[pitch + 3];
+    d[4] = v - c[3];
+    d[5] = v - c[-pitch + 3];
+    d[6] = v - c[-2 * pitch + 2];
+    d[7] = v - c[-3 * pitch + 1];
+    d[8] = v - c[-3 * pitch];
+    d[9] = v - c[-3 * pitch - 1];
+    d[10] = v - c[-2 * pitch - 2];
+    d[11] = v - c[-pitch - 3];
+    d[12] = v - c[-3];
+    d[13] = v - c[pitch - 3];
+    d[14] = v - c[2 * pitch - 2];
+    d[15] = v - c[3 * pitch - 1];
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        lo2[i] = min(d[i], d[(i + 1) & 15]);
+        hi2[i] = max(d[i], d[(i + 1) & 15]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        lo4[i] = min(lo2[i], lo2[(i + 2) & 15]);
+        hi4[i] = max(hi2[i], hi2[(i + 2) & 15]);
+    }
+    int best = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        int lo9 = min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
+        int hi9 = max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
+        best = max(best, max(lo9, -hi9));
+    }
+    return best;
+}
+
+// One CTA per FAST cell (src/ORBextractor.cc:745-780).  Output: ordered survivor records of the cell
+// (x | y<<12 | smax<<24, x/y relative to minBorder) into its staging slot + the cell count.
+__global__ void __launch_bounds__(128)
+    k_fast_cells(const LevelInfo *__restrict__ lv, const Cell *__restrict__ cells, const short *__restrict__ cellLevel,
+                 const uint8_t *__restrict__ pyr, size_t frameStride, int totalCells, int capCell, int iniTh,
+                 int minTh, uint32_t *__restrict__ staging, int *__restrict__ cellCount) {
+    __shared__ uint8_t tile[CELL_TILE * CELL_TILE];
+    __shared__ uint8_t sc[CELL_TILE * CELL_TILE];
+    __shared__ uint8_t sv[CELL_TILE * CELL_TILE];
+    __shared__ int wsum[4];
+    __shared__ int s_any;
+    const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const Cell C = cells[cell];
+    const LevelInfo L = lv[cellLevel[cell]];
+    const int rw = C.x1 - C.x0, rh = C.y1 - C.y0;
+    const int cw = rw - 6, ch = rh - 6;  // detectable area
+    const uint8_t *img = pyr + frame * frameStride + L.offset;
+    for (int p = tid; p < rw * rh; p += 128) {
+        int ry = p / rw, rx = p - ry * rw;
+        tile[ry * CELL_TILE + rx] = img[(size_t)(C.y0 + ry) * L.pitch + C.x0 + rx];
+    }
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    const int np = cw * ch;
+    for (int p = tid; p < np; p += 128) {
+        int cy = p / cw, cx = p - cy * cw;
+        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(tile + (cy + 3) * CELL_TILE + cx + 3, CELL_TILE);
+    }
+    __syncthreads();
+    // in-cell NMS: strict maximum over the 8 neighbours; neighbours outside the cell's ring count as 0
+    int any = 0;
+    for (int p = tid; p < np; p += 128) {
+        int cy = p / cw, cx = p - cy * cw;
+        int s = sc[cy * CELL_TILE + cx];
+        int keep = 0;
+        if (s > minTh) {
+            int m = 0;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    int nx = cx + dx, ny = cy + dy;
+                    if (nx >= 0 && nx < cw && ny >= 0 && ny < ch) m = max(m, (int)sc[ny * CELL_TILE + nx]);
+                }
+            keep = s > m;
+        }
+        sv[cy * CELL_TILE + cx] = keep ? (uint8_t)s : 0;
+        any |= (keep && s > iniTh);
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    const int thr = s_any ? iniTh : minTh;  // FAST(iniThFAST) non-empty, else FAST(minThFAST)
+    uint32_t *out = staging + ((size_t)frame * totalCells + cell) * capCell;
+    const int offX = C.x0 + 3 - MIN_BORDER, offY = C.y0 + 3 - MIN_BORDER;
+    int base = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int p0 = 0; p0 < np; p0 += 128) {
+        int p = p0 + tid;
+        int s = 0, cx = 0, cy = 0;
+        if (p < np) {
+            cy = p / cw;
+            cx = p - cy * cw;
+            s = sv[cy * CELL_TILE + cx];
+        }
+        const bool f = s > thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            int c = wsum[w];
+            if (w < wid) pre += c;
+            tot += c;
+        }
+        if (f) out[base + pre + __popc(bal & ((1u << lane) - 1))] =
+                   (uint32_t)(cx + offX) | ((uint32_t)(cy + offY) << 12) | ((uint32_t)s << 24);
+        base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) cellCount[(size_t)frame * totalCells + cell] = base;
+}
+
+// ------------------------------------------------------------------------------------------ O3
+// DistributeOctTree (src/ORBextractor.cc:531-721) as rounds of parallel quad splits.  The node list is
+// kept in list order in shared memory and rebuilt every round:
+//   new list = reverse(children in creation order) ++ (undivided nodes in old order)
+// which is exactly what push_front/erase produce.  Phase 1 divides every node with >1 keys; once
+// size + 3*nToExpand > N the largest-first phase divides the previous round's multi-key children
+// in (size desc, creation desc) order -- creation desc == list position asc -- up to the node that
+// makes size >= N.  Finally each node keeps its max-response key (first in candidate order on ties).
+struct OctSmem {
+    short4 *rect[2];
+    int *cnt[2];
+    int *pidx;     // eligible enumeration (exclusive scan)
+    int *rank;     // creation order index of eligible node (by pidx)
+    int *ordPos;   // list position by creation order index
+    int *cc;       // 4 child counts per eligible node (by pidx); later reused as child new-position
+    int *flag;     // scan scratch (4 per order index)
+    int *surv;     // survivor scan
+    int *ws;       // block scan scratch (34 ints)
+};
+
+__device__ __forceinline__ int quadrant_of(const short4 r, int x, int y) {
+    // ExtractorNode::DivideNode, src/ORBextractor.cc:477-529
+    const int halfX = (int)ceilf((float)(r.z - r.x) / 2.f);
+    const int halfY = (int)ceilf((float)(r.w - r.y) / 2.f);
+    const int q = (x < r.x + halfX) ? 0 : 1;
+    return (y < r.y + halfY) ? q : q + 2;
+}
+
+__device__ __forceinline__ short4 child_rect(const short4 r, int q) {
+    const int halfX = (int)ceilf((float)(r.z - r.x) / 2.f);
+    const int halfY = (int)ceilf((float)(r.w - r.y) / 2.f);
+    short4 c;
+    c.x = (q & 1) ? r.x + halfX : r.x;
+    c.z = (q & 1) ? r.z : r.x + halfX;
+    c.y = (q & 2) ? r.y + halfY : r.y;
+    c.w = (q & 2) ? r.w : r.y + halfY;
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+    k_octree(const LevelInfo *__restrict__ lv, int nlevels, int totalCells, int capCell,
+             const uint32_t *__restrict__ staging, const int *__restrict__ cellCount, uint32_t *__restrict__ candRec,
+             unsigned short *__restrict__ candNode, int *__restrict__ candCount, LevelKp *__restrict__ lvlKps,
+             int *__restrict__ lvlCount, int kpCapTotal, int maxNodes, int *__restrict__ err) {
+    extern __shared__ int smem_raw[];
+    const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    const LevelInfo L = lv[level];
+    OctSmem S;
+    {
+        int *p = smem_raw;
+        S.rect[0] = (short4 *)p; p += 2 * maxNodes;
+        S.rect[1] = (short4 *)p; p += 2 * maxNodes;
+        S.cnt[0] = p; p += maxNodes;
+        S.cnt[1] = p; p += maxNodes;
+        S.pidx = p; p += maxNodes;
+        S.rank = p; p += maxNodes;
+        S.ordPos = p; p += maxNodes;
+        S.surv = p; p += maxNodes;
+        S.cc = p; p += 4 * maxNodes;
+        S.flag = p; p += 4 * maxNodes;
+        S.ws = p; p += 40;
+    }
+    __shared__ int s_n, s_size, s_phase, s_clast, s_finish, s_J, s_m;
+    uint32_t *rec = candRec + ((size_t)frame * nlevels + level) * CAND_CAP;
+    unsigned short *node = candNode + ((size_t)frame * nlevels + level) * CAND_CAP;
+
+    // ---- gather the ordered candidate list: cells in (row, col) order, row-major inside a cell
+    const int *cc = cellCount + (size_t)frame * totalCells + L.cellBase;
+    int *cellOff = S.flag;  // nCells <= 4*maxNodes is checked on the host
+    for (int c = tid; c < L.nCells; c += nt) cellOff[c] = cc[c];
+    __syncthreads();
+    const int n = block_excl_scan(cellOff, L.nCells, S.ws);
+    if (tid == 0) {
+        s_n = n;
+        candCount[frame * nlevels + level] = n;
+        if (n > CAND_CAP) atomicExch(err, 1);
+    }
+    __syncthreads();
+    if (n > CAND_CAP || n == 0) {
+        if (tid == 0) lvlCount[frame * nlevels + level] = 0;
+        return;
+    }
+    for (int c = tid >> 5; c < L.nCells; c += nt >> 5) {  // one warp per cell
+        const uint32_t *src = staging + ((size_t)frame * totalCells + L.cellBase + c) * capCell;
+        const int k = cc[c], o = cellOff[c];
+        for (int i = tid & 31; i < k; i += 32) rec[o + i] = src[i];
+    }
+    // ---- roots (src/ORBextractor.cc:536-571)
+    const int N = L.nFeatures;
+    for (int i = tid; i < L.nIni; i += nt) {
+        short4 r;
+        r.x = (short)(int)(L.hX * (float)i);
+        r.z = (short)(int)(L.hX * (float)(i + 1));
+        r.y = 0;
+        r.w = (short)L.height;
+        S.rect[0][i] = r;
+        S.cnt[0][i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const int x = rec[i] & 0xfff;
+        const int r = (int)((float)x / L.hX);
+        node[i] = (unsigned short)r;
+        atomicAdd(&S.cnt[0][r], 1);
+    }
+    __syncthreads();
+    int cur = 0;
+    {   // erase empty roots, keep order
+        for (int i = tid; i < L.nIni; i += nt) S.surv[i] = S.cnt[0][i] > 0;
+        __syncthreads();
+        const int live = block_excl_scan(S.surv, L.nIni, S.ws);
+        for (int i = tid; i < L.nIni; i += nt)
+            if (S.cnt[0][i] > 0) {
+                S.rect[1][S.surv[i]] = S.rect[0][i];
+                S.cnt[1][S.surv[i]] = S.cnt[0][i];
+                S.pidx[i] = S.surv[i];
+            } else
+                S.pidx[i] = -1;
+        __syncthreads();
+        if (live != L.nIni)
+            for (int i = tid; i < n; i += nt) node[i] = (unsigned short)S.pidx[node[i]];
+        cur = 1;
+        if (tid == 0) {
+            s_size = live;
+            s_phase = 1;
+            s_clast = 0;
+            s_finish = 0;
+        }
+        __syncthreads();
+    }
+
+    // ---- split rounds
+    for (int round = 0; round < 64; round++) {
+        const short4 *rect = S.rect[cur];
+        const int *cnt = S.cnt[cur];
+        short4 *rect2 = S.rect[cur ^ 1];
+        int *cnt2 = S.cnt[cur ^ 1];
+        const int size = s_size, phase = s_phase, clast = s_clast;
+        // 1. eligible nodes, enumerated by list position
+        for (int p = tid; p < size; p += nt) S.pidx[p] = (cnt[p] > 1) && (phase == 1 || p < clast);
+        __syncthreads();
+        const int m = block_excl_scan(S.pidx, size, S.ws);
+        if (m == 0) break;  // size == prevSize -> bFinish
+        for (int k = tid; k < 4 * m; k += nt) S.cc[k] = 0;
+        __syncthreads();
+        auto eligible = [&](int p) { return (cnt[p] > 1) && (phase == 1 || p < clast); };
+        // 2. child occupancy of every eligible node
+        for (int i = tid; i < n; i += nt) {
+            const int p = node[i];
+            if (eligible(p)) {
+                const uint32_t r = rec[i];
+                atomicAdd(&S.cc[4 * S.pidx[p] + quadrant_of(rect[p], r & 0xfff, (r >> 12) & 0xfff)], 1);
+            }
+        }
+        __syncthreads();
+        // 3. creation order: list order (phase 1) or size desc / position asc (phase 2)
+        for (int p = tid; p < size; p += nt) {
+            if (!eligible(p)) continue;
+            int rk;
+            if (phase == 1)
+                rk = S.pidx[p];
+            else {
+                rk = 0;
+                const int c = cnt[p];
+                for (int p2 = 0; p2 < clast; p2++) {
+                    const int c2 = cnt[p2];
+                    rk += (c2 > 1) && (c2 > c || (c2 == c && p2 < p));
+                }
+            }
+            S.rank[S.pidx[p]] = rk;
+            S.ordPos[rk] = p;
+        }
+        __syncthreads();
+        // 4. cut-off: divide in creation order until size >= N (phase 2 only)
+        int J = m - 1;
+        if (phase == 2) {
+            for (int e = tid; e < m; e += nt) {
+                const int k = S.pidx[S.ordPos[e]];
+                S.flag[e] = (S.cc[4 * k] > 0) + (S.cc[4 * k + 1] > 0) + (S.cc[4 * k + 2] > 0) + (S.cc[4 * k + 3] > 0) - 1;
+            }
+            __syncthreads();
+            block_excl_scan(S.flag, m, S.ws);  // flag[e] = growth before e
+            if (tid == 0) s_J = m - 1;
+            __syncthreads();
+            for (int e = tid; e < m; e += nt) {
+                const int k = S.pidx[S.ordPos[e]];
+                const int nz = (S.cc[4 * k] > 0) + (S.cc[4 * k + 1] > 0) + (S.cc[4 * k + 2] > 0) + (S.cc[4 * k + 3] > 0);
+                const int before = size + S.flag[e], after = before + nz - 1;
+                if (before < N && after >= N) s_J = e;  // unique: first e reaching N
+            }
+            __syncthreads();
+            J = s_J;
+            __syncthreads();
+        }
+        // 5. creation index of every child of the divided nodes
+        for (int k = tid; k < 4 * (J + 1); k += nt) {
+            const int e = k >> 2, q = k & 3;
+            S.flag[k] = S.cc[4 * S.pidx[S.ordPos[e]] + q] > 0;
+        }
+        __syncthreads();
+        const int created = block_excl_scan(S.flag, 4 * (J + 1), S.ws);
+        // 6. survivors keep their relative order behind the new children
+        for (int p = tid; p < size; p += nt) S.surv[p] = !(eligible(p) && S.rank[S.pidx[p]] <= J);
+        __syncthreads();
+        const int nsurv = block_excl_scan(S.surv, size, S.ws);
+        const int newSize = created + nsurv;
+        // 7. build the new list (position = created-1-creationIdx for children)
+        for (int k = tid; k < 4 * (J + 1); k += nt) {
+            const int e = k >> 2, q = k & 3;
+            const int p = S.ordPos[e];
+            const int c = S.cc[4 * S.pidx[p] + q];
+            if (c > 0) {
+                const int np = created - 1 - S.flag[k];
+                rect2[np] = child_rect(rect[p], q);
+                cnt2[np] = c;
+            }
+        }
+        for (int p = tid; p < size; p += nt)
+            if (!(eligible(p) && S.rank[S.pidx[p]] <= J)) {
+                const int np = created + S.surv[p];
+                rect2[np] = rect[p];
+                cnt2[np] = cnt[p];
+            }
+        // 8. move the keys
+        for (int i = tid; i < n; i += nt) {
+            const int p = node[i];
+            int np;
+            if (eligible(p) && S.rank[S.pidx[p]] <= J) {
+                const uint32_t r = rec[i];
+                const int q = quadrant_of(rect[p], r & 0xfff, (r >> 12) & 0xfff);
+                np = created - 1 - S.flag[4 * S.rank[S.pidx[p]] + q];
+            } else
+                np = created + S.surv[p];
+            node[i] = (unsigned short)np;
+        }
+        __syncthreads();
+        // 9. termination / phase switch (src/ORBextractor.cc:641-700)
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        int nexp = 0;
+        for (int p = tid; p < created; p += nt) nexp += cnt2[p] > 1;
+        if (nexp) atomicAdd(&s_m, nexp);
+        __syncthreads();
+        if (tid == 0) {
+            const int nToExpand = s_m;
+            if (newSize >= N || newSize == size)
+                s_finish = 1;
+            else if (phase == 1 && newSize + nToExpand * 3 > N)
+                s_phase = 2;
+            s_size = newSize;
+            s_clast = created;
+        }
+        cur ^= 1;
+        __syncthreads();
+        if (s_finish) break;
+    }
+    __syncthreads();
+    // ---- best key per node: max response, first in candidate order on ties (src/ORBextractor.cc:702-718)
+    const int size = s_size;
+    int *best = S.pidx;
+    for (int p = tid; p < size; p += nt) best[p] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicMax(&best[node[i]], (int)(((rec[i] >> 24) << 16) | (0xffffu - (unsigned)i)));
+    __syncthreads();
+    if (size > L.kpCap) {
+        if (tid == 0) {
+            atomicExch(err, 2);
+            lvlCount[frame * nlevels + level] = 0;
+        }
+        return;
+    }
+    LevelKp *out = lvlKps + (size_t)frame * kpCapTotal + L.kpBase;
+    for (int p = tid; p < size; p += nt) {
+        const uint32_t r = rec[0xffff - (best[p] & 0xffff)];
+        LevelKp k;
+        k.x = (short)((r & 0xfff) + MIN_BORDER);
+        k.y = (short)(((r >> 12) & 0xfff) + MIN_BORDER);
+        k.score = (short)((r >> 24) - 1);
+        k.level = (short)level;
+        out[p] = k;
+    }
+    if (tid == 0) lvlCount[frame * nlevels + level] = size;
+}
+
+// ------------------------------------------------------------------------------------------ O6
+// cv::GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101, 8.8 fixed-point taps {18,34,48,56,48,34,18}.
+constexpr int BLUR_TW = 64, BLUR_TH = 16;
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * (len - 1) - p;
+    return p;
+}
+__global__ void __launch_bounds__(256)
+    k_blur(const LevelInfo *__restrict__ lv, const int *__restrict__ tileBase, int nlevels,
+           const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, size_t frameStride) {
+    __shared__ uint8_t in[(BLUR_TH + 6)][BLUR_TW + 8];
+    __shared__ uint16_t hz[(BLUR_TH + 6)][BLUR_TW];
+    int level = 0;
+    while (level + 1 < nlevels && (int)blockIdx.x >= tileBase[level + 1]) level++;
+    const LevelInfo L = lv[level];
+    const int t = blockIdx.x - tileBase[level];
+    const int tilesX = (L.w + BLUR_TW - 1) / BLUR_TW;
+    const int tx = (t % tilesX) * BLUR_TW, ty = (t / tilesX) * BLUR_TH;
+    const uint8_t *src = pyr + blockIdx.y * frameStride + L.offset;
+    const int tid = threadIdx.x;
+    for (int p = tid; p < (BLUR_TH + 6) * (BLUR_TW + 6); p += 256) {
+        int ry = p / (BLUR_TW + 6), rx = p - ry * (BLUR_TW + 6);
+        int gy = reflect101(ty + ry - 3, L.h), gx = reflect101(tx + rx - 3, L.w);
+        in[ry][rx] = src[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    for (int p = tid; p < (BLUR_TH + 6) * BLUR_TW; p += 256) {
+        int ry = p / BLUR_TW, rx = p - ry * BLUR_TW;
+        const uint8_t *r = &in[ry][rx];
+        hz[ry][rx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    }
+    __syncthreads();
+    uint8_t *dst = blur + blockIdx.y * frameStride + L.offset;
+    for (int p = tid; p < BLUR_TH * BLUR_TW; p += 256) {
+        int ry = p / BLUR_TW, rx = p - ry * BLUR_TW;
+        int gx = tx + rx, gy = ty + ry;
+        if (gx < L.w && gy < L.h) {
+            uint32_t acc = 18u * (hz[ry][rx] + hz[ry + 6][rx]) + 34u * (hz[ry + 1][rx] + hz[ry + 5][rx]) +
+                           48u * (hz[ry + 2][rx] + hz[ry + 4][rx]) + 56u * hz[ry + 3][rx];
+            dst[(size_t)gy * L.pitch + gx] = (uint8_t)((acc + (1u << 15)) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ O5 + O7 + O8
+// cv::fastAtan2 (scalar atan_f32): 7th-order odd polynomial in degrees; no FMA (file built -fmad=false).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = 0.9997878412794807f * (float)(180 / 3.14159265358979323846);
+    const float p3 = -0.3258083974640975f * (float)(180 / 3.14159265358979323846);
+    const float p5 = 0.1555786518463281f * (float)(180 / 3.14159265358979323846);
+    const float p7 = -0.04432655554792128f * (float)(180 / 3.14159265358979323846);
+    const float eps = (float)2.2204460492503131e-16;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// One warp per keypoint.  Level offsets come from an in-kernel prefix over the per-level counts.
+__global__ void __launch_bounds__(256)
+    k_describe(const LevelInfo *__restrict__ lv, int nlevels, const uint8_t *__restrict__ pyr,
+               const uint8_t *__restrict__ blur, size_t frameStride, const LevelKp *__restrict__ lvlKps,
+               const int *__restrict__ lvlCount, int kpCapTotal, int capOut, msl_keypoint *__restrict__ kps,
+               uint8_t *__restrict__ desc, int *__restrict__ counts, int *__restrict__ err) {
+    __shared__ int8_t pat[1024];  // transposed: pat[(k*4 + c)*32 + byte] -> conflict-free per-lane reads
+    __shared__ int lvlOff[MAX_LEVELS + 1];
+    const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 1024; i += 256) {
+        // source layout: byte b (0..31), test k (0..7), component c (x0,y0,x1,y1) at b*32 + k*4 + c
+        int b = i >> 5, kc = i & 31;
+        pat[kc * 32 + b] = c_pattern.v[i];
+    }
+    if (tid == 0) {
+        int o = 0;
+        for (int l = 0; l < nlevels; l++) {
+            lvlOff[l] = o;
+            o += lvlCount[frame * nlevels + l];
+        }
+        lvlOff[nlevels] = o;
+        if (blockIdx.x == 0) {
+            counts[frame] = min(o, capOut);
+            if (o > capOut) atomicExch(err, 3);
+        }
+    }
+    __syncthreads();
+    const int total = min(lvlOff[nlevels], capOut);
+    for (int k = blockIdx.x * 8 + wid; k < total; k += gridDim.x * 8) {
+        int level = 0;
+        while (level + 1 < nlevels && k >= lvlOff[level + 1]) level++;
+        const LevelInfo L = lv[level];
+        const LevelKp kp = lvlKps[(size_t)frame * kpCapTotal + L.kpBase + (k - lvlOff[level])];
+        // IC_Angle (src/ORBextractor.cc:75-99): lanes = columns u in [-15,15], loop rows v
+        const uint8_t *img = pyr + frame * frameStride + L.offset + (size_t)kp.y * L.pitch + kp.x;
+        const int u = lane - HALF_PATCH;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+#pragma unroll 1
+            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+                if (abs(u) <= c_umax[abs(v)]) {
+                    const int val = img[v * L.pitch + u];
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // computeOrbDescriptor (src/ORBextractor.cc:104-149): a=cosf(angle*pi/180), b=sinf(..)
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        const float ang = __fmul_rn(angle, factorPI);
+        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        const uint8_t *ctr = blur + frame * frameStride + L.offset + (size_t)kp.y * L.pitch + kp.x;
+        int val = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const float x0 = (float)pat[(t * 4 + 0) * 32 + lane], y0 = (float)pat[(t * 4 + 1) * 32 + lane];
+            const float x1 = (float)pat[(t * 4 + 2) * 32 + lane], y1 = (float)pat[(t * 4 + 3) * 32 + lane];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = ctr[r0 * L.pitch + c0], t1 = ctr[r1 * L.pitch + c1];
+            val |= (t0 < t1) << t;
+        }
+        desc[((size_t)frame * capOut + k) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            msl_keypoint o;
+            float fx = (float)kp.x, fy = (float)kp.y;
+            if (level != 0) {  // src/ORBextractor.cc:861-866
+                fx = __fmul_rn(fx, L.scale);
+                fy = __fmul_rn(fy, L.scale);
+            }
+            o.x = fx;
+            o.y = fy;
+            o.size = (float)L.scaledPatch;
+            o.angle = angle;
+            o.response = (float)kp.score;
+            o.octave = level;
+            o.class_id = -1;
+            kps[(size_t)frame * capOut + k] = o;
+        }
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+struct msl_orb {
+    msl_orb_params prm;
+    int w, h, maxBatch, device;
+    cudaStream_t stream = nullptr;
+    int nlevels;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> featPerLevel;
+    std::vector<LevelInfo> lv;
+    std::vector<int> blurTileBase;
+    int totalCells = 0, capCell = 0, kpCapTotal = 0, capOut = 0, maxNodes = 0, blurTiles = 0;
+    size_t pyrBytes = 0;
+    size_t octSmem = 0;
+    // device
+    LevelInfo *d_lv = nullptr;
+    Cell *d_cells = nullptr;
+    short *d_cellLevel = nullptr, *d_tab = nullptr;
+    int *d_blurTileBase = nullptr;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    uint32_t *d_staging = nullptr, *d_candRec = nullptr;
+    unsigned short *d_candNode = nullptr;
+    int *d_cellCount = nullptr, *d_candCount = nullptr, *d_lvlCount = nullptr, *d_err = nullptr;
+    LevelKp *d_lvlKps = nullptr;
+    msl_keypoint *d_kps = nullptr;
+    uint8_t *d_desc = nullptr;
+    int *d_counts = nullptr;
+    int lastBatch = 0;
+};
+
+static void orb_free(msl_orb *o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    void *ptrs[] = {o->d_lv, o->d_cells, o->d_cellLevel, o->d_tab, o->d_blurTileBase, o->d_pyr, o->d_blur,
+                    o->d_staging, o->d_candRec, o->d_candNode, o->d_cellCount, o->d_candCount, o->d_lvlCount,
+                    o->d_err, o->d_lvlKps, o->d_kps, o->d_desc, o->d_counts};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (o->stream) cudaStreamDestroy(o->stream);
+    delete o;
+}
+
+extern "C" {
+
+const char *msl_last_error(void) { return g_last_error.c_str(); }
+const char *msl_version(void) { return "manhattanslam_b200 0.1 (sm_100a)"; }
+uint64_t msl_kernel_launch_count(void) { return g_launches.load(); }
+
+int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int device, msl_orb **out) {
+    if (!prm || !out) return fail(MSL_ERR_INVALID, "msl_orb_create: null argument");
+    *out = nullptr;
+    if (prm->nlevels < 1 || prm->nlevels > MAX_LEVELS || prm->nfeatures < 1 || !(prm->scale_factor > 1.0f) ||
+        w < 64 || h < 64 || w > 4095 || h > 4095 || max_batch < 1)
+        return fail(MSL_ERR_INVALID, "msl_orb_create: parameter out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0)
+        return fail(MSL_ERR_CUDA, "msl_orb_create: no usable CUDA device (there is no CPU fallback)");
+    MSL_CUDA(cudaSetDevice(device));
+    msl_orb *o = new msl_orb();
+    o->prm = *prm;
+    o->w = w, o->h = h, o->maxBatch = max_batch, o->device = device;
+    const int nl = o->nlevels = prm->nlevels;
+    // ---- ORBextractor::ORBextractor, src/ORBextractor.cc:412-445 (float/double mix kept literally)
+    const double scaleFactor = prm->scale_factor;
+    o->scale.resize(nl), o->invScale.resize(nl), o->sigma2.resize(nl), o->invSigma2.resize(nl);
+    o->scale[0] = 1.0f, o->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; i++) {
+        o->scale[i] = (float)(o->scale[i - 1] * scaleFactor);
+        o->sigma2[i] = o->scale[i] * o->scale[i];
+    }
+    for (int i = 0; i < nl; i++) {
+        o->invScale[i] = 1.0f / o->scale[i];
+        o->invSigma2[i] = 1.0f / o->sigma2[i];
+    }
+    o->featPerLevel.resize(nl);
+    {
+        float factor = (float)(1.0f / scaleFactor);
+        float nDesired = prm->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; l++) {
+            o->featPerLevel[l] = cv_round_f(nDesired);
+            sum += o->featPerLevel[l];
+            nDesired *= factor;
+        }
+        o->featPerLevel[nl - 1] = std::max(prm->nfeatures - sum, 0);
+    }
+    int umax[16];
+    {   // src/ORBextractor.cc:453-467
+        int v, v0, vmax = cv_floor_d(HALF_PATCH * sqrtf(2.f) / 2 + 1);
+        int vmin = cv_ceil_d(HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) umax[v] = (int)nearbyint(sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+    // ---- level geometry, resize tables, FAST cells
+    o->lv.resize(nl);
+    std::vector<short> tab;
+    std::vector<Cell> cells;
+    std::vector<short> cellLevel;
+    size_t off = 0;
+    int kpBase = 0, maxNodes = 0, capCell = 0, blurTiles = 0;
+    o->blurTileBase.resize(nl + 1);
+    for (int l = 0; l < nl; l++) {
+        LevelInfo &L = o->lv[l];
+        L.w = cv_round_f((float)w * o->invScale[l]);  // src/ORBextractor.cc:875
+        L.h = cv_round_f((float)h * o->invScale[l]);
+        L.pitch = (int)align_up(L.w, 16);
+        L.offset = (int)off;
+        off = align_up(off + (size_t)L.pitch * L.h, 256);
+        L.scale = o->scale[l];
+        L.scaledPatch = (int)(PATCH_SIZE * o->scale[l]);
+        L.nFeatures = o->featPerLevel[l];
+        const int maxBorderX = L.w - EDGE_THRESHOLD + 3, maxBorderY = L.h - EDGE_THRESHOLD + 3;
+        L.width = maxBorderX - MIN_BORDER, L.height = maxBorderY - MIN_BORDER;
+        const float W = 30;
+        const float width = (float)L.width, height = (float)L.height;
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        if (nCols < 1 || nRows < 1 || L.height <= 0) {
+            orb_free(o);
+            return fail(MSL_ERR_INVALID, "msl_orb_create: pyramid level too small for a 30-px FAST cell");
+        }
+        const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+        L.nIni = (int)roundf((float)L.width / (float)L.height);  // src/ORBextractor.cc:535
+        if (L.nIni < 1) {
+            orb_free(o);
+            return fail(MSL_ERR_INVALID, "msl_orb_create: aspect ratio gives zero octree roots");
+        }
+        L.hX = (float)L.width / L.nIni;
+        L.cellBase = (int)cells.size();
+        for (int i = 0; i < nRows; i++) {  // src/ORBextractor.cc:745-761
+            const float iniY = (float)(MIN_BORDER + i * hCell);
+            float maxY = iniY + hCell + 6;
+            if (iniY >= maxBorderY - 3) continue;
+            if (maxY > maxBorderY) maxY = (float)maxBorderY;
+            for (int j = 0; j < nCols; j++) {
+                const float iniX = (float)(MIN_BORDER + j * wCell);
+                float maxX = iniX + wCell + 6;
+                if (iniX >= maxBorderX - 6) continue;
+                if (maxX > maxBorderX) maxX = (float)maxBorderX;
+                Cell c = {(short)iniX, (short)iniY, (short)maxX, (short)maxY};
+                if (c.x1 - c.x0 < 7 || c.y1 - c.y0 < 7) continue;  // cv::FAST on <7 px finds nothing
+                if (c.x1 - c.x0 > CELL_TILE || c.y1 - c.y0 > CELL_TILE) {
+                    orb_free(o);
+                    return fail(MSL_ERR_INVALID, "msl_orb_create: FAST cell exceeds tile");
+                }
+                cells.push_back(c);
+                cellLevel.push_back((short)l);
+            }
+        }
+        L.nCells = (int)cells.size() - L.cellBase;
+        capCell = std::max(capCell, ((wCell + 1) / 2) * ((hCell + 1) / 2));
+        L.kpCap = std::max(L.nFeatures + 3, 4 * L.nIni) + 1;
+        L.kpBase = kpBase;
+        kpBase += L.kpCap;
+        maxNodes = std::max(maxNodes, L.kpCap + 1);
+        o->blurTileBase[l] = blurTiles;
+        blurTiles += cdiv(L.w, BLUR_TW) * cdiv(L.h, BLUR_TH);
+        // resize tables for level l from level l-1 (cv::resize, imgproc/resize.cpp)
+        L.tabOff = (int)tab.size();
+        if (l > 0) {
+            const LevelInfo &P = o->lv[l - 1];
+            const double sx_ = 1. / ((double)L.w / P.w), sy_ = 1. / ((double)L.h / P.h);
+            std::vector<short> xo(L.w), a0(L.w), a1(L.w), yo(L.h), b0(L.h), b1(L.h);
+            for (int dx = 0; dx < L.w; dx++) {
+                float fx = (float)((dx + 0.5) * sx_ - 0.5);
+                int sx = cv_floor_d(fx);
+                fx -= sx;
+                if (sx < 0) fx = 0, sx = 0;
+                if (sx >= P.w - 1) fx = 0, sx = P.w - 1;
+                xo[dx] = (short)sx;
+                a0[dx] = sat_short((1.f - fx) * 2048);
+                a1[dx] = sat_short(fx * 2048);
+            }
+            for (int dy = 0; dy < L.h; dy++) {
+                float fy = (float)((dy + 0.5) * sy_ - 0.5);
+                int sy = cv_floor_d(fy);
+                fy -= sy;
+                yo[dy] = (short)sy;
+                b0[dy] = sat_short((1.f - fy) * 2048);
+                b1[dy] = sat_short(fy * 2048);
+            }
+            for (auto *v : {&xo, &a0, &a1, &yo, &b0, &b1}) tab.insert(tab.end(), v->begin(), v->end());
+        }
+    }
+    o->blurTileBase[nl] = blurTiles;
+    o->blurTiles = blurTiles;
+    o->pyrBytes = align_up(off, 256);
+    o->totalCells = (int)cells.size();
+    o->capCell = capCell;
+    o->kpCapTotal = kpBase;
+    o->capOut = kpBase;
+    o->maxNodes = maxNodes;
+    for (int l = 0; l < nl; l++)
+        if (o->lv[l].nCells > 4 * maxNodes) o->maxNodes = maxNodes = cdiv(o->lv[l].nCells, 4) + 1;
+    o->octSmem = (size_t)(2 * 2 + 2 + 4 + 8) * maxNodes * sizeof(int) + 64 * sizeof(int);
+    if (o->octSmem > 200 * 1024) {
+        orb_free(o);
+        return fail(MSL_ERR_INVALID, "msl_orb_create: nfeatures per level too large for the octree kernel");
+    }
+    if (tab.empty()) tab.push_back(0);
+    // ---- device allocations
+    const size_t B = max_batch;
+#define ALLOC(ptr, bytes)                                   \
+    do {                                                    \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes)); \
+        if (e_ != cudaSuccess) {                            \
+            orb_free(o);                                    \
+            return fail(MSL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); \
+        }                                                   \
+    } while (0)
+    ALLOC(o->d_lv, sizeof(LevelInfo) * nl);
+    ALLOC(o->d_cells, sizeof(Cell) * cells.size());
+    ALLOC(o->d_cellLevel, sizeof(short) * cells.size());
+    ALLOC(o->d_tab, sizeof(short) * tab.size());
+    ALLOC(o->d_blurTileBase, sizeof(int) * (nl + 1));
+    ALLOC(o->d_pyr, B * o->pyrBytes);
+    ALLOC(o->d_blur, B * o->pyrBytes);
+    ALLOC(o->d_staging, B * o->totalCells * (size_t)capCell * sizeof(uint32_t));
+    ALLOC(o->d_candRec, B * nl * (size_t)CAND_CAP * sizeof(uint32_t));
+    ALLOC(o->d_candNode, B * nl * (size_t)CAND_CAP * sizeof(unsigned short));
+    ALLOC(o->d_cellCount, B * o->totalCells * sizeof(int));
+    ALLOC(o->d_candCount, B * nl * sizeof(int));
+    ALLOC(o->d_lvlCount, B * nl * sizeof(int));
+    ALLOC(o->d_err, sizeof(int));
+    ALLOC(o->d_lvlKps, B * o->kpCapTotal * sizeof(LevelKp));
+    ALLOC(o->d_kps, B * o->capOut * sizeof(msl_keypoint));
+    ALLOC(o->d_desc, B * o->capOut * 32);
+    ALLOC(o->d_counts, B * sizeof(int));
+#undef ALLOC
+    MSL_CUDA(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking));
+    MSL_CUDA(cudaMemcpy(o->d_lv, o->lv.data(), sizeof(LevelInfo) * nl, cudaMemcpyHostToDevice));
+    MSL_CUDA(cudaMemcpy(o->d_cells, cells.data(), sizeof(Cell) * cells.size(), cudaMemcpyHostToDevice));
+    MSL_CUDA(cudaMemcpy(o->d_cellLevel, cellLevel.data(), sizeof(short) * cells.size(), cudaMemcpyHostToDevice));
+    MSL_CUDA(cudaMemcpy(o->d_tab, tab.data(), sizeof(short) * tab.size(), cudaMemcpyHostToDevice));
+    MSL_CUDA(cudaMemcpy(o->d_blurTileBase, o->blurTileBase.data(), sizeof(int) * (nl + 1), cudaMemcpyHostToDevice));
+    MSL_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
+    MSL_CUDA(cudaMemset(o->d_err, 0, sizeof(int)));
+    MSL_CUDA(cudaMemset(o->d_pyr, 0, B * o->pyrBytes));
+    MSL_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->octSmem));
+    *out = o;
+    return MSL_OK;
+}
+
+void msl_orb_destroy(msl_orb *o) { orb_free(o); }
+int msl_orb_levels(const msl_orb *o) { return o ? o->nlevels : 0; }
+int msl_orb_capacity(const msl_orb *o) { return o ? o->capOut : 0; }
+void *msl_orb_stream(msl_orb *o) { return o ? (void *)o->stream : nullptr; }
+
+int msl_orb_scale_factors(const msl_orb *o, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2) {
+    if (!o) return fail(MSL_ERR_INVALID, "null handle");
+    for (int i = 0; i < o->nlevels; i++) {
+        if (scale) scale[i] = o->scale[i];
+        if (inv_scale) inv_scale[i] = o->invScale[i];
+        if (sigma2) sigma2[i] = o->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = o->invSigma2[i];
+    }
+    return MSL_OK;
+}
+
+// Enqueue the whole pipeline; level 0 of every frame must already be in d_pyr.
+static int orb_run(msl_orb *o, int batch, msl_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts) {
+    cudaStream_t st = o->stream;
+    const int nl = o->nlevels;
+    for (int l = 1; l < nl; l++) {
+        dim3 g(cdiv(o->lv[l].w, 32), cdiv(o->lv[l].h, 8), batch);
+        k_resize<<<g, dim3(32, 8), 0, st>>>(o->d_lv, l, o->d_pyr, o->pyrBytes, o->d_tab);
+        MSL_LAUNCH_CHECK();
+    }
+    k_fast_cells<<<dim3(o->totalCells, batch), 128, 0, st>>>(o->d_lv, o->d_cells, o->d_cellLevel, o->d_pyr,
+                                                             o->pyrBytes, o->totalCells, o->capCell,
+                                                             o->prm.ini_th_fast, o->prm.min_th_fast, o->d_staging,
+                                                             o->d_cellCount);
+    MSL_LAUNCH_CHECK();
+    k_octree<<<dim3(nl, batch), 256, o->octSmem, st>>>(o->d_lv, nl, o->totalCells, o->capCell, o->d_staging,
+                                                       o->d_cellCount, o->d_candRec, o->d_candNode, o->d_candCount,
+                                                       o->d_lvlKps, o->d_lvlCount, o->kpCapTotal, o->maxNodes,
+                                                       o->d_err);
+    MSL_LAUNCH_CHECK();
+    k_blur<<<dim3(o->blurTiles, batch), 256, 0, st>>>(o->d_lv, o->d_blurTileBase, nl, o->d_pyr, o->d_blur,
+                                                      o->pyrBytes);
+    MSL_LAUNCH_CHECK();
+    k_describe<<<dim3(cdiv(o->capOut, 8), batch), 256, 0, st>>>(o->d_lv, nl, o->d_pyr, o->d_blur, o->pyrBytes,
+                                                                o->d_lvlKps, o->d_lvlCount, o->kpCapTotal, o->capOut,
+                                                                d_kps, d_desc, d_counts, o->d_err);
+    MSL_LAUNCH_CHECK();
+    o->lastBatch = batch;
+    return MSL_OK;
+}
+
+static int orb_check_err(msl_orb *o) {
+    int e = 0;
+    MSL_CUDA(cudaMemcpyAsync(&e, o->d_err, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    MSL_CUDA(cudaStreamSynchronize(o->stream));
+    if (e) {
+        cudaMemsetAsync(o->d_err, 0, sizeof(int), o->stream);
+        return fail(MSL_ERR_CAPACITY, e == 1   ? "ORB: more than 16384 FAST candidates on one pyramid level"
+                                      : e == 2 ? "ORB: octree produced more nodes than the level capacity"
+                                               : "ORB: keypoint output capacity exceeded");
+    }
+    return MSL_OK;
+}
+
+int msl_orb_extract_dev(msl_orb *o, const uint8_t *d_gray, int stride, size_t frame_stride, int batch,
+                        msl_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts) {
+    if (!o || !d_gray || !d_kps || !d_desc || !d_counts) return fail(MSL_ERR_INVALID, "msl_orb_extract_dev: null argument");
+    if (batch < 1 || batch > o->maxBatch || stride < o->w) return fail(MSL_ERR_INVALID, "msl_orb_extract_dev: bad batch/stride");
+    MSL_CUDA(cudaSetDevice(o->device));
+    const int vec = (o->w % 16 == 0) && (stride % 16 == 0) && (frame_stride % 16 == 0) && (((uintptr_t)d_gray) % 16 == 0);
+    k_load_level0<<<dim3(cdiv(o->w, 256 * 16), o->h, batch), 256, 0, o->stream>>>(d_gray, stride, frame_stride, o->d_pyr,
+                                                                               o->lv[0].pitch, o->pyrBytes, o->w, o->h, vec);
+    MSL_LAUNCH_CHECK();
+    return orb_run(o, batch, d_kps, d_desc, d_counts);
+}
+
+int msl_orb_sync(msl_orb *o) {
+    if (!o) return fail(MSL_ERR_INVALID, "null handle");
+    MSL_CUDA(cudaSetDevice(o->device));
+    return orb_check_err(o);
+}
+
+int msl_orb_extract(msl_orb *o, const uint8_t *gray, int stride, size_t frame_stride, int batch, msl_keypoint *kps,
+                    uint8_t *desc, int32_t *counts) {
+    if (!o || !kps || !desc || !counts) return fail(MSL_ERR_INVALID, "msl_orb_extract: null argument");
+    if (batch < 1 || batch > o->maxBatch) return fail(MSL_ERR_INVALID, "msl_orb_extract: bad batch");
+    if (!gray) {  // _image.empty() => silent return, src/ORBextractor.cc:815-816
+        for (int b = 0; b < batch; b++) counts[b] = 0;
+        return MSL_OK;
+    }
+    if (stride < o->w) return fail(MSL_ERR_INVALID, "msl_orb_extract: stride < width");
+    MSL_CUDA(cudaSetDevice(o->device));
+    if (stride == o->w && o->lv[0].pitch == o->w) {  // dense frames: one strided copy, one "row" per frame
+        MSL_CUDA(cudaMemcpy2DAsync(o->d_pyr, o->pyrBytes, gray, frame_stride, (size_t)o->w * o->h, batch,
+                                   cudaMemcpyHostToDevice, o->stream));
+    } else {
+        for (int b = 0; b < batch; b++)
+            MSL_CUDA(cudaMemcpy2DAsync(o->d_pyr + b * o->pyrBytes, o->lv[0].pitch, gray + b * frame_stride, stride,
+                                       o->w, o->h, cudaMemcpyHostToDevice, o->stream));
+    }
+    int rc = orb_run(o, batch, o->d_kps, o->d_desc, o->d_counts);
+    if (rc) return rc;
+    MSL_CUDA(cudaMemcpyAsync(counts, o->d_counts, sizeof(int) * batch, cudaMemcpyDeviceToHost, o->stream));
+    MSL_CUDA(cudaMemcpyAsync(kps, o->d_kps, sizeof(msl_keypoint) * (size_t)batch * o->capOut, cudaMemcpyDeviceToHost, o->stream));
+    MSL_CUDA(cudaMemcpyAsync(desc, o->d_desc, (size_t)batch * o->capOut * 32, cudaMemcpyDeviceToHost, o->stream));
+    return orb_check_err(o);
+}
+
+int msl_orb_debug_level_size(const msl_orb *o, int level, int *w, int *h) {
+    if (!o || level < 0 || level >= o->nlevels) return fail(MSL_ERR_INVALID, "bad level");
+    *w = o->lv[level].w, *h = o->lv[level].h;
+    return MSL_OK;
+}
+
+int msl_orb_debug_level(msl_orb *o, int frame, int level, int blurred, uint8_t *out) {
+    if (!o || level < 0 || level >= o->nlevels || frame < 0 || frame >= o->maxBatch) return fail(MSL_ERR_INVALID, "bad level/frame");
+    MSL_CUDA(cudaSetDevice(o->device));
+    const LevelInfo &L = o->lv[level];
+    const uint8_t *src = (blurred ? o->d_blur : o->d_pyr) + frame * o->pyrBytes + L.offset;
+    MSL_CUDA(cudaStreamSynchronize(o->stream));
+    MSL_CUDA(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return MSL_OK;
+}
+
+int msl_orb_debug_candidates(msl_orb *o, int frame, int level, int32_t *xyr, int cap, int *n) {
+    if (!o || level < 0 || level >= o->nlevels || frame < 0 || frame >= o->maxBatch) return fail(MSL_ERR_INVALID, "bad level/frame");
+    MSL_CUDA(cudaSetDevice(o->device));
+    MSL_CUDA(cudaStreamSynchronize(o->stream));
+    int cnt = 0;
+    MSL_CUDA(cudaMemcpy(&cnt, o->d_candCount + frame * o->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    int m = std::min(std::min(cnt, cap), CAND_CAP);
+    std::vector<uint32_t> rec(m);
+    if (m) MSL_CUDA(cudaMemcpy(rec.data(), o->d_candRec + ((size_t)frame * o->nlevels + level) * CAND_CAP, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) {
+        xyr[3 * i] = rec[i] & 0xfff;
+        xyr[3 * i + 1] = (rec[i] >> 12) & 0xfff;
+        xyr[3 * i + 2] = (int)(rec[i] >> 24) - 1;
+    }
+    return MSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""Seeded synthetic RGB-D inputs: identical bytes feed the CPU oracle and the
+CUDA path in tests and bench.  numpy only."""
+import numpy as np
+
+K_DEFAULT = (525.0, 525.0, 319.5, 239.5)  # fx, fy, cx, cy (Example/TUM3.yaml-style, no distortion)
+
+
+def gray_frame(seed, w=640, h=480):
+    """128 base + 300 random axis-aligned rectangles (8-80 px, delta U(-60,60)) + N(0,2) noise, u8."""
+    r = np.random.default_rng(seed)
+    img = np.full((h, w), 128, np.float32)
+    for _ in range(300):
+        rw, rh = r.integers(8, 81, 2)
+        x = r.integers(0, w)
+        y = r.integers(0, h)
+        img[y:y + rh, x:x + rw] += r.uniform(-60, 60)
+    img += r.normal(0, 2, (h, w)).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def gray_batch(seed0, batch, w=640, h=480):
+    return np.stack([gray_frame(seed0 + i, w, h) for i in range(batch)])
+
+
+def depth_frame(seed, w=640, h=480, K=K_DEFAULT, holes=True):
+    """Piecewise-planar scene: 3-6 random planes (normals within 60 deg of -z, 0.8-4 m) z-buffered
+    through K, + N(0,(1.5e-3 z^2)) noise, 2 % zero holes in 8x8 patches, quantised to u16 (factor 5000).
+    Returns (depth_u16, depth_f32_metres)."""
+    r = np.random.default_rng(seed + 100003)
+    fx, fy, cx, cy = [k * (w / 640.0) for k in K]
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    rx, ry = (u - cx) / fx, (v - cy) / fy
+    z = np.full((h, w), np.inf)
+    for _ in range(int(r.integers(3, 7))):
+        ang = np.deg2rad(r.uniform(0, 60))
+        az = r.uniform(0, 2 * np.pi)
+        n = np.array([np.sin(ang) * np.cos(az), np.sin(ang) * np.sin(az), -np.cos(ang)])
+        d0 = r.uniform(0.8, 4.0)
+        # plane through (x0, y0, d0) on a random ray
+        px, py = r.uniform(-0.5, 0.5), r.uniform(-0.4, 0.4)
+        p0 = np.array([px * d0, py * d0, d0])
+        denom = n[0] * rx + n[1] * ry + n[2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            zz = (n @ p0) / denom
+        zz[(zz < 0.4) | ~np.isfinite(zz)] = np.inf
+        # each plane covers a random half-plane/rectangle so that several stay visible
+        x0, x1 = sorted(r.integers(0, w, 2))
+        y0, y1 = sorted(r.integers(0, h, 2))
+        if x1 - x0 < w // 3:
+            x0, x1 = 0, w
+        if y1 - y0 < h // 3:
+            y0, y1 = 0, h
+        m = np.zeros((h, w), bool)
+        m[y0:y1, x0:x1] = True
+        zz[~m] = np.inf
+        z = np.minimum(z, zz)
+    z[~np.isfinite(z)] = 4.5
+    z = z + r.normal(0, 1.0, (h, w)) * (1.5e-3 * z * z)
+    if holes:
+        nh = int(0.02 * (w // 8) * (h // 8))
+        for _ in range(nh):
+            x = int(r.integers(0, w // 8)) * 8
+            y = int(r.integers(0, h // 8)) * 8
+            z[y:y + 8, x:x + 8] = 0
+    d16 = np.clip(np.rint(z * 5000.0), 0, 65535).astype(np.uint16)
+    # Tracking::GrabImage: imDepth.convertTo(CV_32F, mDepthMapFactor) with factor 1/5000 (src/Tracking.cc:133-137,205-207)
+    dep = (d16.astype(np.float32) * np.float32(1.0 / 5000.0)).astype(np.float32)
+    return d16, dep
+
+
+def membership(seed, w=640, h=480, plane_fraction=0.0):
+    """Half-resolution CV_32SC1 plane membership image: -1 = no plane.  plane_fraction of the pixels
+    (as 20x20 half-res patches) are assigned plane id 0."""
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    m = np.full((h2, w2), -1, np.int32)
+    if plane_fraction > 0:
+        r = np.random.default_rng(seed + 7)
+        n = int(plane_fraction * (w2 // 20) * (h2 // 20))
+        for _ in range(n):
+            x = int(r.integers(0, w2 // 20)) * 20
+            y = int(r.integers(0, h2 // 20)) * 20
+            m[y:y + 20, x:x + 20] = 0
+    return m
+
+
+def pose_walk(seed, n):
+    """Twc random walk (<= 2 cm, <= 1 deg per frame) from identity, float32 row-major 4x4."""
+    r = np.random.default_rng(seed + 31)
+    T = np.eye(4)
+    out = []
+    for _ in range(n):
+        ax = r.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        a = np.deg2rad(r.uniform(0, 1.0))
+        Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = np.eye(3) + np.sin(a) * Kx + (1 - np.cos(a)) * Kx @ Kx
+        dT = np.eye(4)
+        dT[:3, :3] = R
+        dT[:3, 3] = r.uniform(-0.02, 0.02, 3) / np.sqrt(3)
+        T = T @ dT
+        out.append(T.astype(np.float32))
+    return np.stack(out)
+
+
+SURFEL_DTYPE = np.dtype([("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                         ("size", "<f4"), ("color", "<f4"), ("r", "<i4"), ("g", "<i4"), ("b", "<i4"),
+                         ("weight", "<f4"), ("updateTimes", "<i4"), ("lastUpdate", "<i4")])
+
+
+def surfel_map(seed, n, depth_f32, Twc, K=K_DEFAULT, ref_index=100, w=640, h=480):
+    """n surfels sampled on the surface seen in depth_f32 from pose Twc (plus out-of-frustum and
+    perturbed ones): ~35 % project into the frame and agree with the depth, ~10 % hit the
+    unstable-drop rule (lastUpdate old, few updates), the rest are outside the frustum."""
+    r = np.random.default_rng(seed + 1234)
+    fx, fy, cx, cy = K
+    s = np.zeros(n, SURFEL_DTYPE)
+    u = r.uniform(-0.9 * w, 1.9 * w, n)
+    v = r.uniform(-0.9 * h, 1.9 * h, n)
+    ui = np.clip(np.rint(u), 1, w - 2).astype(np.int64)
+    vi = np.clip(np.rint(v), 1, h - 2).astype(np.int64)
+    z = depth_f32[vi, ui].astype(np.float64)
+    z = np.where(z > 0.1, z, r.uniform(0.8, 4.0, n))
+    z = z + r.normal(0, 0.01, n) + (r.random(n) < 0.05) * r.uniform(-1.5, 1.5, n)
+    z = np.maximum(z, 0.3)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z, np.ones(n)], 1)
+    pw = pc @ Twc.astype(np.float64).T
+    s["px"], s["py"], s["pz"] = pw[:, 0], pw[:, 1], pw[:, 2]
+    nc = np.stack([r.normal(0, 0.25, n), r.normal(0, 0.25, n), -np.ones(n)], 1)
+    nc /= np.linalg.norm(nc, axis=1, keepdims=True)
+    nw = nc @ Twc[:3, :3].astype(np.float64).T
+    s["nx"], s["ny"], s["nz"] = nw[:, 0], nw[:, 1], nw[:, 2]
+    s["size"] = r.uniform(0.005, 0.05, n)
+    s["color"] = r.uniform(0, 255, n)
+    s["r"] = r.integers(0, 256, n)
+    s["g"] = r.integers(0, 256, n)
+    s["b"] = r.integers(0, 256, n)
+    s["weight"] = r.uniform(1, 20, n)
+    s["updateTimes"] = r.integers(1, 31, n)
+    s["lastUpdate"] = ref_index - r.integers(0, 9, n)
+    return s
