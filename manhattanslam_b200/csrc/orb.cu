@@ -33,7 +33,6 @@ constexpr int HALF_PATCH = 15;
 constexpr int MIN_BORDER = EDGE_THRESHOLD - 3;  // 16
 constexpr int MAX_LEVELS = 16;
 constexpr int CELL_TILE = 68;  // max ROI edge (wCell < 60, +6 ring, rounded)
-constexpr int CAND_CAP = 16384;  // FAST candidates per (frame, level) fed to the octree
 
 struct LevelInfo {
     int w, h, pitch;     // level image size and row pitch (bytes)
@@ -46,6 +45,7 @@ struct LevelInfo {
     int tabOff;          // offset (in shorts) of the resize tables of this level
     float scale;         // mvScaleFactor[level]
     int kpBase, kpCap;   // slot range of this level in the per-frame level-keypoint array
+    int candBase, candCap;  // slot range of this level in the per-frame candidate arrays (nCells*capCell: cannot overflow)
     int scaledPatch;     // (int)(31 * mvScaleFactor)
 };
 
@@ -151,13 +151,20 @@ __device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch) {
         lo4[i] = min(lo2[i], lo2[(i + 2) & 15]);
         hi4[i] = max(hi2[i], hi2[(i + 2) & 15]);
     }
-    int best = 0;
+    // NOTE: the two polarities are reduced separately and combined once at the end.  Folding them as
+    // max(best, max(lo9, -hi9)) inside the loop is miscompiled by ptxas 12.9 for sm_100a (a negated
+    // operand feeding a fused 3-input VIMNMX3; repro in tools/ptxas_vimnmx3_repro.cu).
+    int a = lo4[0], b = hi4[0];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        int lo9 = min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
-        int hi9 = max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
-        best = max(best, max(lo9, -hi9));
+        const int lo9 = min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
+        const int hi9 = max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
+        a = (i == 0) ? lo9 : max(a, lo9);
+        b = (i == 0) ? hi9 : min(b, hi9);
     }
+    const int dark = 0 - b;
+    int best = a > dark ? a : dark;
+    best = best > 0 ? best : 0;
     return best;
 }
 
@@ -288,8 +295,8 @@ __global__ void __launch_bounds__(256)
     k_octree(const LevelInfo *__restrict__ lv, int nlevels, int totalCells, int capCell,
              const uint32_t *__restrict__ staging, const int *__restrict__ cellCount, uint32_t *__restrict__ candRec,
              unsigned short *__restrict__ candNode, int *__restrict__ candCount, LevelKp *__restrict__ lvlKps,
-             int *__restrict__ lvlCount, int kpCapTotal, int maxNodes, int *__restrict__ err) {
-    extern __shared__ int smem_raw[];
+             int *__restrict__ lvlCount, int kpCapTotal, int candCapTotal, int maxNodes, int *__restrict__ err) {
+    extern __shared__ __align__(16) int smem_raw[];
     const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     const LevelInfo L = lv[level];
     OctSmem S;
@@ -308,8 +315,8 @@ __global__ void __launch_bounds__(256)
         S.ws = p; p += 40;
     }
     __shared__ int s_n, s_size, s_phase, s_clast, s_finish, s_J, s_m;
-    uint32_t *rec = candRec + ((size_t)frame * nlevels + level) * CAND_CAP;
-    unsigned short *node = candNode + ((size_t)frame * nlevels + level) * CAND_CAP;
+    uint32_t *rec = candRec + (size_t)frame * candCapTotal + L.candBase;
+    unsigned short *node = candNode + (size_t)frame * candCapTotal + L.candBase;
 
     // ---- gather the ordered candidate list: cells in (row, col) order, row-major inside a cell
     const int *cc = cellCount + (size_t)frame * totalCells + L.cellBase;
@@ -320,10 +327,9 @@ __global__ void __launch_bounds__(256)
     if (tid == 0) {
         s_n = n;
         candCount[frame * nlevels + level] = n;
-        if (n > CAND_CAP) atomicExch(err, 1);
     }
     __syncthreads();
-    if (n > CAND_CAP || n == 0) {
+    if (n == 0) {
         if (tid == 0) lvlCount[frame * nlevels + level] = 0;
         return;
     }
@@ -504,10 +510,11 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     // ---- best key per node: max response, first in candidate order on ties (src/ORBextractor.cc:702-718)
     const int size = s_size;
-    int *best = S.pidx;
-    for (int p = tid; p < size; p += nt) best[p] = 0;
+    unsigned long long *best = (unsigned long long *)S.cc;  // 8-byte aligned: offset is a multiple of 2 ints
+    for (int p = tid; p < size; p += nt) best[p] = 0ull;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) atomicMax(&best[node[i]], (int)(((rec[i] >> 24) << 16) | (0xffffu - (unsigned)i)));
+    for (int i = tid; i < n; i += nt)
+        atomicMax(&best[node[i]], ((unsigned long long)(rec[i] >> 24) << 32) | (0xffffffffu - (unsigned)i));
     __syncthreads();
     if (size > L.kpCap) {
         if (tid == 0) {
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(256)
     }
     LevelKp *out = lvlKps + (size_t)frame * kpCapTotal + L.kpBase;
     for (int p = tid; p < size; p += nt) {
-        const uint32_t r = rec[0xffff - (best[p] & 0xffff)];
+        const uint32_t r = rec[0xffffffffu - (unsigned)(best[p] & 0xffffffffull)];
         LevelKp k;
         k.x = (short)((r & 0xfff) + MIN_BORDER);
         k.y = (short)(((r >> 12) & 0xfff) + MIN_BORDER);
@@ -699,7 +706,7 @@ struct msl_orb {
     std::vector<int> featPerLevel;
     std::vector<LevelInfo> lv;
     std::vector<int> blurTileBase;
-    int totalCells = 0, capCell = 0, kpCapTotal = 0, capOut = 0, maxNodes = 0, blurTiles = 0;
+    int totalCells = 0, capCell = 0, kpCapTotal = 0, capOut = 0, maxNodes = 0, blurTiles = 0, candCapTotal = 0;
     size_t pyrBytes = 0;
     size_t octSmem = 0;
     // device
@@ -886,6 +893,15 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     o->maxNodes = maxNodes;
     for (int l = 0; l < nl; l++)
         if (o->lv[l].nCells > 4 * maxNodes) o->maxNodes = maxNodes = cdiv(o->lv[l].nCells, 4) + 1;
+    {   // candidate slots per level: every cell can hold at most capCell NMS survivors
+        int cb = 0;
+        for (int l = 0; l < nl; l++) {
+            o->lv[l].candBase = cb;
+            o->lv[l].candCap = o->lv[l].nCells * capCell;
+            cb += (o->lv[l].candCap + 3) & ~3;
+        }
+        o->candCapTotal = cb;
+    }
     o->octSmem = (size_t)(2 * 2 + 2 + 4 + 8) * maxNodes * sizeof(int) + 64 * sizeof(int);
     if (o->octSmem > 200 * 1024) {
         orb_free(o);
@@ -910,8 +926,8 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     ALLOC(o->d_pyr, B * o->pyrBytes);
     ALLOC(o->d_blur, B * o->pyrBytes);
     ALLOC(o->d_staging, B * o->totalCells * (size_t)capCell * sizeof(uint32_t));
-    ALLOC(o->d_candRec, B * nl * (size_t)CAND_CAP * sizeof(uint32_t));
-    ALLOC(o->d_candNode, B * nl * (size_t)CAND_CAP * sizeof(unsigned short));
+    ALLOC(o->d_candRec, B * (size_t)o->candCapTotal * sizeof(uint32_t));
+    ALLOC(o->d_candNode, B * (size_t)o->candCapTotal * sizeof(unsigned short));
     ALLOC(o->d_cellCount, B * o->totalCells * sizeof(int));
     ALLOC(o->d_candCount, B * nl * sizeof(int));
     ALLOC(o->d_lvlCount, B * nl * sizeof(int));
@@ -967,7 +983,7 @@ static int orb_run(msl_orb *o, int batch, msl_keypoint *d_kps, uint8_t *d_desc, 
     MSL_LAUNCH_CHECK();
     k_octree<<<dim3(nl, batch), 256, o->octSmem, st>>>(o->d_lv, nl, o->totalCells, o->capCell, o->d_staging,
                                                        o->d_cellCount, o->d_candRec, o->d_candNode, o->d_candCount,
-                                                       o->d_lvlKps, o->d_lvlCount, o->kpCapTotal, o->maxNodes,
+                                                       o->d_lvlKps, o->d_lvlCount, o->kpCapTotal, o->candCapTotal, o->maxNodes,
                                                        o->d_err);
     MSL_LAUNCH_CHECK();
     k_blur<<<dim3(o->blurTiles, batch), 256, 0, st>>>(o->d_lv, o->d_blurTileBase, nl, o->d_pyr, o->d_blur,
@@ -987,8 +1003,7 @@ static int orb_check_err(msl_orb *o) {
     MSL_CUDA(cudaStreamSynchronize(o->stream));
     if (e) {
         cudaMemsetAsync(o->d_err, 0, sizeof(int), o->stream);
-        return fail(MSL_ERR_CAPACITY, e == 1   ? "ORB: more than 16384 FAST candidates on one pyramid level"
-                                      : e == 2 ? "ORB: octree produced more nodes than the level capacity"
+        return fail(MSL_ERR_CAPACITY, e == 2 ? "ORB: octree produced more nodes than the level capacity"
                                                : "ORB: keypoint output capacity exceeded");
     }
     return MSL_OK;
@@ -1061,9 +1076,9 @@ int msl_orb_debug_candidates(msl_orb *o, int frame, int level, int32_t *xyr, int
     int cnt = 0;
     MSL_CUDA(cudaMemcpy(&cnt, o->d_candCount + frame * o->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
-    int m = std::min(std::min(cnt, cap), CAND_CAP);
+    int m = std::min(std::min(cnt, cap), o->lv[level].candCap);
     std::vector<uint32_t> rec(m);
-    if (m) MSL_CUDA(cudaMemcpy(rec.data(), o->d_candRec + ((size_t)frame * o->nlevels + level) * CAND_CAP, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (m) MSL_CUDA(cudaMemcpy(rec.data(), o->d_candRec + (size_t)frame * o->candCapTotal + o->lv[level].candBase, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (int i = 0; i < m; i++) {
         xyr[3 * i] = rec[i] & 0xfff;
         xyr[3 * i + 1] = (rec[i] >> 12) & 0xfff;

@@ -105,7 +105,7 @@ class ORBextractor:
         return out
 
     def debug_candidates(self, frame, level):
-        cap = 16384
+        cap = 1 << 18
         out = np.zeros((cap, 3), np.int32)
         n = C.c_int()
         check(self._L.msl_orb_debug_candidates(self._h, frame, level, ptr(out), cap, C.byref(n)))
