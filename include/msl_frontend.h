@@ -236,6 +236,16 @@ int msl_surfel_fuse(msl_surfel_fusion *, int reference_frame_index, const uint8_
  * msl_surfel_read_stats. */
 int msl_surfel_fuse_dev(msl_surfel_fusion *, int reference_frame_index, const uint8_t *d_gray, int gray_stride,
                         const float *d_depth, const int32_t *d_membership, const float Twc[16], int compact);
+/* Stream of `batch` consecutive keyframes (reference indices ref0, ref0+1, ...): the map-independent
+ * superpixel stage runs batched over all frames, then fuse/initialise/compact runs frame by frame in
+ * order on the device-resident map -- identical to `batch` consecutive fuseInitializeMap calls.
+ * Twc: batch x 16 floats (host).  stats accumulate over the batch (n_new, n_updated, n_deleted) and
+ * report the final map size. */
+int msl_surfel_fuse_batch(msl_surfel_fusion *, int ref0, const uint8_t *gray, int gray_stride, const float *depth,
+                          const int32_t *membership, const float *Twc, int batch, int compact, int64_t stats[4]);
+int msl_surfel_fuse_batch_dev(msl_surfel_fusion *, int ref0, const uint8_t *d_gray, int gray_stride,
+                              size_t gray_frame_stride, const float *d_depth, const int32_t *d_membership,
+                              const float *Twc, int batch, int compact);
 int msl_surfel_read_stats(msl_surfel_fusion *, int64_t stats[4]);
 int msl_surfel_read_new(msl_surfel_fusion *, msl_surfel *new_surfels, int cap_new, int *n_new);
 int msl_surfel_sync(msl_surfel_fusion *);

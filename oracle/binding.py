@@ -196,3 +196,83 @@ def fast_score_map(img):
 
 def fast_atan2(y, x):
     return lib().orc_fast_atan2(float(y), float(x))
+
+
+# -------------------------------------------------------------------- surfels
+
+@_late("orc_surfel_create")
+def _s1(f):
+    f.restype = C.c_void_p
+    f.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6
+
+
+@_late("orc_surfel_fuse")
+def _s2(f):
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_int64, C.c_void_p, C.c_int, C.c_int]
+
+
+@_late("orc_surfel_compact")
+def _s3(f):
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+
+
+class SurfelOracle:
+    """Mirror of SurfelFusion (include/SurfelFusion.h:44-139) on the CPU oracle."""
+
+    def __init__(self, w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, fuseFar=30.0, fuseNear=0.5):
+        self.L = lib()
+        self.w, self.h = w, h
+        self.nseeds = (w // 8) * (h // 8)
+        self.hd = self.L.orc_surfel_create(w, h, fx, fy, cx, cy, fuseFar, fuseNear)
+        for name in ("orc_surfel_index", "orc_surfel_seeds", "orc_surfel_normmap"):
+            fn = getattr(self.L, name)
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_void_p]
+        for name in ("orc_surfel_seeds_iter", "orc_surfel_index_iter"):
+            fn = getattr(self.L, name)
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_surfel_destroy.argtypes = [C.c_void_p]
+
+    def __del__(self):
+        if getattr(self, "hd", None):
+            self.L.orc_surfel_destroy(self.hd)
+            self.hd = None
+
+    def fuse(self, ref, gray, depth, membership, Twc, local, threads=1):
+        """fuseInitializeMap: local (SURFEL_DTYPE array) is updated in place; returns newSurfels."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        membership = np.ascontiguousarray(membership, np.int32)
+        Twc = np.ascontiguousarray(Twc, np.float32)
+        assert local.dtype == SURFEL_DTYPE and local.flags.c_contiguous
+        new = np.zeros(self.nseeds, SURFEL_DTYPE)
+        n = self.L.orc_surfel_fuse(self.hd, ref, _p(gray), gray.strides[0], _p(depth), _p(membership), _p(Twc),
+                                   _p(local), len(local), _p(new), len(new), threads)
+        return new[:n].copy()
+
+    def _arr(self, ptr, dtype, count):
+        buf = (C.c_uint8 * (np.dtype(dtype).itemsize * count)).from_address(ptr)
+        return np.frombuffer(buf, dtype).copy()
+
+    def seeds(self, it=None):
+        ptr = self.L.orc_surfel_seeds(self.hd) if it is None else self.L.orc_surfel_seeds_iter(self.hd, it)
+        return self._arr(ptr, SEED_DTYPE, self.nseeds)
+
+    def index(self, it=None):
+        ptr = self.L.orc_surfel_index(self.hd) if it is None else self.L.orc_surfel_index_iter(self.hd, it)
+        return self._arr(ptr, np.int32, self.w * self.h).reshape(self.h, self.w)
+
+    def normmap(self):
+        return self._arr(self.L.orc_surfel_normmap(self.hd), np.float32, self.w * self.h * 3).reshape(self.h, self.w, 3)
+
+
+def surfel_compact(local, new):
+    """SurfelMapping::fuseMap tail (src/SurfelMapping.cpp:366-391); returns the new local array."""
+    buf = np.zeros(len(local) + len(new), SURFEL_DTYPE)
+    buf[:len(local)] = local
+    new = np.ascontiguousarray(new)
+    n = lib().orc_surfel_compact(_p(buf), len(local), _p(new), len(new))
+    return buf[:n].copy()
