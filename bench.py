@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- RGB-D front-end frames/s on synthetic 640x480 RGB-D (BASELINE.json metric).
+
+One step = one pass of the front-end over one batch of 64 synthetic RGB-D frames per GPU:
+ORB extraction (+ Hamming match of consecutive frames and the plane pre-stage when built) and the
+projective surfel fusion of the 64-frame stream into a device-resident 5M-surfel map (superpixels
+batched, fuse/initialise/compact frame by frame in order).  Frames are independent across ranks
+(one chunk and one map replica per rank, weak scaling); the only collective is one NCCL all-gather
+of the per-frame keypoint counts + surfel statistics.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference ...                           the reference's CPU path (oracle port)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+METRIC = "rgbd_frontend_frames_per_s"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--surfels", type=int, default=5_000_000, help="surfels in the local map per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "frontend_%dx%d_b%d_map%s" % (W, H, a.batch, ("%dM" % (a.surfels // 1_000_000)) if a.surfels >= 1_000_000 else str(a.surfels))
+
+
+def make_inputs(rank, batch, n_surfels):
+    """Seeded synthetic RGB-D batch + pose walk + surfel map."""
+    from manhattanslam_b200 import synthetic as S
+    seed0 = 1000 * (rank + 1)
+    # 16 distinct frames cycled to the batch size keeps start-up short; every frame is still processed
+    uniq = min(batch, 16)
+    gray_u = [S.gray_frame(seed0 + i) for i in range(uniq)]
+    depth_u = [S.depth_frame(seed0 + i)[1] for i in range(uniq)]
+    gray = np.stack([gray_u[i % uniq] for i in range(batch)])
+    depth = np.stack([depth_u[i % uniq] for i in range(batch)])
+    mem = np.stack([S.membership(seed0 + i) for i in range(batch)])
+    poses = S.pose_walk(seed0, batch)
+    surfels = S.surfel_map(seed0, n_surfels, depth[0], poses[0], ref_index=100)
+    return gray, depth, mem, poses, surfels
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_frontend(gray, depth, mem, poses, surfels, frames, threads):
+    """The reference's CPU path (oracle port): ORB frame-parallel over all host threads (the reference
+    runs one ORB thread per frame), SurfelFusion frame by frame with THREAD_NUM=10 scan threads
+    (include/SurfelFusion.h:34).  Returns (frames/s, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import binding as ob
+    frames = min(frames, len(gray))
+    local = surfels.copy()
+    t0 = time.perf_counter()
+    tl = threading.local()
+
+    def orb(i):
+        if not hasattr(tl, "o"):
+            tl.o = ob.OrbOracle()
+        k, d = tl.o(gray[i])
+        return len(k)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        counts = list(ex.map(orb, range(frames)))
+    so = ob.SurfelOracle(W, H)
+    for i in range(frames):
+        new = so.fuse(100 + i, gray[i], depth[i], mem[i], poses[i], local, threads=min(10, threads))
+        local = ob.surfel_compact(local, new)
+    dt = time.perf_counter() - t0
+    assert sum(counts) > 0
+    return frames / dt, dt
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    gray, depth, mem, poses, surfels = make_inputs(0, a.batch, a.surfels)
+    frames = min(a.cpu_frames, a.batch)
+    for _ in range(min(a.warmup, 1)):
+        cpu_frontend(gray, depth, mem, poses, surfels, min(frames, 4), threads)
+    ts = []
+    for _ in range(a.steps):
+        fps, dt = cpu_frontend(gray, depth, mem, poses, surfels, frames, threads)
+        ts.append(dt)
+    ms = 1e3 * sum(ts) / len(ts)
+    value = frames / (ms / 1e3)
+    sample = "%d of %d frames per step: ORB frame-parallel on %d threads + SurfelFusion (10 scan threads) into a %d-surfel map" % (
+        frames, a.batch, threads, a.surfels)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8+f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "surfels_per_gpu": a.surfels,
+                      "stages": ["orb", "surfel_fuse"]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import manhattanslam_b200 as msl
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.batch
+    gray, depth, mem, poses, surfels = make_inputs(rank, B, a.surfels)
+
+    orb = msl.ORBextractor(width=W, height=H, max_batch=B, device=local_rank)
+    sf = msl.SurfelFusion(W, H, max_surfels=a.surfels + 4 * B * 4800, device=local_rank)
+    sf.upload_map(surfels)
+    cap = orb.capacity
+
+    # pinned host staging (e2e leg) and device-resident inputs (kernel leg)
+    h_gray = torch.from_numpy(gray).pin_memory()
+    h_depth = torch.from_numpy(depth).pin_memory()
+    h_mem = torch.from_numpy(mem).pin_memory()
+    d_gray, d_depth, d_mem = h_gray.to(dev), h_depth.to(dev), h_mem.to(dev)
+    d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    h_kps = torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory()
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_counts = torch.zeros(B, dtype=torch.int32).pin_memory()
+    gathered = torch.zeros((world, B), dtype=torch.int32, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    s_orb = torch.cuda.ExternalStream(orb.stream, device=dev)
+    s_sf = torch.cuda.ExternalStream(sf.stream, device=dev)
+    state = {"ref": 100}
+
+    def step_dev():
+        """inputs resident in HBM; ORB and the surfel stream run on their own CUDA streams and overlap"""
+        if world > 1:
+            s_orb.wait_stream(torch.cuda.current_stream())  # previous all-gather still reads d_counts
+        orb.extract_dev(d_gray.data_ptr(), W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr())
+        sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
+        state["ref"] += B
+        if world > 1:  # the path's single collective: per-frame counts to every rank
+            torch.cuda.current_stream().wait_stream(s_orb)
+            dist.all_gather_into_tensor(gathered.view(-1), d_counts)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_dev()
+    barrier()
+    launches0 = msl.lib().msl_kernel_launch_count()
+    sf.set_timing(True)
+    st0 = sf.read_stats()
+    clk = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_o, ev_s = torch.cuda.Event(), torch.cuda.Event()
+    cur = torch.cuda.current_stream()
+    ev0.record(cur)
+    s_orb.wait_event(ev0)
+    s_sf.wait_event(ev0)
+    upd = dele = 0
+    for _ in range(a.steps):
+        step_dev()
+    ev_o.record(s_orb)
+    ev_s.record(s_sf)
+    cur.wait_event(ev_o)
+    cur.wait_event(ev_s)
+    ev1.record(cur)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = clk.stop()
+    launches = int(msl.lib().msl_kernel_launch_count() - launches0)
+    fuse_ms, fuse_launches = sf.fuse_kernel_time()
+    sf.set_timing(False)
+    st1 = sf.read_stats()
+    orb.sync()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    value = world * B / (ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel (projective fuse scan), measured live with CUDA events
+    n_map = st1[3]
+    # stats accumulate per fuse_batch call: st1 holds the last step's totals over its B launches
+    upd_per_launch = st1[1] / B
+    del_per_launch = st1[2] / B
+    alg_bytes = n_map * 20.0 + upd_per_launch * 64.0 + del_per_launch * 4.0
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    fuse_avg_ms = fuse_ms / max(fuse_launches, 1)
+    achieved = alg_bytes / (fuse_avg_ms * 1e-3) / 1e9 if fuse_launches else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "fuse_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "k_fuse", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_avg_ms, "launches": fuse_launches,
+                "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None}
+
+    # ---- e2e: the public host API with pinned host buffers, H2D of the inputs + D2H of the results every step
+    import ctypes as C
+    from manhattanslam_b200._lib import check, ptr
+
+    def step_e2e():
+        check(orb._L.msl_orb_extract(orb._h, C.c_void_p(h_gray.data_ptr()), C.c_int(W), C.c_size_t(W * H), C.c_int(B),
+                                     C.c_void_p(h_kps.data_ptr()), C.c_void_p(h_desc.data_ptr()),
+                                     C.c_void_p(h_counts.data_ptr())))
+        stats = np.zeros(4, np.int64)
+        check(sf._L.msl_surfel_fuse_batch(sf._h, state["ref"], C.c_void_p(h_gray.data_ptr()), C.c_int(W),
+                                          C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_mem.data_ptr()), ptr(poses),
+                                          C.c_int(B), 1, ptr(stats)))
+        state["ref"] += B
+        return stats
+
+    for _ in range(min(a.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * a.steps / float(t.item())
+    h2d = int(h_gray.numel() + h_depth.numel() * 4 + h_mem.numel() * 4 + 64 * B)
+    d2h = int(h_kps.numel() + h_desc.numel() + h_counts.numel() * 4 + 32)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        frames = min(a.cpu_frames, B)
+        fps, dt = cpu_frontend(gray, depth, mem, poses, surfels, frames, threads)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d frames (%.1f s): oracle ORB frame-parallel on %d threads + oracle SurfelFusion with 10 scan "
+                         "threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8+f32", "data": "synthetic",
+               "config": {"workload": workload_name(a), "batch_per_gpu": B, "surfels_per_gpu": a.surfels,
+                          "stages": ["orb", "surfel_fuse"], "map_size_end": n_map,
+                          "l2": "working set per step (280 MB surfel planes + 190 MB pyramids) exceeds the 126 MB L2",
+                          "collective": "nccl all_gather of per-frame counts" if world > 1 else "none (1 GPU)"},
+               "roofline": roofline, "cpu_baseline": cpu,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    run_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -249,6 +249,11 @@ int msl_surfel_fuse_batch_dev(msl_surfel_fusion *, int ref0, const uint8_t *d_gr
 int msl_surfel_read_stats(msl_surfel_fusion *, int64_t stats[4]);
 int msl_surfel_read_new(msl_surfel_fusion *, msl_surfel *new_surfels, int cap_new, int *n_new);
 int msl_surfel_sync(msl_surfel_fusion *);
+/* Measurement aid: when enabled, every launch of the projective fuse scan is bracketed by CUDA events on
+ * the handle's stream; msl_surfel_fuse_kernel_time synchronises, returns the summed kernel time and the
+ * number of launches since the last query, and resets the tally. */
+int msl_surfel_set_timing(msl_surfel_fusion *, int enable);
+int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *launches);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
 /* Batched superpixel generation only (generateSuperPixels, src/SurfelFusion.cpp:805-816) for `batch`

@@ -98,6 +98,15 @@ class SurfelFusion:
     def sync(self):
         check(self._L.msl_surfel_sync(self._h))
 
+    def set_timing(self, enable=True):
+        check(self._L.msl_surfel_set_timing(self._h, int(enable)))
+
+    def fuse_kernel_time(self):
+        """(total milliseconds, launches) of the projective fuse scan since the last query."""
+        ms, n = C.c_double(), C.c_int()
+        check(self._L.msl_surfel_fuse_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def stream(self):
         return self._L.msl_surfel_stream(self._h)

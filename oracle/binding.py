@@ -15,10 +15,21 @@ _LIB = None
 
 def build(force=False):
     """Compile oracle/libmsl_oracle.so with the committed Makefile (gcc only, no GPU needed)."""
+    import hashlib
     so = os.path.join(_HERE, "libmsl_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h", ".inc"))]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "libmsl_oracle.so"], stdout=subprocess.DEVNULL)
+    stamp = so + ".stamp"
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(_HERE)):
+        if f.endswith((".cpp", ".h", ".inc")) or f == "Makefile":
+            h.update(f.encode())
+            with open(os.path.join(_HERE, f), "rb") as fh:
+                h.update(fh.read())
+    digest = h.hexdigest()
+    # content hash, not mtimes: mtimes do not survive the gpurun snapshot
+    if force or not os.path.exists(so) or not os.path.exists(stamp) or open(stamp).read().strip() != digest:
+        subprocess.check_call(["make", "-B", "-C", _HERE, "libmsl_oracle.so"], stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as fh:
+            fh.write(digest)
     return so
 
 

@@ -94,7 +94,7 @@ def test_fuse_matches_oracle(oracle, msl, n):
     w2 = _cmp(new_o, new_g, FLOAT_SURFEL, INT_SURFEL, "newSurfels")
     assert w1 == 0.0 and w2 == 0.0
     assert np.array_equal(o.seeds()["fused"], sf.debug_seeds()["fused"])
-    n_upd = int(((lo["lastUpdate"] == 100) & (lo["updateTimes"] != local["updateTimes"])).sum())
+    n_upd = int((lo["updateTimes"] == local["updateTimes"] + 1).sum())
     n_del = int(((lo["updateTimes"] == 0) & (local["updateTimes"] != 0)).sum())
     assert stats == (len(new_o), n_upd, n_del, n)
     if n >= 1000:
