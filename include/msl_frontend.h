@@ -110,6 +110,8 @@ typedef struct msl_matcher msl_matcher;
 
 int msl_matcher_create(int max_queries, int max_train, int max_batch, int device, msl_matcher **out);
 void msl_matcher_destroy(msl_matcher *);
+int msl_matcher_sync(msl_matcher *);
+void *msl_matcher_stream(msl_matcher *); /* cudaStream_t */
 
 /* All-pairs Hamming distance of 256-bit descriptors: dist[b][i][j] = popcount(q[b][i] ^ t[b][j]),
  * batch pairs; q: batch x nq x 32, t: batch x nt x 32, dist: batch x nq x nt uint16. */
@@ -128,9 +130,9 @@ int msl_hamming_best2_dev(msl_matcher *, const uint8_t *d_q, int nq, const uint8
  *     32 B), last_octave (mvKeys[i].octave), last_angle (mvKeysUn[i].angle);
  *   Cur side, per keypoint j < n_cur: cur_xy (mvKeysUn pt), cur_octave, cur_angle, cur_uright (mvuRight),
  *     cur_desc (mDescriptors), cur_occupied (mvpMapPoints[j] && Observations()>0 on entry).
- * Output: cur_match[j] = index i of the Last keypoint whose MapPoint now sits in slot j, -1 if none,
- * -2 if the slot was occupied on entry; *nmatches = return value of the reference method (after the
- * rotation-histogram pruning when check_orientation != 0). */
+ * Output: cur_match[j] = index i of the Last keypoint whose MapPoint now sits in slot j, -1 if the slot
+ * was not touched, -2 if it was occupied on entry, -3 if it was matched and then reset to NULL by the
+ * rotation-consistency check; *nmatches = return value of the reference method. */
 int msl_search_by_projection_frame(msl_matcher *, const msl_frame_geom *geom, const float Tcw_cur[16],
                                    const float Tcw_last[16], float th, int check_orientation, int n_last,
                                    const uint8_t *last_has_mp, const uint8_t *last_outlier,

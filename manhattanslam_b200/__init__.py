@@ -8,5 +8,7 @@ include/msl_frontend.h plus the C++ adapters in adapters/.
 from ._lib import MslError, lib  # noqa: F401
 from .orb import ORBextractor, KP_DTYPE  # noqa: F401
 from .surfel import SurfelFusion, SURFEL_DTYPE, SEED_DTYPE  # noqa: F401
+from .plane import PlaneDetection, BLOCK_DTYPE  # noqa: F401
+from .matcher import ORBmatcher, frame_geom, GEOM_DTYPE  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,574 @@
+// match.cu -- B200-native descriptor matching (replaces ORBmatcher::DescriptorDistance and the window
+// searches ORBmatcher::SearchByProjection of src/ORBmatcher.cc:40-117, 548-678, 799-849 with the
+// Frame grid semantics of src/Frame.cc:155-168, 332-381, 418-427 of razayunus/ManhattanSLAM).
+//
+//   k_hamming_best2     all-pairs 256-bit Hamming: one warp per query, train descriptors staged through
+//                       shared memory in 256-descriptor tiles, xor + __popc on 8 x u32, warp-shuffle
+//                       (best, index, second) reduction; ties resolve to the lowest train index
+//   k_hamming_all_pairs full nq x nt distance matrix (uint16)
+//   k_search            one CTA per Frame pair: (1) the 64x48 feature grid as a sorted (cell, index) list --
+//                       reproducing GetFeaturesInArea's candidate order (ix asc, iy asc, insertion asc);
+//                       (2) per-query projection / window / level predicate; (3) the reference's greedy,
+//                       order-dependent slot blocking (Observations()>0) solved as a fixed point:
+//                       query i sees slot j blocked iff an earlier query i' < i holds it -- iterate until
+//                       no assignment changes (unique solution by induction on i); (4) rotation histogram
+//                       + ComputeThreeMaxima pruning.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "msl_common.cuh"
+
+using namespace msl;
+
+namespace {
+
+constexpr int TH_HIGH = 100;      // src/ORBmatcher.cc:33
+constexpr int HISTO_LENGTH = 30;  // :35
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:53-54
+constexpr int NCELLS = GRID_COLS * GRID_ROWS;
+constexpr int MAXK = 4096;  // keypoints per frame handled by k_search
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256)
+    k_hamming_best2(const uint8_t *__restrict__ q, int nq, const uint8_t *__restrict__ t, int nt, int32_t *__restrict__ bestIdx,
+                    int32_t *__restrict__ bestDist, int32_t *__restrict__ secondDist) {
+    __shared__ uint4 tile[256 * 2];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qi = blockIdx.x * 8 + wid;
+    const uint4 *Q = (const uint4 *)(q + (size_t)b * nq * 32);
+    const uint4 *T = (const uint4 *)(t + (size_t)b * nt * 32);
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    if (qi < nq) q0 = __ldg(Q + 2 * qi), q1 = __ldg(Q + 2 * qi + 1);
+    int bd = 257, bi = -1, sd = 257;
+    for (int base = 0; base < nt; base += 256) {
+        const int m = min(256, nt - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < 2 * m; k += 256) tile[k] = __ldg(T + 2 * base + k);
+        __syncthreads();
+        if (qi < nq)
+            for (int j = lane; j < m; j += 32) {
+                const int d = hamming256(q0, q1, tile[2 * j], tile[2 * j + 1]);
+                if (d < bd) {
+                    sd = bd;
+                    bd = d;
+                    bi = base + j;
+                } else if (d < sd)
+                    sd = d;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int obd = __shfl_xor_sync(0xffffffffu, bd, o), obi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int osd = __shfl_xor_sync(0xffffffffu, sd, o);
+        const int ns = min(max(bd, obd), min(sd, osd));
+        if (obd < bd || (obd == bd && (unsigned)obi < (unsigned)bi)) bd = obd, bi = obi;
+        sd = ns;
+    }
+    if (qi < nq && lane == 0) {
+        const size_t o = (size_t)b * nq + qi;
+        bestIdx[o] = bi;
+        bestDist[o] = bd > 256 ? 256 : bd;
+        secondDist[o] = sd > 256 ? 256 : sd;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_hamming_all_pairs(const uint8_t *__restrict__ q, int nq, const uint8_t *__restrict__ t, int nt, uint16_t *__restrict__ dist) {
+    const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= nt) return;
+    const uint4 *Q = (const uint4 *)(q + ((size_t)b * nq + i) * 32);
+    const uint4 *T = (const uint4 *)(t + ((size_t)b * nt + j) * 32);
+    dist[((size_t)b * nq + i) * nt + j] = (uint16_t)hamming256(__ldg(Q), __ldg(Q + 1), __ldg(T), __ldg(T + 1));
+}
+
+// -------------------------------------------------------------------------------- window search
+struct SearchArgs {
+    msl_frame_geom g;
+    int mode;                 // 0: Frame-Frame (:548-678), 1: Frame-MapPoints (:40-117)
+    float th, nnratio;
+    int checkOri;
+    float Rcw[9], tcw[3];
+    int bForward, bBackward;
+    int nq, nc;
+    // query side
+    const uint8_t *q_valid, *q_obs, *q_desc;
+    const float *q_f3;        // mode 0: world xyz; mode 1: (projX, projY, projXR)
+    const int32_t *q_level;   // mode 0: last octave; mode 1: predicted level
+    const float *q_aux;       // mode 0: last angle; mode 1: view cos
+    // current frame
+    const float *c_xy, *c_angle, *c_uright;
+    const int32_t *c_octave;
+    const uint8_t *c_desc, *c_occ;
+    int32_t *c_match, *nmatches;
+    // scratch (global)
+    int32_t *assign, *bin;
+};
+
+struct QueryGeom {
+    float u, v, radius, urOrXr, rEr;
+    int minL, maxL;
+    short cx0, cx1, cy0, cy1;
+    int valid;
+};
+
+__device__ __forceinline__ float gemm_row(const float *R, const float *x, float t) {
+    double s = 0;
+    s += (double)R[0] * (double)x[0];
+    s += (double)R[1] * (double)x[1];
+    s += (double)R[2] * (double)x[2];
+    return (float)(s + (double)t);
+}
+
+__device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int n2) {  // n2 = power of two, whole CTA
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint32_t x = a[i], y = a[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) a[i] = y, a[l] = x;
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
+    __shared__ uint32_t keys[MAXK];          // (cell << 12 | index), sorted; 0xffffffff = not in grid
+    __shared__ unsigned short cellStart[NCELLS + 1];
+    __shared__ int blockedAt[MAXK];           // first query index holding the slot (INF = free)
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_changed, s_n, s_ind[3];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const msl_frame_geom &g = A.g;
+    // ---- (1) grid: AssignFeaturesToGrid (src/Frame.cc:155-168) as a sorted list
+    int n2 = 1;
+    while (n2 < A.nc) n2 <<= 1;
+    for (int i = tid; i < n2; i += nt) {
+        uint32_t key = 0xffffffffu;
+        if (i < A.nc) {
+            const int px = (int)roundf((A.c_xy[2 * i] - g.mnMinX) * g.gridWInv);   // PosInGrid :418-427
+            const int py = (int)roundf((A.c_xy[2 * i + 1] - g.mnMinY) * g.gridHInv);
+            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 12) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_u32(keys, n2);
+    for (int c = tid; c <= NCELLS; c += nt) {  // first position with cell >= c
+        int lo = 0, hi = A.nc;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((keys[mid] >> 12) < (uint32_t)c) lo = mid + 1; else hi = mid;
+        }
+        cellStart[c] = (unsigned short)lo;
+    }
+    for (int j = tid; j < A.nc; j += nt) blockedAt[j] = A.c_occ[j] ? -1 : 0x7fffffff;
+    for (int i = tid; i < A.nq; i += nt) A.assign[i] = -1;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+
+    // ---- (2)+(3) search rounds
+    for (int round = 0; round < A.nq + 2; round++) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < A.nq; i += nt) {
+            int best = -1;
+            if (A.q_valid[i]) {
+                float u, v, radius, urRef, erLim;
+                int minL, maxL;
+                bool ok = true;
+                if (A.mode == 0) {
+                    const float *x3Dw = A.q_f3 + 3 * i;
+                    const float xc = gemm_row(A.Rcw, x3Dw, A.tcw[0]);
+                    const float yc = gemm_row(A.Rcw + 3, x3Dw, A.tcw[1]);
+                    const float invzc = (float)(1.0 / (double)gemm_row(A.Rcw + 6, x3Dw, A.tcw[2]));
+                    if (invzc < 0) ok = false;
+                    u = g.fx * xc * invzc + g.cx;
+                    v = g.fy * yc * invzc + g.cy;
+                    if (u < g.mnMinX || u > g.mnMaxX) ok = false;
+                    if (v < g.mnMinY || v > g.mnMaxY) ok = false;
+                    const int oct = A.q_level[i];
+                    radius = A.th * g.scaleFactors[oct];
+                    if (A.bForward) minL = oct, maxL = -1;
+                    else if (A.bBackward) minL = 0, maxL = oct;
+                    else minL = oct - 1, maxL = oct + 1;
+                    urRef = u - g.mbf * invzc;
+                    erLim = radius;
+                } else {
+                    const int lvl = A.q_level[i];
+                    float r = (A.q_aux[i] > 0.998f) ? 2.5f : 4.0f;  // RadiusByViewingCos :119-124
+                    if (A.th != 1.0f) r *= A.th;
+                    u = A.q_f3[3 * i], v = A.q_f3[3 * i + 1];
+                    radius = r * g.scaleFactors[lvl];
+                    minL = lvl - 1, maxL = lvl;
+                    urRef = A.q_f3[3 * i + 2];
+                    erLim = r * g.scaleFactors[lvl];
+                }
+                if (ok) {
+                    // GetFeaturesInArea, src/Frame.cc:332-381
+                    const int cx0 = max(0, (int)floorf((u - g.mnMinX - radius) * g.gridWInv));
+                    const int cx1 = min(GRID_COLS - 1, (int)ceilf((u - g.mnMinX + radius) * g.gridWInv));
+                    const int cy0 = max(0, (int)floorf((v - g.mnMinY - radius) * g.gridHInv));
+                    const int cy1 = min(GRID_ROWS - 1, (int)ceilf((v - g.mnMinY + radius) * g.gridHInv));
+                    if (cx0 < GRID_COLS && cx1 >= 0 && cy0 < GRID_ROWS && cy1 >= 0) {
+                        const bool checkLevels = (minL > 0) || (maxL >= 0);
+                        const uint4 *Q = (const uint4 *)(A.q_desc + 32 * (size_t)i);
+                        const uint4 q0 = Q[0], q1 = Q[1];
+                        int bestDist = 256, bestDist2 = 256, bestLevel = -1, bestLevel2 = -1;
+                        for (int ix = cx0; ix <= cx1; ix++) {
+                            const int s0 = cellStart[ix * GRID_ROWS + cy0], s1 = cellStart[ix * GRID_ROWS + cy1 + 1];
+                            for (int s = s0; s < s1; s++) {
+                                const int k = keys[s] & 0xfff;
+                                const int oct = A.c_octave[k];
+                                if (checkLevels) {
+                                    if (oct < minL) continue;
+                                    if (maxL >= 0 && oct > maxL) continue;
+                                }
+                                const float dx = A.c_xy[2 * k] - u, dy = A.c_xy[2 * k + 1] - v;
+                                if (!(fabsf(dx) < radius && fabsf(dy) < radius)) continue;
+                                if (blockedAt[k] < i) continue;  // slot holds a MapPoint with Observations()>0
+                                const float ur = A.c_uright[k];
+                                if (ur > 0 && fabsf(urRef - ur) > erLim) continue;
+                                const uint4 *T = (const uint4 *)(A.c_desc + 32 * (size_t)k);
+                                const int d = hamming256(q0, q1, T[0], T[1]);
+                                if (d < bestDist) {
+                                    bestDist2 = bestDist, bestLevel2 = bestLevel;
+                                    bestDist = d, bestLevel = oct, best = k;
+                                } else if (d < bestDist2) {
+                                    bestLevel2 = oct, bestDist2 = d;
+                                }
+                            }
+                        }
+                        if (!(bestDist <= TH_HIGH)) best = -1;
+                        else if (A.mode == 1 && bestLevel == bestLevel2 && (float)bestDist > A.nnratio * (float)bestDist2) best = -1;
+                    }
+                }
+            }
+            if (best != A.assign[i]) {
+                A.assign[i] = best;
+                s_changed = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_changed) break;
+        for (int j = tid; j < A.nc; j += nt) blockedAt[j] = A.c_occ[j] ? -1 : 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < A.nq; i += nt) {
+            const int k = A.assign[i];
+            if (k >= 0 && A.q_obs[i]) atomicMin(&blockedAt[k], i);
+        }
+        __syncthreads();
+    }
+
+    // ---- (4) matches, rotation histogram (:639-675) and ComputeThreeMaxima (:799-830)
+    int *lastAssign = blockedAt;  // reuse: last query assigned to each slot (-1 none)
+    __syncthreads();
+    for (int j = tid; j < A.nc; j += nt) lastAssign[j] = -1;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < A.nq; i += nt) {
+        const int k = A.assign[i];
+        int bin = -1;
+        if (k >= 0) {
+            mine++;
+            atomicMax(&lastAssign[k], i);
+            if (A.mode == 0 && A.checkOri) {
+                float rot = A.q_aux[i] - A.c_angle[k];
+                if (rot < 0.0f) rot += 360.0f;
+                bin = (int)roundf(rot * (1.0f / HISTO_LENGTH));
+                if (bin == HISTO_LENGTH) bin = 0;
+                atomicAdd(&hist[bin], 1);
+            }
+        }
+        A.bin[i] = bin;
+    }
+    if (mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (tid == 0) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        if (A.mode == 0 && A.checkOri) {
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int s = hist[i];
+                if (s > max1) {
+                    max3 = max2, max2 = max1, max1 = s;
+                    ind3 = ind2, ind2 = ind1, ind1 = i;
+                } else if (s > max2) {
+                    max3 = max2, max2 = s;
+                    ind3 = ind2, ind2 = i;
+                } else if (s > max3) {
+                    max3 = s, ind3 = i;
+                }
+            }
+            if ((float)max2 < 0.1f * (float)max1) ind2 = -1, ind3 = -1;
+            else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        }
+        s_ind[0] = ind1, s_ind[1] = ind2, s_ind[2] = ind3;
+    }
+    __syncthreads();
+    for (int j = tid; j < A.nc; j += nt) A.c_match[j] = A.c_occ[j] ? -2 : lastAssign[j];
+    __syncthreads();
+    if (A.mode == 0 && A.checkOri) {
+        int pruned = 0;
+        for (int i = tid; i < A.nq; i += nt) {
+            const int b = A.bin[i];
+            if (b >= 0 && b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) {
+                A.c_match[A.assign[i]] = -3;  // mvpMapPoints[..] = NULL
+                pruned++;
+            }
+        }
+        if (pruned) atomicSub(&s_n, pruned);
+    }
+    __syncthreads();
+    if (tid == 0) *A.nmatches = s_n;
+}
+
+}  // namespace
+
+struct msl_matcher {
+    int maxQ, maxT, maxBatch, device;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_q = nullptr, *d_t = nullptr;
+    int32_t *d_bi = nullptr, *d_bd = nullptr, *d_sd = nullptr;
+    uint16_t *d_dist = nullptr;
+    size_t distCap = 0;
+    uint8_t *d_scr = nullptr;  // arena for the window-search arrays
+    size_t scrCap = 0;
+};
+
+static void matcher_free(msl_matcher *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+// bump allocator over the scratch arena + H2D copy
+struct Arena {
+    uint8_t *base;
+    size_t off, cap;
+    cudaStream_t st;
+    bool ok = true;
+    template <typename T>
+    const T *put(const T *h, size_t n) {
+        off = align_up(off, 16);
+        if (off + n * sizeof(T) > cap) { ok = false; return nullptr; }
+        T *d = (T *)(base + off);
+        off += n * sizeof(T);
+        if (n && cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        return d;
+    }
+    template <typename T>
+    T *get(size_t n) {
+        off = align_up(off, 16);
+        if (off + n * sizeof(T) > cap) { ok = false; return nullptr; }
+        T *d = (T *)(base + off);
+        off += n * sizeof(T);
+        return d;
+    }
+};
+
+static int run_search(msl_matcher *m, SearchArgs &A, int32_t *cur_match, int32_t *nmatches) {
+    k_search<<<1, 1024, 0, m->stream>>>(A);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaMemcpyAsync(cur_match, A.c_match, sizeof(int32_t) * A.nc, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+extern "C" {
+
+int msl_matcher_create(int max_queries, int max_train, int max_batch, int device, msl_matcher **out) {
+    if (!out) return fail(MSL_ERR_INVALID, "msl_matcher_create: null out");
+    *out = nullptr;
+    if (max_queries < 1 || max_train < 1 || max_batch < 1) return fail(MSL_ERR_INVALID, "msl_matcher_create: parameter out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0)
+        return fail(MSL_ERR_CUDA, "msl_matcher_create: no usable CUDA device (there is no CPU fallback)");
+    MSL_CUDA(cudaSetDevice(device));
+    msl_matcher *m = new msl_matcher();
+    m->maxQ = max_queries, m->maxT = max_train, m->maxBatch = max_batch, m->device = device;
+    const size_t B = max_batch;
+    cudaError_t e = cudaMalloc((void **)&m->d_q, B * max_queries * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_t, B * max_train * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_bi, B * max_queries * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_bd, B * max_queries * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_sd, B * max_queries * 4);
+    m->scrCap = (size_t)(max_queries + max_train) * 96 + 4096;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_scr, m->scrCap);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        matcher_free(m);
+        return fail(MSL_ERR_CUDA, std::string("msl_matcher_create: ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return MSL_OK;
+}
+
+void msl_matcher_destroy(msl_matcher *m) { matcher_free(m); }
+void *msl_matcher_stream(msl_matcher *m) { return m ? (void *)m->stream : nullptr; }
+int msl_matcher_sync(msl_matcher *m) {
+    if (!m) return fail(MSL_ERR_INVALID, "null handle");
+    MSL_CUDA(cudaSetDevice(m->device));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+int msl_hamming_best2_dev(msl_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int batch,
+                          int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist) {
+    if (!m || !d_q || !d_t || !d_best_idx || !d_best_dist || !d_second_dist) return fail(MSL_ERR_INVALID, "msl_hamming_best2_dev: null argument");
+    if (nq < 1 || nt < 0 || batch < 1) return fail(MSL_ERR_INVALID, "msl_hamming_best2_dev: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    k_hamming_best2<<<dim3(cdiv(nq, 8), batch), 256, 0, m->stream>>>(d_q, nq, d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+    MSL_LAUNCH_CHECK();
+    return MSL_OK;
+}
+
+int msl_hamming_best2(msl_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, int batch, int32_t *best_idx,
+                      int32_t *best_dist, int32_t *second_dist) {
+    if (!m || !q || !t || !best_idx || !best_dist || !second_dist) return fail(MSL_ERR_INVALID, "msl_hamming_best2: null argument");
+    if (nq < 1 || nq > m->maxQ || nt < 1 || nt > m->maxT || batch < 1 || batch > m->maxBatch) return fail(MSL_ERR_INVALID, "msl_hamming_best2: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    MSL_CUDA(cudaMemcpyAsync(m->d_q, q, (size_t)batch * nq * 32, cudaMemcpyHostToDevice, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(m->d_t, t, (size_t)batch * nt * 32, cudaMemcpyHostToDevice, m->stream));
+    int rc = msl_hamming_best2_dev(m, m->d_q, nq, m->d_t, nt, batch, m->d_bi, m->d_bd, m->d_sd);
+    if (rc) return rc;
+    MSL_CUDA(cudaMemcpyAsync(best_idx, m->d_bi, (size_t)batch * nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(best_dist, m->d_bd, (size_t)batch * nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(second_dist, m->d_sd, (size_t)batch * nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+int msl_hamming_all_pairs(msl_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, int batch, uint16_t *dist) {
+    if (!m || !q || !t || !dist) return fail(MSL_ERR_INVALID, "msl_hamming_all_pairs: null argument");
+    if (nq < 1 || nq > m->maxQ || nt < 1 || nt > m->maxT || batch < 1 || batch > m->maxBatch) return fail(MSL_ERR_INVALID, "msl_hamming_all_pairs: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    const size_t need = (size_t)batch * nq * nt * 2;
+    if (need > m->distCap) {
+        if (m->d_dist) cudaFree(m->d_dist);
+        m->d_dist = nullptr;
+        MSL_CUDA(cudaMalloc((void **)&m->d_dist, need));
+        m->distCap = need;
+    }
+    MSL_CUDA(cudaMemcpyAsync(m->d_q, q, (size_t)batch * nq * 32, cudaMemcpyHostToDevice, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(m->d_t, t, (size_t)batch * nt * 32, cudaMemcpyHostToDevice, m->stream));
+    k_hamming_all_pairs<<<dim3(cdiv(nt, 256), nq, batch), 256, 0, m->stream>>>(m->d_q, nq, m->d_t, nt, m->d_dist);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaMemcpyAsync(dist, m->d_dist, need, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, const float Tcw_cur[16],
+                                   const float Tcw_last[16], float th, int check_orientation, int n_last,
+                                   const uint8_t *last_has_mp, const uint8_t *last_outlier, const uint8_t *last_mp_obs,
+                                   const float *last_mp_world, const uint8_t *last_mp_desc, const int32_t *last_octave,
+                                   const float *last_angle, int n_cur, const float *cur_xy, const int32_t *cur_octave,
+                                   const float *cur_angle, const float *cur_uright, const uint8_t *cur_desc,
+                                   const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches) {
+    if (!m || !geom || !Tcw_cur || !Tcw_last || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_frame: null argument");
+    if (n_last < 0 || n_cur < 0 || n_last > m->maxQ || n_cur > m->maxT || n_cur > MAXK || n_last > 0x7ffffff)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_frame: too many keypoints for this handle");
+    if (n_cur == 0 || n_last == 0) {
+        for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
+        *nmatches = 0;
+        return MSL_OK;
+    }
+    MSL_CUDA(cudaSetDevice(m->device));
+    SearchArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = *geom, A.mode = 0, A.th = th, A.nnratio = 0, A.checkOri = check_orientation, A.nq = n_last, A.nc = n_cur;
+    // :554-568: twc = -Rcw^T tcw; tlc = Rlw twc + tlw (cv::Mat products: double accumulation, one rounding)
+    float Rlw[9], tlw[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw_cur[r * 4 + c], Rlw[r * 3 + c] = Tcw_last[r * 4 + c];
+        A.tcw[r] = Tcw_cur[r * 4 + 3], tlw[r] = Tcw_last[r * 4 + 3];
+    }
+    float twc[3];
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
+        twc[r] = (float)s;
+    }
+    double s2 = 0;
+    for (int k = 0; k < 3; k++) s2 += (double)Rlw[6 + k] * (double)twc[k];
+    const float tlc2 = (float)(s2 + (double)tlw[2]);
+    A.bForward = tlc2 > geom->mb;
+    A.bBackward = -tlc2 > geom->mb;
+    std::vector<uint8_t> valid(n_last);
+    for (int i = 0; i < n_last; i++) valid[i] = last_has_mp[i] && !last_outlier[i];
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.q_valid = ar.put(valid.data(), n_last);
+    A.q_obs = ar.put(last_mp_obs, n_last);
+    A.q_desc = ar.put(last_mp_desc, (size_t)n_last * 32);
+    A.q_f3 = ar.put(last_mp_world, (size_t)n_last * 3);
+    A.q_level = ar.put(last_octave, n_last);
+    A.q_aux = ar.put(last_angle, n_last);
+    A.c_xy = ar.put(cur_xy, (size_t)n_cur * 2);
+    A.c_angle = ar.put(cur_angle, n_cur);
+    A.c_uright = ar.put(cur_uright, n_cur);
+    A.c_octave = ar.put(cur_octave, n_cur);
+    A.c_desc = ar.put(cur_desc, (size_t)n_cur * 32);
+    A.c_occ = ar.put(cur_occupied, n_cur);
+    A.c_match = ar.get<int32_t>(n_cur);
+    A.nmatches = ar.get<int32_t>(1);
+    A.assign = ar.get<int32_t>(n_last);
+    A.bin = ar.get<int32_t>(n_last);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_frame: scratch arena / copy failure");
+    return run_search(m, A, cur_match, nmatches);
+}
+
+int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, float th, float nnratio, int n_mp,
+                                    const uint8_t *mp_valid, const uint8_t *mp_obs, const float *mp_proj_xyr,
+                                    const int32_t *mp_level, const float *mp_viewcos, const uint8_t *mp_desc, int n_cur,
+                                    const float *cur_xy, const int32_t *cur_octave, const float *cur_uright,
+                                    const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match,
+                                    int32_t *nmatches) {
+    if (!m || !geom || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_points: null argument");
+    if (n_mp < 0 || n_cur < 0 || n_mp > m->maxQ || n_cur > m->maxT || n_cur > MAXK)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_points: too many keypoints for this handle");
+    if (n_cur == 0 || n_mp == 0) {
+        for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
+        *nmatches = 0;
+        return MSL_OK;
+    }
+    MSL_CUDA(cudaSetDevice(m->device));
+    SearchArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = *geom, A.mode = 1, A.th = th, A.nnratio = nnratio, A.checkOri = 0, A.nq = n_mp, A.nc = n_cur;
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.q_valid = ar.put(mp_valid, n_mp);
+    A.q_obs = ar.put(mp_obs, n_mp);
+    A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);
+    A.q_f3 = ar.put(mp_proj_xyr, (size_t)n_mp * 3);
+    A.q_level = ar.put(mp_level, n_mp);
+    A.q_aux = ar.put(mp_viewcos, n_mp);
+    A.c_xy = ar.put(cur_xy, (size_t)n_cur * 2);
+    A.c_angle = A.c_xy;  // unused in this mode
+    A.c_uright = ar.put(cur_uright, n_cur);
+    A.c_octave = ar.put(cur_octave, n_cur);
+    A.c_desc = ar.put(cur_desc, (size_t)n_cur * 32);
+    A.c_occ = ar.put(cur_occupied, n_cur);
+    A.c_match = ar.get<int32_t>(n_cur);
+    A.nmatches = ar.get<int32_t>(1);
+    A.assign = ar.get<int32_t>(n_mp);
+    A.bin = ar.get<int32_t>(n_mp);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_points: scratch arena / copy failure");
+    return run_search(m, A, cur_match, nmatches);
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""ORBmatcher mirror (include/ORBmatcher.h:39-55: DescriptorDistance + the two tracking-time
+SearchByProjection overloads) over the CUDA C ABI.  The Frame/MapPoint graph is passed as flat arrays."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, ptr
+
+GEOM_DTYPE = np.dtype([("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4"),
+                       ("mnMinX", "<f4"), ("mnMinY", "<f4"), ("mnMaxX", "<f4"), ("mnMaxY", "<f4"),
+                       ("gridWInv", "<f4"), ("gridHInv", "<f4"), ("mb", "<f4"), ("mbf", "<f4"),
+                       ("nlevels", "<i4"), ("scaleFactors", "<f4", 16)])
+
+
+def frame_geom(width=640, height=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, bf=40.0, scale_factors=None):
+    """Frame constants for an undistorted camera (src/Frame.cc:127-147, 466-493)."""
+    g = np.zeros(1, GEOM_DTYPE)
+    g["fx"], g["fy"], g["cx"], g["cy"] = fx, fy, cx, cy
+    g["mnMinX"], g["mnMinY"], g["mnMaxX"], g["mnMaxY"] = 0.0, 0.0, width, height
+    g["gridWInv"] = np.float32(64) / np.float32(width)
+    g["gridHInv"] = np.float32(48) / np.float32(height)
+    g["mbf"] = bf
+    g["mb"] = np.float32(bf) / np.float32(fx)
+    sf = np.asarray(scale_factors if scale_factors is not None else 1.2 ** np.arange(8), np.float32)
+    g["nlevels"] = len(sf)
+    g["scaleFactors"][0, :len(sf)] = sf
+    return g
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, max_queries=4096, max_train=4096, max_batch=1, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        check(self._L.msl_matcher_create(max_queries, max_train, max_batch, device, C.byref(self._h)))
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        self._L.msl_matcher_stream.restype = C.c_void_p
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.msl_matcher_destroy.argtypes = [C.c_void_p]
+            self._L.msl_matcher_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def hamming_best2(self, q, t):
+        """q: (B, nq, 32), t: (B, nt, 32) uint8 -> best_idx, best_dist, second_dist (B, nq) int32."""
+        q = np.ascontiguousarray(q, np.uint8)
+        t = np.ascontiguousarray(t, np.uint8)
+        if q.ndim == 2:
+            q, t = q[None], t[None]
+        B, nq, nt = q.shape[0], q.shape[1], t.shape[1]
+        bi, bd, sd = (np.zeros((B, nq), np.int32) for _ in range(3))
+        check(self._L.msl_hamming_best2(self._h, ptr(q), nq, ptr(t), nt, B, ptr(bi), ptr(bd), ptr(sd)))
+        return bi, bd, sd
+
+    def hamming_best2_dev(self, d_q, nq, d_t, nt, batch, d_bi, d_bd, d_sd):
+        check(self._L.msl_hamming_best2_dev(self._h, ptr(d_q), nq, ptr(d_t), nt, batch, ptr(d_bi), ptr(d_bd), ptr(d_sd)))
+
+    def hamming_all_pairs(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8)
+        t = np.ascontiguousarray(t, np.uint8)
+        if q.ndim == 2:
+            q, t = q[None], t[None]
+        B, nq, nt = q.shape[0], q.shape[1], t.shape[1]
+        d = np.zeros((B, nq, nt), np.uint16)
+        check(self._L.msl_hamming_all_pairs(self._h, ptr(q), nq, ptr(t), nt, B, ptr(d)))
+        return d
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        return int(np.unpackbits(np.bitwise_xor(np.asarray(a, np.uint8), np.asarray(b, np.uint8))).sum())
+
+    def SearchByProjectionFrame(self, geom, Tcw_cur, Tcw_last, th, last, cur):
+        """SearchByProjection(Frame &Cur, const Frame &Last, th).  last/cur: dicts of flat arrays
+        (see include/msl_frontend.h).  Returns (nmatches, cur_match)."""
+        n_last, n_cur = len(last["octave"]), len(cur["octave"])
+        cm = np.zeros(n_cur, np.int32)
+        nm = C.c_int32()
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        args = [a(last["has_mp"], np.uint8), a(last["outlier"], np.uint8), a(last["mp_obs"], np.uint8),
+                a(last["mp_world"], np.float32), a(last["mp_desc"], np.uint8), a(last["octave"], np.int32),
+                a(last["angle"], np.float32)]
+        cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["angle"], np.float32),
+                 a(cur["uright"], np.float32), a(cur["desc"], np.uint8), a(cur["occupied"], np.uint8)]
+        check(self._L.msl_search_by_projection_frame(
+            self._h, ptr(geom), ptr(a(Tcw_cur, np.float32)), ptr(a(Tcw_last, np.float32)), C.c_float(th),
+            int(self.mbCheckOrientation), n_last, *[ptr(x) for x in args], n_cur, *[ptr(x) for x in cargs], ptr(cm),
+            C.byref(nm)))
+        return nm.value, cm
+
+    def SearchByProjectionPoints(self, geom, th, mps, cur):
+        """SearchByProjection(Frame &F, const vector<MapPoint*> &, th).  Returns (nmatches, cur_match)."""
+        n_mp, n_cur = len(mps["level"]), len(cur["octave"])
+        cm = np.zeros(n_cur, np.int32)
+        nm = C.c_int32()
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        args = [a(mps["valid"], np.uint8), a(mps["obs"], np.uint8), a(mps["proj_xyr"], np.float32),
+                a(mps["level"], np.int32), a(mps["viewcos"], np.float32), a(mps["desc"], np.uint8)]
+        cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["uright"], np.float32),
+                 a(cur["desc"], np.uint8), a(cur["occupied"], np.uint8)]
+        check(self._L.msl_search_by_projection_points(
+            self._h, ptr(geom), C.c_float(th), C.c_float(self.mfNNratio), n_mp, *[ptr(x) for x in args], n_cur,
+            *[ptr(x) for x in cargs], ptr(cm), C.byref(nm)))
+        return nm.value, cm

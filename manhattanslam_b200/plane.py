@@ -1,0 +1,62 @@
+"""PlaneDetection pre-stage mirror (src/PlaneExtractor.cpp:44-76 + peac PlaneSeg/initGraph) over the CUDA C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, ptr
+
+BLOCK_DTYPE = np.dtype([("center", "<f8", 3), ("normal", "<f8", 3), ("mse", "<f8"), ("curvature", "<f8"),
+                        ("N", "<i4"), ("nouse", "<i4")])
+
+
+class PlaneDetection:
+    """readDepthImage(depthImg, K, depthMapFactor) + the data-parallel part of runPlaneDetection():
+    organized half-resolution cloud, per-10x10-block PCA statistics, graph seeds and edges."""
+
+    def __init__(self, width=640, height=480, max_batch=1, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        check(self._L.msl_plane_create(width, height, max_batch, device, C.byref(self._h)))
+        self.width, self.height, self.max_batch = width, height, max_batch
+        self.w2, self.h2 = (width + 1) // 2, (height + 1) // 2
+        self.nblocks = (self.w2 // 10) * (self.h2 // 10)
+        self._L.msl_plane_stream.restype = C.c_void_p
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.msl_plane_destroy.argtypes = [C.c_void_p]
+            self._L.msl_plane_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def prestage(self, depth_u16, K=(525.0, 525.0, 319.5, 239.5), depthMapFactor=1.0 / 5000.0, want_cloud=True):
+        d = np.ascontiguousarray(depth_u16, np.uint16)
+        if d.ndim == 2:
+            d = d[None]
+        B = d.shape[0]
+        assert d.shape[1:] == (self.height, self.width) and B <= self.max_batch
+        cloud = np.zeros((B, self.h2, self.w2, 3), np.float64) if want_cloud else None
+        blocks = np.zeros((B, self.nblocks), BLOCK_DTYPE)
+        seed = np.zeros((B, self.nblocks), np.uint8)
+        edges = np.zeros((B, self.nblocks), np.uint8)
+        Kf = np.asarray(K, np.float32)
+        check(self._L.msl_plane_prestage(self._h, ptr(d), C.c_int(self.width), C.c_size_t(self.width * self.height),
+                                         C.c_int(B), ptr(Kf), C.c_float(depthMapFactor), ptr(cloud), ptr(blocks),
+                                         ptr(seed), ptr(edges)))
+        return cloud, blocks, seed, edges
+
+    def prestage_dev(self, d_depth, batch, K=(525.0, 525.0, 319.5, 239.5), depthMapFactor=1.0 / 5000.0,
+                     d_cloud=None, d_blocks=None, d_seed=None, d_edges=None):
+        Kf = np.asarray(K, np.float32)
+        check(self._L.msl_plane_prestage_dev(self._h, ptr(d_depth), C.c_int(self.width),
+                                             C.c_size_t(self.width * self.height), C.c_int(batch), ptr(Kf),
+                                             C.c_float(depthMapFactor), ptr(d_cloud), ptr(d_blocks), ptr(d_seed),
+                                             ptr(d_edges)))
+
+    def sync(self):
+        check(self._L.msl_plane_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._L.msl_plane_stream(self._h)

@@ -138,3 +138,50 @@ def surfel_map(seed, n, depth_f32, Twc, K=K_DEFAULT, ref_index=100, w=640, h=480
     s["updateTimes"] = r.integers(1, 31, n)
     s["lastUpdate"] = ref_index - r.integers(0, 9, n)
     return s
+
+
+def match_scene(seed, n_cur=1000, n_last=900, w=640, h=480, K=K_DEFAULT, collide=0.3):
+    """Synthetic tracking situation for ORBmatcher::SearchByProjection: current-frame keypoints with
+    random descriptors, and last-frame map points that project (through Tcw_cur) near a chosen current
+    keypoint with a noisy copy of its descriptor.  `collide` = fraction of queries that target a
+    keypoint also targeted by another query (exercises the Observations()>0 slot blocking)."""
+    r = np.random.default_rng(seed + 555)
+    fx, fy, cx, cy = K
+    cur = {"xy": np.stack([r.uniform(2, w - 2, n_cur), r.uniform(2, h - 2, n_cur)], 1).astype(np.float32),
+           "octave": r.integers(0, 8, n_cur).astype(np.int32),
+           "angle": r.uniform(0, 360, n_cur).astype(np.float32),
+           "uright": None,
+           "desc": r.integers(0, 256, (n_cur, 32), dtype=np.uint8),
+           "occupied": (r.random(n_cur) < 0.05).astype(np.uint8)}
+    # poses: small motion between last and current
+    T = pose_walk(seed, 2)
+    Twc_last, Twc_cur = T[0].astype(np.float64), T[1].astype(np.float64)
+    Twc_cur[2, 3] += r.choice([-0.3, 0.0, 0.3])  # exercises bForward / bBackward / neither
+    Tcw_cur = np.linalg.inv(Twc_cur).astype(np.float32)
+    Tcw_last = np.linalg.inv(Twc_last).astype(np.float32)
+    tgt = r.integers(0, n_cur, n_last)
+    ncol = int(collide * n_last)
+    tgt[:ncol] = tgt[ncol:2 * ncol]
+    r.shuffle(tgt)
+    cur_z = r.uniform(1.0, 5.0, n_cur)
+    cur["uright"] = np.where(r.random(n_cur) < 0.7, cur["xy"][:, 0] - 40.0 / cur_z, -1).astype(np.float32)
+    z = cur_z[tgt] * (1.0 + r.normal(0, 0.01, n_last))
+    uv = cur["xy"][tgt].astype(np.float64) + r.normal(0, 2.0, (n_last, 2))
+    pc = np.stack([(uv[:, 0] - cx) / fx * z, (uv[:, 1] - cy) / fy * z, z, np.ones(n_last)], 1)
+    pw = (np.linalg.inv(Tcw_cur.astype(np.float64)) @ pc.T).T[:, :3]
+    desc = cur["desc"][tgt].copy()
+    flips = r.integers(0, 70, n_last)
+    for i in range(n_last):
+        bits = r.choice(256, flips[i], replace=False)
+        for b in bits:
+            desc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    last = {"has_mp": (r.random(n_last) < 0.9).astype(np.uint8), "outlier": (r.random(n_last) < 0.05).astype(np.uint8),
+            "mp_obs": (r.random(n_last) < 0.85).astype(np.uint8), "mp_world": pw.astype(np.float32), "mp_desc": desc,
+            "octave": np.clip(cur["octave"][tgt] + r.integers(-1, 2, n_last), 0, 7).astype(np.int32),
+            "angle": ((cur["angle"][tgt] + r.normal(0, 8, n_last) + (r.random(n_last) < 0.1) * 90) % 360).astype(np.float32)}
+    # map-point flavour (SearchLocalPoints): projections already computed by Frame::isInFrustum
+    invz = 1.0 / z
+    mps = {"valid": (r.random(n_last) < 0.9).astype(np.uint8), "obs": last["mp_obs"],
+           "proj_xyr": np.stack([uv[:, 0], uv[:, 1], uv[:, 0] - 40.0 * invz], 1).astype(np.float32),
+           "level": last["octave"], "viewcos": r.uniform(0.9, 1.0, n_last).astype(np.float32), "desc": desc}
+    return cur, last, mps, Tcw_cur, Tcw_last

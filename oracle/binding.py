@@ -287,3 +287,87 @@ def surfel_compact(local, new):
     new = np.ascontiguousarray(new)
     n = lib().orc_surfel_compact(_p(buf), len(local), _p(new), len(new))
     return buf[:n].copy()
+
+
+# --------------------------------------------------------------- plane pre-stage
+
+@_late("orc_plane_prestage")
+def _p1(f):
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p] * 4
+
+
+def plane_prestage(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0):
+    """-> (cloud[h2,w2,3] f64, blocks[BLOCK_DTYPE], seed[u8], edges[u8])"""
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    h, w = depth_u16.shape
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    nb = (h2 // 10) * (w2 // 10)
+    cloud = np.zeros((h2, w2, 3), np.float64)
+    blocks = np.zeros(nb, BLOCK_DTYPE)
+    seed = np.zeros(nb, np.uint8)
+    edges = np.zeros(nb, np.uint8)
+    lib().orc_plane_prestage(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor,
+                             _p(cloud), _p(blocks), _p(seed), _p(edges))
+    return cloud, blocks, seed, edges
+
+
+def eig33sym(K):
+    lib().orc_eig33sym.argtypes = [C.c_void_p] * 3
+    K = np.ascontiguousarray(K, np.float64).reshape(9)
+    s = np.zeros(3)
+    V = np.zeros(9)
+    lib().orc_eig33sym(_p(K), _p(s), _p(V))
+    return s, V.reshape(3, 3)
+
+
+# ------------------------------------------------------------------- matcher
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    lib().orc_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def features_in_area(geom, kp_xy, kp_octave, x, y, r, minLevel=-1, maxLevel=-1):
+    L = lib()
+    L.orc_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_int]
+    kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+    kp_octave = np.ascontiguousarray(kp_octave, np.int32)
+    out = np.zeros(len(kp_octave), np.int32)
+    n = L.orc_features_in_area(_p(geom), _p(kp_xy), _p(kp_octave), len(kp_octave), x, y, r, minLevel, maxLevel, _p(out),
+                               len(out))
+    return out[:n].copy()
+
+
+def search_by_projection_frame(geom, Tcw_cur, Tcw_last, th, check_ori, last, cur):
+    L = lib()
+    L.orc_search_by_projection_frame.argtypes = ([C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_int] + [C.c_void_p] * 7 +
+                                                 [C.c_int] + [C.c_void_p] * 7)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    largs = [a(last["has_mp"], np.uint8), a(last["outlier"], np.uint8), a(last["mp_obs"], np.uint8),
+             a(last["mp_world"], np.float32), a(last["mp_desc"], np.uint8), a(last["octave"], np.int32),
+             a(last["angle"], np.float32)]
+    cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["angle"], np.float32),
+             a(cur["uright"], np.float32), a(cur["desc"], np.uint8), a(cur["occupied"], np.uint8)]
+    cm = np.zeros(len(cur["octave"]), np.int32)
+    n = L.orc_search_by_projection_frame(_p(geom), _p(a(Tcw_cur, np.float32)), _p(a(Tcw_last, np.float32)), th,
+                                         int(check_ori), len(last["octave"]), *[_p(x) for x in largs],
+                                         len(cur["octave"]), *[_p(x) for x in cargs], _p(cm))
+    return n, cm
+
+
+def search_by_projection_points(geom, th, nnratio, mps, cur):
+    L = lib()
+    L.orc_search_by_projection_points.argtypes = ([C.c_void_p, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 6 +
+                                                  [C.c_int] + [C.c_void_p] * 6)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    margs = [a(mps["valid"], np.uint8), a(mps["obs"], np.uint8), a(mps["proj_xyr"], np.float32),
+             a(mps["level"], np.int32), a(mps["viewcos"], np.float32), a(mps["desc"], np.uint8)]
+    cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["uright"], np.float32),
+             a(cur["desc"], np.uint8), a(cur["occupied"], np.uint8)]
+    cm = np.zeros(len(cur["octave"]), np.int32)
+    n = L.orc_search_by_projection_points(_p(geom), th, nnratio, len(mps["level"]), *[_p(x) for x in margs],
+                                          len(cur["octave"]), *[_p(x) for x in cargs], _p(cm))
+    return n, cm

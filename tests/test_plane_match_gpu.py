@@ -1,0 +1,112 @@
+"""GPU parity: plane pre-stage and matcher (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from manhattanslam_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_blocks(bo, bg):
+    assert np.array_equal(bo["N"], bg["N"]) and np.array_equal(bo["nouse"], bg["nouse"])
+    ok = bo["N"] >= 4
+    assert np.array_equal(np.isnan(bo["mse"]), np.isnan(bg["mse"]))
+    worst = 0.0
+    for f in ("center", "normal", "mse", "curvature"):
+        a, b = bo[f][ok], bg[f][ok]
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-12), f  # north_star tolerance for float fields
+        worst = max(worst, float(np.abs(a - b).max()) if a.size else 0.0)
+    return worst
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_plane_prestage_matches_oracle(oracle, msl, seed):
+    d16, _ = S.depth_frame(seed)
+    co, bo, so, eo = oracle.plane_prestage(d16)
+    pd = msl.PlaneDetection(max_batch=1)
+    cg, bg, sg, eg = pd.prestage(d16)
+    assert np.array_equal(co, cg[0])  # cloud: same fp64 operations -> bit-exact
+    worst = _cmp_blocks(bo, bg[0])
+    assert worst < 1e-12
+    assert np.array_equal(so, sg[0]) and np.array_equal(eo, eg[0])
+    assert so.sum() > 300
+
+
+def test_plane_prestage_batch_and_holes(oracle, msl):
+    B = 6
+    ds = np.stack([S.depth_frame(30 + b)[0] for b in range(B)])
+    ds[1] = 0  # no depth at all: every block rejected
+    ds[2, ::7, ::5] = 0  # scattered holes
+    pd = msl.PlaneDetection(max_batch=B)
+    cg, bg, sg, eg = pd.prestage(ds, want_cloud=False)
+    for b in range(B):
+        co, bo, so, eo = oracle.plane_prestage(ds[b])
+        _cmp_blocks(bo, bg[b])
+        assert np.array_equal(so, sg[b]) and np.array_equal(eo, eg[b])
+    assert sg[1].sum() == 0
+
+
+def test_plane_other_size(oracle, msl):
+    d16, _ = S.depth_frame(4, 1280, 960)
+    K = (1050.0, 1050.0, 639.5, 479.5)
+    co, bo, so, eo = oracle.plane_prestage(d16, K)
+    cg, bg, sg, eg = msl.PlaneDetection(1280, 960).prestage(d16, K)
+    assert np.array_equal(co, cg[0]) and np.array_equal(so, sg[0]) and np.array_equal(eo, eg[0])
+    _cmp_blocks(bo, bg[0])
+
+
+def test_hamming_best2_and_all_pairs(oracle, msl):
+    r = np.random.default_rng(0)
+    B, nq, nt = 3, 777, 1003
+    q = r.integers(0, 256, (B, nq, 32), dtype=np.uint8)
+    t = r.integers(0, 256, (B, nt, 32), dtype=np.uint8)
+    t[0, 5] = q[0, 9]  # exact match
+    t[0, 700] = q[0, 9]  # duplicate: tie -> lowest index
+    m = msl.ORBmatcher(max_queries=1024, max_train=1024, max_batch=B)
+    d = m.hamming_all_pairs(q, t)
+    ref = np.unpackbits(q[:, :, None, :] ^ t[:, None, :, :], axis=3).sum(3).astype(np.uint16)
+    assert np.array_equal(d, ref)
+    assert d[0, 9, 5] == 0 and oracle.descriptor_distance(q[1, 3], t[1, 4]) == ref[1, 3, 4]
+    bi, bd, sd = m.hamming_best2(q, t)
+    assert np.array_equal(bi, ref.argmin(2)) and np.array_equal(bd, ref.min(2))
+    assert np.array_equal(sd, np.sort(ref, 2)[:, :, 1])
+    assert bi[0, 9] == 5 and sd[0, 9] == 0
+
+
+@pytest.mark.parametrize("seed,th", [(1, 15.0), (2, 30.0), (3, 7.0), (4, 15.0)])
+def test_search_by_projection_frame(oracle, msl, seed, th):
+    cur, last, mps, Tc, Tl = S.match_scene(seed)
+    g = msl.frame_geom()
+    m = msl.ORBmatcher()
+    for check in (True, False):
+        m.mbCheckOrientation = check
+        n_o, cm_o = oracle.search_by_projection_frame(g, Tc, Tl, th, check, last, cur)
+        n_g, cm_g = m.SearchByProjectionFrame(g, Tc, Tl, th, last, cur)
+        assert n_o == n_g and np.array_equal(cm_o, cm_g)
+        assert n_o > 100
+
+
+@pytest.mark.parametrize("seed,th", [(1, 1.0), (2, 3.0), (5, 5.0)])
+def test_search_by_projection_points(oracle, msl, seed, th):
+    cur, last, mps, Tc, Tl = S.match_scene(seed, collide=0.5)
+    g = msl.frame_geom()
+    m = msl.ORBmatcher(nnratio=0.8)
+    n_o, cm_o = oracle.search_by_projection_points(g, th, 0.8, mps, cur)
+    n_g, cm_g = m.SearchByProjectionPoints(g, th, mps, cur)
+    assert n_o == n_g and np.array_equal(cm_o, cm_g)
+    assert n_o > 50
+
+
+def test_search_edge_cases(oracle, msl):
+    cur, last, mps, Tc, Tl = S.match_scene(9, n_cur=50, n_last=40)
+    g = msl.frame_geom()
+    m = msl.ORBmatcher()
+    # no usable query at all
+    last2 = dict(last)
+    last2["has_mp"] = np.zeros_like(last["has_mp"])
+    assert m.SearchByProjectionFrame(g, Tc, Tl, 15.0, last2, cur)[0] == oracle.search_by_projection_frame(g, Tc, Tl, 15.0, True, last2, cur)[0] == 0
+    # every slot occupied on entry
+    cur2 = dict(cur)
+    cur2["occupied"] = np.ones_like(cur["occupied"])
+    n, cm = m.SearchByProjectionFrame(g, Tc, Tl, 15.0, last, cur2)
+    assert n == 0 and (cm == -2).all()
