@@ -40,3 +40,26 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def stages():
+    """Stage-level golden vectors produced by the oracle (self-consistency across compilers/builds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_stages import _surfel_case
+    from manhattanslam_b200.matcher import frame_geom
+    g, d, m, T, local = _surfel_case()
+    lo = local.copy()
+    o = ob.SurfelOracle()
+    new = o.fuse(20, g, d, m, T, lo)
+    d16, _ = S.depth_frame(3)
+    cloud, blocks, seed, edges = ob.plane_prestage(d16)
+    cur, last, mps, Tc, Tl = S.match_scene(3)
+    n, cm = ob.search_by_projection_frame(frame_geom(), Tc, Tl, 15.0, True, last, cur)
+    np.savez_compressed(os.path.join(HERE, "stages.npz"), sp_index=o.index(), sp_seeds=o.seeds().view(np.uint8),
+                        local_after=lo.view(np.uint8), new=new.view(np.uint8), plane_seed=seed, plane_edges=edges,
+                        plane_normals=blocks["normal"][seed == 1], match_n=n, match_cm=cm)
+    print("stage golden written")
+
+
+if __name__ == "__main__":
+    stages()
