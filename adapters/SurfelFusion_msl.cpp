@@ -1,0 +1,54 @@
+// SurfelFusion_msl.cpp -- SurfelFusion on the B200 front-end (drop-in for src/SurfelFusion.cpp).
+// SurfelMapping::fuseMap (src/SurfelMapping.cpp:353-364) is unchanged.  This is the exact drop-in: the host
+// vector Map::mvLocalSurfels stays authoritative, so every call uploads it, fuses on the device and downloads it
+// again (one PCIe round trip of 56 B/surfel per keyframe).  INTEGRATION.md describes the device-resident mode
+// (compaction on the device, no round trip) that msl_surfel_fuse(..., compact=1) provides once
+// SurfelMapping::moveAddSurfels is routed through the ABI as well.
+#include <mutex>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "SurfelFusion.h"
+#include "msl_frontend.h"
+
+static_assert(sizeof(Surfel) == sizeof(msl_surfel), "include/Surfel.h layout == msl_surfel");
+
+namespace {
+std::mutex g_mu;
+std::unordered_map<const SurfelFusion *, msl_surfel_fusion *> g_h;  // one instance, SurfelMapping thread only
+}
+
+SurfelFusion::SurfelFusion(int width, int height, float _fx, float _fy, float _cx, float _cy, float _fuseFar, float _fuseNear)
+    : imageWidth(width), imageHeight(height), spWidth(width / SP_SIZE), spHeight(height / SP_SIZE), fx(_fx), fy(_fy),
+      cx(_cx), cy(_cy), fuseFar(_fuseFar), fuseNear(_fuseNear) {
+    msl_surfel_fusion *h = nullptr;
+    if (msl_surfel_create(width, height, _fx, _fy, _cx, _cy, _fuseFar, _fuseNear, 32ll << 20, 0, &h) != MSL_OK)
+        throw std::runtime_error(msl_last_error());
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_h[this] = h;
+}
+
+void SurfelFusion::fuseInitializeMap(const int referenceFrameIndex, const cv::Mat &inputImage, const cv::Mat &inputDepth,
+                                     const cv::Mat &inputPlaneMembershipImg, const Eigen::Matrix4f &pose,
+                                     std::vector<Surfel> &localSurfels, std::vector<Surfel> &newSurfels) {
+    msl_surfel_fusion *h;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        h = g_h.at(this);
+    }
+    CV_Assert(inputImage.type() == CV_8UC1 && inputDepth.type() == CV_32F && inputDepth.isContinuous() &&
+              inputPlaneMembershipImg.type() == CV_32SC1 && inputPlaneMembershipImg.isContinuous());
+    const Eigen::Matrix<float, 4, 4, Eigen::RowMajor> Twc = pose;  // the ABI takes row-major
+    if (msl_surfel_upload_map(h, reinterpret_cast<const msl_surfel *>(localSurfels.data()), (int64_t)localSurfels.size()) != MSL_OK)
+        throw std::runtime_error(msl_last_error());
+    newSurfels.resize((size_t)spWidth * spHeight);
+    int64_t stats[4];
+    if (msl_surfel_fuse(h, referenceFrameIndex, inputImage.data, (int)inputImage.step, inputDepth.ptr<float>(),
+                        inputPlaneMembershipImg.ptr<int32_t>(), Twc.data(), reinterpret_cast<msl_surfel *>(newSurfels.data()),
+                        (int)newSurfels.size(), /*compact=*/0, stats) != MSL_OK)
+        throw std::runtime_error(msl_last_error());
+    newSurfels.resize((size_t)stats[0]);
+    int64_t n = 0;
+    if (msl_surfel_download_map(h, reinterpret_cast<msl_surfel *>(localSurfels.data()), (int64_t)localSurfels.size(), &n) != MSL_OK)
+        throw std::runtime_error(msl_last_error());
+}
