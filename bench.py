@@ -2,9 +2,10 @@
 """bench.py -- RGB-D front-end frames/s on synthetic 640x480 RGB-D (BASELINE.json metric).
 
 One step = one pass of the front-end over one batch of 64 synthetic RGB-D frames per GPU:
-ORB extraction (+ Hamming match of consecutive frames and the plane pre-stage when built) and the
-projective surfel fusion of the 64-frame stream into a device-resident 5M-surfel map (superpixels
-batched, fuse/initialise/compact frame by frame in order).  Frames are independent across ranks
+ORB extraction, brute-force Hamming match of every frame's descriptors against the next frame's (BASELINE.json
+config 2), the plane pre-stage on the u16 depth (config 3) and the projective surfel fusion of the 64-frame
+stream into a device-resident 5M-surfel map (config 4: superpixels batched, fuse/initialise/compact frame by
+frame in order).  Frames are independent across ranks
 (one chunk and one map replica per rank, weak scaling); the only collective is one NCCL all-gather
 of the per-frame keypoint counts + surfel statistics.
 
@@ -56,9 +57,11 @@ def make_inputs(rank, batch, n_surfels):
     # 16 distinct frames cycled to the batch size keeps start-up short; every frame is still processed
     uniq = min(batch, 16)
     gray_u = [S.gray_frame(seed0 + i) for i in range(uniq)]
-    depth_u = [S.depth_frame(seed0 + i)[1] for i in range(uniq)]
+    dd = [S.depth_frame(seed0 + i) for i in range(uniq)]
+    depth_u = [d[1] for d in dd]
     gray = np.stack([gray_u[i % uniq] for i in range(batch)])
     depth = np.stack([depth_u[i % uniq] for i in range(batch)])
+    make_inputs.depth16 = np.stack([dd[i % uniq][0] for i in range(batch)])
     mem = np.stack([S.membership(seed0 + i) for i in range(batch)])
     poses = S.pose_walk(seed0, batch)
     surfels = S.surfel_map(seed0, n_surfels, depth[0], poses[0], ref_index=100)
@@ -77,14 +80,23 @@ def cpu_frontend(gray, depth, mem, poses, surfels, frames, threads):
     t0 = time.perf_counter()
     tl = threading.local()
 
-    def orb(i):
+    depth16 = make_inputs.depth16
+    descs = [None] * frames
+
+    def orb(i):  # ORB + plane pre-stage of frame i (independent per frame)
         if not hasattr(tl, "o"):
             tl.o = ob.OrbOracle()
         k, d = tl.o(gray[i])
+        descs[i] = d
+        ob.plane_prestage(depth16[i])
         return len(k)
+
+    def match(i):  # brute-force Hamming best-2 of frame i against frame i+1
+        return int(ob.hamming_best2(descs[i], descs[i + 1])[1].sum())
 
     with ThreadPoolExecutor(max_workers=threads) as ex:
         counts = list(ex.map(orb, range(frames)))
+        list(ex.map(match, range(frames - 1)))
     so = ob.SurfelOracle(W, H)
     for i in range(frames):
         new = so.fuse(100 + i, gray[i], depth[i], mem[i], poses[i], local, threads=min(10, threads))
@@ -108,13 +120,13 @@ def run_reference(a, rank, world):
         ts.append(dt)
     ms = 1e3 * sum(ts) / len(ts)
     value = frames / (ms / 1e3)
-    sample = "%d of %d frames per step: ORB frame-parallel on %d threads + SurfelFusion (10 scan threads) into a %d-surfel map" % (
+    sample = "%d of %d frames per step: ORB + plane pre-stage + Hamming match frame-parallel on %d threads, SurfelFusion (10 scan threads) into a %d-surfel map" % (
         frames, a.batch, threads, a.surfels)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8+f32", "data": "synthetic",
            "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "surfels_per_gpu": a.surfels,
-                      "stages": ["orb", "surfel_fuse"]},
+                      "stages": ["orb", "hamming_match", "plane_prestage", "surfel_fuse"]},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -177,12 +189,25 @@ def run_ours(a, rank, world, local_rank):
     sf = msl.SurfelFusion(W, H, max_surfels=a.surfels + 4 * B * 4800, device=local_rank)
     sf.upload_map(surfels)
     cap = orb.capacity
+    matcher = msl.ORBmatcher(max_queries=cap, max_train=cap, max_batch=B, device=local_rank)
+    plane = msl.PlaneDetection(W, H, max_batch=B, device=local_rank)
+    depth16 = make_inputs.depth16
+    nblk = plane.nblocks
 
     # pinned host staging (e2e leg) and device-resident inputs (kernel leg)
     h_gray = torch.from_numpy(gray).pin_memory()
     h_depth = torch.from_numpy(depth).pin_memory()
     h_mem = torch.from_numpy(mem).pin_memory()
-    d_gray, d_depth, d_mem = h_gray.to(dev), h_depth.to(dev), h_mem.to(dev)
+    h_d16 = torch.from_numpy(depth16.view(np.int16)).pin_memory()
+    d_gray, d_depth, d_mem, d_d16 = h_gray.to(dev), h_depth.to(dev), h_mem.to(dev), h_d16.to(dev)
+    d_bi = torch.zeros((B, cap), dtype=torch.int32, device=dev)
+    d_bd, d_sd = torch.zeros_like(d_bi), torch.zeros_like(d_bi)
+    d_blocks = torch.zeros((B, nblk, 72), dtype=torch.uint8, device=dev)
+    d_seedm = torch.zeros((B, nblk), dtype=torch.uint8, device=dev)
+    d_edges = torch.zeros((B, nblk), dtype=torch.uint8, device=dev)
+    h_match = torch.zeros((3, B, cap), dtype=torch.int32).pin_memory()
+    h_blocks = torch.zeros((B, nblk, 72), dtype=torch.uint8).pin_memory()
+    h_seedm = torch.zeros((2, B, nblk), dtype=torch.uint8).pin_memory()
     d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
     d_counts = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -194,6 +219,8 @@ def run_ours(a, rank, world, local_rank):
 
     s_orb = torch.cuda.ExternalStream(orb.stream, device=dev)
     s_sf = torch.cuda.ExternalStream(sf.stream, device=dev)
+    s_pl = torch.cuda.ExternalStream(plane.stream, device=dev)
+    K4 = (525.0, 525.0, 319.5, 239.5)
     state = {"ref": 100}
 
     def step_dev():
@@ -201,6 +228,12 @@ def run_ours(a, rank, world, local_rank):
         if world > 1:
             s_orb.wait_stream(torch.cuda.current_stream())  # previous all-gather still reads d_counts
         orb.extract_dev(d_gray.data_ptr(), W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr())
+        # frame b vs frame b+1, chained on the ORB stream (no host sync between extraction and matching)
+        matcher.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_counts.data_ptr(),
+                                         d_counts.data_ptr() + 4, B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr(),
+                                         stream=orb.stream)
+        plane.prestage_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, None, d_blocks.data_ptr(), d_seedm.data_ptr(),
+                           d_edges.data_ptr())
         sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
         state["ref"] += B
         if world > 1:  # the path's single collective: per-frame counts to every rank
@@ -221,18 +254,20 @@ def run_ours(a, rank, world, local_rank):
     st0 = sf.read_stats()
     clk = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev_o, ev_s = torch.cuda.Event(), torch.cuda.Event()
+    ev_o, ev_s, ev_p = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     cur = torch.cuda.current_stream()
     ev0.record(cur)
     s_orb.wait_event(ev0)
     s_sf.wait_event(ev0)
-    upd = dele = 0
+    s_pl.wait_event(ev0)
     for _ in range(a.steps):
         step_dev()
     ev_o.record(s_orb)
     ev_s.record(s_sf)
+    ev_p.record(s_pl)
     cur.wait_event(ev_o)
     cur.wait_event(ev_s)
+    cur.wait_event(ev_p)
     ev1.record(cur)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -268,7 +303,7 @@ def run_ours(a, rank, world, local_rank):
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_fuse", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_fuse_scan+k_fuse_apply", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_avg_ms, "launches": fuse_launches,
                 "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None}
@@ -281,6 +316,16 @@ def run_ours(a, rank, world, local_rank):
         check(orb._L.msl_orb_extract(orb._h, C.c_void_p(h_gray.data_ptr()), C.c_int(W), C.c_size_t(W * H), C.c_int(B),
                                      C.c_void_p(h_kps.data_ptr()), C.c_void_p(h_desc.data_ptr()),
                                      C.c_void_p(h_counts.data_ptr())))
+        # matching on the descriptors just produced (device-resident copy inside the ORB handle is not exposed, so the
+        # host API path re-uploads them: that is what a host-side caller of the C ABI pays)
+        check(matcher._L.msl_hamming_best2(matcher._h, C.c_void_p(h_desc.data_ptr()), C.c_int(cap),
+                                           C.c_void_p(h_desc.data_ptr() + cap * 32), C.c_int(cap), C.c_int(B - 1),
+                                           C.c_void_p(h_match[0].data_ptr()), C.c_void_p(h_match[1].data_ptr()),
+                                           C.c_void_p(h_match[2].data_ptr())))
+        Kf = np.asarray(K4, np.float32)
+        check(plane._L.msl_plane_prestage(plane._h, C.c_void_p(h_d16.data_ptr()), C.c_int(W), C.c_size_t(W * H), C.c_int(B),
+                                          ptr(Kf), C.c_float(1.0 / 5000.0), None, C.c_void_p(h_blocks.data_ptr()),
+                                          C.c_void_p(h_seedm[0].data_ptr()), C.c_void_p(h_seedm[1].data_ptr())))
         stats = np.zeros(4, np.int64)
         check(sf._L.msl_surfel_fuse_batch(sf._h, state["ref"], C.c_void_p(h_gray.data_ptr()), C.c_int(W),
                                           C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_mem.data_ptr()), ptr(poses),
@@ -300,8 +345,9 @@ def run_ours(a, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * a.steps / float(t.item())
-    h2d = int(h_gray.numel() + h_depth.numel() * 4 + h_mem.numel() * 4 + 64 * B)
-    d2h = int(h_kps.numel() + h_desc.numel() + h_counts.numel() * 4 + 32)
+    h2d = int(h_gray.numel() + h_depth.numel() * 4 + h_mem.numel() * 4 + h_d16.numel() * 2 + 2 * (B - 1) * cap * 32 + 64 * B)
+    d2h = int(h_kps.numel() + h_desc.numel() + h_counts.numel() * 4 + 3 * (B - 1) * cap * 4 + h_blocks.numel() +
+              2 * B * nblk + 32)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -309,15 +355,15 @@ def run_ours(a, rank, world, local_rank):
         frames = min(a.cpu_frames, B)
         fps, dt = cpu_frontend(gray, depth, mem, poses, surfels, frames, threads)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d frames (%.1f s): oracle ORB frame-parallel on %d threads + oracle SurfelFusion with 10 scan "
-                         "threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
+               "sample": "%d frames (%.1f s): oracle ORB + plane pre-stage + Hamming match frame-parallel on %d threads, oracle "
+                         "SurfelFusion with 10 scan threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8+f32", "data": "synthetic",
                "config": {"workload": workload_name(a), "batch_per_gpu": B, "surfels_per_gpu": a.surfels,
-                          "stages": ["orb", "surfel_fuse"], "map_size_end": n_map,
+                          "stages": ["orb", "hamming_match", "plane_prestage", "surfel_fuse"], "map_size_end": n_map,
                           "l2": "working set per step (280 MB surfel planes + 190 MB pyramids) exceeds the 126 MB L2",
                           "collective": "nccl all_gather of per-frame counts" if world > 1 else "none (1 GPU)"},
                "roofline": roofline, "cpu_baseline": cpu,

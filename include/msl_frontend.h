@@ -122,6 +122,12 @@ int msl_hamming_best2(msl_matcher *, const uint8_t *q, int nq, const uint8_t *t,
                       int32_t *best_idx, int32_t *best_dist, int32_t *second_dist);
 int msl_hamming_best2_dev(msl_matcher *, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int batch,
                           int32_t *d_best_idx, int32_t *d_best_dist, int32_t *d_second_dist);
+/* Same on the ragged output of msl_orb_extract_dev: every batch entry reserves `rows` descriptor rows (and
+ * `rows` output slots), of which d_qcounts[b] / d_tcounts[b] are filled.  stream = cudaStream_t to enqueue on
+ * (NULL = the handle's stream), e.g. the ORB handle's stream to chain extraction -> matching without a sync. */
+int msl_hamming_best2_counts_dev(msl_matcher *, const uint8_t *d_q, const uint8_t *d_t, int rows,
+                                 const int32_t *d_qcounts, const int32_t *d_tcounts, int batch, int32_t *d_best_idx,
+                                 int32_t *d_best_dist, int32_t *d_second_dist, void *stream);
 
 /* ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th) (src/ORBmatcher.cc:548-678).
  * The adapter flattens the Frame/MapPoint graph into arrays:

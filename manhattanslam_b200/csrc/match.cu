@@ -36,13 +36,17 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 }
 
 __global__ void __launch_bounds__(256)
-    k_hamming_best2(const uint8_t *__restrict__ q, int nq, const uint8_t *__restrict__ t, int nt, int32_t *__restrict__ bestIdx,
+    k_hamming_best2(const uint8_t *__restrict__ q, int nqMax, int qRows, const uint8_t *__restrict__ t, int ntMax, int tRows,
+                    const int32_t *__restrict__ qCounts, const int32_t *__restrict__ tCounts, int32_t *__restrict__ bestIdx,
                     int32_t *__restrict__ bestDist, int32_t *__restrict__ secondDist) {
     __shared__ uint4 tile[256 * 2];
     const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int qi = blockIdx.x * 8 + wid;
-    const uint4 *Q = (const uint4 *)(q + (size_t)b * nq * 32);
-    const uint4 *T = (const uint4 *)(t + (size_t)b * nt * 32);
+    // qRows/tRows = descriptor rows reserved per batch entry; counts (optional) = rows actually filled
+    const int nq = qCounts ? min(qCounts[b], nqMax) : nqMax, nt = tCounts ? min(tCounts[b], ntMax) : ntMax;
+    if (blockIdx.x * 8 >= nq) return;
+    const uint4 *Q = (const uint4 *)(q + (size_t)b * qRows * 32);
+    const uint4 *T = (const uint4 *)(t + (size_t)b * tRows * 32);
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
     if (qi < nq) q0 = __ldg(Q + 2 * qi), q1 = __ldg(Q + 2 * qi + 1);
     int bd = 257, bi = -1, sd = 257;
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(256)
         sd = ns;
     }
     if (qi < nq && lane == 0) {
-        const size_t o = (size_t)b * nq + qi;
+        const size_t o = (size_t)b * qRows + qi;
         bestIdx[o] = bi;
         bestDist[o] = bd > 256 ? 256 : bd;
         secondDist[o] = sd > 256 ? 256 : sd;
@@ -432,7 +436,21 @@ int msl_hamming_best2_dev(msl_matcher *m, const uint8_t *d_q, int nq, const uint
     if (!m || !d_q || !d_t || !d_best_idx || !d_best_dist || !d_second_dist) return fail(MSL_ERR_INVALID, "msl_hamming_best2_dev: null argument");
     if (nq < 1 || nt < 0 || batch < 1) return fail(MSL_ERR_INVALID, "msl_hamming_best2_dev: bad size");
     MSL_CUDA(cudaSetDevice(m->device));
-    k_hamming_best2<<<dim3(cdiv(nq, 8), batch), 256, 0, m->stream>>>(d_q, nq, d_t, nt, d_best_idx, d_best_dist, d_second_dist);
+    k_hamming_best2<<<dim3(cdiv(nq, 8), batch), 256, 0, m->stream>>>(d_q, nq, nq, d_t, nt, nt, nullptr, nullptr, d_best_idx,
+                                                                      d_best_dist, d_second_dist);
+    MSL_LAUNCH_CHECK();
+    return MSL_OK;
+}
+
+int msl_hamming_best2_counts_dev(msl_matcher *m, const uint8_t *d_q, const uint8_t *d_t, int rows, const int32_t *d_qcounts,
+                                 const int32_t *d_tcounts, int batch, int32_t *d_best_idx, int32_t *d_best_dist,
+                                 int32_t *d_second_dist, void *stream) {
+    if (!m || !d_q || !d_t || !d_best_idx || !d_best_dist || !d_second_dist) return fail(MSL_ERR_INVALID, "msl_hamming_best2_counts_dev: null argument");
+    if (rows < 1 || batch < 1) return fail(MSL_ERR_INVALID, "msl_hamming_best2_counts_dev: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    k_hamming_best2<<<dim3(cdiv(rows, 8), batch), 256, 0, st>>>(d_q, rows, rows, d_t, rows, rows, d_qcounts, d_tcounts, d_best_idx,
+                                                                 d_best_dist, d_second_dist);
     MSL_LAUNCH_CHECK();
     return MSL_OK;
 }

@@ -59,6 +59,10 @@ class ORBmatcher:
     def hamming_best2_dev(self, d_q, nq, d_t, nt, batch, d_bi, d_bd, d_sd):
         check(self._L.msl_hamming_best2_dev(self._h, ptr(d_q), nq, ptr(d_t), nt, batch, ptr(d_bi), ptr(d_bd), ptr(d_sd)))
 
+    def hamming_best2_counts_dev(self, d_q, d_t, rows, d_qcounts, d_tcounts, batch, d_bi, d_bd, d_sd, stream=None):
+        check(self._L.msl_hamming_best2_counts_dev(self._h, ptr(d_q), ptr(d_t), rows, ptr(d_qcounts), ptr(d_tcounts), batch,
+                                                   ptr(d_bi), ptr(d_bd), ptr(d_sd), C.c_void_p(stream or 0)))
+
     def hamming_all_pairs(self, q, t):
         q = np.ascontiguousarray(q, np.uint8)
         t = np.ascontiguousarray(t, np.uint8)

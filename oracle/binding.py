@@ -329,6 +329,16 @@ def descriptor_distance(a, b):
     return lib().orc_descriptor_distance(_p(a), _p(b))
 
 
+def hamming_best2(q, t):
+    L = lib()
+    L.orc_hamming_best2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    bi, bd, sd = (np.zeros(len(q), np.int32) for _ in range(3))
+    L.orc_hamming_best2(_p(q), len(q), _p(t), len(t), _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
 def features_in_area(geom, kp_xy, kp_octave, x, y, r, minLevel=-1, maxLevel=-1):
     L = lib()
     L.orc_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,

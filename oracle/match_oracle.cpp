@@ -112,6 +112,21 @@ extern "C" {
 
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) { return descriptor_distance(a, b); }
 
+// brute-force best / second-best over all train descriptors (ties: lowest index); the CPU counterpart of the
+// all-pairs Hamming search of BASELINE.json config 2
+void orc_hamming_best2(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist,
+                       int32_t *second_dist) {
+    for (int i = 0; i < nq; i++) {
+        int bd = 257, bi = -1, sd = 257;
+        for (int j = 0; j < nt; j++) {
+            const int d = descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (d < bd) sd = bd, bd = d, bi = j;
+            else if (d < sd) sd = d;
+        }
+        best_idx[i] = bi, best_dist[i] = bd > 256 ? 256 : bd, second_dist[i] = sd > 256 ? 256 : sd;
+    }
+}
+
 int orc_features_in_area(const orc_frame_geom *g, const float *kp_xy, const int32_t *kp_octave, int n, float x, float y,
                          float r, int minLevel, int maxLevel, int32_t *out, int cap) {
     Grid G;

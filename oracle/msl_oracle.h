@@ -80,6 +80,8 @@ int orc_cv_round_f(float v);
 
 /* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:835-849 */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
+void orc_hamming_best2(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist,
+                       int32_t *second_dist);
 
 typedef struct {
     float fx, fy, cx, cy;

@@ -110,3 +110,32 @@ def test_search_edge_cases(oracle, msl):
     cur2["occupied"] = np.ones_like(cur["occupied"])
     n, cm = m.SearchByProjectionFrame(g, Tc, Tl, 15.0, last, cur2)
     assert n == 0 and (cm == -2).all()
+
+
+def test_hamming_best2_ragged_device(oracle, msl):
+    """Ragged batch (per-entry row counts, as produced by msl_orb_extract_dev) through the device entry point."""
+    import torch
+    r = np.random.default_rng(3)
+    B, rows = 5, 300
+    desc = r.integers(0, 256, (B, rows, 32), dtype=np.uint8)
+    counts = np.array([300, 17, 0, 123, 256], np.int32)
+    d_desc = torch.from_numpy(desc).cuda()
+    d_counts = torch.from_numpy(counts).cuda()
+    d_bi = torch.full((B, rows), -7, dtype=torch.int32, device="cuda")
+    d_bd, d_sd = torch.zeros_like(d_bi), torch.zeros_like(d_bi)
+    m = msl.ORBmatcher(max_queries=rows, max_train=rows, max_batch=B)
+    # entry b: frame b (query) vs frame b+1 (train)
+    m.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + rows * 32, rows, d_counts.data_ptr(),
+                               d_counts.data_ptr() + 4, B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr())
+    m._L.msl_matcher_sync(m._h)
+    bi, bd, sd = d_bi.cpu().numpy(), d_bd.cpu().numpy(), d_sd.cpu().numpy()
+    for b in range(B - 1):
+        nq, nt = counts[b], counts[b + 1]
+        if nq == 0:
+            continue
+        if nt == 0:
+            assert (bi[b, :nq] == -1).all() and (bd[b, :nq] == 256).all()
+            continue
+        obi, obd, osd = oracle.hamming_best2(desc[b, :nq], desc[b + 1, :nt])
+        assert np.array_equal(bi[b, :nq], obi) and np.array_equal(bd[b, :nq], obd) and np.array_equal(sd[b, :nq], osd)
+        assert (bi[b, nq:] == -7).all()  # rows beyond the count are not touched

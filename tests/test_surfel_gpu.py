@@ -48,9 +48,7 @@ def test_superpixels_match_oracle(oracle, msl, seed, pf):
     assert np.array_equal(index[0], o.index()), "superpixelIndex"
     so = o.seeds()
     worst = _cmp(so, seeds[0], FLOAT_SEED, INT_SEED, "seed")
-    # same float operation order (only the fp64 normal-equation sums use a warp tree): differences, if any, are
-    # last-bit float roundings far inside the 1e-4 bar
-    assert worst <= 1e-5, worst
+    assert worst == 0.0, worst  # same operation order => bit-exact in practice (regression guard)
     assert so["stable"].sum() > 100  # the stable/fixed-point path was exercised
 
 
@@ -94,7 +92,7 @@ def test_fuse_matches_oracle(oracle, msl, n):
     got = sf.download_map()
     w1 = _cmp(lo, got, FLOAT_SURFEL, INT_SURFEL, "localSurfels")
     w2 = _cmp(new_o, new_g, FLOAT_SURFEL, INT_SURFEL, "newSurfels")
-    assert w1 <= 1e-5 and w2 <= 1e-5
+    assert w1 == 0.0 and w2 == 0.0
     assert np.array_equal(o.seeds()["fused"], sf.debug_seeds()["fused"])
     n_upd = int((lo["updateTimes"] == local["updateTimes"] + 1).sum())
     n_del = int(((lo["updateTimes"] == 0) & (local["updateTimes"] != 0)).sum())
@@ -122,14 +120,14 @@ def test_fuse_with_compaction_stream(oracle, msl, n):
         _, stats = sf.fuseInitializeMap(50 + k, fr[k][0], fr[k][1], fr[k][2], T[k], compact=True)
     got = sf.download_map()
     assert stats[3] == len(lo) == len(got)
-    assert _cmp(lo, got, FLOAT_SURFEL, INT_SURFEL, "map after stream") <= 1e-5
+    assert _cmp(lo, got, FLOAT_SURFEL, INT_SURFEL, "map after stream") == 0.0
     # batched stream API (superpixels batched, fuse in order)
     sf2 = msl.SurfelFusion(max_surfels=n + K * 4800)
     sf2.upload_map(local)
     st2 = sf2.fuse_batch(50, np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr]), np.stack([f[2] for f in fr]), T)
     got2 = sf2.download_map()
     assert st2[3] == len(lo)
-    assert _cmp(lo, got2, FLOAT_SURFEL, INT_SURFEL, "map after batched stream") <= 1e-5
+    assert _cmp(lo, got2, FLOAT_SURFEL, INT_SURFEL, "map after batched stream") == 0.0
 
 
 def test_compaction_many_deleted(oracle, msl):
@@ -149,7 +147,7 @@ def test_compaction_many_deleted(oracle, msl):
     _, stats = sf.fuseInitializeMap(100, g, d, m, T, compact=True)
     got = sf.download_map()
     assert len(got) == len(lo) == stats[3]
-    assert _cmp(lo, got, FLOAT_SURFEL, INT_SURFEL, "compacted map") <= 1e-5
+    assert _cmp(lo, got, FLOAT_SURFEL, INT_SURFEL, "compacted map") == 0.0
 
 
 def test_upload_download_roundtrip(msl):
