@@ -274,6 +274,7 @@ def run_ours(a, rank, world, local_rank):
     clocks = clk.stop()
     launches = int(msl.lib().msl_kernel_launch_count() - launches0)
     fuse_ms, fuse_launches = sf.fuse_kernel_time()
+    chain, chain_frames = sf.chain_times()
     sf.set_timing(False)
     st1 = sf.read_stats()
     orb.sync()
@@ -306,7 +307,8 @@ def run_ours(a, rank, world, local_rank):
     roofline = {"kernel": "k_fuse_scan+k_fuse_apply", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_avg_ms, "launches": fuse_launches,
-                "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None}
+                "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None,
+                "chain_us_per_frame": {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}}
 
     # ---- e2e: the public host API with pinned host buffers, H2D of the inputs + D2H of the results every step
     import ctypes as C

@@ -262,6 +262,8 @@ int msl_surfel_sync(msl_surfel_fusion *);
  * number of launches since the last query, and resets the tally. */
 int msl_surfel_set_timing(msl_surfel_fusion *, int enable);
 int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *launches);
+/* per-kernel split of the per-frame chain (compact mode): out = {scan, apply, post, list, cmp_apply} in ms */
+int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
 /* Batched superpixel generation only (generateSuperPixels, src/SurfelFusion.cpp:805-816) for `batch`

@@ -101,6 +101,13 @@ class SurfelFusion:
     def set_timing(self, enable=True):
         check(self._L.msl_surfel_set_timing(self._h, int(enable)))
 
+    def chain_times(self):
+        """per-frame-chain kernel times in ms: dict(scan, apply, post, list, cmp_apply), frames"""
+        out = (C.c_double * 5)()
+        n = C.c_int()
+        check(self._L.msl_surfel_chain_times(self._h, out, C.byref(n)))
+        return dict(zip(("scan", "apply", "post", "list", "cmp_apply"), [float(v) for v in out])), n.value
+
     def fuse_kernel_time(self):
         """(total milliseconds, launches) of the projective fuse scan since the last query."""
         ms, n = C.c_double(), C.c_int()
