@@ -121,8 +121,18 @@ __global__ void __launch_bounds__(256) k_resize(const LevelInfo *__restrict__ lv
 // ------------------------------------------------------------------------------------------ O2
 // Threshold-free FAST-9-16 score: S_max = max over the 16 nine-pixel arcs, both polarities, of the
 // minimum signed difference; cv::FAST's response is S_max-1 and "corner at t" <=> S_max > t.
-__device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch) {
+// minTh: scores <= minTh are never used (a candidate needs S_max > minTh and NMS only ever compares a candidate
+// against neighbours whose true score is below its own when they are <= minTh), so they are returned as 0 after a
+// cheap test: any 9-arc of the 16-ring contains two of the four compass pixels (0, 4, 8, 12) that are 4 apart or
+// three of them, so S_max > minTh needs >= 2 compass pixels beyond the threshold on the same side.
+__device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch, int minTh) {
     const int v = c[0];
+    {
+        const int c0 = v - c[3 * pitch], c4 = v - c[3], c8 = v - c[-3 * pitch], c12 = v - c[-3];
+        const int pos = (c0 > minTh) + (c4 > minTh) + (c8 > minTh) + (c12 > minTh);
+        const int neg = (c0 < -minTh) + (c4 < -minTh) + (c8 < -minTh) + (c12 < -minTh);
+        if (pos < 2 && neg < 2) return 0;
+    }
     int d[16];
     d[0] = v - c[3 * pitch];
     d[1] = v - c[3 * pitch + 1];
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(128)
     const int np = cw * ch;
     for (int p = tid; p < np; p += 128) {
         int cy = p / cw, cx = p - cy * cw;
-        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(tile + (cy + 3) * CELL_TILE + cx + 3, CELL_TILE);
+        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(tile + (cy + 3) * CELL_TILE + cx + 3, CELL_TILE, min(minTh, iniTh));
     }
     __syncthreads();
     // in-cell NMS: strict maximum over the 8 neighbours; neighbours outside the cell's ring count as 0
