@@ -108,14 +108,23 @@ SURFEL_DTYPE = np.dtype([("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("nx", "<f
 
 
 def surfel_map(seed, n, depth_f32, Twc, K=K_DEFAULT, ref_index=100, w=640, h=480):
-    """n surfels sampled on the surface seen in depth_f32 from pose Twc (plus out-of-frustum and
-    perturbed ones): ~35 % project into the frame and agree with the depth, ~10 % hit the
-    unstable-drop rule (lastUpdate old, few updates), the rest are outside the frustum."""
+    """n surfels laid out the way a real local map is: the back-projected superpixel seeds
+    (80x60 raster, ~4800 each) of ceil(n/4800) synthetic keyframes whose views overlap the current one, keyframe
+    after keyframe -- so neighbours in memory are neighbours in space.  ~35 % project into the frame and agree
+    with the depth, ~10 % hit the unstable-drop rule (old lastUpdate, few updates), the rest are out of view."""
     r = np.random.default_rng(seed + 1234)
     fx, fy, cx, cy = K
     s = np.zeros(n, SURFEL_DTYPE)
-    u = r.uniform(-0.9 * w, 1.9 * w, n)
-    v = r.uniform(-0.9 * h, 1.9 * h, n)
+    spw, sph = w // 8, h // 8
+    per = spw * sph
+    nkf = (n + per - 1) // per
+    col = np.tile(np.arange(spw), sph).astype(np.float64)
+    row = np.repeat(np.arange(sph), spw).astype(np.float64)
+    ou = r.uniform(-0.9 * w, 0.9 * w, nkf)
+    ov = r.uniform(-0.9 * h, 0.9 * h, nkf)
+    sc = r.uniform(0.8, 1.25, nkf)
+    u = (ou[:, None] + sc[:, None] * (8 * col[None, :] + 4)).reshape(-1)[:n] + r.uniform(-2, 2, n)
+    v = (ov[:, None] + sc[:, None] * (8 * row[None, :] + 4)).reshape(-1)[:n] + r.uniform(-2, 2, n)
     ui = np.clip(np.rint(u), 1, w - 2).astype(np.int64)
     vi = np.clip(np.rint(v), 1, h - 2).astype(np.int64)
     z = depth_f32[vi, ui].astype(np.float64)
