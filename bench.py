@@ -289,7 +289,9 @@ def run_ours(a, rank, world, local_rank):
     # stats accumulate per fuse_batch call: st1 holds the last step's totals over its B launches
     upd_per_launch = st1[1] / B
     del_per_launch = st1[2] / B
-    alg_bytes = n_map * 20.0 + upd_per_launch * 64.0 + del_per_launch * 4.0
+    # k_fuse_scan: 20 B per surfel streamed (lastUpdate, updateTimes, px, py, pz) + 4 B per surfel it kills; the
+    # survivor queue (12 B per in-view surfel) and the sparse fuse writes of k_fuse_apply are not counted
+    alg_bytes = n_map * 20.0 + del_per_launch * 4.0
     peak, peak_src = FALLBACK_HBM_GBS, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -304,7 +306,7 @@ def run_ours(a, rank, world, local_rank):
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_fuse_scan+k_fuse_apply", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_fuse_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_avg_ms, "launches": fuse_launches,
                 "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None,
