@@ -284,6 +284,19 @@ def run_ours(a, rank, world, local_rank):
     ms_step = float(t.item()) / a.steps
     value = world * B / (ms_step / 1e3)
 
+    # ---- the same kernel timed alone (one extra stream call after a full sync: its superpixel stage precedes its
+    # chain and no other stream is busy), to separate the kernel's own efficiency from SM sharing in the timed region
+    barrier()
+    orb.sync()
+    plane.sync()
+    sf.set_timing(True)
+    sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
+    state["ref"] += B
+    iso_ms, iso_launches = sf.fuse_kernel_time()
+    iso_chain, iso_frames = sf.chain_times()
+    sf.set_timing(False)
+    st1 = sf.read_stats()
+
     # ---- roofline of the dominant kernel (projective fuse scan), measured live with CUDA events
     n_map = st1[3]
     # stats accumulate per fuse_batch call: st1 holds the last step's totals over its B launches
@@ -303,14 +316,20 @@ def run_ours(a, rank, world, local_rank):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fuse_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f)["dram_bytes_per_surfel"] * n_map  # ncu capture scaled to this run's map size
     except Exception:
         pass
     roofline = {"kernel": "k_fuse_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_avg_ms, "launches": fuse_launches,
                 "share_of_step": fuse_ms / (ms_step * a.steps) if ms_step else None,
-                "chain_us_per_frame": {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}}
+                "chain_us_per_frame": {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()},
+                "isolated": {"avg_launch_ms": iso_ms / max(iso_launches, 1),
+                             "achieved": alg_bytes / (iso_ms / max(iso_launches, 1) * 1e-3) / 1e9 if iso_launches else None,
+                             "frac": alg_bytes / (iso_ms / max(iso_launches, 1) * 1e-3) / 1e9 / peak if iso_launches else None,
+                             "chain_us_per_frame": {k: 1e3 * v / max(iso_frames, 1) for k, v in iso_chain.items()},
+                             "note": "same kernel, same map, no other stream active"},
+                "note": "timed-region launches share the SMs with the next batch's superpixel kernels (stream overlap)"}
 
     # ---- e2e: the public host API with pinned host buffers, H2D of the inputs + D2H of the results every step
     import ctypes as C
