@@ -114,13 +114,6 @@ struct SearchArgs {
     int32_t *assign, *bin;
 };
 
-struct QueryGeom {
-    float u, v, radius, urOrXr, rEr;
-    int minL, maxL;
-    short cx0, cx1, cy0, cy1;
-    int valid;
-};
-
 __device__ __forceinline__ float gemm_row(const float *R, const float *x, float t) {
     double s = 0;
     s += (double)R[0] * (double)x[0];

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256)
         S.flag = p; p += 4 * maxNodes;
         S.ws = p; p += 40;
     }
-    __shared__ int s_n, s_size, s_phase, s_clast, s_finish, s_J, s_m;
+    __shared__ int s_size, s_phase, s_clast, s_finish, s_J, s_m;
     uint32_t *rec = candRec + (size_t)frame * candCapTotal + L.candBase;
     unsigned short *node = candNode + (size_t)frame * candCapTotal + L.candBase;
 
@@ -334,10 +334,7 @@ __global__ void __launch_bounds__(256)
     for (int c = tid; c < L.nCells; c += nt) cellOff[c] = cc[c];
     __syncthreads();
     const int n = block_excl_scan(cellOff, L.nCells, S.ws);
-    if (tid == 0) {
-        s_n = n;
-        candCount[frame * nlevels + level] = n;
-    }
+    if (tid == 0) candCount[frame * nlevels + level] = n;
     __syncthreads();
     if (n == 0) {
         if (tid == 0) lvlCount[frame * nlevels + level] = 0;
