@@ -181,6 +181,7 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line (no version banner)
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
     gray, depth, mem, poses, surfels = make_inputs(rank, B, a.surfels)
