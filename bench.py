@@ -134,11 +134,14 @@ def run_reference(a, rank, world):
 
 # ------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; started before the warm-up (nvidia-smi needs a few
+    hundred ms to come up) and filtered to the wall-clock window of the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
@@ -146,30 +149,43 @@ class ClockSampler:
         except OSError:
             pass
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             out = self.p.communicate(timeout=5)[0]
         except Exception:
             out = ""
-        sm, mx, reasons = [], 0, set()
+        import datetime
+        sm, allsm, mx, reasons = [], [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk = float(f[1])
+                mx = max(mx, float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            allsm.append(clk)
+            if self.t0 is not None and (ts < self.t0 - 0.02 or ts > self.t1 + 0.02):
+                continue
+            sm.append(clk)
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+        use = sm if sm else allsm[-5:]
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
@@ -247,16 +263,17 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank)
     for _ in range(a.warmup):
         step_dev()
     barrier()
     launches0 = msl.lib().msl_kernel_launch_count()
     sf.set_timing(True)
     st0 = sf.read_stats()
-    clk = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_o, ev_s, ev_p = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     cur = torch.cuda.current_stream()
+    clk.begin()
     ev0.record(cur)
     s_orb.wait_event(ev0)
     s_sf.wait_event(ev0)
@@ -271,6 +288,7 @@ def run_ours(a, rank, world, local_rank):
     cur.wait_event(ev_p)
     ev1.record(cur)
     barrier()
+    clk.end()
     ms_total = ev0.elapsed_time(ev1)
     clocks = clk.stop()
     launches = int(msl.lib().msl_kernel_launch_count() - launches0)

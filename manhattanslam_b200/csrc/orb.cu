@@ -16,6 +16,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved through cudaGetDriverEntryPoint, no -lcuda)
+
 #include "msl_common.cuh"
 
 namespace msl {
@@ -180,31 +182,76 @@ __device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch, int minTh)
 
 // One CTA per FAST cell (src/ORBextractor.cc:745-780).  Output: ordered survivor records of the cell
 // (x | y<<12 | smax<<24, x/y relative to minBorder) into its staging slot + the cell count.
+// ---- TMA (tensor-map) helpers for the FAST cell tiles: SASS UTMALDG + SYNCS
+__device__ __forceinline__ uint32_t orb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool orb_mbar_wait_bounded(uint64_t *b, uint32_t parity) {
+    // bounded spin: a malformed descriptor must surface as an error code, never as a hung GPU
+    for (int it = 0; it < (1 << 20); it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(orb_smem_u32(b)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// TMA tiled loads trap ("illegal instruction") unless innermost-coordinate * elemSize is 16-byte aligned (measured on
+// B200, driver 580): the box starts at x0 & ~15 and is wide enough for ROI width (<= 66) + 15, rounded up to 16.
+constexpr int TILE_W_MAX = 96;
+
+// One CTA per FAST cell (src/ORBextractor.cc:745-780).  The cell's ROI (cell + 3-px FAST ring) is staged into
+// shared memory by ONE 3-D TMA tensor load (x, y, frame) of the level image; out-of-image columns/rows are
+// zero-filled by the TMA unit and never read.  Output: ordered survivor records of the cell
+// (x | y<<12 | smax<<24, x/y relative to minBorder) into its staging slot + the cell count.
 __global__ void __launch_bounds__(128)
     k_fast_cells(const LevelInfo *__restrict__ lv, const Cell *__restrict__ cells, const short *__restrict__ cellLevel,
-                 const uint8_t *__restrict__ pyr, size_t frameStride, int totalCells, int capCell, int iniTh,
-                 int minTh, uint32_t *__restrict__ staging, int *__restrict__ cellCount) {
-    __shared__ uint8_t tile[CELL_TILE * CELL_TILE];
+                 const uint8_t *__restrict__ pyr, size_t frameStride, const CUtensorMap *__restrict__ tmaps, int tileW,
+                 int tileBytes, int totalCells, int capCell, int iniTh, int minTh, uint32_t *__restrict__ staging,
+                 int *__restrict__ cellCount, int *__restrict__ err) {
+    __shared__ __align__(128) uint8_t tile[TILE_W_MAX * CELL_TILE];
     __shared__ uint8_t sc[CELL_TILE * CELL_TILE];
     __shared__ uint8_t sv[CELL_TILE * CELL_TILE];
+    __shared__ __align__(8) uint64_t mbar;
     __shared__ int wsum[4];
     __shared__ int s_any;
     const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
     const Cell C = cells[cell];
-    const LevelInfo L = lv[cellLevel[cell]];
+    const int level = cellLevel[cell];
+    const LevelInfo L = lv[level];
     const int rw = C.x1 - C.x0, rh = C.y1 - C.y0;
     const int cw = rw - 6, ch = rh - 6;  // detectable area
-    const uint8_t *img = pyr + frame * frameStride + L.offset;
-    for (int p = tid; p < rw * rh; p += 128) {
-        int ry = p / rw, rx = p - ry * rw;
-        tile[ry * CELL_TILE + rx] = img[(size_t)(C.y0 + ry) * L.pitch + C.x0 + rx];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(orb_smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(orb_smem_u32(&mbar)), "r"(tileBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                orb_smem_u32(tile)),
+            "l"((unsigned long long)(tmaps + level)), "r"((int)C.x0 & ~15), "r"((int)C.y0), "r"(frame), "r"(orb_smem_u32(&mbar))
+            : "memory");
     }
+    __syncthreads();
+    if (!orb_mbar_wait_bounded(&mbar, 0)) {  // should never happen; keep the result correct and report it
+        if (tid == 0) atomicExch(err, 4);
+        const uint8_t *img = pyr + frame * frameStride + L.offset;
+        for (int p = tid; p < rw * rh; p += 128) {
+            int ry = p / rw, rx = p - ry * rw;
+            tile[ry * tileW + (C.x0 & 15) + rx] = img[(size_t)(C.y0 + ry) * L.pitch + C.x0 + rx];
+        }
+    }
+    const uint8_t *roi = tile + (C.x0 & 15);  // ROI origin inside the 16-byte aligned box
     if (tid == 0) s_any = 0;
     __syncthreads();
     const int np = cw * ch;
     for (int p = tid; p < np; p += 128) {
         int cy = p / cw, cx = p - cy * cw;
-        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(tile + (cy + 3) * CELL_TILE + cx + 3, CELL_TILE, min(minTh, iniTh));
+        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(roi + (cy + 3) * tileW + cx + 3, tileW, min(minTh, iniTh));
     }
     __syncthreads();
     // in-cell NMS: strict maximum over the 8 neighbours; neighbours outside the cell's ring count as 0
@@ -714,6 +761,8 @@ struct msl_orb {
     std::vector<LevelInfo> lv;
     std::vector<int> blurTileBase;
     int totalCells = 0, capCell = 0, kpCapTotal = 0, capOut = 0, maxNodes = 0, blurTiles = 0, candCapTotal = 0;
+    int tileW = 0, tileH = 0;   // TMA box of the FAST cell tiles
+    CUtensorMap *d_tmaps = nullptr;
     size_t pyrBytes = 0;
     size_t octSmem = 0;
     // device
@@ -737,7 +786,7 @@ static void orb_free(msl_orb *o) {
     cudaSetDevice(o->device);
     void *ptrs[] = {o->d_lv, o->d_cells, o->d_cellLevel, o->d_tab, o->d_blurTileBase, o->d_pyr, o->d_blur,
                     o->d_staging, o->d_candRec, o->d_candNode, o->d_cellCount, o->d_candCount, o->d_lvlCount,
-                    o->d_err, o->d_lvlKps, o->d_kps, o->d_desc, o->d_counts};
+                    o->d_err, o->d_lvlKps, o->d_kps, o->d_desc, o->d_counts, o->d_tmaps};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (o->stream) cudaStreamDestroy(o->stream);
@@ -853,6 +902,8 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
                 }
                 cells.push_back(c);
                 cellLevel.push_back((short)l);
+                o->tileW = std::max(o->tileW, (int)align_up(c.x1 - c.x0 + 15, 16));
+                o->tileH = std::max(o->tileH, c.y1 - c.y0);
             }
         }
         L.nCells = (int)cells.size() - L.cellBase;
@@ -950,6 +1001,39 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     MSL_CUDA(cudaMemcpy(o->d_cellLevel, cellLevel.data(), sizeof(short) * cells.size(), cudaMemcpyHostToDevice));
     MSL_CUDA(cudaMemcpy(o->d_tab, tab.data(), sizeof(short) * tab.size(), cudaMemcpyHostToDevice));
     MSL_CUDA(cudaMemcpy(o->d_blurTileBase, o->blurTileBase.data(), sizeof(int) * (nl + 1), cudaMemcpyHostToDevice));
+    {   // one 3-D tensor map (x, y, frame) per pyramid level for the TMA tile loads of k_fast_cells
+        typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess || o->tileW > TILE_W_MAX || o->tileH > CELL_TILE) {
+            orb_free(o);
+            return fail(MSL_ERR_CUDA, "msl_orb_create: cuTensorMapEncodeTiled unavailable (TMA is required)");
+        }
+        std::vector<CUtensorMap> maps(nl);
+        for (int l = 0; l < nl; l++) {
+            const LevelInfo &L = o->lv[l];
+            const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)max_batch};
+            const cuuint64_t gstr[2] = {(cuuint64_t)L.pitch, (cuuint64_t)o->pyrBytes};
+            const cuuint32_t box[3] = {(cuuint32_t)o->tileW, (cuuint32_t)o->tileH, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = ((EncodeTiled)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, o->d_pyr + L.offset, gdim, gstr, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                orb_free(o);
+                return fail(MSL_ERR_CUDA, "msl_orb_create: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+            }
+        }
+        cudaError_t e_ = cudaMalloc((void **)&o->d_tmaps, sizeof(CUtensorMap) * nl);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(o->d_tmaps, maps.data(), sizeof(CUtensorMap) * nl, cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) {
+            orb_free(o);
+            return fail(MSL_ERR_CUDA, std::string("tensor maps: ") + cudaGetErrorString(e_));
+        }
+    }
     MSL_CUDA(cudaMemcpyToSymbol(c_umax, umax, sizeof(umax)));
     MSL_CUDA(cudaMemset(o->d_err, 0, sizeof(int)));
     MSL_CUDA(cudaMemset(o->d_pyr, 0, B * o->pyrBytes));
@@ -984,9 +1068,9 @@ static int orb_run(msl_orb *o, int batch, msl_keypoint *d_kps, uint8_t *d_desc, 
         MSL_LAUNCH_CHECK();
     }
     k_fast_cells<<<dim3(o->totalCells, batch), 128, 0, st>>>(o->d_lv, o->d_cells, o->d_cellLevel, o->d_pyr,
-                                                             o->pyrBytes, o->totalCells, o->capCell,
-                                                             o->prm.ini_th_fast, o->prm.min_th_fast, o->d_staging,
-                                                             o->d_cellCount);
+                                                             o->pyrBytes, o->d_tmaps, o->tileW, o->tileW * o->tileH,
+                                                             o->totalCells, o->capCell, o->prm.ini_th_fast,
+                                                             o->prm.min_th_fast, o->d_staging, o->d_cellCount, o->d_err);
     MSL_LAUNCH_CHECK();
     k_octree<<<dim3(nl, batch), 256, o->octSmem, st>>>(o->d_lv, nl, o->totalCells, o->capCell, o->d_staging,
                                                        o->d_cellCount, o->d_candRec, o->d_candNode, o->d_candCount,
@@ -1010,6 +1094,7 @@ static int orb_check_err(msl_orb *o) {
     MSL_CUDA(cudaStreamSynchronize(o->stream));
     if (e) {
         cudaMemsetAsync(o->d_err, 0, sizeof(int), o->stream);
+        if (e == 4) return fail(MSL_ERR_CUDA, "ORB: TMA tile load did not complete (fallback loads were used)");
         return fail(MSL_ERR_CAPACITY, e == 2 ? "ORB: octree produced more nodes than the level capacity"
                                                : "ORB: keypoint output capacity exceeded");
     }
