@@ -1,12 +1,14 @@
 // ORBmatcher_msl.cc -- the tracking-time searches of ORB_SLAM2::ORBmatcher on the B200 front-end.
-// Build together with the reference's src/ORBmatcher.cc compiled with -DMSL_FRONTEND, where the three
-// definitions below are wrapped in `#ifndef MSL_FRONTEND` (INTEGRATION.md shows the patch); every other
-// method (SearchByBoW, SearchForTriangulation, Fuse, ...) stays as is.  Callers are unchanged
-// (src/Tracking.cc:956,963,1253,1262,1693).
+// Build together with the reference's src/ORBmatcher.cc compiled with -DMSL_FRONTEND, where the four
+// definitions below (three SearchByProjection overloads + DescriptorDistance) are wrapped in
+// `#ifndef MSL_FRONTEND` (INTEGRATION.md shows the patch); every other method (SearchByBoW, SearchForTriangulation, Fuse, ...) stays as is.  Callers are unchanged
+// (src/Tracking.cc:956,963,1253,1262,1693,2006,2019).
+#include <set>
 #include <stdexcept>
 #include <vector>
 
 #include "Frame.h"
+#include "KeyFrame.h"
 #include "MapPoint.h"
 #include "ORBmatcher.h"
 #include "msl_frontend.h"
@@ -108,6 +110,52 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMa
         throw std::runtime_error(msl_last_error());
     for (int j = 0; j < nc; j++)
         if (match[j] >= 0) F.mvpMapPoints[j] = vpMapPoints[match[j]];
+    return nmatches;
+}
+
+namespace {
+// MapPoint::mfMinDistance / mfMaxDistance are protected (include/MapPoint.h:135-136) and only exposed scaled by
+// 0.8f / 1.2f; PredictScale needs the raw value.  A derived struct may name them, which yields plain
+// pointers-to-member of MapPoint -- no change to the reference header.
+struct MapPointDistances : MapPoint {
+    static float MapPoint::*minPtr() { return &MapPointDistances::mfMinDistance; }
+    static float MapPoint::*maxPtr() { return &MapPointDistances::mfMaxDistance; }
+};
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound,
+                                   const float th, const int ORBdist) {  // :680-797
+    const std::vector<MapPoint *> vpMPs = pKF->GetMapPointMatches();
+    const int nk = (int)vpMPs.size(), nc = CurrentFrame.N;
+    std::vector<uint8_t> valid(nk), desc((size_t)nk * 32), occ(nc);
+    std::vector<float> world(3 * (size_t)nk), dist(2 * (size_t)nk), ang(nk);
+    for (int i = 0; i < nk; i++) {
+        MapPoint *p = vpMPs[i];
+        ang[i] = pKF->mvKeysUn[i].angle;
+        valid[i] = p && !p->isBad() && !sAlreadyFound.count(p);
+        if (!valid[i]) continue;
+        cv::Mat x = p->GetWorldPos();
+        world[3 * i] = x.at<float>(0), world[3 * i + 1] = x.at<float>(1), world[3 * i + 2] = x.at<float>(2);
+        dist[2 * i] = p->*MapPointDistances::minPtr(), dist[2 * i + 1] = p->*MapPointDistances::maxPtr();
+        memcpy(&desc[(size_t)i * 32], p->GetDescriptor().ptr(), 32);
+    }
+    CurArrays C(CurrentFrame);
+    for (int j = 0; j < nc; j++) occ[j] = CurrentFrame.mvpMapPoints[j] != nullptr;  // :741-742
+    std::vector<int32_t> match(nc);
+    int32_t nmatches = 0;
+    msl_frame_geom g = geom_of(CurrentFrame);
+    g.nlevels = CurrentFrame.mnScaleLevels;
+    cv::Mat Tc;
+    CurrentFrame.mTcw.convertTo(Tc, CV_32F);
+    if (msl_search_by_projection_keyframe(matcher(), &g, Tc.ptr<float>(), th, ORBdist, mbCheckOrientation,
+                                          CurrentFrame.mfLogScaleFactor, nk, valid.data(), world.data(), desc.data(),
+                                          dist.data(), ang.data(), nc, C.xy.data(), C.octave.data(), C.angle.data(),
+                                          CurrentFrame.mDescriptors.ptr(), occ.data(), match.data(), &nmatches) != MSL_OK)
+        throw std::runtime_error(msl_last_error());
+    for (int j = 0; j < nc; j++) {
+        if (match[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[match[j]];
+        else if (match[j] == -3) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint *>(NULL);
+    }
     return nmatches;
 }
 

@@ -94,7 +94,7 @@ int msl_orb_debug_candidates(msl_orb *, int frame, int level, int32_t *xyr, int 
 
 /* -------------------------------------------------------------------------------------- matcher
  * Replaces ORBmatcher::DescriptorDistance and the window searches of ORBmatcher::SearchByProjection
- * (src/ORBmatcher.cc:40-117, 548-678, 835-849) including Frame::GetFeaturesInArea semantics
+ * (src/ORBmatcher.cc:40-117, 548-678, 680-797, 835-849) including Frame::GetFeaturesInArea semantics
  * (src/Frame.cc:155-168, 332-381, 418-427). */
 
 typedef struct {
@@ -159,6 +159,22 @@ int msl_search_by_projection_points(msl_matcher *, const msl_frame_geom *geom, f
                                     const uint8_t *mp_desc, int n_cur, const float *cur_xy,
                                     const int32_t *cur_octave, const float *cur_uright, const uint8_t *cur_desc,
                                     const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame &Cur, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * (src/ORBmatcher.cc:680-797, relocalisation; called at src/Tracking.cc:2006,2019) including
+ * MapPoint::PredictScale (src/MapPoint.cc:350-364) and Get{Min,Max}DistanceInvariance (:324-332).
+ *   KeyFrame side, per keypoint i < n_kf (pKF->GetMapPointMatches()): kf_valid (pMP && !pMP->isBad() &&
+ *     !sAlreadyFound.count(pMP)), kf_mp_world (GetWorldPos), kf_mp_desc (GetDescriptor), kf_mp_dist
+ *     (2 floats: mfMinDistance, mfMaxDistance), kf_angle (pKF->mvKeysUn[i].angle);
+ *   Cur side: cur_occupied[j] = (mvpMapPoints[j] != NULL) -- this overload has no Observations() test.
+ *   log_scale_factor = Frame::mfLogScaleFactor; geom->nlevels = Frame::mnScaleLevels.
+ * cur_match / nmatches as for msl_search_by_projection_frame. */
+int msl_search_by_projection_keyframe(msl_matcher *, const msl_frame_geom *geom, const float Tcw_cur[16], float th,
+                                      int orb_dist, int check_orientation, float log_scale_factor, int n_kf,
+                                      const uint8_t *kf_valid, const float *kf_mp_world, const uint8_t *kf_mp_desc,
+                                      const float *kf_mp_dist, const float *kf_angle, int n_cur, const float *cur_xy,
+                                      const int32_t *cur_octave, const float *cur_angle, const uint8_t *cur_desc,
+                                      const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches);
 
 /* ----------------------------------------------------------------------------- plane pre-stage
  * Replaces PlaneDetection::readDepthImage (src/PlaneExtractor.cpp:44-76) and the peac pre-stage:

@@ -1,5 +1,5 @@
 // match.cu -- B200-native descriptor matching (replaces ORBmatcher::DescriptorDistance and the window
-// searches ORBmatcher::SearchByProjection of src/ORBmatcher.cc:40-117, 548-678, 799-849 with the
+// searches ORBmatcher::SearchByProjection of src/ORBmatcher.cc:40-117, 548-678, 680-797, 799-849 with the
 // Frame grid semantics of src/Frame.cc:155-168, 332-381, 418-427 of razayunus/ManhattanSLAM).
 //
 //   k_hamming_best2     all-pairs 256-bit Hamming: one warp per query, train descriptors staged through
@@ -94,15 +94,18 @@ __global__ void __launch_bounds__(256)
 // -------------------------------------------------------------------------------- window search
 struct SearchArgs {
     msl_frame_geom g;
-    int mode;                 // 0: Frame-Frame (:548-678), 1: Frame-MapPoints (:40-117)
+    int mode;                 // 0: Frame-Frame (:548-678), 1: Frame-MapPoints (:40-117), 2: Frame-KeyFrame (:680-797)
     float th, nnratio;
     int checkOri;
     float Rcw[9], tcw[3];
+    float Ow[3], logScale;    // mode 2: camera centre, Frame::mfLogScaleFactor
+    int distTh;               // TH_HIGH (modes 0, 1) or ORBdist (mode 2)
     int bForward, bBackward;
     int nq, nc;
     // query side
     const uint8_t *q_valid, *q_obs, *q_desc;
-    const float *q_f3;        // mode 0: world xyz; mode 1: (projX, projY, projXR)
+    const float *q_f3;        // modes 0, 2: world xyz; mode 1: (projX, projY, projXR)
+    const float *q_f2;        // mode 2: (mfMinDistance, mfMaxDistance)
     const int32_t *q_level;   // mode 0: last octave; mode 1: predicted level
     const float *q_aux;       // mode 0: last angle; mode 1: view cos
     // current frame
@@ -200,6 +203,36 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
                     else minL = oct - 1, maxL = oct + 1;
                     urRef = u - g.mbf * invzc;
                     erLim = radius;
+                } else if (A.mode == 2) {
+                    const float *x3Dw = A.q_f3 + 3 * i;
+                    const float xc = gemm_row(A.Rcw, x3Dw, A.tcw[0]);
+                    const float yc = gemm_row(A.Rcw + 3, x3Dw, A.tcw[1]);
+                    const float invzc = (float)(1.0 / (double)gemm_row(A.Rcw + 6, x3Dw, A.tcw[2]));  // no invzc<0 test (:705)
+                    u = g.fx * xc * invzc + g.cx;
+                    v = g.fy * yc * invzc + g.cy;
+                    if (u < g.mnMinX || u > g.mnMaxX) ok = false;
+                    if (v < g.mnMinY || v > g.mnMaxY) ok = false;
+                    // :717-718 cv::norm(x3Dw - Ow): float differences, double accumulation, double sqrt
+                    double s2 = 0;
+                    for (int k = 0; k < 3; k++) {
+                        const float po = x3Dw[k] - A.Ow[k];
+                        s2 += (double)po * (double)po;
+                    }
+                    const float dist3D = (float)sqrt(s2);
+                    const float minD = A.q_f2[2 * i], maxD = A.q_f2[2 * i + 1];
+                    if (dist3D < 0.8f * minD || dist3D > 1.2f * maxD) ok = false;  // src/MapPoint.cc:324-332
+                    // MapPoint::PredictScale (src/MapPoint.cc:350-364): ceil(logf(ratio) / logScale).  logf is taken as the
+                    // rounded fp64 logarithm (glibc's logf is correctly rounded in all but ~1e-8 of its inputs)
+                    const float ratio = maxD / dist3D;
+                    int lvl = 0;
+                    if (ok) {
+                        lvl = (int)ceilf((float)log((double)ratio) / A.logScale);
+                        if (lvl < 0) lvl = 0;
+                        else if (lvl >= g.nlevels) lvl = g.nlevels - 1;
+                    }
+                    radius = A.th * g.scaleFactors[lvl];
+                    minL = lvl - 1, maxL = lvl + 1;
+                    urRef = 0.f, erLim = 0.f;
                 } else {
                     const int lvl = A.q_level[i];
                     float r = (A.q_aux[i] > 0.998f) ? 2.5f : 4.0f;  // RadiusByViewingCos :119-124
@@ -234,7 +267,7 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
                                 if (!(fabsf(dx) < radius && fabsf(dy) < radius)) continue;
                                 if (blockedAt[k] < i) continue;  // slot holds a MapPoint with Observations()>0
                                 const float ur = A.c_uright[k];
-                                if (ur > 0 && fabsf(urRef - ur) > erLim) continue;
+                                if (A.mode != 2 && ur > 0 && fabsf(urRef - ur) > erLim) continue;
                                 const uint4 *T = (const uint4 *)(A.c_desc + 32 * (size_t)k);
                                 const int d = hamming256(q0, q1, T[0], T[1]);
                                 if (d < bestDist) {
@@ -245,7 +278,7 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
                                 }
                             }
                         }
-                        if (!(bestDist <= TH_HIGH)) best = -1;
+                        if (!(bestDist <= A.distTh)) best = -1;
                         else if (A.mode == 1 && bestLevel == bestLevel2 && (float)bestDist > A.nnratio * (float)bestDist2) best = -1;
                     }
                 }
@@ -278,7 +311,7 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
         if (k >= 0) {
             mine++;
             atomicMax(&lastAssign[k], i);
-            if (A.mode == 0 && A.checkOri) {
+            if (A.mode != 1 && A.checkOri) {
                 float rot = A.q_aux[i] - A.c_angle[k];
                 if (rot < 0.0f) rot += 360.0f;
                 bin = (int)roundf(rot * (1.0f / HISTO_LENGTH));
@@ -292,7 +325,7 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
     __syncthreads();
     if (tid == 0) {
         int ind1 = -1, ind2 = -1, ind3 = -1;
-        if (A.mode == 0 && A.checkOri) {
+        if (A.mode != 1 && A.checkOri) {
             int max1 = 0, max2 = 0, max3 = 0;
             for (int i = 0; i < HISTO_LENGTH; i++) {
                 const int s = hist[i];
@@ -314,7 +347,7 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
     __syncthreads();
     for (int j = tid; j < A.nc; j += nt) A.c_match[j] = A.c_occ[j] ? -2 : lastAssign[j];
     __syncthreads();
-    if (A.mode == 0 && A.checkOri) {
+    if (A.mode != 1 && A.checkOri) {
         int pruned = 0;
         for (int i = tid; i < A.nq; i += nt) {
             const int b = A.bin[i];
@@ -503,6 +536,7 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
     SearchArgs A;
     memset(&A, 0, sizeof(A));
     A.g = *geom, A.mode = 0, A.th = th, A.nnratio = 0, A.checkOri = check_orientation, A.nq = n_last, A.nc = n_cur;
+    A.distTh = TH_HIGH;
     // :554-568: twc = -Rcw^T tcw; tlc = Rlw twc + tlw (cv::Mat products: double accumulation, one rounding)
     float Rlw[9], tlw[3];
     for (int r = 0; r < 3; r++) {
@@ -561,6 +595,7 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
     SearchArgs A;
     memset(&A, 0, sizeof(A));
     A.g = *geom, A.mode = 1, A.th = th, A.nnratio = nnratio, A.checkOri = 0, A.nq = n_mp, A.nc = n_cur;
+    A.distTh = TH_HIGH;
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(mp_valid, n_mp);
     A.q_obs = ar.put(mp_obs, n_mp);
@@ -579,6 +614,59 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
     A.assign = ar.get<int32_t>(n_mp);
     A.bin = ar.get<int32_t>(n_mp);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_points: scratch arena / copy failure");
+    return run_search(m, A, cur_match, nmatches);
+}
+
+int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom, const float Tcw_cur[16], float th,
+                                      int orb_dist, int check_orientation, float log_scale_factor, int n_kf,
+                                      const uint8_t *kf_valid, const float *kf_mp_world, const uint8_t *kf_mp_desc,
+                                      const float *kf_mp_dist, const float *kf_angle, int n_cur, const float *cur_xy,
+                                      const int32_t *cur_octave, const float *cur_angle, const uint8_t *cur_desc,
+                                      const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches) {
+    if (!m || !geom || !Tcw_cur || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: null argument");
+    if (n_kf < 0 || n_cur < 0 || n_kf > m->maxQ || n_cur > m->maxT || n_cur > MAXK)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: too many keypoints for this handle");
+    if (geom->nlevels < 1 || geom->nlevels > 16 || !(log_scale_factor > 0.f) || orb_dist < 0 || orb_dist > 255)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: parameter out of range");
+    if (n_cur == 0 || n_kf == 0) {
+        for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
+        *nmatches = 0;
+        return MSL_OK;
+    }
+    MSL_CUDA(cudaSetDevice(m->device));
+    SearchArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = *geom, A.mode = 2, A.th = th, A.nnratio = 0, A.checkOri = check_orientation, A.nq = n_kf, A.nc = n_cur;
+    A.distTh = orb_dist, A.logScale = log_scale_factor;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw_cur[r * 4 + c];
+        A.tcw[r] = Tcw_cur[r * 4 + 3];
+    }
+    for (int r = 0; r < 3; r++) {  // :686 Ow = -Rcw^T tcw (one cv gemm: double accumulation, one rounding)
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
+        A.Ow[r] = (float)s;
+    }
+    std::vector<uint8_t> ones(n_kf, 1);  // every slot assigned by this overload blocks later queries (:741-742)
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.q_valid = ar.put(kf_valid, n_kf);
+    A.q_obs = ar.put(ones.data(), n_kf);
+    A.q_desc = ar.put(kf_mp_desc, (size_t)n_kf * 32);
+    A.q_f3 = ar.put(kf_mp_world, (size_t)n_kf * 3);
+    A.q_f2 = ar.put(kf_mp_dist, (size_t)n_kf * 2);
+    A.q_level = nullptr;
+    A.q_aux = ar.put(kf_angle, n_kf);
+    A.c_xy = ar.put(cur_xy, (size_t)n_cur * 2);
+    A.c_angle = ar.put(cur_angle, n_cur);
+    A.c_uright = A.c_angle;  // unused in this mode
+    A.c_octave = ar.put(cur_octave, n_cur);
+    A.c_desc = ar.put(cur_desc, (size_t)n_cur * 32);
+    A.c_occ = ar.put(cur_occupied, n_cur);
+    A.c_match = ar.get<int32_t>(n_cur);
+    A.nmatches = ar.get<int32_t>(1);
+    A.assign = ar.get<int32_t>(n_kf);
+    A.bin = ar.get<int32_t>(n_kf);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_keyframe: scratch arena / copy failure");
     return run_search(m, A, cur_match, nmatches);
 }
 

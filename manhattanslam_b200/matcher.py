@@ -1,5 +1,5 @@
 """ORBmatcher mirror (include/ORBmatcher.h:39-55: DescriptorDistance + the two tracking-time
-SearchByProjection overloads) over the CUDA C ABI.  The Frame/MapPoint graph is passed as flat arrays."""
+SearchByProjection overloads + the relocalisation overload) over the CUDA C ABI.  The Frame/MapPoint graph is passed as flat arrays."""
 import ctypes as C
 
 import numpy as np
@@ -108,4 +108,24 @@ class ORBmatcher:
         check(self._L.msl_search_by_projection_points(
             self._h, ptr(geom), C.c_float(th), C.c_float(self.mfNNratio), n_mp, *[ptr(x) for x in args], n_cur,
             *[ptr(x) for x in cargs], ptr(cm), C.byref(nm)))
+        return nm.value, cm
+
+    def SearchByProjectionKeyFrame(self, geom, Tcw_cur, th, ORBdist, kf, cur, log_scale_factor=None):
+        """SearchByProjection(Frame &Cur, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+        (src/ORBmatcher.cc:680-797).  kf/cur: dicts of flat arrays (include/msl_frontend.h).
+        Returns (nmatches, cur_match)."""
+        n_kf, n_cur = len(kf["angle"]), len(cur["octave"])
+        if log_scale_factor is None:  # Frame::mfLogScaleFactor = log(mfScaleFactor), src/Frame.cc:82
+            log_scale_factor = float(np.float32(np.log(np.float64(np.float32(geom["scaleFactors"][0, 1])))))
+        cm = np.zeros(n_cur, np.int32)
+        nm = C.c_int32()
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        args = [a(kf["valid"], np.uint8), a(kf["mp_world"], np.float32), a(kf["mp_desc"], np.uint8),
+                a(kf["mp_dist"], np.float32), a(kf["angle"], np.float32)]
+        cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["angle"], np.float32), a(cur["desc"], np.uint8),
+                 a(cur["occupied"], np.uint8)]
+        check(self._L.msl_search_by_projection_keyframe(
+            self._h, ptr(geom), ptr(a(Tcw_cur, np.float32)), C.c_float(th), int(ORBdist), int(self.mbCheckOrientation),
+            C.c_float(log_scale_factor), n_kf, *[ptr(x) for x in args], n_cur, *[ptr(x) for x in cargs], ptr(cm),
+            C.byref(nm)))
         return nm.value, cm

@@ -194,3 +194,29 @@ def match_scene(seed, n_cur=1000, n_last=900, w=640, h=480, K=K_DEFAULT, collide
            "proj_xyr": np.stack([uv[:, 0], uv[:, 1], uv[:, 0] - 40.0 * invz], 1).astype(np.float32),
            "level": last["octave"], "viewcos": r.uniform(0.9, 1.0, n_last).astype(np.float32), "desc": desc}
     return cur, last, mps, Tcw_cur, Tcw_last
+
+
+def reloc_scene(seed, n_cur=1000, n_kf=900, collide=0.3, negative_depth=0.02):
+    """Relocalisation flavour of match_scene for ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist)
+    (src/ORBmatcher.cc:680-797): KeyFrame map points with scale-invariance distances (mfMinDistance, mfMaxDistance)
+    chosen so that MapPoint::PredictScale lands near the target keypoint's octave; a few points lie outside their
+    distance range or behind the camera (that overload has no invzc<0 test)."""
+    cur, last, _, Tcw_cur, _ = match_scene(seed, n_cur, n_kf, collide=collide)
+    r = np.random.default_rng(seed + 777)
+    Twc = np.linalg.inv(Tcw_cur.astype(np.float64))
+    Ow = Twc[:3, 3]
+    pw = last["mp_world"].astype(np.float64).copy()
+    nneg = int(negative_depth * n_kf)
+    if nneg:  # mirror a few points through the camera centre: z < 0 but the projection stays in the image
+        pw[:nneg] = 2 * Ow[None, :] - pw[:nneg]
+    dist = np.linalg.norm(pw - Ow[None, :], axis=1)
+    lvl = np.clip(last["octave"] + r.integers(-1, 2, n_kf), 0, 7)
+    maxd = dist * 1.2 ** (lvl - r.uniform(0.05, 0.95, n_kf))       # ceil(log(max/dist)/log 1.2) == lvl
+    mind = maxd / 1.2 ** 7
+    far = r.random(n_kf) < 0.05
+    maxd = np.where(far, dist / 1.3, maxd)                           # outside [0.8 min, 1.2 max]
+    kf = {"valid": (r.random(n_kf) < 0.9).astype(np.uint8), "mp_world": pw.astype(np.float32), "mp_desc": last["mp_desc"],
+          "mp_dist": np.stack([mind, maxd], 1).astype(np.float32), "angle": last["angle"]}
+    cur = dict(cur)
+    cur["occupied"] = (r.random(n_cur) < 0.1).astype(np.uint8)      # mvpMapPoints[j] != NULL on entry
+    return cur, kf, Tcw_cur

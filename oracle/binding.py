@@ -381,3 +381,19 @@ def search_by_projection_points(geom, th, nnratio, mps, cur):
     n = L.orc_search_by_projection_points(_p(geom), th, nnratio, len(mps["level"]), *[_p(x) for x in margs],
                                           len(cur["octave"]), *[_p(x) for x in cargs], _p(cm))
     return n, cm
+
+
+def search_by_projection_keyframe(geom, Tcw_cur, th, orb_dist, check_ori, log_scale_factor, kf, cur):
+    L = lib()
+    L.orc_search_by_projection_keyframe.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int] +
+                                                    [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    kargs = [a(kf["valid"], np.uint8), a(kf["mp_world"], np.float32), a(kf["mp_desc"], np.uint8),
+             a(kf["mp_dist"], np.float32), a(kf["angle"], np.float32)]
+    cargs = [a(cur["xy"], np.float32), a(cur["octave"], np.int32), a(cur["angle"], np.float32), a(cur["desc"], np.uint8),
+             a(cur["occupied"], np.uint8)]
+    cm = np.zeros(len(cur["octave"]), np.int32)
+    n = L.orc_search_by_projection_keyframe(_p(geom), _p(a(Tcw_cur, np.float32)), th, int(orb_dist), int(check_ori),
+                                            log_scale_factor, len(kf["angle"]), *[_p(x) for x in kargs],
+                                            len(cur["octave"]), *[_p(x) for x in cargs], _p(cm))
+    return n, cm

@@ -1,6 +1,6 @@
 // match_oracle.cpp -- CPU oracle (TEST INFRASTRUCTURE, see msl_oracle.h) restating
-// ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:835-849), the two tracking-time
-// ORBmatcher::SearchByProjection overloads (:40-117, :548-678), ComputeThreeMaxima (:799-830) and the
+// ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:835-849), the three Frame-side
+// ORBmatcher::SearchByProjection overloads (:40-117, :548-678, :680-797), ComputeThreeMaxima (:799-830) and the
 // Frame grid they search through (src/Frame.cc:155-168, 332-381, 418-427).
 // The Frame/MapPoint object graph is flattened into arrays (see msl_oracle.h); cv::Mat products are
 // evaluated as OpenCV's gemm does for CV_32F (double accumulation, one rounding) -- "parity unpinned".
@@ -277,6 +277,102 @@ int orc_search_by_projection_points(const orc_frame_geom *g, float th, float nnr
             blocked[bestIdx] = mp_obs[iMP];
             nmatches++;
         }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+// src/ORBmatcher.cc:680-797 (relocalisation) with MapPoint::PredictScale (src/MapPoint.cc:350-364) and
+// MapPoint::GetMin/MaxDistanceInvariance (:324-332).  Differences from the Frame-Frame overload that are kept:
+// no invzc<0 rejection, any non-NULL slot blocks (:741-742, no Observations() test), no uRight test, threshold
+// ORBdist instead of TH_HIGH, level window nPredictedLevel-1..+1.
+int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_cur[16], float th, int orb_dist,
+                                      int check_orientation, float log_scale_factor, int n_kf, const uint8_t *kf_valid,
+                                      const float *kf_mp_world, const uint8_t *kf_mp_desc, const float *kf_mp_dist,
+                                      const float *kf_angle, int n_cur, const float *cur_xy, const int32_t *cur_octave,
+                                      const float *cur_angle, const uint8_t *cur_desc, const uint8_t *cur_occupied,
+                                      int32_t *cur_match) {
+    int nmatches = 0;
+    float Rcw[9], tcw[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Rcw[r * 3 + c] = Tcw_cur[r * 4 + c];
+        tcw[r] = Tcw_cur[r * 4 + 3];
+    }
+    float Ow[3];  // :686  Ow = -Rcw.t() * tcw (one gemm)
+    for (int r = 0; r < 3; r++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)(-Rcw[k * 3 + r]) * (double)tcw[k];
+        Ow[r] = (float)s;
+    }
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    Grid G;
+    assign_grid(g, cur_xy, n_cur, G);
+    std::vector<uint8_t> blocked(cur_occupied, cur_occupied + n_cur);  // mvpMapPoints[i2] != NULL
+    for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n_kf; i++) {
+        if (!kf_valid[i]) continue;  // pMP && !pMP->isBad() && !sAlreadyFound.count(pMP)
+        const float *x3Dw = kf_mp_world + 3 * i;
+        const float xc = gemm_row(Rcw, x3Dw, tcw[0]);
+        const float yc = gemm_row(Rcw + 3, x3Dw, tcw[1]);
+        const float invzc = (float)(1.0 / gemm_row(Rcw + 6, x3Dw, tcw[2]));
+        const float u = g->fx * xc * invzc + g->cx;
+        const float v = g->fy * yc * invzc + g->cy;
+        if (u < g->mnMinX || u > g->mnMaxX) continue;
+        if (v < g->mnMinY || v > g->mnMaxY) continue;
+        // :717-718  PO = x3Dw - Ow; dist3D = cv::norm(PO)  (CV_32F L2 norm: double accumulation, sqrt in double)
+        double s2 = 0;
+        for (int k = 0; k < 3; k++) {
+            const float po = x3Dw[k] - Ow[k];
+            s2 += (double)po * (double)po;
+        }
+        const float dist3D = (float)std::sqrt(s2);
+        const float mfMinDistance = kf_mp_dist[2 * i], mfMaxDistance = kf_mp_dist[2 * i + 1];
+        const float maxDistance = 1.2f * mfMaxDistance;  // src/MapPoint.cc:329-332
+        const float minDistance = 0.8f * mfMinDistance;  // :324-327
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        // MapPoint::PredictScale(dist3D, &CurrentFrame) :350-364 (std::log(float), std::ceil(float))
+        const float ratio = mfMaxDistance / dist3D;
+        int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= g->nlevels) nPredictedLevel = g->nlevels - 1;
+        const float radius = th * g->scaleFactors[nPredictedLevel];
+        features_in_area(g, G, cur_xy, cur_octave, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t *dMP = kf_mp_desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t k = 0; k < vIndices2.size(); k++) {
+            const int i2 = vIndices2[k];
+            if (blocked[i2]) continue;
+            const int dist = descriptor_distance(dMP, cur_desc + 32 * (size_t)i2);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx2 = i2;
+            }
+        }
+        if (bestDist <= orb_dist && bestIdx2 >= 0) {  // bestIdx2 == -1 with ORBdist >= 256 would index [-1] in the reference
+            cur_match[bestIdx2] = i;
+            blocked[bestIdx2] = 1;
+            nmatches++;
+            if (check_orientation) {
+                float rot = kf_angle[i] - cur_angle[bestIdx2];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    cur_match[rotHist[i][j]] = -3;
+                    nmatches--;
+                }
     }
     return nmatches;
 }

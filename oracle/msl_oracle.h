@@ -124,6 +124,18 @@ int orc_search_by_projection_points(const orc_frame_geom *g, float th, float nnr
                                     const float *cur_uright, const uint8_t *cur_desc, const uint8_t *cur_occupied,
                                     int32_t *cur_match);
 
+/* ORBmatcher::SearchByProjection(Frame&Cur, KeyFrame*, const set<MapPoint*>&sAlreadyFound, th, ORBdist),
+ * src/ORBmatcher.cc:680-797 (relocalisation).  Per KeyFrame keypoint i: kf_valid[i] = (pMP && !isBad() &&
+ * !sAlreadyFound.count(pMP)), world position, descriptor, kf_mp_dist[2i..] = (mfMinDistance, mfMaxDistance),
+ * kf_angle = pKF->mvKeysUn[i].angle.  cur_occupied[j] = (mvpMapPoints[j] != NULL).  log_scale_factor =
+ * Frame::mfLogScaleFactor, g->nlevels = Frame::mnScaleLevels.  Output cur_match as above.  Returns nmatches. */
+int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_cur[16], float th, int orb_dist,
+                                      int check_orientation, float log_scale_factor,
+                                      int n_kf, const uint8_t *kf_valid, const float *kf_mp_world,
+                                      const uint8_t *kf_mp_desc, const float *kf_mp_dist, const float *kf_angle,
+                                      int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle,
+                                      const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match);
+
 /* ---------------------------------------------------- plane pre-stage --- */
 
 typedef struct {

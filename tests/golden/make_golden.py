@@ -59,6 +59,11 @@ def stages():
                         local_after=lo.view(np.uint8), new=new.view(np.uint8), plane_seed=seed, plane_edges=edges,
                         plane_normals=blocks["normal"][seed == 1], match_n=n, match_cm=cm)
     print("stage golden written")
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    cur, kf, Tc = S.reloc_scene(3)
+    n, cm = ob.search_by_projection_keyframe(frame_geom(), Tc, 15.0, 100, True, lsf, kf, cur)
+    np.savez_compressed(os.path.join(HERE, "reloc.npz"), match_n=n, match_cm=cm)
+    print("reloc golden written", n)
 
 
 if __name__ == "__main__":

@@ -89,6 +89,89 @@ def test_search_by_projection_invariants(oracle):
     assert n2 <= n and (cm2 == -3).sum() >= 1
 
 
+def _py_search_keyframe(oracle, g, Tcw, th, orb_dist, check_ori, lsf, kf, cur):
+    """Independent numpy/Python restatement of src/ORBmatcher.cc:680-797 (float32 scalar arithmetic, candidate lists
+    from the grid oracle), used to pin the C++ oracle's control flow on a small case."""
+    f32, f64 = np.float32, np.float64
+    T = np.asarray(Tcw, f32)
+    R, t = T[:3, :3], T[:3, 3]
+    Ow = np.array([f32(sum(f64(-R[k, r]) * f64(t[k]) for k in range(3))) for r in range(3)], f32)
+    gg = {k: g[k][0] for k in g.dtype.names}
+    n_cur = len(cur["octave"])
+    slot = np.where(cur["occupied"] == 1, -2, -1).astype(np.int32)
+    blocked = cur["occupied"].astype(bool).copy()
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for i in range(len(kf["angle"])):
+        if not kf["valid"][i]:
+            continue
+        x = kf["mp_world"][i].astype(f32)
+        row = lambda r: f32(sum(f64(R[r, k]) * f64(x[k]) for k in range(3)) + f64(t[r]))
+        xc, yc = row(0), row(1)
+        with np.errstate(divide="ignore"):
+            invz = f32(f64(1.0) / f64(row(2)))
+        u = f32(f32(f32(gg["fx"] * xc) * invz) + gg["cx"])
+        v = f32(f32(f32(gg["fy"] * yc) * invz) + gg["cy"])
+        if u < gg["mnMinX"] or u > gg["mnMaxX"] or v < gg["mnMinY"] or v > gg["mnMaxY"]:
+            continue
+        po = (x - Ow).astype(f32)
+        d3 = f32(np.sqrt(sum(f64(p) * f64(p) for p in po)))
+        mind, maxd = kf["mp_dist"][i].astype(f32)
+        if d3 < f32(0.8) * mind or d3 > f32(1.2) * maxd:
+            continue
+        lvl = int(np.ceil(f32(np.log(f32(maxd / d3))) / f32(lsf)))
+        lvl = min(max(lvl, 0), int(gg["nlevels"]) - 1)
+        radius = f32(f32(th) * gg["scaleFactors"][lvl])
+        cand = oracle.features_in_area(g, cur["xy"], cur["octave"], float(u), float(v), float(radius), lvl - 1, lvl + 1)
+        best, bi = 256, -1
+        for j in cand:
+            if blocked[j]:
+                continue
+            d = int(np.unpackbits(kf["mp_desc"][i] ^ cur["desc"][j]).sum())
+            if d < best:
+                best, bi = d, int(j)
+        if best <= orb_dist:
+            slot[bi] = i
+            blocked[bi] = True
+            nm += 1
+            if check_ori:
+                rot = f32(kf["angle"][i]) - f32(cur["angle"][bi])
+                if rot < 0:
+                    rot = f32(rot + f32(360.0))
+                b = int(np.floor(f64(f32(rot * f32(1.0 / 30))) + 0.5))  # round(): half away from zero, rot >= 0
+                hist[0 if b == 30 else b].append(bi)
+    if check_ori:
+        sizes = [len(h) for h in hist]
+        order = sorted(range(30), key=lambda k: (-sizes[k], k))[:3]
+        m1 = sizes[order[0]]
+        keep = [order[0]] + [k for k in order[1:] if not sizes[k] < 0.1 * m1]
+        if len(keep) == 2 and keep[1] == order[2]:  # max2 pruned implies max3 pruned
+            keep = keep[:1]
+        for k in range(30):
+            if k not in keep:
+                for j in hist[k]:
+                    slot[j] = -3
+                    nm -= 1
+    return nm, slot
+
+
+def test_search_by_projection_keyframe_vs_python(oracle):
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    for seed, th, od in ((21, 15.0, 100), (22, 10.0, 64)):
+        cur, kf, Tc = S.reloc_scene(seed, n_cur=300, n_kf=260)
+        g = frame_geom()
+        for check in (False, True):
+            n, cm = oracle.search_by_projection_keyframe(g, Tc, th, od, check, lsf, kf, cur)
+            n_py, cm_py = _py_search_keyframe(oracle, g, Tc, th, od, check, lsf, kf, cur)
+            assert n == n_py and np.array_equal(cm, cm_py)
+            assert n > 40
+        # behind-camera points are not rejected by this overload (no invzc<0 test, :705)
+        Twc = np.linalg.inv(Tc.astype(np.float64))
+        zc = (kf["mp_world"].astype(np.float64) @ np.linalg.inv(Twc)[:3, :3].T + np.linalg.inv(Twc)[:3, 3])[:, 2]
+        n0, cm0 = oracle.search_by_projection_keyframe(g, Tc, th, od, False, lsf, kf, cur)
+        assert np.isin(np.nonzero(zc < 0)[0], cm0[cm0 >= 0]).any()
+
+
 def _surfel_case():
     g = S.gray_frame(3)
     _, d = S.depth_frame(3)
@@ -140,4 +223,12 @@ def test_golden_stages(oracle):
     assert np.allclose(blocks["normal"][seed == 1], gold["plane_normals"], rtol=0, atol=1e-12)
     cur, last, mps, Tc, Tl = S.match_scene(3)
     n, cm = oracle.search_by_projection_frame(frame_geom(), Tc, Tl, 15.0, True, last, cur)
+    assert n == int(gold["match_n"]) and np.array_equal(cm, gold["match_cm"])
+
+
+def test_golden_reloc(oracle):
+    gold = np.load(os.path.join(GOLD, "reloc.npz"))
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    cur, kf, Tc = S.reloc_scene(3)
+    n, cm = oracle.search_by_projection_keyframe(frame_geom(), Tc, 15.0, 100, True, lsf, kf, cur)
     assert n == int(gold["match_n"]) and np.array_equal(cm, gold["match_cm"])

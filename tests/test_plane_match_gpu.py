@@ -112,6 +112,43 @@ def test_search_edge_cases(oracle, msl):
     assert n == 0 and (cm == -2).all()
 
 
+LSF = float(np.float32(np.log(np.float64(np.float32(1.2)))))  # Frame::mfLogScaleFactor (src/Frame.cc:82)
+
+
+@pytest.mark.parametrize("seed,th,orb_dist", [(1, 15.0, 100), (2, 10.0, 64), (3, 3.0, 100), (4, 30.0, 50)])
+def test_search_by_projection_keyframe(oracle, msl, seed, th, orb_dist):
+    """Relocalisation overload (src/ORBmatcher.cc:680-797): bit-exact match table and count."""
+    cur, kf, Tc = S.reloc_scene(seed, collide=0.4)
+    g = msl.frame_geom()
+    m = msl.ORBmatcher()
+    for check in (True, False):
+        m.mbCheckOrientation = check
+        n_o, cm_o = oracle.search_by_projection_keyframe(g, Tc, th, orb_dist, check, LSF, kf, cur)
+        n_g, cm_g = m.SearchByProjectionKeyFrame(g, Tc, th, orb_dist, kf, cur, LSF)
+        assert n_o == n_g and np.array_equal(cm_o, cm_g)
+        assert n_o > 50
+
+
+def test_search_keyframe_edge_cases(oracle, msl):
+    cur, kf, Tc = S.reloc_scene(9, n_cur=60, n_kf=50)
+    g = msl.frame_geom()
+    m = msl.ORBmatcher()
+    kf2 = dict(kf)
+    kf2["valid"] = np.zeros_like(kf["valid"])  # every point bad / already found
+    assert m.SearchByProjectionKeyFrame(g, Tc, 15.0, 100, kf2, cur, LSF)[0] == 0
+    cur2 = dict(cur)
+    cur2["occupied"] = np.ones_like(cur["occupied"])  # every slot already holds a MapPoint
+    n, cm = m.SearchByProjectionKeyFrame(g, Tc, 15.0, 100, kf, cur2, LSF)
+    assert n == 0 and (cm == -2).all()
+    # single-level pyramid: PredictScale clamps to level 0 and the level window is [-1, 1]
+    g1 = msl.frame_geom(scale_factors=[1.0])
+    n_o, cm_o = oracle.search_by_projection_keyframe(g1, Tc, 15.0, 100, True, LSF, kf, cur)
+    n_g, cm_g = m.SearchByProjectionKeyFrame(g1, Tc, 15.0, 100, kf, cur, LSF)
+    assert n_o == n_g and np.array_equal(cm_o, cm_g)
+    with pytest.raises(Exception):
+        m.SearchByProjectionKeyFrame(g, Tc, 15.0, 300, kf, cur, LSF)  # ORBdist out of range
+
+
 def test_hamming_best2_ragged_device(oracle, msl):
     """Ragged batch (per-entry row counts, as produced by msl_orb_extract_dev) through the device entry point."""
     import torch
