@@ -22,11 +22,14 @@ def gray_batch(seed0, batch, w=640, h=480):
     return np.stack([gray_frame(seed0 + i, w, h) for i in range(batch)])
 
 
-def depth_frame(seed, w=640, h=480, K=K_DEFAULT, holes=True):
+def depth_frame(seed, w=640, h=480, K=K_DEFAULT, holes=True, scene=None):
     """Piecewise-planar scene: 3-6 random planes (normals within 60 deg of -z, 0.8-4 m) z-buffered
     through K, + N(0,(1.5e-3 z^2)) noise, 2 % zero holes in 8x8 patches, quantised to u16 (factor 5000).
+    scene=None: planes, noise and holes all come from `seed` (independent frames).  scene=s: the planes come
+    from seed s and only the sensor noise / holes from `seed` -- consecutive frames of ONE scene, which is what
+    a keyframe stream into a local surfel map looks like.
     Returns (depth_u16, depth_f32_metres)."""
-    r = np.random.default_rng(seed + 100003)
+    r = np.random.default_rng((seed if scene is None else scene) + 100003)
     fx, fy, cx, cy = [k * (w / 640.0) for k in K]
     u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
     rx, ry = (u - cx) / fx, (v - cy) / fy
@@ -55,6 +58,8 @@ def depth_frame(seed, w=640, h=480, K=K_DEFAULT, holes=True):
         zz[~m] = np.inf
         z = np.minimum(z, zz)
     z[~np.isfinite(z)] = 4.5
+    if scene is not None:
+        r = np.random.default_rng(seed + 200003)
     z = z + r.normal(0, 1.0, (h, w)) * (1.5e-3 * z * z)
     if holes:
         nh = int(0.02 * (w // 8) * (h // 8))
