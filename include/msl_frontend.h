@@ -207,8 +207,9 @@ int msl_plane_sync(msl_plane *);
 void *msl_plane_stream(msl_plane *);
 
 /* ------------------------------------------------------------------------------------- surfels
- * Replaces SurfelFusion (include/SurfelFusion.h:44-139, src/SurfelFusion.cpp) and the compaction
- * tail of SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391). */
+ * Replaces SurfelFusion (include/SurfelFusion.h:44-139, src/SurfelFusion.cpp), the compaction tail of
+ * SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391) and SurfelMapping::moveAddSurfels (:194-304), so that
+ * Map::mvLocalSurfels and Map::mvInactiveSurfels can stay on the device between keyframes. */
 
 typedef struct {
     float px, py, pz;
@@ -246,6 +247,20 @@ void msl_surfel_destroy(msl_surfel_fusion *);
 int msl_surfel_upload_map(msl_surfel_fusion *, const msl_surfel *local, int64_t n);
 int msl_surfel_download_map(msl_surfel_fusion *, msl_surfel *local, int64_t cap, int64_t *n);
 int64_t msl_surfel_map_size(const msl_surfel_fusion *);
+
+/* SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304) on the device-resident maps.  poses_to_remove /
+ * poses_to_add are what SurfelMapping::getAddRemovePoses (:306-326) returned (that walk over the pose graph stays on
+ * the host).  Moving out: local surfels with updateTimes > 0 && lastUpdate == pose are appended -- pose after pose, map
+ * order inside a pose -- to the device-side Map::mvInactiveSurfels (= PoseElement::attachedSurfels) and their local slot
+ * keeps updateTimes = 0 until the next fuse compacts it, as in the reference.  Moving in: the attached surfels of the
+ * poses to add are appended to the local map in list order and leave the inactive store.
+ *   stats (may be NULL): {moved_out, moved_in, local size afterwards (dead slots included)}.
+ * MSL_ERR_STATE if a pose to add was never moved out or a pose to remove is already inactive. */
+int msl_surfel_move_add(msl_surfel_fusion *, const int32_t *poses_to_remove, int n_remove, const int32_t *poses_to_add,
+                        int n_add, int64_t stats[3]);
+/* Map::mvInactiveSurfels in the reference's order (poses in the order they were moved out, minus those moved back) */
+int64_t msl_surfel_inactive_size(const msl_surfel_fusion *);
+int msl_surfel_download_inactive(msl_surfel_fusion *, msl_surfel *out, int64_t cap, int64_t *n);
 
 /* SurfelFusion::fuseInitializeMap (src/SurfelFusion.cpp:40-73) on the device-resident map.
  *   gray (CV_8UC1, row stride gray_stride), depth (CV_32F metres, dense w*h), membership (CV_32SC1,

@@ -60,6 +60,23 @@ class SurfelFusion:
         check(self._L.msl_surfel_download_map(self._h, ptr(out), C.c_int64(len(out)), C.byref(n)))
         return out
 
+    def moveAddSurfels(self, poses_to_remove, poses_to_add):
+        """SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304) on the device-resident maps; the two lists
+        are getAddRemovePoses' outputs.  Returns (moved_out, moved_in, local_size)."""
+        rem = np.ascontiguousarray(poses_to_remove, np.int32)
+        add = np.ascontiguousarray(poses_to_add, np.int32)
+        stats = np.zeros(3, np.int64)
+        check(self._L.msl_surfel_move_add(self._h, ptr(rem), C.c_int(len(rem)), ptr(add), C.c_int(len(add)), ptr(stats)))
+        return tuple(int(v) for v in stats)
+
+    def download_inactive(self):
+        """Map::mvInactiveSurfels in the reference's order."""
+        n = C.c_int64()
+        check(self._L.msl_surfel_download_inactive(self._h, None, C.c_int64(0), C.byref(n)))
+        out = np.zeros(n.value, SURFEL_DTYPE)
+        check(self._L.msl_surfel_download_inactive(self._h, ptr(out), C.c_int64(len(out)), C.byref(n)))
+        return out
+
     def fuseInitializeMap(self, referenceFrameIndex, image, depth, planeMembershipImg, pose, compact=False):
         """Returns (newSurfels, stats) with stats = (n_new, n_updated, n_deleted, map_size)."""
         image = np.ascontiguousarray(image, np.uint8)

@@ -397,3 +397,42 @@ def search_by_projection_keyframe(geom, Tcw_cur, th, orb_dist, check_ori, log_sc
                                             log_scale_factor, len(kf["angle"]), *[_p(x) for x in kargs],
                                             len(cur["octave"]), *[_p(x) for x in cargs], _p(cm))
     return n, cm
+
+
+class SurfelMappingOracle:
+    """The part of SurfelMapping that moveAddSurfels touches (src/SurfelMapping.cpp:194-304)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.L.orc_mapping_create.restype = C.c_void_p
+        self.L.orc_mapping_destroy.argtypes = [C.c_void_p]
+        self.L.orc_move_add_surfels.restype = C.c_int64
+        self.L.orc_move_add_surfels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.L.orc_mapping_inactive.restype = C.c_int64
+        self.L.orc_mapping_inactive.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        self.hd = self.L.orc_mapping_create()
+
+    def __del__(self):
+        if getattr(self, "hd", None):
+            self.L.orc_mapping_destroy(self.hd)
+            self.hd = None
+
+    def move_add(self, local, poses_to_remove, poses_to_add, extra=0):
+        """Returns the new local array (moved-out surfels stay as updateTimes == 0 slots)."""
+        rem = np.ascontiguousarray(poses_to_remove, np.int32)
+        add = np.ascontiguousarray(poses_to_add, np.int32)
+        cap = len(local) + self.inactive_size() + extra
+        buf = np.zeros(cap, SURFEL_DTYPE)
+        buf[:len(local)] = local
+        n = self.L.orc_move_add_surfels(self.hd, _p(buf), len(local), cap, _p(rem), len(rem), _p(add), len(add))
+        if n < 0:
+            raise RuntimeError("orc_move_add_surfels failed: %d" % n)
+        return buf[:n].copy()
+
+    def inactive_size(self):
+        return int(self.L.orc_mapping_inactive(self.hd, None, 0))
+
+    def inactive(self):
+        out = np.zeros(self.inactive_size(), SURFEL_DTYPE)
+        self.L.orc_mapping_inactive(self.hd, _p(out), len(out))
+        return out

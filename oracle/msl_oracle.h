@@ -211,6 +211,19 @@ const int32_t *orc_surfel_index_iter(const orc_surfel_fusion *, int it);
  * local must have room for n_local + n_new.  Returns the new local size. */
 int64_t orc_surfel_compact(orc_surfel *local, int64_t n_local, const orc_surfel *new_surfels, int n_new);
 
+/* SurfelMapping::moveAddSurfels, src/SurfelMapping.cpp:194-304, on the state it touches (posesDatabase's
+ * attachedSurfels / pointsBeginIndex / pointsPoseIndex, pointcloudPoseIndex, Map::mvInactiveSurfels).  The two pose
+ * lists are what getAddRemovePoses (:306-326) returned.  local has room for cap_local surfels.  Returns the new
+ * local size (surfels moved out stay as updateTimes == 0 slots, as in the reference), -1 if a pose to add was never
+ * moved out, -2 if cap_local is too small. */
+typedef struct orc_surfel_mapping orc_surfel_mapping;
+orc_surfel_mapping *orc_mapping_create(void);
+void orc_mapping_destroy(orc_surfel_mapping *);
+int64_t orc_move_add_surfels(orc_surfel_mapping *, orc_surfel *local, int64_t n_local, int64_t cap_local,
+                             const int32_t *posesToRemove, int n_remove, const int32_t *posesToAdd, int n_add);
+/* Map::mvInactiveSurfels (copied to out, at most cap entries); returns its size */
+int64_t orc_mapping_inactive(const orc_surfel_mapping *, orc_surfel *out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -733,4 +733,104 @@ int64_t orc_surfel_compact(orc_surfel *local, int64_t n_local, const orc_surfel 
     return size;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304) with the state it touches: posesDatabase
+// (include/SurfelMapping.h:39-46: attachedSurfels, pointsBeginIndex, pointsPoseIndex), pointcloudPoseIndex and
+// Map::mvInactiveSurfels.  posesToAdd / posesToRemove (getAddRemovePoses :306-326, a walk over the pose graph)
+// are inputs.  linkedPoseIndex / localSurfelsIndexs are the caller's business.
+struct orc_surfel_mapping {
+    struct PoseElement {
+        std::vector<orc_surfel> attachedSurfels;
+        int pointsBeginIndex = -1, pointsPoseIndex = -1;
+    };
+    std::vector<PoseElement> posesDatabase;
+    std::vector<int> pointcloudPoseIndex;
+    std::vector<orc_surfel> inactive;  // Map::mvInactiveSurfels
+};
+
+orc_surfel_mapping *orc_mapping_create() { return new orc_surfel_mapping(); }
+void orc_mapping_destroy(orc_surfel_mapping *m) { delete m; }
+
+int64_t orc_move_add_surfels(orc_surfel_mapping *m, orc_surfel *local, int64_t n_local, int64_t cap_local,
+                             const int32_t *posesToRemove, int n_remove, const int32_t *posesToAdd, int n_add) {
+    auto &posesDatabase = m->posesDatabase;
+    auto &pointcloudPoseIndex = m->pointcloudPoseIndex;
+    int maxPose = -1;
+    for (int i = 0; i < n_remove; i++) maxPose = std::max(maxPose, posesToRemove[i]);
+    for (int i = 0; i < n_add; i++) maxPose = std::max(maxPose, posesToAdd[i]);
+    if ((int)posesDatabase.size() < maxPose + 1) posesDatabase.resize(maxPose + 1);
+    if (n_remove > 0) {  // :200-229
+        for (int r = 0; r < n_remove; r++) {
+            const int inactiveIndex = posesToRemove[r];
+            posesDatabase[inactiveIndex].pointsBeginIndex = (int)m->inactive.size();
+            posesDatabase[inactiveIndex].pointsPoseIndex = (int)pointcloudPoseIndex.size();
+            pointcloudPoseIndex.push_back(inactiveIndex);
+            for (int64_t i = 0; i < n_local; i++) {
+                orc_surfel &localSurfel = local[i];
+                if (localSurfel.updateTimes > 0 && localSurfel.lastUpdate == inactiveIndex) {
+                    posesDatabase[inactiveIndex].attachedSurfels.push_back(localSurfel);
+                    m->inactive.push_back(localSurfel);
+                    localSurfel.updateTimes = 0;  // delete the surfel from the local map
+                }
+            }
+        }
+    }
+    if (n_add > 0) {  // :230-303
+        std::vector<std::pair<int, int>> removeInfo;
+        for (int addI = 0; addI < n_add; addI++) {
+            const int addIndex = posesToAdd[addI];
+            if (posesDatabase[addIndex].pointsPoseIndex < 0) return -1;  // never moved out: the reference would index [-1]
+            removeInfo.push_back(std::make_pair(posesDatabase[addIndex].pointsPoseIndex, addIndex));
+        }
+        std::sort(removeInfo.begin(), removeInfo.end(),
+                  [](const std::pair<int, int> &first, const std::pair<int, int> &second) { return first.first < second.first; });
+        int removeBeginIndex = removeInfo[0].second;
+        int removePointsSize = (int)posesDatabase[removeBeginIndex].attachedSurfels.size();
+        int removePoseSize = 1;
+        for (int removeI = 1; removeI <= (int)removeInfo.size(); removeI++) {
+            bool needRemove = false;
+            if (removeI == (int)removeInfo.size()) needRemove = true;
+            if (removeI < (int)removeInfo.size())
+                if (removeInfo[removeI].first != (removeInfo[removeI - 1].first + 1)) needRemove = true;
+            if (!needRemove) {
+                const int thisPoseIndex = removeInfo[removeI].second;
+                removePointsSize += (int)posesDatabase[thisPoseIndex].attachedSurfels.size();
+                removePoseSize += 1;
+                continue;
+            }
+            const int removeEndIndex = removeInfo[removeI - 1].second;
+            auto beginPtr = m->inactive.begin() + posesDatabase[removeBeginIndex].pointsBeginIndex;
+            m->inactive.erase(beginPtr, beginPtr + removePointsSize);
+            for (int pi = posesDatabase[removeEndIndex].pointsPoseIndex + 1; pi < (int)pointcloudPoseIndex.size(); pi++) {
+                posesDatabase[pointcloudPoseIndex[pi]].pointsBeginIndex -= removePointsSize;
+                posesDatabase[pointcloudPoseIndex[pi]].pointsPoseIndex -= removePoseSize;
+            }
+            pointcloudPoseIndex.erase(pointcloudPoseIndex.begin() + posesDatabase[removeBeginIndex].pointsPoseIndex,
+                                      pointcloudPoseIndex.begin() + posesDatabase[removeEndIndex].pointsPoseIndex + 1);
+            if (removeI < (int)removeInfo.size()) {
+                removeBeginIndex = removeInfo[removeI].second;
+                removePointsSize = (int)posesDatabase[removeBeginIndex].attachedSurfels.size();
+                removePoseSize = 1;
+            }
+        }
+        for (int pi = 0; pi < n_add; pi++) {  // :292-302 append to mvLocalSurfels
+            const int pose_index = posesToAdd[pi];
+            auto &att = posesDatabase[pose_index].attachedSurfels;
+            if (n_local + (int64_t)att.size() > cap_local) return -2;
+            for (const orc_surfel &e : att) local[n_local++] = e;
+            att.clear();
+            posesDatabase[pose_index].pointsBeginIndex = -1;
+            posesDatabase[pose_index].pointsPoseIndex = -1;
+        }
+    }
+    return n_local;
+}
+
+int64_t orc_mapping_inactive(const orc_surfel_mapping *m, orc_surfel *out, int64_t cap) {
+    const int64_t n = (int64_t)m->inactive.size();
+    if (out)
+        for (int64_t i = 0; i < n && i < cap; i++) out[i] = m->inactive[i];
+    return n;
+}
+
 }  // extern "C"

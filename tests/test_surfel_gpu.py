@@ -157,3 +157,77 @@ def test_upload_download_roundtrip(msl):
     sf.upload_map(local)
     assert sf.map_size() == 12345
     assert np.array_equal(sf.download_map(), local)
+
+
+def _pose_stamped_map(seed, n, depth, T, ref, n_poses=12):
+    """A local map whose lastUpdate values spread over n_poses keyframe indices, with some dead slots."""
+    r = np.random.default_rng(seed)
+    local = S.surfel_map(seed, n, depth, T, ref_index=ref)
+    local["lastUpdate"] = ref - r.integers(0, n_poses, n)
+    local["updateTimes"][r.random(n) < 0.03] = 0
+    return local
+
+
+@pytest.mark.parametrize("n", [3000, 70001])
+def test_move_add_surfels_matches_oracle(oracle, msl, n):
+    """SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304): local map and mvInactiveSurfels, record for
+    record and in order, over a sequence of move-out / move-in steps interleaved with fuse + compaction."""
+    img = S.gray_frame(5)
+    _, depth = S.depth_frame(5)
+    mem = S.membership(5)
+    T = S.pose_walk(5, 1)[0]
+    ref = 40
+    local = _pose_stamped_map(5, n, depth, T, ref)
+    mo = oracle.SurfelMappingOracle()
+    so = oracle.SurfelOracle()
+    sf = msl.SurfelFusion(max_surfels=3 * n + 20000)
+    sf.upload_map(local)
+    lo = local.copy()
+    steps = [([29, 31, 33], []), ([30], [31]), ([], []), ([32, 34], [29, 30]), ([], [33, 32, 34])]
+    for k, (rem, add) in enumerate(steps):
+        lo = mo.move_add(lo, rem, add)
+        out, inn, size = sf.moveAddSurfels(rem, add)
+        got = sf.download_map()
+        assert size == len(lo) == len(got)
+        assert np.array_equal(got.view(np.uint8), lo.view(np.uint8)), "local map differs after step %d" % k
+        assert np.array_equal(sf.download_inactive().view(np.uint8), mo.inactive().view(np.uint8)), "inactive differs after step %d" % k
+        if rem:
+            assert out > 0
+        # a keyframe in between: fuse + compaction refill the dead slots the move-out left behind
+        new = so.fuse(ref + 1 + k, img, depth, mem, T, lo)
+        lo = oracle.surfel_compact(lo, new)
+        sf.fuseInitializeMap(ref + 1 + k, img, depth, mem, T, compact=True)
+        got = sf.download_map()
+        assert len(got) == len(lo)
+        for f in got.dtype.names:
+            if got.dtype[f].kind == "i":
+                assert np.array_equal(got[f], lo[f]), f
+            else:
+                assert np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6), f
+        lo = got.copy()  # continue from identical bits on both sides
+
+
+def test_move_add_many_poses_and_errors(oracle, msl):
+    _, depth = S.depth_frame(6)
+    T = S.pose_walk(6, 1)[0]
+    local = _pose_stamped_map(6, 20000, depth, T, 100, n_poses=40)
+    mo = oracle.SurfelMappingOracle()
+    sf = msl.SurfelFusion(max_surfels=80000)
+    sf.upload_map(local)
+    rem = list(range(61, 101, 1))[:37]  # more than one pass of 16 poses
+    lo = mo.move_add(local.copy(), rem, [])
+    sf.moveAddSurfels(rem, [])
+    assert np.array_equal(sf.download_map().view(np.uint8), lo.view(np.uint8))
+    assert np.array_equal(sf.download_inactive().view(np.uint8), mo.inactive().view(np.uint8))
+    with pytest.raises(Exception):
+        sf.moveAddSurfels([], [5])          # never moved out
+    with pytest.raises(Exception):
+        sf.moveAddSurfels([rem[0]], [])     # already inactive
+    back = rem[::-3]
+    lo = mo.move_add(lo, [], back)
+    out, inn, size = sf.moveAddSurfels([], back)
+    assert out == 0 and inn > 0 and size == len(lo)
+    assert np.array_equal(sf.download_map().view(np.uint8), lo.view(np.uint8))
+    assert np.array_equal(sf.download_inactive().view(np.uint8), mo.inactive().view(np.uint8))
+    # empty call is a no-op
+    assert sf.moveAddSurfels([], []) == (0, 0, len(lo))
