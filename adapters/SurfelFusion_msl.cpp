@@ -2,8 +2,7 @@
 // SurfelMapping::fuseMap (src/SurfelMapping.cpp:353-364) is unchanged.  This is the exact drop-in: the host
 // vector Map::mvLocalSurfels stays authoritative, so every call uploads it, fuses on the device and downloads it
 // again (one PCIe round trip of 56 B/surfel per keyframe).  INTEGRATION.md describes the device-resident mode
-// (compaction on the device, no round trip) that msl_surfel_fuse(..., compact=1) provides once
-// SurfelMapping::moveAddSurfels is routed through the ABI as well.
+// (compaction and SurfelMapping::moveAddSurfels on the device, no round trip): adapters/SurfelMapping_msl.cpp.
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -16,6 +15,12 @@ static_assert(sizeof(Surfel) == sizeof(msl_surfel), "include/Surfel.h layout == 
 namespace {
 std::mutex g_mu;
 std::unordered_map<const SurfelFusion *, msl_surfel_fusion *> g_h;  // one instance, SurfelMapping thread only
+}
+
+// handle of a SurfelFusion object, for adapters/SurfelMapping_msl.cpp (device-resident mode)
+msl_surfel_fusion *msl_handle_of(const SurfelFusion *f) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_h.at(f);
 }
 
 SurfelFusion::SurfelFusion(int width, int height, float _fx, float _fy, float _cx, float _cy, float _fuseFar, float _fuseNear)

@@ -297,6 +297,12 @@ int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *laun
 int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
+/* Validation aid: k_fuse_scan divides by the camera-frame depth with a hand-scheduled IEEE sequence that shares one
+ * reciprocal between the two image coordinates; this compares it bit for bit with the compiler's division on n random
+ * operand triples (divisor in [c_lo, c_hi], numerators in [-a_max, a_max]) and returns the number of mismatches. */
+int msl_surfel_selftest_div(msl_surfel_fusion *, int64_t n, uint64_t seed, float c_lo, float c_hi, float a_max,
+                            int64_t *mismatches);
+
 /* Batched superpixel generation only (generateSuperPixels, src/SurfelFusion.cpp:805-816) for `batch`
  * independent frames: seeds (batch x (w/8)*(h/8) msl_seed), index (batch x w*h int32, may be NULL). */
 int msl_surfel_superpixels(msl_surfel_fusion *, const uint8_t *gray, int gray_stride, const float *depth,

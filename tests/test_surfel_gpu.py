@@ -231,3 +231,15 @@ def test_move_add_many_poses_and_errors(oracle, msl):
     assert np.array_equal(sf.download_inactive().view(np.uint8), mo.inactive().view(np.uint8))
     # empty call is a no-op
     assert sf.moveAddSurfels([], []) == (0, 0, len(lo))
+
+
+def test_scan_division_is_ieee(msl):
+    """The scan's shared-reciprocal division equals div.rn.f32 bit for bit over the operand ranges it sees."""
+    import ctypes as C
+    sf = msl.SurfelFusion(max_surfels=2000)
+    L = msl.lib()
+    for seed, (lo, hi, amax) in enumerate([(0.5, 30.0, 3.0e4), (0.5, 30.0, 50.0), (0.01, 100.0, 1.0e6), (0.5, 2.0, 1e-3)]):
+        bad = C.c_int64(-1)
+        rc = L.msl_surfel_selftest_div(sf._h, C.c_int64(200_000_000), C.c_uint64(seed + 1), C.c_float(lo), C.c_float(hi),
+                                       C.c_float(amax), C.byref(bad))
+        assert rc == 0 and bad.value == 0, (lo, hi, amax, bad.value)
