@@ -340,11 +340,11 @@ def run_ours(a, rank, world, local_rank):
     except Exception:
         ncu_traffic = {}
     # algorithmic bytes per launch:
-    #   k_fuse_scan : 20 B per surfel streamed (lastUpdate, updateTimes, px, py, pz) + 4 B per surfel it kills; the
-    #                 survivor queue (8 B per in-view surfel) is not counted
-    #   k_fuse_apply: per fused surfel 8 B queue entry + 9 plane words read + 14 plane words written = 100 B; the
-    #                 80-byte seed records stay in L1/L2 and are not counted
-    alg = {"k_fuse_scan": n_map * 20.0 + del_per_launch * 4.0, "k_fuse_apply": upd_per_launch * 100.0}
+    #   k_fuse_scan : 24 B per surfel streamed (the {px, py, pz, size} quad, updateTimes, lastUpdate) + 4 B per surfel
+    #                 it kills; the survivor queue (8 B per in-view surfel) is not counted
+    #   k_fuse_apply: per fused surfel 8 B queue entry + 36 B read (two quads + updateTimes) + 56 B written (three
+    #                 quads + updateTimes + lastUpdate) = 100 B; the 80-byte seed records stay in L1/L2, not counted
+    alg = {"k_fuse_scan": n_map * 24.0 + del_per_launch * 4.0, "k_fuse_apply": upd_per_launch * 100.0}
     unit_of = {"k_fuse_scan": ("dram_bytes_per_surfel", n_map), "k_fuse_apply": ("dram_bytes_per_fused", upd_per_launch)}
 
     def entry(kernel, key, times, frames, iso_times, iso_n):

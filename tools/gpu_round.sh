@@ -1,7 +1,7 @@
 #!/bin/bash
-# One gpurun call's worth of evidence: GPU parity tests, the bench line, scan-kernel A/B over its tuning knobs,
-# the ncu launch list of a short bench run and ncu --set full captures of the two fuse kernels.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r02a'
+# One gpurun call's worth of evidence: GPU parity tests, the bench line, A/B over the tuning knobs of the two fuse
+# kernels, the ncu launch list of a short bench run and ncu --set full captures of the two fuse kernels.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r02a [ab] [notest] [noncu]'
 # Everything lands in gpurun_out/<tag>_*; nothing printed under ncu is a bench value.
 TAG=${1:-run}
 shift
@@ -17,24 +17,16 @@ if [[ " $* " != *" notest "* ]]; then
 fi
 
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-tail -c 2500 $OUT/${TAG}_bench.json
+tail -c 3000 $OUT/${TAG}_bench.json
 
 if [[ " $* " == *" ab "* ]]; then
-  for cfg in "1 3" "2 3" "2 5" "3 2" "4 2"; do
-    set -- $cfg
-    MSL_SCAN_STAGES=$1 MSL_SCAN_CTAS=$2 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
-      > $OUT/${TAG}_ab_s$1_c$2.json 2>> $OUT/${TAG}_bench.err
-    python - "$OUT/${TAG}_ab_s$1_c$2.json" "$cfg" <<'EOF'
-import json, sys
-try:
-    j = json.load(open(sys.argv[1]))
-    r = j["roofline"]
-    print("AB stages,ctas=%s  value %.0f  scan %.1f us (isolated %.1f)  chain iso %s" % (
-        sys.argv[2], j["value"], 1e3 * r["avg_launch_ms"], 1e3 * r["isolated"]["avg_launch_ms"],
-        {k: round(v, 1) for k, v in r["isolated"]["chain_us_per_frame"].items()}))
-except Exception as e:
-    print("AB", sys.argv[2], "failed", e)
-EOF
+  # pairs of (MSL_SCAN_STAGES, MSL_APPLY_CTAS)
+  for cfg in "1_4" "0_3" "0_5"; do
+    S=${cfg%_*}
+    A=${cfg#*_}
+    MSL_SCAN_STAGES=$S MSL_APPLY_CTAS=$A timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
+      > $OUT/${TAG}_ab_s${S}_a${A}.json 2>> $OUT/${TAG}_bench.err
+    python tools/ab_line.py $OUT/${TAG}_ab_s${S}_a${A}.json "scan_stages=$S apply_ctas=$A"
   done
 fi
 
