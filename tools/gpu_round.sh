@@ -21,7 +21,7 @@ tail -c 3000 $OUT/${TAG}_bench.json
 
 if [[ " $* " == *" ab "* ]]; then
   # pairs of (MSL_SCAN_STAGES, MSL_APPLY_CTAS)
-  for cfg in "1_4" "0_3" "0_5"; do
+  for cfg in "0_3" "0_5"; do
     S=${cfg%_*}
     A=${cfg#*_}
     MSL_SCAN_STAGES=$S MSL_APPLY_CTAS=$A timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
@@ -37,8 +37,10 @@ if [[ " $* " != *" noncu "* ]]; then
   python tools/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt 2>&1
   head -30 $OUT/${TAG}_launches_summary.txt
   # full captures of the two fuse kernels (one launch each, a frame in the steady state of the stream)
-  for kn in k_fuse_scan k_fuse_apply; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s 40 -c 1 -f -o $OUT/${TAG}_$kn \
+  for kn in k_fuse_scan k_fuse_apply k_sp_fit; do
+    SKIP=40
+    [[ $kn == k_sp_* ]] && SKIP=2
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $SKIP -c 1 -f -o $OUT/${TAG}_$kn \
       python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline >> $OUT/${TAG}_ncu_bench.log 2>&1
     python tools/ncu_brief.py $OUT/${TAG}_$kn.ncu-rep > $OUT/${TAG}_${kn}_brief.txt 2>&1
     cat $OUT/${TAG}_${kn}_brief.txt
