@@ -20,13 +20,12 @@ timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 tail -c 3000 $OUT/${TAG}_bench.json
 
 if [[ " $* " == *" ab "* ]]; then
-  # pairs of (MSL_SCAN_STAGES, MSL_APPLY_CTAS)
-  for cfg in "0_3" "0_5"; do
-    S=${cfg%_*}
-    A=${cfg#*_}
-    MSL_SCAN_STAGES=$S MSL_APPLY_CTAS=$A timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
-      > $OUT/${TAG}_ab_s${S}_a${A}.json 2>> $OUT/${TAG}_bench.err
-    python tools/ab_line.py $OUT/${TAG}_ab_s${S}_a${A}.json "scan_stages=$S apply_ctas=$A"
+  # triples MSL_SCAN_STAGES _ MSL_APPLY_CTAS _ MSL_APPLY_ILP (override the list with AB_CFGS="0_2_4 0_4_2 ...")
+  for cfg in ${AB_CFGS:-0_2_4 0_4_2 0_3_2 0_4_1}; do
+    IFS=_ read S A I <<< "$cfg"
+    MSL_SCAN_STAGES=$S MSL_APPLY_CTAS=$A MSL_APPLY_ILP=$I timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
+      > $OUT/${TAG}_ab_$cfg.json 2>> $OUT/${TAG}_bench.err
+    python tools/ab_line.py $OUT/${TAG}_ab_$cfg.json "scan_stages=$S apply_ctas=$A apply_ilp=$I"
   done
 fi
 
@@ -37,7 +36,7 @@ if [[ " $* " != *" noncu "* ]]; then
   python tools/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt 2>&1
   head -30 $OUT/${TAG}_launches_summary.txt
   # full captures of the two fuse kernels (one launch each, a frame in the steady state of the stream)
-  for kn in k_fuse_scan k_fuse_apply k_sp_fit; do
+  for kn in ${NCU_KERNELS:-k_fuse_scan k_fuse_apply}; do
     SKIP=40
     [[ $kn == k_sp_* ]] && SKIP=2
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $SKIP -c 1 -f -o $OUT/${TAG}_$kn \
