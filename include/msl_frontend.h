@@ -176,6 +176,39 @@ int msl_search_by_projection_keyframe(msl_matcher *, const msl_frame_geom *geom,
                                       const int32_t *cur_octave, const float *cur_angle, const uint8_t *cur_desc,
                                       const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches);
 
+/* ---------------------------------------------------------------------------------- frame glue
+ * The per-frame steps either side of the ORB extractor, so that a frame can stay on the device from decode to the
+ * feature grid: Tracking::GrabImage's cvtColor and depth conversion (src/Tracking.cc:184-211),
+ * Frame::UndistortKeyPoints (src/Frame.cc:437-463) and Frame::ComputeStereoFromRGBD (src/Frame.cc:495-513). */
+
+typedef struct msl_glue msl_glue;
+
+int msl_glue_create(int w, int h, int max_batch, int device, msl_glue **out);
+void msl_glue_destroy(msl_glue *);
+int msl_glue_sync(msl_glue *);
+void *msl_glue_stream(msl_glue *); /* cudaStream_t */
+
+/* cvtColor(mImGray, mImGray, CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY | CV_BGRA2GRAY) (src/Tracking.cc:189-200):
+ * channels = 3 or 4, rgb_order = Tracking::mbRGB.  src rows `stride` bytes apart; gray dense w*h per frame. */
+int msl_glue_cvt_gray(msl_glue *, const uint8_t *src, int stride, int channels, int rgb_order, int batch, uint8_t *gray);
+int msl_glue_cvt_gray_dev(msl_glue *, const uint8_t *d_src, int stride, size_t frame_stride, int channels, int rgb_order,
+                          int batch, uint8_t *d_gray, int gray_stride, size_t gray_frame_stride);
+/* mImDepth.convertTo(mImDepth, CV_32F, mDepthMapFactor) (src/Tracking.cc:205-207) on CV_16U depth */
+int msl_glue_depth_to_float(msl_glue *, const uint16_t *depth16, int batch, float factor, float *depth);
+int msl_glue_depth_to_float_dev(msl_glue *, const uint16_t *d_depth16, int64_t n, float factor, float *d_depth);
+/* Frame::UndistortKeyPoints + Frame::ComputeStereoFromRGBD for one frame's keypoints (mvKeys as returned by
+ * msl_orb_extract): K4 = fx, fy, cx, cy; D5 = k1, k2, p1, p2, k3 (NULL or D5[0] == 0: mvKeysUn = mvKeys);
+ * depth = CV_32F metres, dense w*h, or NULL to skip the stereo part; mbf = Frame::mbf.
+ * Outputs: xy_un (2 floats per keypoint, may be NULL), uright = mvuRight, kdepth = mvDepth (-1 where depth <= 0). */
+int msl_glue_keypoints(msl_glue *, const msl_keypoint *kps, int n, const float K4[4], const float D5[5],
+                       const float *depth, float mbf, float *xy_un, float *uright, float *kdepth);
+/* Batched device form on the ragged output of msl_orb_extract_dev (`rows` keypoint rows reserved per frame, d_counts
+ * filled); d_depth: batch dense frames; stream = cudaStream_t to enqueue on (NULL = the handle's), e.g. the ORB
+ * handle's stream to chain extraction -> glue without a sync. */
+int msl_glue_keypoints_dev(msl_glue *, const msl_keypoint *d_kps, int rows, const int32_t *d_counts, int batch,
+                           const float K4[4], const float D5[5], const float *d_depth, float mbf, float *d_xy_un,
+                           float *d_uright, float *d_kdepth, void *stream);
+
 /* ----------------------------------------------------------------------------- plane pre-stage
  * Replaces PlaneDetection::readDepthImage (src/PlaneExtractor.cpp:44-76) and the peac pre-stage:
  * PlaneSeg ctor + Stats::compute per 10x10 block (include/peac/AHCPlaneSeg.hpp:148-181, 235-312)

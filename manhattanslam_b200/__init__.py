@@ -12,3 +12,4 @@ from .plane import PlaneDetection, BLOCK_DTYPE  # noqa: F401
 from .matcher import ORBmatcher, frame_geom, GEOM_DTYPE  # noqa: F401
 
 __version__ = "0.1.0"
+from .glue import FrameGlue  # noqa: F401

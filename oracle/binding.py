@@ -436,3 +436,48 @@ class SurfelMappingOracle:
         out = np.zeros(self.inactive_size(), SURFEL_DTYPE)
         self.L.orc_mapping_inactive(self.hd, _p(out), len(out))
         return out
+
+
+# ------------------------------------------------------------------- frame glue
+
+def cvt_gray(img, rgb_order=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.zeros((h, w), np.uint8)
+    L = lib()
+    L.orc_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.orc_cvt_gray(_p(img), w, h, img.strides[0], ch, int(rgb_order), _p(out), w)
+    return out
+
+
+def depth_to_float(d16, factor):
+    d16 = np.ascontiguousarray(d16, np.uint16)
+    out = np.zeros(d16.shape, np.float32)
+    L = lib()
+    L.orc_depth_to_float.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+    L.orc_depth_to_float(_p(d16), d16.size, factor, _p(out))
+    return out
+
+
+def undistort_keypoints(xy, K4, D5, force=False):
+    xy = np.ascontiguousarray(xy, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float32)
+    D5 = np.ascontiguousarray(D5, np.float32)
+    out = np.zeros_like(xy)
+    L = lib()
+    fn = L.orc_undistort_points if force else L.orc_undistort_keypoints
+    fn.argtypes = [C.c_int] + [C.c_void_p] * 4
+    fn(len(xy), _p(xy), _p(K4), _p(D5), _p(out))
+    return out
+
+
+def stereo_from_rgbd(kp_xy, kpun_xy, depth, mbf):
+    kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+    kpun_xy = np.ascontiguousarray(kpun_xy, np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    n = len(kp_xy)
+    ur, kd = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    L = lib()
+    L.orc_stereo_from_rgbd.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_float] + [C.c_void_p] * 2
+    L.orc_stereo_from_rgbd(n, _p(kp_xy), _p(kpun_xy), _p(depth), depth.shape[1], mbf, _p(ur), _p(kd))
+    return ur, kd

@@ -224,6 +224,19 @@ int64_t orc_move_add_surfels(orc_surfel_mapping *, orc_surfel *local, int64_t n_
 /* Map::mvInactiveSurfels (copied to out, at most cap entries); returns its size */
 int64_t orc_mapping_inactive(const orc_surfel_mapping *, orc_surfel *out, int64_t cap);
 
+/* ------------------------------------------------------------ frame glue --- */
+/* cv::cvtColor RGB/BGR(A) -> GRAY on CV_8U (src/Tracking.cc:189-200); channels 3|4, rgb_order 1 = R first */
+void orc_cvt_gray(const uint8_t *src, int w, int h, int stride, int channels, int rgb_order, uint8_t *dst, int dstride);
+/* Mat::convertTo(CV_32F, factor) on CV_16U depth (src/Tracking.cc:205-207) */
+void orc_depth_to_float(const uint16_t *src, int64_t n, float factor, float *dst);
+/* cv::undistortPoints(src, dst, K, D, noArray(), K) with K4 = fx,fy,cx,cy and D5 = k1,k2,p1,p2,k3 */
+void orc_undistort_points(int n, const float *xy, const float K4[4], const float D5[5], float *out);
+/* Frame::UndistortKeyPoints (src/Frame.cc:437-463): copy when D5[0] == 0 */
+void orc_undistort_keypoints(int n, const float *xy, const float K4[4], const float D5[5], float *out);
+/* Frame::ComputeStereoFromRGBD (src/Frame.cc:495-513): kp_xy = mvKeys, kpun_xy = mvKeysUn, dense w-wide depth */
+void orc_stereo_from_rgbd(int n, const float *kp_xy, const float *kpun_xy, const float *depth, int w, float mbf,
+                          float *uright, float *kdepth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,15 @@ def main():
     np.savez_compressed(os.path.join(HERE, "orb_frame.npz"), seed=seed, kps=kps.view(np.uint8).reshape(len(kps), -1),
                         desc=desc)
     print("golden written; cv2", cv2.__version__, "kps", len(kps))
+    # frame glue: cvtColor + undistortPoints (TUM1.yaml camera)
+    rgb = r.integers(0, 256, (33, 64, 3), dtype=np.uint8)
+    K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+    D5 = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    pts = np.stack([r.uniform(-20, 660, 1000), r.uniform(-20, 500, 1000)], 1).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "glue.npz"), cv2_version=cv2.__version__, rgb=rgb,
+                        gray_rgb=cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY), gray_bgr=cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY),
+                        K4=K4, D5=D5, pts=pts, undist=cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D5, None, K).reshape(-1, 2))
 
 
 if __name__ == "__main__":
