@@ -321,12 +321,14 @@ int msl_surfel_fuse_batch_dev(msl_surfel_fusion *, int ref0, const uint8_t *d_gr
 int msl_surfel_read_stats(msl_surfel_fusion *, int64_t stats[4]);
 int msl_surfel_read_new(msl_surfel_fusion *, msl_surfel *new_surfels, int cap_new, int *n_new);
 int msl_surfel_sync(msl_surfel_fusion *);
-/* Measurement aid: when enabled, every launch of the projective fuse scan is bracketed by CUDA events on
- * the handle's stream; msl_surfel_fuse_kernel_time synchronises, returns the summed kernel time and the
- * number of launches since the last query, and resets the tally. */
-int msl_surfel_set_timing(msl_surfel_fusion *, int enable);
+/* Measurement aid: CUDA events on the handle's stream around the kernels of the per-frame chain.  One event record
+ * costs about 2.7 us of stream time, so mode 1 -- meant for use inside a timed region -- marks only k_fuse_scan and
+ * k_fuse_apply (3 events) on every 8th frame, mode 2 marks all six points of every frame, mode 0 is off.
+ * msl_surfel_fuse_kernel_time synchronises and returns the summed k_fuse_scan time and the number of timed launches;
+ * msl_surfel_chain_times returns out = {scan, apply, post, list, cmp_apply} in ms summed over the timed frames
+ * (mode 1: scan and apply only) and resets the tally. */
+int msl_surfel_set_timing(msl_surfel_fusion *, int mode);
 int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *launches);
-/* per-kernel split of the per-frame chain (compact mode): out = {scan, apply, post, list, cmp_apply} in ms */
 int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
 void *msl_surfel_stream(msl_surfel_fusion *);
 

@@ -115,8 +115,9 @@ class SurfelFusion:
     def sync(self):
         check(self._L.msl_surfel_sync(self._h))
 
-    def set_timing(self, enable=True):
-        check(self._L.msl_surfel_set_timing(self._h, int(enable)))
+    def set_timing(self, mode=1):
+        """0 off, 1 scan + apply on every 8th frame (light: for use inside a timed region), 2 every mark of every frame"""
+        check(self._L.msl_surfel_set_timing(self._h, int(mode)))
 
     def chain_times(self):
         """per-frame-chain kernel times in ms: dict(scan, apply, post, list, cmp_apply), frames"""
