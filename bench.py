@@ -203,7 +203,9 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line (no version banner)
+        # stdout carries the single JSON line only: NCCL's version banner / debug output (printed whenever NCCL_DEBUG is
+        # set, e.g. by the launcher's environment) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
     gray, depth, mem, poses, surfels = make_inputs(rank, B, a.surfels)
