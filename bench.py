@@ -371,6 +371,10 @@ def run_ours(a, rank, world, local_rank):
     roofline["chain_us_per_frame"] = {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}
     roofline["isolated"]["chain_us_per_frame"] = {k: 1e3 * v / max(iso_frames, 1) for k, v in iso_chain.items()}
     roofline["fused_per_launch"] = upd_per_launch
+    # share_of_step is against the wall time of a step in which three streams overlap (the shares of all kernels sum to
+    # more than 1); the ncu launch list serialises every stream.  The split of the fuse chain itself is comparable:
+    tot = chain["scan"] + chain["apply"]
+    roofline["share_of_fuse_chain"] = {"k_fuse_scan": chain["scan"] / tot, "k_fuse_apply": chain["apply"] / tot} if tot else None
     roofline["note"] = "timed-region launches share the SMs with the next batch's superpixel kernels (stream overlap)"
 
     # ---- e2e: the public host API with pinned host buffers, H2D of the inputs + D2H of the results every step
