@@ -276,7 +276,6 @@ def run_ours(a, rank, world, local_rank):
         step_dev()
     barrier()
     launches0 = msl.lib().msl_kernel_launch_count()
-    sf.scan_tile_stats()  # reset
     sf.set_timing(1)  # light: scan + apply marks on every 8th frame (an event record costs ~2.7 us of stream time)
     st0 = sf.read_stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,7 +303,6 @@ def run_ours(a, rank, world, local_rank):
     fuse_ms, fuse_launches = sf.fuse_kernel_time()
     chain, chain_frames = sf.chain_times()
     sf.set_timing(0)
-    tiles_scanned, tiles_covered, scan_launches = sf.scan_tile_stats()
     st1 = sf.read_stats()
     orb.sync()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -344,16 +342,12 @@ def run_ours(a, rank, world, local_rank):
     except Exception:
         ncu_traffic = {}
     # algorithmic bytes per launch:
-    #   k_fuse_scan : 24 B per surfel of the tiles it scans (the {px, py, pz, size} quad, updateTimes, lastUpdate) + 32 B of
-    #                 tile metadata per tile looked at + 4 B per surfel it kills; tiles culled by their bounding box are
-    #                 not read and not counted; the survivor queue (8 B per in-view surfel) is not counted
+    #   k_fuse_scan : 24 B per surfel streamed (the {px, py, pz, size} quad, updateTimes, lastUpdate) + 4 B per surfel
+    #                 it kills; the survivor queue (8 B per in-view surfel) is not counted
     #   k_fuse_apply: per fused surfel 8 B queue entry + 36 B read (two quads + updateTimes) + 56 B written (three
     #                 quads + updateTimes + lastUpdate) = 100 B; the 80-byte seed records stay in L1/L2, not counted
-    scanned_frac = tiles_scanned / max(tiles_covered, 1)
-    alg = {"k_fuse_scan": n_map * scanned_frac * 24.0 + (tiles_covered / max(scan_launches, 1)) * 36.0 + del_per_launch * 4.0,
-           "k_fuse_apply": upd_per_launch * 100.0}
-    unit_of = {"k_fuse_scan": ("dram_bytes_per_surfel", n_map * scanned_frac), "k_fuse_apply": ("dram_bytes_per_fused", upd_per_launch)}
-
+    alg = {"k_fuse_scan": n_map * 24.0 + del_per_launch * 4.0, "k_fuse_apply": upd_per_launch * 100.0}
+    unit_of = {"k_fuse_scan": ("dram_bytes_per_surfel", n_map), "k_fuse_apply": ("dram_bytes_per_fused", upd_per_launch)}
 
     def entry(kernel, key, times, frames, iso_times, iso_n):
         ms = times[key] / max(frames, 1)
@@ -377,8 +371,6 @@ def run_ours(a, rank, world, local_rank):
     roofline["chain_us_per_frame"] = {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}
     roofline["isolated"]["chain_us_per_frame"] = {k: 1e3 * v / max(iso_frames, 1) for k, v in iso_chain.items()}
     roofline["fused_per_launch"] = upd_per_launch
-    roofline["scan_tiles"] = {"scanned_fraction": scanned_frac, "tiles_per_launch": tiles_covered / max(scan_launches, 1),
-                              "note": "k_fuse_scan skips clean tiles whose bounding box cannot reach the frustum; only scanned tiles count as algorithmic bytes"}
     # share_of_step is against the wall time of a step in which three streams overlap (the shares of all kernels sum to
     # more than 1); the ncu launch list serialises every stream.  The split of the fuse chain itself is comparable:
     tot = chain["scan"] + chain["apply"]

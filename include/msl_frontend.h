@@ -332,13 +332,6 @@ int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *laun
 int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
-/* Tile culling of the projective scan: k_fuse_scan keeps, per 1024-surfel tile it has scanned, the bounding box of the
- * live surfels, the oldest lastUpdate among the not yet established ones and the dead count, and skips a tile that is
- * unwritten since, cannot reach the frustum, holds no dead slot and no surfel due for the unstable-drop rule -- results
- * are identical to scanning everything.  Returns, since the last query: tiles actually scanned, tiles covered by the
- * launches, and the number of launches (the bench derives the algorithmic bytes of the scan from these). */
-int msl_surfel_scan_tile_stats(msl_surfel_fusion *, int64_t *scanned, int64_t *covered, int64_t *launches);
-
 /* Validation aid: k_fuse_scan divides by the camera-frame depth with a hand-scheduled IEEE sequence that shares one
  * reciprocal between the two image coordinates; this compares it bit for bit with the compiler's division on n random
  * operand triples (divisor in [c_lo, c_hi], numerators in [-a_max, a_max]) and returns the number of mismatches. */

@@ -126,12 +126,6 @@ class SurfelFusion:
         check(self._L.msl_surfel_chain_times(self._h, out, C.byref(n)))
         return dict(zip(("scan", "apply", "post", "list", "cmp_apply"), [float(v) for v in out])), n.value
 
-    def scan_tile_stats(self):
-        """(tiles scanned, tiles covered, launches) of k_fuse_scan since the last query (tile culling)."""
-        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
-        check(self._L.msl_surfel_scan_tile_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
-
     def fuse_kernel_time(self):
         """(total milliseconds, launches) of the projective fuse scan since the last query."""
         ms, n = C.c_double(), C.c_int()
