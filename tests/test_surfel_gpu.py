@@ -243,3 +243,33 @@ def test_scan_division_is_ieee(msl):
         rc = L.msl_surfel_selftest_div(sf._h, C.c_int64(200_000_000), C.c_uint64(seed + 1), C.c_float(lo), C.c_float(hi),
                                        C.c_float(amax), C.byref(bad))
         assert rc == 0 and bad.value == 0, (lo, hi, amax, bad.value)
+
+
+def test_fuse_stream_with_panning_camera(oracle, msl):
+    """A camera that pans away and comes back: surfels leave and re-enter the frustum, new surfels are spawned at the
+    borders, the unstable-drop rule fires on the ones left behind -- every frame's map must equal the oracle's."""
+    img = S.gray_frame(21)
+    frames = [S.depth_frame(21 + k, scene=21)[1] for k in range(3)]
+    mem = S.membership(21)
+    T0 = S.pose_walk(21, 1)[0].astype(np.float64)
+    local = S.surfel_map(21, 90001, frames[0], T0.astype(np.float32), ref_index=50)
+    sf = msl.SurfelFusion(max_surfels=200000)
+    sf.upload_map(local)
+    so = oracle.SurfelOracle()
+    lo = local.copy()
+    for k, yaw in enumerate([0, 12, 25, 40, 40, 25, 12, 0, -15, -30, 0, 0]):  # degrees about the camera's y axis
+        a = np.deg2rad(yaw)
+        R = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]])
+        T = (T0 @ R).astype(np.float32)
+        ref = 51 + k
+        new = so.fuse(ref, img, frames[k % 3], mem, T, lo)
+        lo = oracle.surfel_compact(lo, new)
+        _, stats = sf.fuseInitializeMap(ref, img, frames[k % 3], mem, T, compact=True)
+        got = sf.download_map()
+        assert len(got) == len(lo) == stats[3], "frame %d" % k
+        for f in got.dtype.names:
+            if got.dtype[f].kind == "i":
+                assert np.array_equal(got[f], lo[f]), (k, f)
+            else:
+                assert np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6), (k, f)
+        lo = got.copy()
