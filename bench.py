@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--surfels", type=int, default=5_000_000, help="surfels in the local map per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
+    ap.add_argument("--only", default="", help="diagnostic: comma list of stages (orb,match,plane,surfel) the device-resident "
+                                               "step runs; the default (empty) is the full front-end -- anything else is not a bench value")
     return ap.parse_args()
 
 
@@ -248,18 +250,24 @@ def run_ours(a, rank, world, local_rank):
     K4 = (525.0, 525.0, 319.5, 239.5)
     state = {"ref": 100}
 
+    only = set(x for x in a.only.split(",") if x) or {"orb", "match", "plane", "surfel"}
+
     def step_dev():
         """inputs resident in HBM; ORB and the surfel stream run on their own CUDA streams and overlap"""
         if world > 1:
             s_orb.wait_stream(torch.cuda.current_stream())  # previous all-gather still reads d_counts
-        orb.extract_dev(d_gray.data_ptr(), W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr())
+        if "orb" in only:
+            orb.extract_dev(d_gray.data_ptr(), W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr())
         # frame b vs frame b+1, chained on the ORB stream (no host sync between extraction and matching)
-        matcher.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_counts.data_ptr(),
-                                         d_counts.data_ptr() + 4, B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr(),
-                                         stream=orb.stream)
-        plane.prestage_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, None, d_blocks.data_ptr(), d_seedm.data_ptr(),
-                           d_edges.data_ptr())
-        sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
+        if "match" in only:
+            matcher.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_counts.data_ptr(),
+                                             d_counts.data_ptr() + 4, B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr(),
+                                             stream=orb.stream)
+        if "plane" in only:
+            plane.prestage_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, None, d_blocks.data_ptr(), d_seedm.data_ptr(),
+                               d_edges.data_ptr())
+        if "surfel" in only:
+            sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
         state["ref"] += B
         if world > 1:  # the path's single collective: per-frame counts to every rank
             torch.cuda.current_stream().wait_stream(s_orb)
@@ -346,8 +354,12 @@ def run_ours(a, rank, world, local_rank):
     #                 it kills; the survivor queue (8 B per in-view surfel) is not counted
     #   k_fuse_apply: per fused surfel 8 B queue entry + 36 B read (two quads + updateTimes) + 56 B written (three
     #                 quads + updateTimes + lastUpdate) = 100 B; the 80-byte seed records stay in L1/L2, not counted
-    alg = {"k_fuse_scan": n_map * 24.0 + del_per_launch * 4.0, "k_fuse_apply": upd_per_launch * 100.0}
-    unit_of = {"k_fuse_scan": ("dram_bytes_per_surfel", n_map), "k_fuse_apply": ("dram_bytes_per_fused", upd_per_launch)}
+    #   k_fuse_one  : (default) both in one kernel: 24 B per surfel streamed + 4 B per killed surfel + per fused surfel
+    #                 16 B read (the normal/weight quad) + 56 B written = 72 B; no queue, no second read of q0 / updateTimes
+    alg = {"k_fuse_scan": n_map * 24.0 + del_per_launch * 4.0, "k_fuse_apply": upd_per_launch * 100.0,
+           "k_fuse_one": n_map * 24.0 + del_per_launch * 4.0 + upd_per_launch * 72.0}
+    unit_of = {"k_fuse_scan": ("dram_bytes_per_surfel", n_map), "k_fuse_apply": ("dram_bytes_per_fused", upd_per_launch),
+               "k_fuse_one": ("dram_bytes_per_surfel", n_map)}
 
     def entry(kernel, key, times, frames, iso_times, iso_n):
         ms = times[key] / max(frames, 1)
@@ -364,17 +376,24 @@ def run_ours(a, rank, world, local_rank):
                 "isolated": {"avg_launch_ms": iso, "achieved": ach_iso, "frac": ach_iso / peak if ach_iso else None,
                              "note": "same kernel, same map, no other stream active"}}
 
-    r_scan = entry("k_fuse_scan", "scan", chain, chain_frames, iso_chain, iso_frames)
-    r_apply = entry("k_fuse_apply", "apply", chain, chain_frames, iso_chain, iso_frames)
-    roofline, other = (r_apply, r_scan) if chain["apply"] >= chain["scan"] else (r_scan, r_apply)
-    roofline["other_kernel"] = other
+    if sf.fuse_kernels() == 1:
+        # the "scan" interval of the timing aid brackets k_fuse_one; "apply" is an empty interval (one event record)
+        roofline = entry("k_fuse_one", "scan", chain, chain_frames, iso_chain, iso_frames)
+        tot = chain["scan"]
+        roofline["share_of_fuse_chain"] = {"k_fuse_one": 1.0}
+    else:
+        r_scan = entry("k_fuse_scan", "scan", chain, chain_frames, iso_chain, iso_frames)
+        r_apply = entry("k_fuse_apply", "apply", chain, chain_frames, iso_chain, iso_frames)
+        roofline, other = (r_apply, r_scan) if chain["apply"] >= chain["scan"] else (r_scan, r_apply)
+        roofline["other_kernel"] = other
+        # share_of_step is against the wall time of a step in which three streams overlap (the shares of all kernels sum to
+        # more than 1); the ncu launch list serialises every stream.  The split of the fuse chain itself is comparable:
+        tot = chain["scan"] + chain["apply"]
+        roofline["share_of_fuse_chain"] = {"k_fuse_scan": chain["scan"] / tot, "k_fuse_apply": chain["apply"] / tot} if tot else None
     roofline["chain_us_per_frame"] = {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}
     roofline["isolated"]["chain_us_per_frame"] = {k: 1e3 * v / max(iso_frames, 1) for k, v in iso_chain.items()}
     roofline["fused_per_launch"] = upd_per_launch
-    # share_of_step is against the wall time of a step in which three streams overlap (the shares of all kernels sum to
-    # more than 1); the ncu launch list serialises every stream.  The split of the fuse chain itself is comparable:
-    tot = chain["scan"] + chain["apply"]
-    roofline["share_of_fuse_chain"] = {"k_fuse_scan": chain["scan"] / tot, "k_fuse_apply": chain["apply"] / tot} if tot else None
+    roofline["killed_per_launch"] = del_per_launch
     roofline["note"] = "timed-region launches share the SMs with the next batch's superpixel kernels (stream overlap)"
 
     # ---- e2e: the public host API with pinned host buffers, H2D of the inputs + D2H of the results every step
@@ -449,7 +468,7 @@ def run_ours(a, rank, world, local_rank):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8+f32", "data": "synthetic",
-               "config": {"workload": workload_name(a), "batch_per_gpu": B, "surfels_per_gpu": a.surfels,
+               "config": {"workload": workload_name(a) + ("" if not a.only else "_DIAGNOSTIC_only_" + a.only), "batch_per_gpu": B, "surfels_per_gpu": a.surfels,
                           "stages": ["orb", "hamming_match", "plane_prestage", "surfel_fuse"], "map_size_end": n_map,
                           "l2": "working set per step (280 MB surfel planes + 190 MB pyramids) exceeds the 126 MB L2",
                           "collective": "nccl all_gather of per-frame counts" if world > 1 else "none (1 GPU)"},

@@ -330,6 +330,10 @@ int msl_surfel_sync(msl_surfel_fusion *);
 int msl_surfel_set_timing(msl_surfel_fusion *, int mode);
 int msl_surfel_fuse_kernel_time(msl_surfel_fusion *, double *total_ms, int *launches);
 int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
+/* Number of kernels fuseSurfelsKernel (src/SurfelFusion.cpp:167-283) runs as: 1 = k_fuse_one (scan and fuse in one
+ * kernel; the "scan" interval of the timing aid is that kernel and "apply" is empty), 2 = k_fuse_scan + k_fuse_apply
+ * (environment MSL_FUSE_ONE=0). */
+int msl_surfel_fuse_kernels(const msl_surfel_fusion *);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
 /* Validation aid: k_fuse_scan divides by the camera-frame depth with a hand-scheduled IEEE sequence that shares one

@@ -126,6 +126,10 @@ class SurfelFusion:
         check(self._L.msl_surfel_chain_times(self._h, out, C.byref(n)))
         return dict(zip(("scan", "apply", "post", "list", "cmp_apply"), [float(v) for v in out])), n.value
 
+    def fuse_kernels(self):
+        """1: fuseSurfelsKernel runs as k_fuse_one; 2: as k_fuse_scan + k_fuse_apply (MSL_FUSE_ONE=0)"""
+        return int(self._L.msl_surfel_fuse_kernels(self._h))
+
     def fuse_kernel_time(self):
         """(total milliseconds, launches) of the projective fuse scan since the last query."""
         ms, n = C.c_double(), C.c_int()

@@ -271,5 +271,7 @@ def test_fuse_stream_with_panning_camera(oracle, msl):
             if got.dtype[f].kind == "i":
                 assert np.array_equal(got[f], lo[f]), (k, f)
             else:
-                assert np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6), (k, f)
+                # this scene has two seeds whose plane fit degenerates to NaN (0/0 in the reference's arithmetic as well):
+                # the NaNs must sit in the same records
+                assert np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6, equal_nan=True), (k, f)
         lo = got.copy()
