@@ -36,7 +36,7 @@ if [[ " $* " != *" noncu "* ]]; then
   python tools/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt 2>&1
   head -30 $OUT/${TAG}_launches_summary.txt
   # full captures of the two fuse kernels (one launch each, a frame in the steady state of the stream)
-  for kn in ${NCU_KERNELS:-k_fuse_scan k_fuse_apply}; do
+  for kn in ${NCU_KERNELS:-k_fuse_one}; do
     SKIP=40
     [[ $kn == k_sp_* ]] && SKIP=2
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $SKIP -c 1 -f -o $OUT/${TAG}_$kn \
