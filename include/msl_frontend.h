@@ -176,6 +176,50 @@ int msl_search_by_projection_keyframe(msl_matcher *, const msl_frame_geom *geom,
                                       const int32_t *cur_octave, const float *cur_angle, const uint8_t *cur_desc,
                                       const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (src/ORBmatcher.cc:146-255;
+ * called at src/Tracking.cc:859,1158,1942).  The two DBoW2::FeatureVector maps (pKF->mFeatVec, F.mFeatVec) in CSR form:
+ * node ids in ascending (std::map) order, node k owns the feature indices feat[off[k] .. off[k+1]) in their stored
+ * order.  kf_valid[i] = (vpMapPointsKF[i] && !isBad()); kf_angle = pKF->mvKeysUn[i].angle; f_angle = F.mvKeys[j].angle.
+ * f_match[j] = index i of the KeyFrame keypoint whose MapPoint now sits in vpMapPointMatches[j], -1 none, -3 assigned
+ * and then reset to NULL by the rotation-consistency check; *nmatches = return value of the reference method.
+ * MSL_ERR_INVALID for a malformed feature vector (ids not ascending, offsets not monotone, index out of range). */
+int msl_search_by_bow(msl_matcher *, float nnratio, int check_orientation, int n_nodes_kf, const uint32_t *kf_node_id,
+                      const int32_t *kf_node_off, const int32_t *kf_node_feat, int n_nodes_f, const uint32_t *f_node_id,
+                      const int32_t *f_node_off, const int32_t *f_node_feat, int n_kf, const uint8_t *kf_valid,
+                      const uint8_t *kf_desc, const float *kf_angle, int n_f, const uint8_t *f_desc, const float *f_angle,
+                      int32_t *f_match, int32_t *nmatches);
+
+/* ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
+ * (src/ORBmatcher.cc:257-406, with CheckDistEpipolarLine :127-144; called at src/LocalMapping.cc:351).
+ * F12 row-major 3x3; Cw1 = pKF1->GetCameraCenter(); Tcw2 = pKF2's pose (row-major 4x4); K2 = pKF2 fx, fy, cx, cy;
+ * scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2 (nlevels entries); feature vectors as above;
+ * has_mp = (GetMapPoint(idx) != NULL); uright = mvuRight; xy / angle / octave = mvKeysUn.
+ * matches12[idx1] = idx2 (vMatchedPairs = the pairs with matches12 >= 0 in idx1 order), -1 none, -3 removed by the
+ * rotation check; *nmatches = return value. */
+int msl_search_for_triangulation(msl_matcher *, const float F12[9], const float Cw1[3], const float Tcw2[16],
+                                 const float K2[4], int only_stereo, int check_orientation, int nlevels,
+                                 const float *scale_factors2, const float *level_sigma2_2, int n_nodes1,
+                                 const uint32_t *node_id1, const int32_t *node_off1, const int32_t *node_feat1,
+                                 int n_nodes2, const uint32_t *node_id2, const int32_t *node_off2,
+                                 const int32_t *node_feat2, int n1, const uint8_t *has_mp1, const float *uright1,
+                                 const float *xy1, const float *angle1, const uint8_t *desc1, int n2,
+                                 const uint8_t *has_mp2, const float *uright2, const float *xy2, const int32_t *octave2,
+                                 const float *angle2, const uint8_t *desc2, int32_t *matches12, int32_t *nmatches);
+
+/* The search part of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th)
+ * (src/ORBmatcher.cc:408-519; called at src/LocalMapping.cc:549,569): per map point the best keypoint of the KeyFrame.
+ * geom = the KeyFrame's intrinsics, image bounds, grid and scale factors; Tcw = its pose; inv_level_sigma2 =
+ * pKF->mvInvLevelSigma2; log_scale_factor = pKF->mfLogScaleFactor.  Per map point: mp_valid (pMP && !isBad() &&
+ * !IsInKeyFrame(pKF)), mp_world (GetWorldPos), mp_normal (GetNormal), mp_dist (mfMinDistance, mfMaxDistance),
+ * mp_desc (GetDescriptor).  KeyFrame keypoints: kf_xy / kf_octave = mvKeysUn, kf_uright = mvuRight, kf_desc.
+ * best_idx[i] = bestIdx (-1 none), best_dist[i] = bestDist (256 none).  The caller applies :521-541 (Replace /
+ * AddObservation / AddMapPoint) to every map point with best_dist <= TH_LOW (50), in order; *nfused = their number. */
+int msl_fuse_search(msl_matcher *, const msl_frame_geom *geom, const float Tcw[16], float th, float log_scale_factor,
+                    const float *inv_level_sigma2, int n_mp, const uint8_t *mp_valid, const float *mp_world,
+                    const float *mp_normal, const float *mp_dist, const uint8_t *mp_desc, int n_kf, const float *kf_xy,
+                    const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
+                    int32_t *best_dist, int32_t *nfused);
+
 /* ---------------------------------------------------------------------------------- frame glue
  * The per-frame steps either side of the ORB extractor, so that a frame can stay on the device from decode to the
  * feature grid: Tracking::GrabImage's cvtColor and depth conversion (src/Tracking.cc:184-211),

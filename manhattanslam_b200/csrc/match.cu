@@ -1,6 +1,7 @@
 // match.cu -- B200-native descriptor matching (replaces ORBmatcher::DescriptorDistance and the window
 // searches ORBmatcher::SearchByProjection of src/ORBmatcher.cc:40-117, 548-678, 680-797, 799-849 with the
-// Frame grid semantics of src/Frame.cc:155-168, 332-381, 418-427 of razayunus/ManhattanSLAM).
+// Frame grid semantics of src/Frame.cc:155-168, 332-381, 418-427 of razayunus/ManhattanSLAM; the vocabulary-node
+// searches SearchByBoW :146-255 and SearchForTriangulation :257-406, and the search part of Fuse :408-519).
 //
 //   k_hamming_best2     all-pairs 256-bit Hamming: one warp per query, train descriptors staged through
 //                       shared memory in 256-descriptor tiles, xor + __popc on 8 x u32, warp-shuffle
@@ -13,6 +14,13 @@
 //                       query i sees slot j blocked iff an earlier query i' < i holds it -- iterate until
 //                       no assignment changes (unique solution by induction on i); (4) rotation histogram
 //                       + ComputeThreeMaxima pruning.
+//   k_node_search       SearchByBoW / SearchForTriangulation: the two FeatureVectors in CSR form; one warp per
+//                       vocabulary node of the first (binary search for the same id in the second), queries of a node
+//                       in order (SearchByBoW's "slot already matched" only couples queries of one node, because a
+//                       feature belongs to exactly one node), lanes over the node's candidates, warp-shuffle
+//                       reduction under the reference's tie rules; rotation histogram + ComputeThreeMaxima.
+//   k_fuse_search       Fuse: the KeyFrame grid as in k_search, one thread per map point (projection, distance /
+//                       viewing-angle / scale tests, chi-square gate per candidate, strict-< best).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -25,6 +33,7 @@ using namespace msl;
 namespace {
 
 constexpr int TH_HIGH = 100;      // src/ORBmatcher.cc:33
+constexpr int TH_LOW = 50;        // :34
 constexpr int HISTO_LENGTH = 30;  // :35
 constexpr int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:53-54
 constexpr int NCELLS = GRID_COLS * GRID_ROWS;
@@ -362,6 +371,278 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
     if (tid == 0) *A.nmatches = s_n;
 }
 
+// ------------------------------------------------------------- vocabulary-node searches (SearchByBoW, SearchForTriangulation)
+__device__ __forceinline__ void three_maxima(const int *hist, int &ind1, int &ind2, int &ind3) {  // :799-830
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = hist[i];
+        if (s > max1) {
+            max3 = max2, max2 = max1, max1 = s;
+            ind3 = ind2, ind2 = ind1, ind1 = i;
+        } else if (s > max2) {
+            max3 = max2, max2 = s;
+            ind3 = ind2, ind2 = i;
+        } else if (s > max3) {
+            max3 = s, ind3 = i;
+        }
+    }
+    if ((float)max2 < 0.1f * (float)max1) ind2 = -1, ind3 = -1;
+    else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+}
+
+struct NodeArgs {
+    int mode;  // 0: SearchByBoW (A = KeyFrame, B = Frame; out indexed by B), 1: SearchForTriangulation (A = KF1, B = KF2; out by A)
+    float nnratio;
+    int checkOri, onlyStereo;
+    int nNodesA, nNodesB, nA, nB;
+    const uint32_t *idA, *idB;
+    const int32_t *offA, *featA, *offB, *featB;
+    const uint8_t *a_flag, *a_desc;  // mode 0: kf_valid; mode 1: has_mp1
+    const float *a_angle, *a_xy, *a_uright;
+    const uint8_t *b_flag, *b_desc;  // mode 1: has_mp2
+    const float *b_angle, *b_xy, *b_uright;
+    const int32_t *b_octave;
+    float F12[9], ex, ey, scale2[16], sigma2[16];
+    int32_t *out, *bin, *nmatches;
+};
+
+__global__ void __launch_bounds__(1024) k_node_search(NodeArgs A) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_n, s_ind[3];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int nOut = A.mode == 0 ? A.nB : A.nA;
+    for (int j = tid; j < nOut; j += blockDim.x) A.out[j] = -1, A.bin[j] = -1;
+    if (tid < HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (int na = wid; na < A.nNodesA; na += nw) {
+        // the node of the same id on the B side (the reference's merge with lower_bound visits exactly the common ids)
+        const uint32_t id = A.idA[na];
+        int lo = 0, hi = A.nNodesB;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A.idB[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= A.nNodesB || A.idB[lo] != id) continue;
+        const int b0 = A.offB[lo], b1 = A.offB[lo + 1];
+        for (int ia = A.offA[na]; ia < A.offA[na + 1]; ia++) {
+            const int idxA = A.featA[ia];
+            if (A.mode == 0) {
+                if (!A.a_flag[idxA]) continue;  // !pMP || pMP->isBad()
+            } else {
+                if (A.a_flag[idxA]) continue;   // pMP1 != NULL
+            }
+            const bool stereoA = A.mode == 1 && A.a_uright[idxA] >= 0;
+            if (A.mode == 1 && A.onlyStereo && !stereoA) continue;
+            const uint4 *Q = (const uint4 *)(A.a_desc + 32 * (size_t)idxA);
+            const uint4 q0 = __ldg(Q), q1 = __ldg(Q + 1);
+            int bd = A.mode == 0 ? 256 : TH_LOW + 1, bp = -1, sd = 256;
+            float la = 0, lb = 0, lc = 0, den = 0, ax = 0, ay = 0;
+            if (A.mode == 1) {  // epipolar line of kp1 in the second image (CheckDistEpipolarLine :127-144)
+                ax = A.a_xy[2 * idxA], ay = A.a_xy[2 * idxA + 1];
+                la = ax * A.F12[0] + ay * A.F12[3] + A.F12[6];
+                lb = ax * A.F12[1] + ay * A.F12[4] + A.F12[7];
+                lc = ax * A.F12[2] + ay * A.F12[5] + A.F12[8];
+                den = la * la + lb * lb;
+            }
+            for (int ib = b0 + lane; ib < b1; ib += 32) {
+                const int idxB = A.featB[ib];
+                if (A.mode == 0) {
+                    if (A.out[idxB] >= 0) continue;  // vpMapPointMatches[realIdxF] set by an earlier query of this node
+                } else {
+                    if (A.b_flag[idxB]) continue;     // pMP2 != NULL (vbMatched2 is never set in the reference)
+                    if (A.onlyStereo && !(A.b_uright[idxB] >= 0)) continue;
+                }
+                const uint4 *T = (const uint4 *)(A.b_desc + 32 * (size_t)idxB);
+                const int d = hamming256(q0, q1, __ldg(T), __ldg(T + 1));
+                if (A.mode == 0) {
+                    if (d < bd) sd = bd, bd = d, bp = ib;
+                    else if (d < sd) sd = d;
+                } else {
+                    if (d > TH_LOW) continue;
+                    const float bx = A.b_xy[2 * idxB], by = A.b_xy[2 * idxB + 1];
+                    const int oct = A.b_octave[idxB];
+                    if (!stereoA && !(A.b_uright[idxB] >= 0)) {
+                        const float distex = A.ex - bx, distey = A.ey - by;
+                        if (distex * distex + distey * distey < 100.0f * A.scale2[oct]) continue;
+                    }
+                    const float num = la * bx + lb * by + lc;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (!((double)dsqr < 3.84 * (double)A.sigma2[oct])) continue;
+                    if (d <= bd) bd = d, bp = ib;  // `dist > bestDist` (:336): the later of two equal candidates wins
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int obd = __shfl_xor_sync(0xffffffffu, bd, o), obp = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int osd = __shfl_xor_sync(0xffffffffu, sd, o);
+                if (A.mode == 0) {
+                    const int ns = min(max(bd, obd), min(sd, osd));
+                    if (obd < bd || (obd == bd && (unsigned)obp < (unsigned)bp)) bd = obd, bp = obp;
+                    sd = ns;
+                } else {
+                    if (obd < bd || (obd == bd && obp > bp)) bd = obd, bp = obp;
+                }
+            }
+            bool hit;
+            if (A.mode == 0) hit = bp >= 0 && bd <= TH_LOW && (float)bd < A.nnratio * (float)sd;
+            else hit = bp >= 0;
+            if (hit && lane == 0) {
+                const int idxB = A.featB[bp];
+                const int slot = A.mode == 0 ? idxB : idxA;
+                A.out[slot] = A.mode == 0 ? idxA : idxB;
+                atomicAdd(&s_n, 1);
+                if (A.checkOri) {
+                    float rot = A.a_angle[idxA] - A.b_angle[idxB];
+                    if (rot < 0.0f) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    A.bin[slot] = bin;
+                    atomicAdd(&hist[bin], 1);
+                }
+            }
+            __syncwarp();  // lane 0's write of out[] is visible to the warp's next query
+        }
+    }
+    __syncthreads();
+    if (A.checkOri) {
+        if (tid == 0) three_maxima(hist, s_ind[0], s_ind[1], s_ind[2]);
+        __syncthreads();
+        int pruned = 0;
+        for (int j = tid; j < nOut; j += blockDim.x) {
+            const int b = A.bin[j];
+            if (b >= 0 && b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) {
+                A.out[j] = -3;
+                pruned++;
+            }
+        }
+        if (pruned) atomicSub(&s_n, pruned);
+        __syncthreads();
+    }
+    if (tid == 0) *A.nmatches = s_n;
+}
+
+// ------------------------------------------------------------------------------- Fuse (search part)
+struct FuseArgs {
+    msl_frame_geom g;
+    float th, logScale;
+    float Rcw[9], tcw[3], Ow[3], invSigma2[16];
+    int nq, nc;
+    const uint8_t *q_valid, *q_desc;
+    const float *q_world, *q_normal, *q_dist;
+    const float *c_xy, *c_uright;
+    const int32_t *c_octave;
+    const uint8_t *c_desc;
+    int32_t *bestIdx, *bestDist, *nFused;
+};
+
+__global__ void __launch_bounds__(1024) k_fuse_search(FuseArgs A) {
+    __shared__ uint32_t keys[MAXK];  // (cell << 12 | index), sorted; 0xffffffff = not in grid
+    __shared__ unsigned short cellStart[NCELLS + 1];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const msl_frame_geom &g = A.g;
+    // the KeyFrame's grid (copied from its Frame: AssignFeaturesToGrid, src/Frame.cc:155-168) as a sorted list
+    int n2 = 1;
+    while (n2 < A.nc) n2 <<= 1;
+    for (int i = tid; i < n2; i += nt) {
+        uint32_t key = 0xffffffffu;
+        if (i < A.nc) {
+            const int px = (int)roundf((A.c_xy[2 * i] - g.mnMinX) * g.gridWInv);
+            const int py = (int)roundf((A.c_xy[2 * i + 1] - g.mnMinY) * g.gridHInv);
+            if (!(px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS)) key = ((uint32_t)(px * GRID_ROWS + py) << 12) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    bitonic_sort_u32(keys, n2);
+    for (int c = tid; c <= NCELLS; c += nt) {
+        int lo = 0, hi = A.nc;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((keys[mid] >> 12) < (uint32_t)c) lo = mid + 1; else hi = mid;
+        }
+        cellStart[c] = (unsigned short)lo;
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < A.nq; i += nt) {
+        int best = -1, bestDist = 256;
+        if (A.q_valid[i]) {
+            const float *p3Dw = A.q_world + 3 * i;
+            const float pc0 = gemm_row(A.Rcw, p3Dw, A.tcw[0]), pc1 = gemm_row(A.Rcw + 3, p3Dw, A.tcw[1]);
+            const float pc2 = gemm_row(A.Rcw + 6, p3Dw, A.tcw[2]);
+            bool ok = !(pc2 < 0.0f);  // :431
+            const float invz = 1.0f / pc2;
+            const float x = pc0 * invz, y = pc1 * invz;
+            const float u = g.fx * x + g.cx, v = g.fy * y + g.cy;
+            if (!(u >= g.mnMinX && u < g.mnMaxX && v >= g.mnMinY && v < g.mnMaxY)) ok = false;  // KeyFrame::IsInImage
+            const float ur = u - g.mbf * invz;
+            const float minD = 0.8f * A.q_dist[2 * i], maxD = 1.2f * A.q_dist[2 * i + 1];
+            float PO[3];
+            double s2 = 0;
+            for (int k = 0; k < 3; k++) {
+                PO[k] = p3Dw[k] - A.Ow[k];
+                s2 += (double)PO[k] * (double)PO[k];
+            }
+            const float dist3D = (float)sqrt(s2);
+            if (dist3D < minD || dist3D > maxD) ok = false;
+            double dot = 0;
+            for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)A.q_normal[3 * i + k];
+            if (dot < 0.5 * (double)dist3D) ok = false;  // viewing angle > 60 deg (:459-462)
+            if (ok) {
+                // MapPoint::PredictScale(dist3D, pKF) src/MapPoint.cc:334-348 (logf as the rounded fp64 logarithm, see k_search)
+                const float ratio = A.q_dist[2 * i + 1] / dist3D;
+                int lvl = (int)ceilf((float)log((double)ratio) / A.logScale);
+                if (lvl < 0) lvl = 0;
+                else if (lvl >= g.nlevels) lvl = g.nlevels - 1;
+                const float radius = A.th * g.scaleFactors[lvl];
+                // KeyFrame::GetFeaturesInArea src/KeyFrame.cc:469-504
+                const int cx0 = max(0, (int)floorf((u - g.mnMinX - radius) * g.gridWInv));
+                const int cx1 = min(GRID_COLS - 1, (int)ceilf((u - g.mnMinX + radius) * g.gridWInv));
+                const int cy0 = max(0, (int)floorf((v - g.mnMinY - radius) * g.gridHInv));
+                const int cy1 = min(GRID_ROWS - 1, (int)ceilf((v - g.mnMinY + radius) * g.gridHInv));
+                if (cx0 < GRID_COLS && cx1 >= 0 && cy0 < GRID_ROWS && cy1 >= 0) {
+                    const uint4 *Q = (const uint4 *)(A.q_desc + 32 * (size_t)i);
+                    const uint4 q0 = Q[0], q1 = Q[1];
+                    for (int ix = cx0; ix <= cx1; ix++) {
+                        const int s0 = cellStart[ix * GRID_ROWS + cy0], s1 = cellStart[ix * GRID_ROWS + cy1 + 1];
+                        for (int s = s0; s < s1; s++) {
+                            const int k = keys[s] & 0xfff;
+                            const float kpx = A.c_xy[2 * k], kpy = A.c_xy[2 * k + 1];
+                            if (!(fabsf(kpx - u) < radius && fabsf(kpy - v) < radius)) continue;
+                            const int kpLevel = A.c_octave[k];
+                            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+                            const float ex = u - kpx, ey = v - kpy;
+                            const float kpr = A.c_uright[k];
+                            if (kpr >= 0) {  // chi-square gate, stereo (:488-499) / mono (:500-509)
+                                const float er = ur - kpr;
+                                const float e2 = ex * ex + ey * ey + er * er;
+                                if ((double)(e2 * A.invSigma2[kpLevel]) > 7.8) continue;
+                            } else {
+                                const float e2 = ex * ex + ey * ey;
+                                if ((double)(e2 * A.invSigma2[kpLevel]) > 5.99) continue;
+                            }
+                            const uint4 *T = (const uint4 *)(A.c_desc + 32 * (size_t)k);
+                            const int d = hamming256(q0, q1, T[0], T[1]);
+                            if (d < bestDist) bestDist = d, best = k;
+                        }
+                    }
+                }
+            }
+        }
+        A.bestIdx[i] = best, A.bestDist[i] = bestDist;
+        if (bestDist <= TH_LOW) mine++;
+    }
+    if (mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (tid == 0) *A.nFused = s_n;
+}
+
 }  // namespace
 
 struct msl_matcher {
@@ -668,6 +949,163 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
     A.bin = ar.get<int32_t>(n_kf);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_keyframe: scratch arena / copy failure");
     return run_search(m, A, cur_match, nmatches);
+}
+
+static bool csr_ok(int nNodes, const uint32_t *id, const int32_t *off, const int32_t *feat, int nFeat) {
+    if (nNodes < 0) return false;
+    if (nNodes == 0) return true;
+    if (!id || !off || off[0] != 0) return false;
+    for (int k = 0; k < nNodes; k++) {
+        if (off[k + 1] < off[k]) return false;
+        if (k && !(id[k - 1] < id[k])) return false;  // std::map order
+    }
+    if (off[nNodes] && !feat) return false;
+    for (int e = 0; e < off[nNodes]; e++)
+        if (feat[e] < 0 || feat[e] >= nFeat) return false;
+    return true;
+}
+
+static int run_node_search(msl_matcher *m, NodeArgs &A, int nOut, int32_t *out, int32_t *nmatches) {
+    k_node_search<<<1, 1024, 0, m->stream>>>(A);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaMemcpyAsync(out, A.out, sizeof(int32_t) * nOut, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int n_nodes_kf, const uint32_t *kf_node_id,
+                      const int32_t *kf_node_off, const int32_t *kf_node_feat, int n_nodes_f, const uint32_t *f_node_id,
+                      const int32_t *f_node_off, const int32_t *f_node_feat, int n_kf, const uint8_t *kf_valid,
+                      const uint8_t *kf_desc, const float *kf_angle, int n_f, const uint8_t *f_desc, const float *f_angle,
+                      int32_t *f_match, int32_t *nmatches) {
+    if (!m || !f_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_bow: null argument");
+    if (n_kf < 0 || n_f < 0 || n_kf > m->maxQ || n_f > m->maxT) return fail(MSL_ERR_INVALID, "msl_search_by_bow: too many keypoints for this handle");
+    if (!csr_ok(n_nodes_kf, kf_node_id, kf_node_off, kf_node_feat, n_kf) || !csr_ok(n_nodes_f, f_node_id, f_node_off, f_node_feat, n_f))
+        return fail(MSL_ERR_INVALID, "msl_search_by_bow: malformed feature vector (ids must ascend, offsets must be monotone, indices in range)");
+    if (n_kf == 0 || n_f == 0 || n_nodes_kf == 0 || n_nodes_f == 0) {
+        for (int j = 0; j < n_f; j++) f_match[j] = -1;
+        *nmatches = 0;
+        return MSL_OK;
+    }
+    if (!kf_valid || !kf_desc || !kf_angle || !f_desc || !f_angle) return fail(MSL_ERR_INVALID, "msl_search_by_bow: null argument");
+    MSL_CUDA(cudaSetDevice(m->device));
+    NodeArgs A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 0, A.nnratio = nnratio, A.checkOri = check_orientation, A.nNodesA = n_nodes_kf, A.nNodesB = n_nodes_f;
+    A.nA = n_kf, A.nB = n_f;
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.idA = ar.put(kf_node_id, n_nodes_kf), A.offA = ar.put(kf_node_off, n_nodes_kf + 1);
+    A.featA = ar.put(kf_node_feat, kf_node_off[n_nodes_kf]);
+    A.idB = ar.put(f_node_id, n_nodes_f), A.offB = ar.put(f_node_off, n_nodes_f + 1);
+    A.featB = ar.put(f_node_feat, f_node_off[n_nodes_f]);
+    A.a_flag = ar.put(kf_valid, n_kf), A.a_desc = ar.put(kf_desc, (size_t)n_kf * 32), A.a_angle = ar.put(kf_angle, n_kf);
+    A.b_desc = ar.put(f_desc, (size_t)n_f * 32), A.b_angle = ar.put(f_angle, n_f);
+    A.out = ar.get<int32_t>(n_f), A.bin = ar.get<int32_t>(n_f), A.nmatches = ar.get<int32_t>(1);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_bow: scratch arena / copy failure");
+    return run_node_search(m, A, n_f, f_match, nmatches);
+}
+
+int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float Cw1[3], const float Tcw2[16],
+                                 const float K2[4], int only_stereo, int check_orientation, int nlevels,
+                                 const float *scale_factors2, const float *level_sigma2_2, int n_nodes1,
+                                 const uint32_t *node_id1, const int32_t *node_off1, const int32_t *node_feat1,
+                                 int n_nodes2, const uint32_t *node_id2, const int32_t *node_off2,
+                                 const int32_t *node_feat2, int n1, const uint8_t *has_mp1, const float *uright1,
+                                 const float *xy1, const float *angle1, const uint8_t *desc1, int n2,
+                                 const uint8_t *has_mp2, const float *uright2, const float *xy2, const int32_t *octave2,
+                                 const float *angle2, const uint8_t *desc2, int32_t *matches12, int32_t *nmatches) {
+    if (!m || !F12 || !Cw1 || !Tcw2 || !K2 || !scale_factors2 || !level_sigma2_2 || !matches12 || !nmatches)
+        return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: null argument");
+    if (n1 < 0 || n2 < 0 || n1 > m->maxQ || n2 > m->maxT) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: too many keypoints for this handle");
+    if (nlevels < 1 || nlevels > 16) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: nlevels out of range");
+    if (!csr_ok(n_nodes1, node_id1, node_off1, node_feat1, n1) || !csr_ok(n_nodes2, node_id2, node_off2, node_feat2, n2))
+        return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: malformed feature vector");
+    if (n1 == 0 || n2 == 0 || n_nodes1 == 0 || n_nodes2 == 0) {
+        for (int i = 0; i < n1; i++) matches12[i] = -1;
+        *nmatches = 0;
+        return MSL_OK;
+    }
+    if (!has_mp1 || !uright1 || !xy1 || !angle1 || !desc1 || !has_mp2 || !uright2 || !xy2 || !octave2 || !angle2 || !desc2)
+        return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: null argument");
+    for (int j = 0; j < n2; j++)
+        if (octave2[j] < 0 || octave2[j] >= nlevels) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: octave out of range");
+    MSL_CUDA(cudaSetDevice(m->device));
+    NodeArgs A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 1, A.checkOri = check_orientation, A.onlyStereo = only_stereo, A.nNodesA = n_nodes1, A.nNodesB = n_nodes2;
+    A.nA = n1, A.nB = n2;
+    memcpy(A.F12, F12, sizeof(float) * 9);
+    for (int l = 0; l < nlevels; l++) A.scale2[l] = scale_factors2[l], A.sigma2[l] = level_sigma2_2[l];
+    {   // :263-270 epipole in the second image: C2 = R2w * Cw + t2w (one cv gemm: double accumulation, one rounding)
+        float C2[3];
+        for (int r = 0; r < 3; r++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += (double)Tcw2[r * 4 + k] * (double)Cw1[k];
+            C2[r] = (float)(s + (double)Tcw2[r * 4 + 3]);
+        }
+        const float invz = 1.0f / C2[2];
+        A.ex = K2[0] * C2[0] * invz + K2[2];
+        A.ey = K2[1] * C2[1] * invz + K2[3];
+    }
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.idA = ar.put(node_id1, n_nodes1), A.offA = ar.put(node_off1, n_nodes1 + 1), A.featA = ar.put(node_feat1, node_off1[n_nodes1]);
+    A.idB = ar.put(node_id2, n_nodes2), A.offB = ar.put(node_off2, n_nodes2 + 1), A.featB = ar.put(node_feat2, node_off2[n_nodes2]);
+    A.a_flag = ar.put(has_mp1, n1), A.a_desc = ar.put(desc1, (size_t)n1 * 32), A.a_angle = ar.put(angle1, n1);
+    A.a_xy = ar.put(xy1, (size_t)n1 * 2), A.a_uright = ar.put(uright1, n1);
+    A.b_flag = ar.put(has_mp2, n2), A.b_desc = ar.put(desc2, (size_t)n2 * 32), A.b_angle = ar.put(angle2, n2);
+    A.b_xy = ar.put(xy2, (size_t)n2 * 2), A.b_uright = ar.put(uright2, n2), A.b_octave = ar.put(octave2, n2);
+    A.out = ar.get<int32_t>(n1), A.bin = ar.get<int32_t>(n1), A.nmatches = ar.get<int32_t>(1);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_for_triangulation: scratch arena / copy failure");
+    return run_node_search(m, A, n1, matches12, nmatches);
+}
+
+int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[16], float th, float log_scale_factor,
+                    const float *inv_level_sigma2, int n_mp, const uint8_t *mp_valid, const float *mp_world,
+                    const float *mp_normal, const float *mp_dist, const uint8_t *mp_desc, int n_kf, const float *kf_xy,
+                    const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
+                    int32_t *best_dist, int32_t *nfused) {
+    if (!m || !geom || !Tcw || !inv_level_sigma2 || !best_idx || !best_dist || !nfused) return fail(MSL_ERR_INVALID, "msl_fuse_search: null argument");
+    if (n_mp < 0 || n_kf < 0 || n_mp > m->maxQ || n_kf > m->maxT || n_kf > MAXK) return fail(MSL_ERR_INVALID, "msl_fuse_search: too many keypoints for this handle");
+    if (geom->nlevels < 1 || geom->nlevels > 16 || !(log_scale_factor > 0.f)) return fail(MSL_ERR_INVALID, "msl_fuse_search: parameter out of range");
+    if (n_mp == 0 || n_kf == 0) {
+        for (int i = 0; i < n_mp; i++) best_idx[i] = -1, best_dist[i] = 256;
+        *nfused = 0;
+        return MSL_OK;
+    }
+    if (!mp_valid || !mp_world || !mp_normal || !mp_dist || !mp_desc || !kf_xy || !kf_octave || !kf_uright || !kf_desc)
+        return fail(MSL_ERR_INVALID, "msl_fuse_search: null argument");
+    for (int j = 0; j < n_kf; j++)
+        if (kf_octave[j] < 0 || kf_octave[j] >= geom->nlevels) return fail(MSL_ERR_INVALID, "msl_fuse_search: octave out of range");
+    MSL_CUDA(cudaSetDevice(m->device));
+    FuseArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g = *geom, A.th = th, A.logScale = log_scale_factor, A.nq = n_mp, A.nc = n_kf;
+    for (int l = 0; l < geom->nlevels; l++) A.invSigma2[l] = inv_level_sigma2[l];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw[r * 4 + c];
+        A.tcw[r] = Tcw[r * 4 + 3];
+    }
+    for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose: Ow = -Rwc * tcw (one cv gemm)
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
+        A.Ow[r] = (float)s;
+    }
+    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    A.q_valid = ar.put(mp_valid, n_mp), A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);
+    A.q_world = ar.put(mp_world, (size_t)n_mp * 3), A.q_normal = ar.put(mp_normal, (size_t)n_mp * 3);
+    A.q_dist = ar.put(mp_dist, (size_t)n_mp * 2);
+    A.c_xy = ar.put(kf_xy, (size_t)n_kf * 2), A.c_uright = ar.put(kf_uright, n_kf), A.c_octave = ar.put(kf_octave, n_kf);
+    A.c_desc = ar.put(kf_desc, (size_t)n_kf * 32);
+    A.bestIdx = ar.get<int32_t>(n_mp), A.bestDist = ar.get<int32_t>(n_mp), A.nFused = ar.get<int32_t>(1);
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_fuse_search: scratch arena / copy failure");
+    k_fuse_search<<<1, 1024, 0, m->stream>>>(A);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(best_dist, A.bestDist, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaMemcpyAsync(nfused, A.nFused, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
 }
 
 }  // extern "C"

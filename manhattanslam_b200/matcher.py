@@ -1,5 +1,6 @@
-"""ORBmatcher mirror (include/ORBmatcher.h:39-55: DescriptorDistance + the two tracking-time
-SearchByProjection overloads + the relocalisation overload) over the CUDA C ABI.  The Frame/MapPoint graph is passed as flat arrays."""
+"""ORBmatcher mirror (include/ORBmatcher.h:39-79: DescriptorDistance, the two tracking-time SearchByProjection
+overloads, the relocalisation overload, SearchByBoW, SearchForTriangulation and the search part of Fuse) over the CUDA
+C ABI.  The Frame / KeyFrame / MapPoint graph is passed as flat arrays, DBoW2 feature vectors in CSR form."""
 import ctypes as C
 
 import numpy as np
@@ -129,3 +130,69 @@ class ORBmatcher:
             C.c_float(log_scale_factor), n_kf, *[ptr(x) for x in args], n_cur, *[ptr(x) for x in cargs], ptr(cm),
             C.byref(nm)))
         return nm.value, cm
+
+    @staticmethod
+    def _csr(fv):
+        """DBoW2::FeatureVector (dict node id -> feature indices) -> (ids u32 ascending, offsets i32, features i32)"""
+        items = sorted(fv.items())
+        ids = np.asarray([k for k, _ in items], np.uint32)
+        off = np.zeros(len(items) + 1, np.int32)
+        for i, (_, v) in enumerate(items):
+            off[i + 1] = off[i] + len(v)
+        feat = np.asarray([x for _, v in items for x in v], np.int32)
+        return ids, off, feat
+
+    def SearchByBoW(self, kf, f):
+        """SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (src/ORBmatcher.cc:146-255).
+        kf: dict(featvec, valid, desc, angle); f: dict(featvec, desc, angle).  Returns (nmatches, f_match)."""
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        kid, koff, kfeat = self._csr(kf["featvec"])
+        fid, foff, ffeat = self._csr(f["featvec"])
+        kv, kd, ka = a(kf["valid"], np.uint8), a(kf["desc"], np.uint8), a(kf["angle"], np.float32)
+        fd, fa = a(f["desc"], np.uint8), a(f["angle"], np.float32)
+        fm = np.zeros(len(fa), np.int32)
+        nm = C.c_int32()
+        check(self._L.msl_search_by_bow(self._h, C.c_float(self.mfNNratio), int(self.mbCheckOrientation), len(kid), ptr(kid),
+                                        ptr(koff), ptr(kfeat), len(fid), ptr(fid), ptr(foff), ptr(ffeat), len(ka), ptr(kv),
+                                        ptr(kd), ptr(ka), len(fa), ptr(fd), ptr(fa), ptr(fm), C.byref(nm)))
+        return nm.value, fm
+
+    def SearchForTriangulation(self, kf1, kf2, F12, Cw1, Tcw2, K2, scale_factors2, level_sigma2_2, bOnlyStereo=False):
+        """SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
+        (src/ORBmatcher.cc:257-406).  kf1: dict(featvec, has_mp, uright, xy, angle, desc); kf2: the same + octave.
+        Returns (nmatches, matches12); vMatchedPairs = [(i, matches12[i]) for i where matches12[i] >= 0]."""
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        id1, off1, ft1 = self._csr(kf1["featvec"])
+        id2, off2, ft2 = self._csr(kf2["featvec"])
+        sf, ls = a(scale_factors2, np.float32), a(level_sigma2_2, np.float32)
+        a1 = [a(kf1["has_mp"], np.uint8), a(kf1["uright"], np.float32), a(kf1["xy"], np.float32), a(kf1["angle"], np.float32),
+              a(kf1["desc"], np.uint8)]
+        a2 = [a(kf2["has_mp"], np.uint8), a(kf2["uright"], np.float32), a(kf2["xy"], np.float32), a(kf2["octave"], np.int32),
+              a(kf2["angle"], np.float32), a(kf2["desc"], np.uint8)]
+        m12 = np.zeros(len(a1[0]), np.int32)
+        nm = C.c_int32()
+        check(self._L.msl_search_for_triangulation(
+            self._h, ptr(a(F12, np.float32)), ptr(a(Cw1, np.float32)), ptr(a(Tcw2, np.float32)), ptr(a(K2, np.float32)),
+            int(bOnlyStereo), int(self.mbCheckOrientation), len(sf), ptr(sf), ptr(ls), len(id1), ptr(id1), ptr(off1), ptr(ft1),
+            len(id2), ptr(id2), ptr(off2), ptr(ft2), len(a1[0]), *[ptr(x) for x in a1], len(a2[0]), *[ptr(x) for x in a2],
+            ptr(m12), C.byref(nm)))
+        return nm.value, m12
+
+    def Fuse(self, geom, Tcw, mps, kf, inv_level_sigma2, th=3.0, log_scale_factor=None):
+        """The search part of Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:408-519).
+        mps: dict(valid, world, normal, dist, desc); kf: dict(xy, octave, uright, desc).
+        Returns (nFused, best_idx, best_dist); the Replace / AddObservation bookkeeping (:521-541) is the caller's."""
+        if log_scale_factor is None:
+            log_scale_factor = float(np.float32(np.log(np.float64(np.float32(geom["scaleFactors"][0, 1])))))
+        a = lambda x, dt: np.ascontiguousarray(x, dt)
+        ils = a(inv_level_sigma2, np.float32)
+        margs = [a(mps["valid"], np.uint8), a(mps["world"], np.float32), a(mps["normal"], np.float32),
+                 a(mps["dist"], np.float32), a(mps["desc"], np.uint8)]
+        kargs = [a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["uright"], np.float32), a(kf["desc"], np.uint8)]
+        bi = np.zeros(len(margs[0]), np.int32)
+        bd = np.zeros(len(margs[0]), np.int32)
+        nf = C.c_int32()
+        check(self._L.msl_fuse_search(self._h, ptr(geom), ptr(a(Tcw, np.float32)), C.c_float(th), C.c_float(log_scale_factor),
+                                      ptr(ils), len(margs[0]), *[ptr(x) for x in margs], len(kargs[1]), *[ptr(x) for x in kargs],
+                                      ptr(bi), ptr(bd), C.byref(nf)))
+        return nf.value, bi, bd

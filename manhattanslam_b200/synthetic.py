@@ -225,3 +225,146 @@ def reloc_scene(seed, n_cur=1000, n_kf=900, collide=0.3, negative_depth=0.02):
     cur = dict(cur)
     cur["occupied"] = (r.random(n_cur) < 0.1).astype(np.uint8)      # mvpMapPoints[j] != NULL on entry
     return cur, kf, Tcw_cur
+
+
+def _noisy_desc(r, desc, max_flips):
+    """copies of 32-byte descriptors with 0..max_flips-1 random bits flipped per row"""
+    out = desc.copy()
+    flips = r.integers(0, max_flips, len(desc))
+    for i in range(len(desc)):
+        for b in r.choice(256, flips[i], replace=False):
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def _feature_vector(node_of_feature, order_rng=None):
+    """DBoW2::FeatureVector as a dict node id -> list of feature indices (ascending, as FeatureVector::addFeature builds
+    it when features are transformed in index order; shuffled inside a node if order_rng is given)."""
+    fv = {}
+    for i, nd in enumerate(node_of_feature):
+        fv.setdefault(int(nd), []).append(i)
+    if order_rng is not None:
+        for v in fv.values():
+            order_rng.shuffle(v)
+    return fv
+
+
+def bow_scene(seed, n_kf=1000, n_f=1000, n_nodes=120, collide=0.3, shuffle=False):
+    """Synthetic ORBmatcher::SearchByBoW situation (src/ORBmatcher.cc:146-255): a Frame with random descriptors spread
+    over vocabulary nodes (sparse 32-bit node ids), and a KeyFrame most of whose keypoints are noisy copies of a Frame
+    keypoint in the same node.  `collide` = fraction of KeyFrame keypoints that target a Frame keypoint another one
+    targets too (exercises the "slot already matched" skip); some nodes exist on one side only."""
+    r = np.random.default_rng(seed + 4242)
+    ids = np.sort(r.choice(100000, n_nodes + 20, replace=False)).astype(np.uint32)
+    f_nodes = ids[r.integers(0, n_nodes, n_f)]                       # the last 20 ids never occur in the Frame
+    f = {"desc": r.integers(0, 256, (n_f, 32), dtype=np.uint8), "angle": r.uniform(0, 360, n_f).astype(np.float32)}
+    tgt = r.integers(0, n_f, n_kf)
+    ncol = int(collide * n_kf) // 2
+    tgt[:ncol] = tgt[ncol:2 * ncol]
+    r.shuffle(tgt)
+    linked = r.random(n_kf) < 0.8
+    kf_nodes = np.where(linked, f_nodes[tgt], ids[r.integers(10, n_nodes + 20, n_kf)])
+    desc = _noisy_desc(r, f["desc"][tgt], 70)
+    desc[~linked] = r.integers(0, 256, (int((~linked).sum()), 32), dtype=np.uint8)
+    # exact duplicates of a Frame descriptor in the same node: best == second best, the ratio test must reject
+    dup = r.choice(n_f, 10, replace=False)
+    for d in dup:
+        same = np.nonzero(f_nodes == f_nodes[d])[0]
+        if len(same) > 1:
+            f["desc"][same[0]] = f["desc"][d]
+    ang = (f["angle"][tgt] + r.normal(0, 6, n_kf) + (r.random(n_kf) < 0.1) * 90) % 360
+    kf = {"valid": (r.random(n_kf) < 0.9).astype(np.uint8), "desc": desc, "angle": ang.astype(np.float32),
+          "featvec": _feature_vector(kf_nodes, r if shuffle else None)}
+    f["featvec"] = _feature_vector(f_nodes, r if shuffle else None)
+    return kf, f
+
+
+def triangulation_scene(seed, n=900, n_nodes=100, K=K_DEFAULT, w=640, h=480):
+    """Two KeyFrames for ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:257-406): 3-D points seen by both, the
+    fundamental matrix F12 = K1^-T [t12]x R12 K2^-1 (LocalMapping::ComputeF12, src/LocalMapping.cc), keypoints =
+    projections + noise, descriptors = noisy copies, a few exact duplicates in KeyFrame 2 (equal distances: the later
+    candidate wins, :336), mixed stereo / monocular keypoints, some keypoints with MapPoints already.
+    Returns (kf1, kf2, F12, Cw1, Tcw2, K2, scale_factors, level_sigma2)."""
+    r = np.random.default_rng(seed + 9090)
+    fx, fy, cx, cy = K
+    Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    T = pose_walk(seed + 3, 2)
+    Twc1 = T[0].astype(np.float64)
+    Twc2 = T[1].astype(np.float64)
+    Twc2[:3, 3] += np.array([0.25, 0.02, 0.05])  # a baseline, as between neighbouring keyframes
+    Tcw1, Tcw2 = np.linalg.inv(Twc1), np.linalg.inv(Twc2)
+    uv1 = np.stack([r.uniform(20, w - 20, n), r.uniform(20, h - 20, n)], 1)
+    z = r.uniform(1.0, 6.0, n)
+    pc1 = np.stack([(uv1[:, 0] - cx) / fx * z, (uv1[:, 1] - cy) / fy * z, z, np.ones(n)], 1)
+    pw = (Twc1 @ pc1.T).T
+    pc2 = (Tcw2 @ pw.T).T
+    uv2 = np.stack([fx * pc2[:, 0] / pc2[:, 2] + cx, fy * pc2[:, 1] / pc2[:, 2] + cy], 1) + r.normal(0, 0.7, (n, 2))
+    bad = r.random(n) < 0.15                      # off the epipolar line
+    uv2[bad] += r.normal(0, 25, (int(bad.sum()), 2))
+    R12 = Tcw1[:3, :3] @ Tcw2[:3, :3].T
+    t12 = -R12 @ Tcw2[:3, 3] + Tcw1[:3, 3]
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    F12 = (np.linalg.inv(Kmat).T @ tx @ R12 @ np.linalg.inv(Kmat)).astype(np.float32)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    ids = np.sort(r.choice(50000, n_nodes, replace=False)).astype(np.uint32)
+    nodes1 = ids[r.integers(0, n_nodes, n)]
+    nodes2 = np.where(r.random(n) < 0.85, nodes1, ids[r.integers(0, n_nodes, n)])
+    desc1 = r.integers(0, 256, (n, 32), dtype=np.uint8)
+    desc2 = _noisy_desc(r, desc1, 60)
+    oct2 = r.integers(0, 8, n).astype(np.int32)
+    ang1 = r.uniform(0, 360, n)
+    ang2 = (ang1 + r.normal(0, 6, n) + (r.random(n) < 0.1) * 120) % 360
+    # duplicates: keypoint j+1 of KeyFrame 2 repeats keypoint j (same node, same descriptor, almost the same place)
+    for j in r.choice(n - 1, 25, replace=False):
+        nodes2[j + 1], desc2[j + 1], uv2[j + 1], oct2[j + 1] = nodes2[j], desc2[j], uv2[j] + 0.1, oct2[j]
+    kf1 = {"has_mp": (r.random(n) < 0.3).astype(np.uint8), "uright": np.where(r.random(n) < 0.6, uv1[:, 0] - 40.0 / z, -1).astype(np.float32),
+           "xy": uv1.astype(np.float32), "angle": ang1.astype(np.float32), "desc": desc1, "featvec": _feature_vector(nodes1)}
+    perm = r.permutation(n)                      # KeyFrame 2 lists its keypoints in another order
+    inv = np.argsort(perm)
+    kf2 = {"has_mp": (r.random(n) < 0.3).astype(np.uint8), "uright": np.where(r.random(n) < 0.6, uv2[perm, 0] - 40.0 / pc2[perm, 2], -1).astype(np.float32),
+           "xy": uv2[perm].astype(np.float32), "octave": oct2[perm], "angle": ang2[perm].astype(np.float32), "desc": desc2[perm],
+           "featvec": _feature_vector(nodes2[perm]), "truth": inv}
+    Cw1 = Twc1[:3, 3].astype(np.float32)
+    return kf1, kf2, F12, Cw1, Tcw2.astype(np.float32), np.asarray(K, np.float32), sf, (sf * sf).astype(np.float32)
+
+
+def fuse_scene(seed, n_mp=1200, n_kf=1000, K=K_DEFAULT, w=640, h=480):
+    """ORBmatcher::Fuse (src/ORBmatcher.cc:408-546): a KeyFrame's keypoints and map points of its neighbours that
+    project near them.  Covers: points behind the camera / outside the image / outside their scale-invariance range /
+    seen at more than 60 degrees, stereo and monocular keypoints (two chi-square gates), level window.
+    Returns (mps, kf, Tcw, inv_level_sigma2)."""
+    r = np.random.default_rng(seed + 6060)
+    fx, fy, cx, cy = K
+    sf = 1.2 ** np.arange(8)
+    Twc = pose_walk(seed + 11, 1)[0].astype(np.float64)
+    Tcw = np.linalg.inv(Twc)
+    xy = np.stack([r.uniform(2, w - 2, n_kf), r.uniform(2, h - 2, n_kf)], 1)
+    octv = r.integers(0, 8, n_kf)
+    zk = r.uniform(1.0, 6.0, n_kf)
+    kf = {"xy": xy.astype(np.float32), "octave": octv.astype(np.int32),
+          "uright": np.where(r.random(n_kf) < 0.6, xy[:, 0] - 40.0 / zk, -1).astype(np.float32),
+          "desc": r.integers(0, 256, (n_kf, 32), dtype=np.uint8)}
+    tgt = r.integers(0, n_kf, n_mp)
+    z = zk[tgt] * (1.0 + r.normal(0, 0.004, n_mp))
+    uv = xy[tgt] + r.normal(0, 0.8, (n_mp, 2)) * sf[octv[tgt]][:, None]
+    far_off = r.random(n_mp) < 0.08
+    uv[far_off] += r.normal(0, 60, (int(far_off.sum()), 2))       # some leave the image
+    pc = np.stack([(uv[:, 0] - cx) / fx * z, (uv[:, 1] - cy) / fy * z, z, np.ones(n_mp)], 1)
+    behind = r.random(n_mp) < 0.03
+    pc[behind, :3] *= -1
+    pw = (Twc @ pc.T).T[:, :3]
+    Ow = Twc[:3, 3]
+    dist = np.linalg.norm(pw - Ow, axis=1)
+    lvl = np.clip(octv[tgt] + r.integers(0, 2, n_mp), 0, 7)       # predicted level = keypoint level or one above
+    maxd = dist * 1.2 ** (lvl - r.uniform(0.05, 0.95, n_mp))
+    mind = maxd / 1.2 ** 7
+    out_of_range = r.random(n_mp) < 0.05
+    maxd = np.where(out_of_range, dist / 1.3, maxd)
+    normal = (pw - Ow) / dist[:, None] + r.normal(0, 0.25, (n_mp, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    oblique = r.random(n_mp) < 0.08
+    normal[oblique] = -normal[oblique]                              # PO . Pn < 0.5 dist
+    mps = {"valid": (r.random(n_mp) < 0.9).astype(np.uint8), "world": pw.astype(np.float32), "normal": normal.astype(np.float32),
+           "dist": np.stack([mind, maxd], 1).astype(np.float32), "desc": _noisy_desc(r, kf["desc"][tgt], 80)}
+    inv_sigma2 = (1.0 / (sf * sf)).astype(np.float32)
+    return mps, kf, Tcw.astype(np.float32), inv_sigma2

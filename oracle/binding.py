@@ -399,6 +399,72 @@ def search_by_projection_keyframe(geom, Tcw_cur, th, orb_dist, check_ori, log_sc
     return n, cm
 
 
+def _csr(fv):
+    """FeatureVector dict/list of (node id, [feature indices]) -> (ids u32, offsets i32, features i32), ascending ids."""
+    items = sorted(fv.items()) if isinstance(fv, dict) else sorted(fv)
+    ids = np.asarray([k for k, _ in items], np.uint32)
+    off = np.zeros(len(items) + 1, np.int32)
+    for i, (_, v) in enumerate(items):
+        off[i + 1] = off[i] + len(v)
+    feat = np.asarray([x for _, v in items for x in v], np.int32)
+    return ids, off, feat
+
+
+def search_by_bow(nnratio, check_ori, kf, f):
+    """kf: dict(featvec, valid, desc, angle); f: dict(featvec, desc, angle) -> (nmatches, f_match)"""
+    L = lib()
+    L.orc_search_by_bow.argtypes = ([C.c_float, C.c_int] + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 +
+                                    [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    kid, koff, kfeat = _csr(kf["featvec"])
+    fid, foff, ffeat = _csr(f["featvec"])
+    kv, kd, ka = a(kf["valid"], np.uint8), a(kf["desc"], np.uint8), a(kf["angle"], np.float32)
+    fd, fa = a(f["desc"], np.uint8), a(f["angle"], np.float32)
+    fm = np.zeros(len(fa), np.int32)
+    n = L.orc_search_by_bow(nnratio, int(check_ori), len(kid), _p(kid), _p(koff), _p(kfeat), len(fid), _p(fid), _p(foff),
+                            _p(ffeat), len(ka), _p(kv), _p(kd), _p(ka), len(fa), _p(fd), _p(fa), _p(fm))
+    return n, fm
+
+
+def search_for_triangulation(F12, Cw1, Tcw2, K2, only_stereo, check_ori, scale_factors2, level_sigma2_2, kf1, kf2):
+    """kf1: dict(featvec, has_mp, uright, xy, angle, desc); kf2: the same + octave -> (nmatches, matches12)"""
+    L = lib()
+    L.orc_search_for_triangulation.argtypes = ([C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 3 +
+                                               [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int] +
+                                               [C.c_void_p] * 6 + [C.c_void_p])
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    id1, off1, ft1 = _csr(kf1["featvec"])
+    id2, off2, ft2 = _csr(kf2["featvec"])
+    sf, ls = a(scale_factors2, np.float32), a(level_sigma2_2, np.float32)
+    a1 = [a(kf1["has_mp"], np.uint8), a(kf1["uright"], np.float32), a(kf1["xy"], np.float32), a(kf1["angle"], np.float32),
+          a(kf1["desc"], np.uint8)]
+    a2 = [a(kf2["has_mp"], np.uint8), a(kf2["uright"], np.float32), a(kf2["xy"], np.float32), a(kf2["octave"], np.int32),
+          a(kf2["angle"], np.float32), a(kf2["desc"], np.uint8)]
+    m12 = np.zeros(len(a1[0]), np.int32)
+    n = L.orc_search_for_triangulation(_p(a(F12, np.float32)), _p(a(Cw1, np.float32)), _p(a(Tcw2, np.float32)),
+                                       _p(a(K2, np.float32)), int(only_stereo), int(check_ori), len(sf), _p(sf), _p(ls),
+                                       len(id1), _p(id1), _p(off1), _p(ft1), len(id2), _p(id2), _p(off2), _p(ft2),
+                                       len(a1[0]), *[_p(x) for x in a1], len(a2[0]), *[_p(x) for x in a2], _p(m12))
+    return n, m12
+
+
+def fuse_search(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf):
+    """mps: dict(valid, world, normal, dist, desc); kf: dict(xy, octave, uright, desc) -> (nfused, best_idx, best_dist)"""
+    L = lib()
+    L.orc_fuse_search.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int] + [C.c_void_p] * 5 +
+                                  [C.c_int] + [C.c_void_p] * 4 + [C.c_void_p] * 2)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    ils = a(inv_level_sigma2, np.float32)
+    margs = [a(mps["valid"], np.uint8), a(mps["world"], np.float32), a(mps["normal"], np.float32), a(mps["dist"], np.float32),
+             a(mps["desc"], np.uint8)]
+    kargs = [a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["uright"], np.float32), a(kf["desc"], np.uint8)]
+    bi = np.zeros(len(margs[0]), np.int32)
+    bd = np.zeros(len(margs[0]), np.int32)
+    n = L.orc_fuse_search(_p(geom), _p(a(Tcw, np.float32)), th, log_scale_factor, _p(ils), len(margs[0]),
+                          *[_p(x) for x in margs], len(kargs[1]), *[_p(x) for x in kargs], _p(bi), _p(bd))
+    return n, bi, bd
+
+
 class SurfelMappingOracle:
     """The part of SurfelMapping that moveAddSurfels touches (src/SurfelMapping.cpp:194-304)."""
 

@@ -1,7 +1,9 @@
 // match_oracle.cpp -- CPU oracle (TEST INFRASTRUCTURE, see msl_oracle.h) restating
 // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:835-849), the three Frame-side
-// ORBmatcher::SearchByProjection overloads (:40-117, :548-678, :680-797), ComputeThreeMaxima (:799-830) and the
-// Frame grid they search through (src/Frame.cc:155-168, 332-381, 418-427).
+// ORBmatcher::SearchByProjection overloads (:40-117, :548-678, :680-797), SearchByBoW (:146-255),
+// SearchForTriangulation (:257-406) with CheckDistEpipolarLine (:127-144), the search part of Fuse (:408-546),
+// ComputeThreeMaxima (:799-830) and the Frame / KeyFrame grid they search through (src/Frame.cc:155-168, 332-381,
+// 418-427; src/KeyFrame.cc:469-504).
 // The Frame/MapPoint object graph is flattened into arrays (see msl_oracle.h); cv::Mat products are
 // evaluated as OpenCV's gemm does for CV_32F (double accumulation, one rounding) -- "parity unpinned".
 #include "msl_oracle.h"
@@ -13,6 +15,7 @@
 namespace {
 
 const int TH_HIGH = 100;      // src/ORBmatcher.cc:33
+const int TH_LOW = 50;        // :34
 const int HISTO_LENGTH = 30;  // :35
 const int GRID_COLS = 64, GRID_ROWS = 48;  // include/Frame.h:53-54
 
@@ -375,6 +378,256 @@ int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_c
                 }
     }
     return nmatches;
+}
+
+
+// ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches), src/ORBmatcher.cc:146-255.
+// The two DBoW2::FeatureVector maps (node id -> feature indices, ascending node id) arrive in CSR form; the merge
+// loop with lower_bound (:164-233) visits exactly the node ids present in both, in ascending order.
+int orc_search_by_bow(float nnratio, int check_orientation, int n_nodes_kf, const uint32_t *kf_node_id,
+                      const int32_t *kf_node_off, const int32_t *kf_node_feat, int n_nodes_f, const uint32_t *f_node_id,
+                      const int32_t *f_node_off, const int32_t *f_node_feat, int n_kf, const uint8_t *kf_valid,
+                      const uint8_t *kf_desc, const float *kf_angle, int n_f, const uint8_t *f_desc, const float *f_angle,
+                      int32_t *f_match) {
+    (void)n_kf;
+    for (int j = 0; j < n_f; j++) f_match[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < n_nodes_kf && b < n_nodes_f) {
+        if (kf_node_id[a] == f_node_id[b]) {
+            for (int iKF = kf_node_off[a]; iKF < kf_node_off[a + 1]; iKF++) {
+                const int realIdxKF = kf_node_feat[iKF];
+                if (!kf_valid[realIdxKF]) continue;  // !pMP || pMP->isBad()
+                const uint8_t *dKF = kf_desc + 32 * (size_t)realIdxKF;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_node_off[b]; iF < f_node_off[b + 1]; iF++) {
+                    const int realIdxF = f_node_feat[iF];
+                    if (f_match[realIdxF] >= 0) continue;  // vpMapPointMatches[realIdxF] != NULL
+                    const int dist = descriptor_distance(dKF, f_desc + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) {
+                        bestDist2 = bestDist1;
+                        bestDist1 = dist;
+                        bestIdxF = realIdxF;
+                    } else if (dist < bestDist2) {
+                        bestDist2 = dist;
+                    }
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        f_match[bestIdxF] = realIdxKF;
+                        if (check_orientation) {
+                            float rot = kf_angle[realIdxKF] - f_angle[bestIdxF];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)std::round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rotHist[bin].push_back(bestIdxF);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            a++, b++;
+        } else if (kf_node_id[a] < f_node_id[b]) {
+            while (a < n_nodes_kf && kf_node_id[a] < f_node_id[b]) a++;  // lower_bound
+        } else {
+            while (b < n_nodes_f && f_node_id[b] < kf_node_id[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    f_match[rotHist[i][j]] = -3;  // = static_cast<MapPoint*>(NULL)
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo),
+// src/ORBmatcher.cc:257-406, with CheckDistEpipolarLine :127-144.  vbMatched2 is never set in the reference (:276, :322),
+// so a KeyFrame-2 feature can be the match of several KeyFrame-1 features; `dist > bestDist` (:336) lets a later
+// candidate of equal distance replace an earlier one.  matches12[idx1] = idx2, -1 none, -3 removed by the rotation check.
+int orc_search_for_triangulation(const float F12[9], const float Cw1[3], const float Tcw2[16], const float K2[4],
+                                 int only_stereo, int check_orientation, int nlevels, const float *scale_factors2,
+                                 const float *level_sigma2_2, int n_nodes1, const uint32_t *node_id1,
+                                 const int32_t *node_off1, const int32_t *node_feat1, int n_nodes2,
+                                 const uint32_t *node_id2, const int32_t *node_off2, const int32_t *node_feat2, int n1,
+                                 const uint8_t *has_mp1, const float *uright1, const float *xy1, const float *angle1,
+                                 const uint8_t *desc1, int n2, const uint8_t *has_mp2, const float *uright2,
+                                 const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
+                                 int32_t *matches12) {
+    (void)nlevels, (void)n2;
+    // :263-270 epipole in the second image: C2 = R2w * Cw + t2w (one gemm)
+    float R2w[9], t2w[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) R2w[r * 3 + c] = Tcw2[r * 4 + c];
+        t2w[r] = Tcw2[r * 4 + 3];
+    }
+    const float C2[3] = {gemm_row(R2w, Cw1, t2w[0]), gemm_row(R2w + 3, Cw1, t2w[1]), gemm_row(R2w + 6, Cw1, t2w[2])};
+    const float invz = 1.0f / C2[2];
+    const float ex = K2[0] * C2[0] * invz + K2[2];
+    const float ey = K2[1] * C2[1] * invz + K2[3];
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < n_nodes1 && b < n_nodes2) {
+        if (node_id1[a] == node_id2[b]) {
+            for (int i1 = node_off1[a]; i1 < node_off1[a + 1]; i1++) {
+                const int idx1 = node_feat1[i1];
+                if (has_mp1[idx1]) continue;
+                const bool bStereo1 = uright1[idx1] >= 0;
+                if (only_stereo)
+                    if (!bStereo1) continue;
+                const float kp1x = xy1[2 * idx1], kp1y = xy1[2 * idx1 + 1];
+                const uint8_t *d1 = desc1 + 32 * (size_t)idx1;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = node_off2[b]; i2 < node_off2[b + 1]; i2++) {
+                    const int idx2 = node_feat2[i2];
+                    if (has_mp2[idx2]) continue;  // vbMatched2[idx2] is always false
+                    const bool bStereo2 = uright2[idx2] >= 0;
+                    if (only_stereo)
+                        if (!bStereo2) continue;
+                    const int dist = descriptor_distance(d1, desc2 + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const float kp2x = xy2[2 * idx2], kp2y = xy2[2 * idx2 + 1];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2x, distey = ey - kp2y;
+                        if (distex * distex + distey * distey < 100 * scale_factors2[octave2[idx2]]) continue;
+                    }
+                    // CheckDistEpipolarLine :127-144
+                    const float la = kp1x * F12[0] + kp1y * F12[3] + F12[6];
+                    const float lb = kp1x * F12[1] + kp1y * F12[4] + F12[7];
+                    const float lc = kp1x * F12[2] + kp1y * F12[5] + F12[8];
+                    const float num = la * kp2x + lb * kp2y + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * level_sigma2_2[octave2[idx2]]) {
+                        bestIdx2 = idx2;
+                        bestDist = dist;
+                    }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_orientation) {
+                        float rot = angle1[idx1] - angle2[bestIdx2];
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            a++, b++;
+        } else if (node_id1[a] < node_id2[b]) {
+            while (a < n_nodes1 && node_id1[a] < node_id2[b]) a++;
+        } else {
+            while (b < n_nodes2 && node_id2[b] < node_id1[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    matches12[rotHist[i][j]] = -3;  // the reference writes -1 (:391)
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+// The search part of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th), src/ORBmatcher.cc:408-519:
+// per map point the best keypoint of the KeyFrame (bestIdx, bestDist).  What follows in the reference (:522-541,
+// Replace / AddObservation / AddMapPoint on the pointer graph, whenever bestDist <= TH_LOW) stays with the caller; it
+// does not feed back into the search of later map points.  KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:469-504) is the
+// Frame grid query without a level filter; KeyFrame::IsInImage :540-542; MapPoint::PredictScale(dist, KeyFrame*)
+// src/MapPoint.cc:334-348.  mp_dist = (mfMinDistance, mfMaxDistance).  Returns the number of map points with
+// bestDist <= TH_LOW (= nFused of the reference when no map point is listed twice).
+int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, float log_scale_factor,
+                    const float *inv_level_sigma2, int n_mp, const uint8_t *mp_valid, const float *mp_world,
+                    const float *mp_normal, const float *mp_dist, const uint8_t *mp_desc, int n_kf, const float *kf_xy,
+                    const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
+                    int32_t *best_dist) {
+    float Rcw[9], tcw[3], Ow[3];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Rcw[r * 3 + c] = Tcw[r * 4 + c];
+        tcw[r] = Tcw[r * 4 + 3];
+    }
+    for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose: Ow = -Rwc * tcw (one gemm)
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)(-Rcw[k * 3 + r]) * (double)tcw[k];
+        Ow[r] = (float)s;
+    }
+    Grid G;
+    assign_grid(g, kf_xy, n_kf, G);
+    std::vector<int> vIndices;
+    int nFused = 0;
+    for (int i = 0; i < n_mp; i++) {
+        best_idx[i] = -1, best_dist[i] = 256;
+        if (!mp_valid[i]) continue;  // !pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)
+        const float *p3Dw = mp_world + 3 * i;
+        const float pc0 = gemm_row(Rcw, p3Dw, tcw[0]), pc1 = gemm_row(Rcw + 3, p3Dw, tcw[1]), pc2 = gemm_row(Rcw + 6, p3Dw, tcw[2]);
+        if (pc2 < 0.0f) continue;
+        const float invz = 1 / pc2;
+        const float x = pc0 * invz, y = pc1 * invz;
+        const float u = g->fx * x + g->cx, v = g->fy * y + g->cy;
+        if (!(u >= g->mnMinX && u < g->mnMaxX && v >= g->mnMinY && v < g->mnMaxY)) continue;
+        const float ur = u - g->mbf * invz;
+        const float maxDistance = 1.2f * mp_dist[2 * i + 1], minDistance = 0.8f * mp_dist[2 * i];
+        float PO[3];
+        double s2 = 0;
+        for (int k = 0; k < 3; k++) {
+            PO[k] = p3Dw[k] - Ow[k];
+            s2 += (double)PO[k] * (double)PO[k];
+        }
+        const float dist3D = (float)std::sqrt(s2);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        double dot = 0;  // cv::Mat::dot on 3 floats: double products, double accumulation
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)mp_normal[3 * i + k];
+        if (dot < 0.5 * dist3D) continue;
+        const float ratio = mp_dist[2 * i + 1] / dist3D;
+        int nPredictedLevel = (int)std::ceil(std::log(ratio) / log_scale_factor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= g->nlevels) nPredictedLevel = g->nlevels - 1;
+        const float radius = th * g->scaleFactors[nPredictedLevel];
+        features_in_area(g, G, kf_xy, kf_octave, u, v, radius, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t *dMP = mp_desc + 32 * (size_t)i;
+        int bestDist = 256, bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const int idx = vIndices[k];
+            const int kpLevel = kf_octave[idx];
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const float kpx = kf_xy[2 * idx], kpy = kf_xy[2 * idx + 1];
+            if (kf_uright[idx] >= 0) {
+                const float ex = u - kpx, ey = v - kpy, er = ur - kf_uright[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u - kpx, ey = v - kpy;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = descriptor_distance(dMP, kf_desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = idx;
+            }
+        }
+        best_idx[i] = bestIdx, best_dist[i] = bestDist;
+        if (bestDist <= TH_LOW) nFused++;
+    }
+    return nFused;
 }
 
 }  // extern "C"

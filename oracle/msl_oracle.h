@@ -136,6 +136,41 @@ int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_c
                                       int n_cur, const float *cur_xy, const int32_t *cur_octave, const float *cur_angle,
                                       const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match);
 
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:146-255.  The two
+ * DBoW2::FeatureVector maps in CSR form (node ids ascending; node k owns features feat[off[k] .. off[k+1]) in their
+ * stored order).  kf_valid[i] = (pMP && !pMP->isBad()); kf_angle = pKF->mvKeysUn[i].angle; f_angle = F.mvKeys[j].angle.
+ * Output f_match[j] = index of the KeyFrame keypoint whose MapPoint was assigned to F's slot j, -1 none, -3 assigned
+ * and then reset by the rotation check.  Returns nmatches. */
+int orc_search_by_bow(float nnratio, int check_orientation, int n_nodes_kf, const uint32_t *kf_node_id,
+                      const int32_t *kf_node_off, const int32_t *kf_node_feat, int n_nodes_f, const uint32_t *f_node_id,
+                      const int32_t *f_node_off, const int32_t *f_node_feat, int n_kf, const uint8_t *kf_valid,
+                      const uint8_t *kf_desc, const float *kf_angle, int n_f, const uint8_t *f_desc, const float *f_angle,
+                      int32_t *f_match);
+
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:257-406 (+ CheckDistEpipolarLine :127-144).  F12 row-major 3x3,
+ * Cw1 = pKF1->GetCameraCenter(), Tcw2 = pKF2 pose (row-major 4x4), K2 = pKF2 fx, fy, cx, cy; scale_factors2 /
+ * level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2; has_mp = (GetMapPoint(idx) != NULL); xy / angle = mvKeysUn.
+ * Output matches12[idx1] = idx2, -1 none, -3 removed by the rotation check.  Returns nmatches. */
+int orc_search_for_triangulation(const float F12[9], const float Cw1[3], const float Tcw2[16], const float K2[4],
+                                 int only_stereo, int check_orientation, int nlevels, const float *scale_factors2,
+                                 const float *level_sigma2_2, int n_nodes1, const uint32_t *node_id1,
+                                 const int32_t *node_off1, const int32_t *node_feat1, int n_nodes2,
+                                 const uint32_t *node_id2, const int32_t *node_off2, const int32_t *node_feat2, int n1,
+                                 const uint8_t *has_mp1, const float *uright1, const float *xy1, const float *angle1,
+                                 const uint8_t *desc1, int n2, const uint8_t *has_mp2, const float *uright2,
+                                 const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2,
+                                 int32_t *matches12);
+
+/* The search part of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:408-519: per map
+ * point the best KeyFrame keypoint (best_idx -1 / best_dist 256 if none).  mp_valid[i] = (pMP && !pMP->isBad() &&
+ * !pMP->IsInKeyFrame(pKF)); mp_dist = (mfMinDistance, mfMaxDistance); g = the KeyFrame's intrinsics, image bounds, grid
+ * and scale factors; Tcw = its pose.  Returns the number of map points with best_dist <= TH_LOW. */
+int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, float log_scale_factor,
+                    const float *inv_level_sigma2, int n_mp, const uint8_t *mp_valid, const float *mp_world,
+                    const float *mp_normal, const float *mp_dist, const uint8_t *mp_desc, int n_kf, const float *kf_xy,
+                    const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
+                    int32_t *best_dist);
+
 /* ---------------------------------------------------- plane pre-stage --- */
 
 typedef struct {

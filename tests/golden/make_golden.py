@@ -77,3 +77,23 @@ def stages():
 
 if __name__ == "__main__":
     stages()
+
+
+def node_searches():
+    """SearchByBoW / SearchForTriangulation / Fuse golden vectors (oracle output, after the oracle has been cross-checked
+    against the independent Python restatements of tests/test_oracle_stages.py)."""
+    from manhattanslam_b200.matcher import frame_geom
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    kf, f = S.bow_scene(3)
+    nb, fm = ob.search_by_bow(0.7, True, kf, f)
+    kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(3)
+    nt, m12 = ob.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2)
+    mps, kfs, Tcw, ils = S.fuse_scene(3)
+    nf, bi, bd = ob.fuse_search(frame_geom(), Tcw, 3.0, lsf, ils, mps, kfs)
+    np.savez_compressed(os.path.join(HERE, "node_searches.npz"), bow_n=nb, bow_match=fm, tri_n=nt, tri_match=m12, fuse_n=nf,
+                        fuse_idx=bi, fuse_dist=bd)
+    print("node search golden written", nb, nt, nf)
+
+
+if __name__ == "__main__":
+    node_searches()

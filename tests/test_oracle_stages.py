@@ -232,3 +232,242 @@ def test_golden_reloc(oracle):
     cur, kf, Tc = S.reloc_scene(3)
     n, cm = oracle.search_by_projection_keyframe(frame_geom(), Tc, 15.0, 100, True, lsf, kf, cur)
     assert n == int(gold["match_n"]) and np.array_equal(cm, gold["match_cm"])
+
+
+# ---- independent Python restatements of the vocabulary-node searches and of Fuse (small cases pin the C++ oracle's control flow)
+def _pop(a, b):
+    return int(np.unpackbits(np.asarray(a, np.uint8) ^ np.asarray(b, np.uint8)).sum())
+
+
+def _rot_prune(hist, clear):
+    """ComputeThreeMaxima (src/ORBmatcher.cc:799-830) + the pruning loops; returns the number of removed matches"""
+    sizes = [len(h) for h in hist]
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+        elif s > m2:
+            m3, m2, i3, i2 = m2, s, i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if m2 < np.float32(0.1) * np.float32(m1):
+        i2 = i3 = -1
+    elif m3 < np.float32(0.1) * np.float32(m1):
+        i3 = -1
+    removed = 0
+    for i in range(30):
+        if i not in (i1, i2, i3):
+            for j in hist[i]:
+                clear(j)
+                removed += 1
+    return removed
+
+
+def _bin(a, b):
+    f32, f64 = np.float32, np.float64
+    rot = f32(f32(a) - f32(b))
+    if rot < 0:
+        rot = f32(rot + f32(360.0))
+    k = int(np.floor(f64(f32(rot * f32(1.0 / 30))) + 0.5))
+    return 0 if k == 30 else k
+
+
+def _py_bow(nnratio, check, kf, f):
+    fm = np.full(len(f["angle"]), -1, np.int32)
+    hist = [[] for _ in range(30)]
+    n = 0
+    for node in sorted(set(kf["featvec"]) & set(f["featvec"])):
+        for ik in kf["featvec"][node]:
+            if not kf["valid"][ik]:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for jf in f["featvec"][node]:
+                if fm[jf] >= 0:
+                    continue
+                d = _pop(kf["desc"][ik], f["desc"][jf])
+                if d < b1:
+                    b2, b1, bi = b1, d, jf
+                elif d < b2:
+                    b2 = d
+            if b1 <= 50 and np.float32(b1) < np.float32(nnratio) * np.float32(b2):
+                fm[bi] = ik
+                n += 1
+                if check:
+                    hist[_bin(kf["angle"][ik], f["angle"][bi])].append(bi)
+    if check:
+        def clear(j):
+            fm[j] = -3
+        n -= _rot_prune(hist, clear)
+    return n, fm
+
+
+def _py_triangulation(F12, Cw1, Tcw2, K2, only_stereo, check, sf, ls, kf1, kf2):
+    f32, f64 = np.float32, np.float64
+    T = np.asarray(Tcw2, f32).reshape(4, 4)
+    C2 = [f32(sum(f64(T[r, k]) * f64(Cw1[k]) for k in range(3)) + f64(T[r, 3])) for r in range(3)]
+    invz = f32(f32(1.0) / C2[2])
+    ex = f32(f32(f32(K2[0] * C2[0]) * invz) + K2[2])
+    ey = f32(f32(f32(K2[1] * C2[1]) * invz) + K2[3])
+    F = np.asarray(F12, f32).reshape(3, 3)
+    m12 = np.full(len(kf1["angle"]), -1, np.int32)
+    hist = [[] for _ in range(30)]
+    n = 0
+    for node in sorted(set(kf1["featvec"]) & set(kf2["featvec"])):
+        for i1 in kf1["featvec"][node]:
+            if kf1["has_mp"][i1]:
+                continue
+            st1 = kf1["uright"][i1] >= 0
+            if only_stereo and not st1:
+                continue
+            x1, y1 = kf1["xy"][i1]
+            a = f32(f32(f32(x1 * F[0, 0]) + f32(y1 * F[1, 0])) + F[2, 0])
+            b = f32(f32(f32(x1 * F[0, 1]) + f32(y1 * F[1, 1])) + F[2, 1])
+            c = f32(f32(f32(x1 * F[0, 2]) + f32(y1 * F[1, 2])) + F[2, 2])
+            best, bi = 50, -1
+            for i2 in kf2["featvec"][node]:
+                if kf2["has_mp"][i2]:
+                    continue
+                st2 = kf2["uright"][i2] >= 0
+                if only_stereo and not st2:
+                    continue
+                d = _pop(kf1["desc"][i1], kf2["desc"][i2])
+                if d > 50 or d > best:
+                    continue
+                x2, y2 = kf2["xy"][i2]
+                o2 = kf2["octave"][i2]
+                if not st1 and not st2:
+                    dx, dy = f32(ex - x2), f32(ey - y2)
+                    if f32(f32(dx * dx) + f32(dy * dy)) < f32(f32(100) * sf[o2]):
+                        continue
+                num = f32(f32(f32(a * x2) + f32(b * y2)) + c)
+                den = f32(f32(a * a) + f32(b * b))
+                if den == 0:
+                    continue
+                dsqr = f32(f32(num * num) / den)
+                if f64(dsqr) < 3.84 * f64(ls[o2]):
+                    bi, best = i2, d
+            if bi >= 0:
+                m12[i1] = bi
+                n += 1
+                if check:
+                    hist[_bin(kf1["angle"][i1], kf2["angle"][bi])].append(i1)
+    if check:
+        def clear(j):
+            m12[j] = -3
+        n -= _rot_prune(hist, clear)
+    return n, m12
+
+
+def _py_fuse(oracle, g, Tcw, th, lsf, ils, mps, kf):
+    f32, f64 = np.float32, np.float64
+    T = np.asarray(Tcw, f32).reshape(4, 4)
+    R, t = T[:3, :3], T[:3, 3]
+    Ow = np.array([f32(sum(f64(-R[k, r]) * f64(t[k]) for k in range(3))) for r in range(3)], f32)
+    gg = {k: g[k][0] for k in g.dtype.names}
+    n_mp = len(mps["valid"])
+    bi, bd = np.full(n_mp, -1, np.int32), np.full(n_mp, 256, np.int32)
+    nf = 0
+    for i in range(n_mp):
+        if not mps["valid"][i]:
+            continue
+        x = mps["world"][i].astype(f32)
+        row = lambda r: f32(sum(f64(R[r, k]) * f64(x[k]) for k in range(3)) + f64(t[r]))
+        p0, p1, p2 = row(0), row(1), row(2)
+        if p2 < 0:
+            continue
+        with np.errstate(divide="ignore", invalid="ignore"):
+            invz = f32(f32(1) / p2)
+            u = f32(f32(gg["fx"] * f32(p0 * invz)) + gg["cx"])
+            v = f32(f32(gg["fy"] * f32(p1 * invz)) + gg["cy"])
+        if not (u >= gg["mnMinX"] and u < gg["mnMaxX"] and v >= gg["mnMinY"] and v < gg["mnMaxY"]):
+            continue
+        ur = f32(u - f32(gg["mbf"] * invz))
+        mind, maxd = mps["dist"][i].astype(f32)
+        po = (x - Ow).astype(f32)
+        d3 = f32(np.sqrt(sum(f64(p) * f64(p) for p in po)))
+        if d3 < f32(0.8) * mind or d3 > f32(1.2) * maxd:
+            continue
+        if sum(f64(po[k]) * f64(mps["normal"][i][k]) for k in range(3)) < 0.5 * f64(d3):
+            continue
+        lvl = int(np.ceil(f32(np.log(f32(maxd / d3))) / f32(lsf)))
+        lvl = min(max(lvl, 0), int(gg["nlevels"]) - 1)
+        radius = f32(f32(th) * gg["scaleFactors"][lvl])
+        best, b = 256, -1
+        for j in oracle.features_in_area(g, kf["xy"], kf["octave"], float(u), float(v), float(radius)):
+            kl = int(kf["octave"][j])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            ex, ey = f32(u - kf["xy"][j][0]), f32(v - kf["xy"][j][1])
+            if kf["uright"][j] >= 0:
+                er = f32(ur - kf["uright"][j])
+                e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                if f64(f32(e2 * ils[kl])) > 7.8:
+                    continue
+            else:
+                e2 = f32(f32(ex * ex) + f32(ey * ey))
+                if f64(f32(e2 * ils[kl])) > 5.99:
+                    continue
+            d = _pop(mps["desc"][i], kf["desc"][j])
+            if d < best:
+                best, b = d, int(j)
+        bi[i], bd[i] = b, best
+        if best <= 50:
+            nf += 1
+    return nf, bi, bd
+
+
+def test_search_by_bow_vs_python(oracle):
+    for seed, shuffle in ((31, False), (32, True)):
+        kf, f = S.bow_scene(seed, n_kf=260, n_f=240, n_nodes=30, shuffle=shuffle)
+        for check in (False, True):
+            n, fm = oracle.search_by_bow(0.7, check, kf, f)
+            n_py, fm_py = _py_bow(0.7, check, kf, f)
+            assert n == n_py and np.array_equal(fm, fm_py)
+            assert n > 40 and n == (fm >= 0).sum()
+        # a Frame slot is matched at most once, and only by a valid KeyFrame keypoint of the same node
+        node_of_f = {j: nd for nd, v in f["featvec"].items() for j in v}
+        node_of_k = {i: nd for nd, v in kf["featvec"].items() for i in v}
+        for j in np.nonzero(fm >= 0)[0]:
+            assert kf["valid"][fm[j]] and node_of_f[j] == node_of_k[fm[j]]
+
+
+def test_search_for_triangulation_vs_python(oracle):
+    for seed in (41, 42):
+        kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(seed, n=280, n_nodes=24)
+        for only_stereo in (False, True):
+            for check in (False, True):
+                n, m = oracle.search_for_triangulation(F12, Cw1, Tcw2, K2, only_stereo, check, sf, ls, kf1, kf2)
+                n_py, m_py = _py_triangulation(F12, Cw1, Tcw2, K2, only_stereo, check, sf, ls, kf1, kf2)
+                assert n == n_py and np.array_equal(m, m_py)
+                assert n == (m >= 0).sum()
+        n, m = oracle.search_for_triangulation(F12, Cw1, Tcw2, K2, False, False, sf, ls, kf1, kf2)
+        ok = np.nonzero(m >= 0)[0]
+        assert len(ok) > 40 and (kf2["truth"][ok] == m[ok]).mean() > 0.9     # mostly the true correspondences
+        assert not kf1["has_mp"][ok].any() and not kf2["has_mp"][m[ok]].any()
+
+
+def test_fuse_search_vs_python(oracle):
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    for seed, th in ((51, 3.0), (52, 5.0)):
+        mps, kf, Tcw, ils = S.fuse_scene(seed, n_mp=300, n_kf=260)
+        g = frame_geom()
+        n, bi, bd = oracle.fuse_search(g, Tcw, th, lsf, ils, mps, kf)
+        n_py, bi_py, bd_py = _py_fuse(oracle, g, Tcw, th, lsf, ils, mps, kf)
+        assert n == n_py and np.array_equal(bi, bi_py) and np.array_equal(bd, bd_py)
+        assert n > 60 and n == (bd <= 50).sum() and ((bi >= 0) == (bd < 256)).all()
+        assert (bi[mps["valid"] == 0] == -1).all()
+
+
+def test_golden_node_searches(oracle):
+    gold = np.load(os.path.join(GOLD, "node_searches.npz"))
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+    kf, f = S.bow_scene(3)
+    n, fm = oracle.search_by_bow(0.7, True, kf, f)
+    assert n == int(gold["bow_n"]) and np.array_equal(fm, gold["bow_match"])
+    kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(3)
+    n, m = oracle.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2)
+    assert n == int(gold["tri_n"]) and np.array_equal(m, gold["tri_match"])
+    mps, kfs, Tcw, ils = S.fuse_scene(3)
+    n, bi, bd = oracle.fuse_search(frame_geom(), Tcw, 3.0, lsf, ils, mps, kfs)
+    assert n == int(gold["fuse_n"]) and np.array_equal(bi, gold["fuse_idx"]) and np.array_equal(bd, gold["fuse_dist"])
