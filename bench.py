@@ -120,8 +120,10 @@ def run_reference(a, rank, world):
     threads = os.cpu_count() or 1
     gray, depth, mem, poses, surfels = make_inputs(0, a.batch, a.surfels)
     frames = min(a.cpu_frames, a.batch)
-    for _ in range(min(a.warmup, 1)):
-        cpu_frontend(gray, depth, mem, poses, surfels, min(frames, 4), threads)
+    # bounded sample: one short untimed pass estimates the host's speed, then the frames per step are chosen so that the
+    # K timed steps together take about two and a half minutes (never more than --cpu-frames, never fewer than 4)
+    fps_est, _ = cpu_frontend(gray, depth, mem, poses, surfels, min(frames, 4), threads)
+    frames = max(4, min(frames, int(fps_est * 150.0 / max(a.steps, 1))))
     ts = []
     for _ in range(a.steps):
         fps, dt = cpu_frontend(gray, depth, mem, poses, surfels, frames, threads)
