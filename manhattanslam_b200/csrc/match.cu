@@ -126,12 +126,12 @@ struct SearchArgs {
     int32_t *assign, *bin;
 };
 
-__device__ __forceinline__ float gemm_row(const float *R, const float *x, float t) {
-    double s = 0;
-    s += (double)R[0] * (double)x[0];
-    s += (double)R[1] * (double)x[1];
-    s += (double)R[2] * (double)x[2];
-    return (float)(s + (double)t);
+// cv::Mat (3x3) * (3x1) + (3x1), CV_32F, as ONE cv::gemm with flags == 0: OpenCV's small-matrix path forms the row sum in
+// float, t0 = a0*b0 + a1*b1 + a2*b2, and stores (float)(t0*alpha + c*beta) evaluated in double (pinned against cv2.gemm,
+// tests/test_oracle_primitives.py::test_cv_gemm_semantics).  Built with -fmad=false: no contraction.
+__host__ __device__ __forceinline__ float gemm_row(const float *R, const float *x, float t) {
+    const float t0 = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+    return (float)((double)t0 * 1.0 + (double)t * 1.0);
 }
 
 __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int n2) {  // n2 = power of two, whole CTA
@@ -818,7 +818,8 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
     memset(&A, 0, sizeof(A));
     A.g = *geom, A.mode = 0, A.th = th, A.nnratio = 0, A.checkOri = check_orientation, A.nq = n_last, A.nc = n_cur;
     A.distTh = TH_HIGH;
-    // :554-568: twc = -Rcw^T tcw; tlc = Rlw twc + tlw (cv::Mat products: double accumulation, one rounding)
+    // :554-568: twc = -Rcw.t() * tcw (transposed operand: cv::gemm's general path, double accumulation, one rounding);
+    // tlc = Rlw * twc + tlw (flags == 0: the small-matrix path, gemm_row)
     float Rlw[9], tlw[3];
     for (int r = 0; r < 3; r++) {
         for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw_cur[r * 4 + c], Rlw[r * 3 + c] = Tcw_last[r * 4 + c];
@@ -830,9 +831,7 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
         for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
         twc[r] = (float)s;
     }
-    double s2 = 0;
-    for (int k = 0; k < 3; k++) s2 += (double)Rlw[6 + k] * (double)twc[k];
-    const float tlc2 = (float)(s2 + (double)tlw[2]);
+    const float tlc2 = gemm_row(Rlw + 6, twc, tlw[2]);
     A.bForward = tlc2 > geom->mb;
     A.bBackward = -tlc2 > geom->mb;
     std::vector<uint8_t> valid(n_last);
@@ -923,7 +922,7 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
         for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw_cur[r * 4 + c];
         A.tcw[r] = Tcw_cur[r * 4 + 3];
     }
-    for (int r = 0; r < 3; r++) {  // :686 Ow = -Rcw^T tcw (one cv gemm: double accumulation, one rounding)
+    for (int r = 0; r < 3; r++) {  // :686 Ow = -Rcw.t() * tcw (transposed operand: general path, double accumulation, one rounding)
         double s = 0;
         for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
         A.Ow[r] = (float)s;
@@ -1037,13 +1036,9 @@ int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float
     A.nA = n1, A.nB = n2;
     memcpy(A.F12, F12, sizeof(float) * 9);
     for (int l = 0; l < nlevels; l++) A.scale2[l] = scale_factors2[l], A.sigma2[l] = level_sigma2_2[l];
-    {   // :263-270 epipole in the second image: C2 = R2w * Cw + t2w (one cv gemm: double accumulation, one rounding)
+    {   // :263-270 epipole in the second image: C2 = R2w * Cw + t2w (one cv gemm, small-matrix path)
         float C2[3];
-        for (int r = 0; r < 3; r++) {
-            double s = 0;
-            for (int k = 0; k < 3; k++) s += (double)Tcw2[r * 4 + k] * (double)Cw1[k];
-            C2[r] = (float)(s + (double)Tcw2[r * 4 + 3]);
-        }
+        for (int r = 0; r < 3; r++) C2[r] = gemm_row(Tcw2 + 4 * r, Cw1, Tcw2[4 * r + 3]);
         const float invz = 1.0f / C2[2];
         A.ex = K2[0] * C2[0] * invz + K2[2];
         A.ey = K2[1] * C2[1] * invz + K2[3];
@@ -1086,10 +1081,9 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
         for (int c = 0; c < 3; c++) A.Rcw[r * 3 + c] = Tcw[r * 4 + c];
         A.tcw[r] = Tcw[r * 4 + 3];
     }
-    for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose: Ow = -Rwc * tcw (one cv gemm)
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += (double)(-A.Rcw[k * 3 + r]) * (double)A.tcw[k];
-        A.Ow[r] = (float)s;
+    for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose (src/KeyFrame.cc:79-80): Rwc = Rcw.t(); Ow = -Rwc * tcw -- flags == 0, alpha = -1
+        const float t0 = A.Rcw[0 * 3 + r] * A.tcw[0] + A.Rcw[1 * 3 + r] * A.tcw[1] + A.Rcw[2 * 3 + r] * A.tcw[2];
+        A.Ow[r] = (float)((double)t0 * -1.0);
     }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(mp_valid, n_mp), A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);

@@ -329,6 +329,37 @@ def descriptor_distance(a, b):
     return lib().orc_descriptor_distance(_p(a), _p(b))
 
 
+def cv_rx_plus_t(R, x, t):
+    """cv::Mat R * x + t for 3x3 / 3x1 CV_32F as the oracle evaluates it"""
+    L = lib()
+    out = np.zeros(3, np.float32)
+    L.orc_cv_rx_plus_t(_p(np.ascontiguousarray(R, np.float32)), _p(np.ascontiguousarray(x, np.float32)),
+                       _p(np.ascontiguousarray(t, np.float32)), _p(out))
+    return out
+
+
+def cv_neg_rt_times_t(R, t):
+    """-R.t() * t (transposed operand)"""
+    L = lib()
+    out = np.zeros(3, np.float32)
+    L.orc_cv_neg_rt_times_t(_p(np.ascontiguousarray(R, np.float32)), _p(np.ascontiguousarray(t, np.float32)), _p(out))
+    return out
+
+
+def cv_neg_rwc_times_t(Rcw, t):
+    """Rwc = Rcw.t(); -Rwc * t (KeyFrame::SetPose)"""
+    L = lib()
+    out = np.zeros(3, np.float32)
+    L.orc_cv_neg_rwc_times_t(_p(np.ascontiguousarray(Rcw, np.float32)), _p(np.ascontiguousarray(t, np.float32)), _p(out))
+    return out
+
+
+def cv_norm3(v):
+    L = lib()
+    L.orc_cv_norm3.restype = C.c_double
+    return float(L.orc_cv_norm3(_p(np.ascontiguousarray(v, np.float32))))
+
+
 def hamming_best2(q, t):
     L = lib()
     L.orc_hamming_best2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -4,8 +4,13 @@
 // SearchForTriangulation (:257-406) with CheckDistEpipolarLine (:127-144), the search part of Fuse (:408-546),
 // ComputeThreeMaxima (:799-830) and the Frame / KeyFrame grid they search through (src/Frame.cc:155-168, 332-381,
 // 418-427; src/KeyFrame.cc:469-504).
-// The Frame/MapPoint object graph is flattened into arrays (see msl_oracle.h); cv::Mat products are
-// evaluated as OpenCV's gemm does for CV_32F (double accumulation, one rounding) -- "parity unpinned".
+// The Frame/MapPoint object graph is flattened into arrays (see msl_oracle.h).  cv::Mat products are evaluated as
+// cv::gemm does for 3x3 / 3x1 CV_32F operands -- PINNED bit-exactly against cv2.gemm 4.13.0 in
+// tests/test_oracle_primitives.py::test_cv_gemm_semantics:
+//   * flags == 0 (R * x + t, -Rwc * t): the small-matrix path, FLOAT products and sums a0*b0 + a1*b1 + a2*b2, then
+//     (float)(t0 * alpha + c * beta) in double;
+//   * a transposed operand (-Rcw.t() * tcw): the general path, double accumulation, one rounding;
+//   * cv::norm of a 3-vector: double accumulation of squares, sqrt in double.
 #include "msl_oracle.h"
 
 #include <cmath>
@@ -102,11 +107,29 @@ void three_maxima(const std::vector<int> *histo, int L, int &ind1, int &ind2, in
     }
 }
 
-// cv::Mat (3x3 float) * (3x1 float) + (3x1 float) as one gemm: double accumulation, single rounding
+// cv::Mat (3x3 float) * (3x1 float) + (3x1 float) as ONE cv::gemm with flags == 0: OpenCV's small-matrix path
+// (modules/core/src/matmul: len == 3) forms the row sum in float, t0 = a0*b0 + a1*b1 + a2*b2, and stores
+// (float)(t0*alpha + c*beta) evaluated in double.
 inline float gemm_row(const float *R, const float *x, float t) {
+    const float t0 = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+    return (float)((double)t0 * 1.0 + (double)t * 1.0);
+}
+// row r of -R.t() * t (GEMM_1_T, alpha = -1): the general path, double accumulation, one rounding
+inline float gemm_neg_rt_row(const float *R, int r, const float *t) {
     double s = 0;
-    for (int k = 0; k < 3; k++) s += (double)R[k] * (double)x[k];
-    return (float)(s + (double)t);
+    for (int k = 0; k < 3; k++) s += (double)R[k * 3 + r] * (double)t[k];
+    return (float)(-1.0 * s);
+}
+// row r of -Rwc * t with Rwc = Rcw.t() materialised first (KeyFrame::SetPose, src/KeyFrame.cc:79-80): flags == 0, alpha = -1
+inline float gemm_neg_rwc_row(const float *Rcw, int r, const float *t) {
+    const float t0 = Rcw[0 * 3 + r] * t[0] + Rcw[1 * 3 + r] * t[1] + Rcw[2 * 3 + r] * t[2];
+    return (float)((double)t0 * -1.0);
+}
+// cv::norm(v) of a 3x1 CV_32F
+inline double norm3(const float *v) {
+    double s2 = 0;
+    for (int k = 0; k < 3; k++) s2 += (double)v[k] * (double)v[k];
+    return std::sqrt(s2);
 }
 
 }  // namespace
@@ -114,6 +137,18 @@ inline float gemm_row(const float *R, const float *x, float t) {
 extern "C" {
 
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b) { return descriptor_distance(a, b); }
+
+// the cv::Mat arithmetic conventions above, exported so that tests can pin them against cv2 (R row-major 3x3)
+void orc_cv_rx_plus_t(const float R[9], const float x[3], const float t[3], float out[3]) {
+    for (int r = 0; r < 3; r++) out[r] = gemm_row(R + 3 * r, x, t[r]);
+}
+void orc_cv_neg_rt_times_t(const float R[9], const float t[3], float out[3]) {
+    for (int r = 0; r < 3; r++) out[r] = gemm_neg_rt_row(R, r, t);
+}
+void orc_cv_neg_rwc_times_t(const float Rcw[9], const float t[3], float out[3]) {
+    for (int r = 0; r < 3; r++) out[r] = gemm_neg_rwc_row(Rcw, r, t);
+}
+double orc_cv_norm3(const float v[3]) { return norm3(v); }
 
 // brute-force best / second-best over all train descriptors (ties: lowest index); the CPU counterpart of the
 // all-pairs Hamming search of BASELINE.json config 2
@@ -161,11 +196,7 @@ int orc_search_by_projection_frame(const orc_frame_geom *g, const float Tcw_cur[
         tcw[r] = Tcw_cur[r * 4 + 3], tlw[r] = Tcw_last[r * 4 + 3];
     }
     float twc[3];
-    for (int r = 0; r < 3; r++) {
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += (double)(-Rcw[k * 3 + r]) * (double)tcw[k];
-        twc[r] = (float)s;
-    }
+    for (int r = 0; r < 3; r++) twc[r] = gemm_neg_rt_row(Rcw, r, tcw);
     const float tlc2 = gemm_row(Rlw + 6, twc, tlw[2]);
     const bool bForward = tlc2 > g->mb;
     const bool bBackward = -tlc2 > g->mb;
@@ -301,12 +332,8 @@ int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_c
         for (int c = 0; c < 3; c++) Rcw[r * 3 + c] = Tcw_cur[r * 4 + c];
         tcw[r] = Tcw_cur[r * 4 + 3];
     }
-    float Ow[3];  // :686  Ow = -Rcw.t() * tcw (one gemm)
-    for (int r = 0; r < 3; r++) {
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += (double)(-Rcw[k * 3 + r]) * (double)tcw[k];
-        Ow[r] = (float)s;
-    }
+    float Ow[3];  // :686  Ow = -Rcw.t() * tcw (one gemm, transposed operand)
+    for (int r = 0; r < 3; r++) Ow[r] = gemm_neg_rt_row(Rcw, r, tcw);
     std::vector<int> rotHist[HISTO_LENGTH];
     const float factor = 1.0f / HISTO_LENGTH;
     Grid G;
@@ -325,12 +352,8 @@ int orc_search_by_projection_keyframe(const orc_frame_geom *g, const float Tcw_c
         if (u < g->mnMinX || u > g->mnMaxX) continue;
         if (v < g->mnMinY || v > g->mnMaxY) continue;
         // :717-718  PO = x3Dw - Ow; dist3D = cv::norm(PO)  (CV_32F L2 norm: double accumulation, sqrt in double)
-        double s2 = 0;
-        for (int k = 0; k < 3; k++) {
-            const float po = x3Dw[k] - Ow[k];
-            s2 += (double)po * (double)po;
-        }
-        const float dist3D = (float)std::sqrt(s2);
+        const float PO[3] = {x3Dw[0] - Ow[0], x3Dw[1] - Ow[1], x3Dw[2] - Ow[2]};
+        const float dist3D = (float)norm3(PO);
         const float mfMinDistance = kf_mp_dist[2 * i], mfMaxDistance = kf_mp_dist[2 * i + 1];
         const float maxDistance = 1.2f * mfMaxDistance;  // src/MapPoint.cc:329-332
         const float minDistance = 0.8f * mfMinDistance;  // :324-327
@@ -563,11 +586,7 @@ int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, floa
         for (int c = 0; c < 3; c++) Rcw[r * 3 + c] = Tcw[r * 4 + c];
         tcw[r] = Tcw[r * 4 + 3];
     }
-    for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose: Ow = -Rwc * tcw (one gemm)
-        double s = 0;
-        for (int k = 0; k < 3; k++) s += (double)(-Rcw[k * 3 + r]) * (double)tcw[k];
-        Ow[r] = (float)s;
-    }
+    for (int r = 0; r < 3; r++) Ow[r] = gemm_neg_rwc_row(Rcw, r, tcw);  // KeyFrame::SetPose: Rwc = Rcw.t(); Ow = -Rwc * tcw
     Grid G;
     assign_grid(g, kf_xy, n_kf, G);
     std::vector<int> vIndices;
@@ -584,13 +603,8 @@ int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, floa
         if (!(u >= g->mnMinX && u < g->mnMaxX && v >= g->mnMinY && v < g->mnMaxY)) continue;
         const float ur = u - g->mbf * invz;
         const float maxDistance = 1.2f * mp_dist[2 * i + 1], minDistance = 0.8f * mp_dist[2 * i];
-        float PO[3];
-        double s2 = 0;
-        for (int k = 0; k < 3; k++) {
-            PO[k] = p3Dw[k] - Ow[k];
-            s2 += (double)PO[k] * (double)PO[k];
-        }
-        const float dist3D = (float)std::sqrt(s2);
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist3D = (float)norm3(PO);
         if (dist3D < minDistance || dist3D > maxDistance) continue;
         double dot = 0;  // cv::Mat::dot on 3 floats: double products, double accumulation
         for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)mp_normal[3 * i + k];

@@ -80,6 +80,13 @@ int orc_cv_round_f(float v);
 
 /* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:835-849 */
 int orc_descriptor_distance(const uint8_t *a, const uint8_t *b);
+/* cv::Mat arithmetic as the matcher restatements evaluate it (pinned against cv2.gemm / cv2.norm):
+ * R * x + t (flags 0: float row sums), -R.t() * t (transposed operand: double accumulation),
+ * -Rwc * t with Rwc = Rcw.t() materialised (flags 0, alpha -1), cv::norm of a 3-vector. */
+void orc_cv_rx_plus_t(const float R[9], const float x[3], const float t[3], float out[3]);
+void orc_cv_neg_rt_times_t(const float R[9], const float t[3], float out[3]);
+void orc_cv_neg_rwc_times_t(const float Rcw[9], const float t[3], float out[3]);
+double orc_cv_norm3(const float v[3]);
 void orc_hamming_best2(const uint8_t *q, int nq, const uint8_t *t, int nt, int32_t *best_idx, int32_t *best_dist,
                        int32_t *second_dist);
 

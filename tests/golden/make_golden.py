@@ -97,3 +97,24 @@ def node_searches():
 
 if __name__ == "__main__":
     node_searches()
+
+
+def cv_gemm():
+    """cv::gemm / cv::norm outputs of cv2 for the 3x3 / 3x1 products of the matcher (see test_cv_gemm_semantics)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_primitives import _cv_gemm_cases
+    Ts, xs, a, b, c, n = [], [], [], [], [], []
+    for T, x in _cv_gemm_cases(512, seed=6):
+        Rcw, tcw = T[:3, :3], T[:3, 3:4]
+        Ts.append(T), xs.append(x)
+        a.append(cv2.gemm(Rcw, x.reshape(3, 1), 1.0, tcw, 1.0).ravel())
+        b.append(cv2.gemm(Rcw, tcw, -1.0, None, 0.0, flags=cv2.GEMM_1_T).ravel())
+        c.append(cv2.gemm(np.ascontiguousarray(Rcw.T), tcw, -1.0, None, 0.0).ravel())
+        n.append(cv2.norm(x.reshape(3, 1), cv2.NORM_L2))
+    np.savez_compressed(os.path.join(HERE, "cv_gemm.npz"), cv2_version=cv2.__version__, T=np.stack(Ts), x=np.stack(xs),
+                        rx_t=np.stack(a), neg_rt_t=np.stack(b), neg_rwc_t=np.stack(c), norm=np.asarray(n, np.float64))
+    print("cv_gemm golden written")
+
+
+if __name__ == "__main__":
+    cv_gemm()

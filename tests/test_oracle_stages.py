@@ -106,7 +106,8 @@ def _py_search_keyframe(oracle, g, Tcw, th, orb_dist, check_ori, lsf, kf, cur):
         if not kf["valid"][i]:
             continue
         x = kf["mp_world"][i].astype(f32)
-        row = lambda r: f32(sum(f64(R[r, k]) * f64(x[k]) for k in range(3)) + f64(t[r]))
+        # cv::gemm small-matrix path: float row sum, then (float)(t0 + c) in double (test_cv_gemm_semantics)
+        row = lambda r: f32(f64(f32(f32(f32(R[r, 0] * x[0]) + f32(R[r, 1] * x[1])) + f32(R[r, 2] * x[2]))) + f64(t[r]))
         xc, yc = row(0), row(1)
         with np.errstate(divide="ignore"):
             invz = f32(f64(1.0) / f64(row(2)))
@@ -305,7 +306,8 @@ def _py_bow(nnratio, check, kf, f):
 def _py_triangulation(F12, Cw1, Tcw2, K2, only_stereo, check, sf, ls, kf1, kf2):
     f32, f64 = np.float32, np.float64
     T = np.asarray(Tcw2, f32).reshape(4, 4)
-    C2 = [f32(sum(f64(T[r, k]) * f64(Cw1[k]) for k in range(3)) + f64(T[r, 3])) for r in range(3)]
+    Cw = np.asarray(Cw1, f32)
+    C2 = [f32(f64(f32(f32(f32(T[r, 0] * Cw[0]) + f32(T[r, 1] * Cw[1])) + f32(T[r, 2] * Cw[2]))) + f64(T[r, 3])) for r in range(3)]
     invz = f32(f32(1.0) / C2[2])
     ex = f32(f32(f32(K2[0] * C2[0]) * invz) + K2[2])
     ey = f32(f32(f32(K2[1] * C2[1]) * invz) + K2[3])
@@ -363,7 +365,8 @@ def _py_fuse(oracle, g, Tcw, th, lsf, ils, mps, kf):
     f32, f64 = np.float32, np.float64
     T = np.asarray(Tcw, f32).reshape(4, 4)
     R, t = T[:3, :3], T[:3, 3]
-    Ow = np.array([f32(sum(f64(-R[k, r]) * f64(t[k]) for k in range(3))) for r in range(3)], f32)
+    # KeyFrame::SetPose: Rwc = Rcw.t(); Ow = -Rwc * tcw (small-matrix path, alpha = -1)
+    Ow = np.array([-f32(f32(f32(R[0, r] * t[0]) + f32(R[1, r] * t[1])) + f32(R[2, r] * t[2])) for r in range(3)], f32)
     gg = {k: g[k][0] for k in g.dtype.names}
     n_mp = len(mps["valid"])
     bi, bd = np.full(n_mp, -1, np.int32), np.full(n_mp, 256, np.int32)
@@ -372,7 +375,8 @@ def _py_fuse(oracle, g, Tcw, th, lsf, ils, mps, kf):
         if not mps["valid"][i]:
             continue
         x = mps["world"][i].astype(f32)
-        row = lambda r: f32(sum(f64(R[r, k]) * f64(x[k]) for k in range(3)) + f64(t[r]))
+        # cv::gemm small-matrix path: float row sum, then (float)(t0 + c) in double (test_cv_gemm_semantics)
+        row = lambda r: f32(f64(f32(f32(f32(R[r, 0] * x[0]) + f32(R[r, 1] * x[1])) + f32(R[r, 2] * x[2]))) + f64(t[r]))
         p0, p1, p2 = row(0), row(1), row(2)
         if p2 < 0:
             continue
