@@ -199,6 +199,51 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def widened_ops(msl, reps=20):
+    """SURVEY.md section 8(f) rows built beyond the step (the vocabulary-node searches and the Fuse search of ORBmatcher):
+    wall time of one call through the host C ABI (H2D of the flat arrays, kernel, D2H, sync) next to the CPU oracle on the
+    same inputs, and whether the two agree.  Reported beside the headline numbers, never part of them; any failure is
+    reported as text instead of numbers."""
+    try:
+        from manhattanslam_b200 import synthetic as S
+        from oracle import binding as ob
+        lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+        m = msl.ORBmatcher(nnratio=0.7)
+
+        def timed(fn, n):
+            fn()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                out = fn()
+                ts.append(time.perf_counter() - t0)
+            return 1e6 * float(np.median(ts)), out
+
+        res = {}
+        kf, f = S.bow_scene(1)
+        g_us, (n_g, fm_g) = timed(lambda: m.SearchByBoW(kf, f), reps)
+        c_us, (n_c, fm_c) = timed(lambda: ob.search_by_bow(0.7, True, kf, f), 3)
+        res["SearchByBoW_1000x1000"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nmatches": int(n_g),
+                                        "equal": bool(n_g == n_c and np.array_equal(fm_g, fm_c))}
+        kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(1)
+        g_us, (n_g, m_g) = timed(lambda: m.SearchForTriangulation(kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls), reps)
+        c_us, (n_c, m_c) = timed(lambda: ob.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2), 3)
+        res["SearchForTriangulation_900x900"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nmatches": int(n_g),
+                                                 "equal": bool(n_g == n_c and np.array_equal(m_g, m_c))}
+        mps, kfs, Tcw, ils = S.fuse_scene(1)
+        geom = msl.frame_geom()
+        g_us, (n_g, bi_g, bd_g) = timed(lambda: m.Fuse(geom, Tcw, mps, kfs, ils, th=3.0, log_scale_factor=lsf), reps)
+        c_us, (n_c, bi_c, bd_c) = timed(lambda: ob.fuse_search(geom, Tcw, 3.0, lsf, ils, mps, kfs), 3)
+        res["Fuse_1200x1000"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nfused": int(n_g),
+                                 "equal": bool(n_g == n_c and np.array_equal(bi_g, bi_c) and np.array_equal(bd_g, bd_c))}
+        res["note"] = ("one call through the host C ABI incl. the Python mirror's array packing, H2D, kernel, D2H and sync; "
+                       "cpu_oracle = the oracle restatement, single thread; not part of the step")
+        m.close()
+        return res
+    except Exception as e:  # noqa: BLE001 -- diagnostics only: never take the bench line down
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -466,6 +511,8 @@ def run_ours(a, rank, world, local_rank):
                "sample": "%d frames (%.1f s): oracle ORB + plane pre-stage + Hamming match frame-parallel on %d threads, oracle "
                          "SurfelFusion with 10 scan threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
 
+    widened = widened_ops(msl) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -476,7 +523,7 @@ def run_ours(a, rank, world, local_rank):
                           "collective": "nccl all_gather of per-frame counts" if world > 1 else "none (1 GPU)"},
                "roofline": roofline, "cpu_baseline": cpu,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": launches, "clocks": clocks}
+               "gpu_launches": launches, "clocks": clocks, "widened": widened}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
