@@ -19,10 +19,19 @@
 namespace ORB_SLAM2 {
 
 namespace {
+// One handle (stream + scratch arena) per calling thread: the Tracking thread runs the SearchByProjection overloads and
+// SearchByBoW while the LocalMapping thread runs SearchForTriangulation and Fuse (src/LocalMapping.cc:351,549,569), and a
+// handle is not thread-safe (include/msl_frontend.h).  The handles live as long as their threads.
 msl_matcher *matcher() {
-    static msl_matcher *m = nullptr;  // Tracking thread only (one ORBmatcher call at a time)
-    if (!m && msl_matcher_create(4096, 4096, 1, 0, &m) != MSL_OK) throw std::runtime_error(msl_last_error());
-    return m;
+    struct Holder {
+        msl_matcher *m = nullptr;
+        ~Holder() {
+            if (m) msl_matcher_destroy(m);
+        }
+    };
+    static thread_local Holder h;
+    if (!h.m && msl_matcher_create(4096, 4096, 1, 0, &h.m) != MSL_OK) throw std::runtime_error(msl_last_error());
+    return h.m;
 }
 msl_frame_geom geom_of(const Frame &F) {
     msl_frame_geom g = {};
