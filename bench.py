@@ -236,6 +236,11 @@ def widened_ops(msl, reps=20):
         c_us, (n_c, bi_c, bd_c) = timed(lambda: ob.fuse_search(geom, Tcw, 3.0, lsf, ils, mps, kfs), 3)
         res["Fuse_1200x1000"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nfused": int(n_g),
                                  "equal": bool(n_g == n_c and np.array_equal(bi_g, bi_c) and np.array_equal(bd_g, bd_c))}
+        sets = S.observation_sets(1)
+        g_us, (bi_g, bm_g) = timed(lambda: m.ComputeDistinctiveDescriptors(sets), reps)
+        c_us, (bi_c, bm_c) = timed(lambda: ob.distinctive_descriptors(sets), 3)
+        res["ComputeDistinctiveDescriptors_400_points"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us,
+                                                           "equal": bool(np.array_equal(bi_g, bi_c) and np.array_equal(bm_g, bm_c))}
         res["note"] = ("one call through the host C ABI incl. the Python mirror's array packing, H2D, kernel, D2H and sync; "
                        "cpu_oracle = the oracle restatement, single thread; not part of the step")
         m.close()

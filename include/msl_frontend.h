@@ -220,6 +220,15 @@ int msl_fuse_search(msl_matcher *, const msl_frame_geom *geom, const float Tcw[1
                     const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
                     int32_t *best_dist, int32_t *nfused);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263; called per map point at src/LocalMapping.cc and
+ * src/Tracking.cc after observations change) for a BATCH of map points: point k owns the descriptors
+ * desc[offsets[k] .. offsets[k+1]) x 32 bytes -- its observations in non-bad KeyFrames, in std::map order (:228-234).
+ * best_idx[k] = BestIdx (the row with the least median distance to the rest, first such row; -1 for a point without
+ * descriptors, which the reference leaves untouched); best_median (optional) = BestMedian.  The caller copies
+ * descriptor best_idx[k] into mDescriptor (:255-258). */
+int msl_distinctive_descriptors(msl_matcher *, int n_points, const int32_t *offsets, const uint8_t *desc,
+                                int32_t *best_idx, int32_t *best_median);
+
 /* ---------------------------------------------------------------------------------- frame glue
  * The per-frame steps either side of the ORB extractor, so that a frame can stay on the device from decode to the
  * feature grid: Tracking::GrabImage's cvtColor and depth conversion (src/Tracking.cc:184-211),

@@ -643,6 +643,47 @@ __global__ void __launch_bounds__(1024) k_fuse_search(FuseArgs A) {
     if (tid == 0) *A.nFused = s_n;
 }
 
+// --------------------------------------------------- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263), batched
+// One CTA (4 warps) per map point, one warp per row i of the point's N x N distance matrix.  The row's median -- the
+// element of rank r = (int)(0.5 * (N - 1)) of the sorted row, diagonal 0 included -- is found without sorting: it is
+// the smallest v in [0, 256] with #{j : d(i, j) <= v} > r, by bisection on v with one warp-wide count per step (at most
+// 9 steps; the distances are recomputed, 8 xor + popc each).  BestIdx = the first row with the smallest median (:247-251).
+__global__ void __launch_bounds__(128)
+    k_distinctive(const int32_t *__restrict__ off, const uint8_t *__restrict__ desc, int32_t *__restrict__ bestIdx,
+                  int32_t *__restrict__ bestMedian) {
+    __shared__ int s_med[4], s_row[4];
+    const int p = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int o0 = off[p], N = off[p + 1] - o0;
+    if (N <= 0) {  // uniform for the CTA: the reference returns without touching the map point
+        if (threadIdx.x == 0) bestIdx[p] = -1, bestMedian[p] = 0x7fffffff;
+        return;
+    }
+    const uint4 *D = (const uint4 *)(desc + 32 * (size_t)o0);
+    const int r = (int)(0.5 * (double)(N - 1));
+    int myMed = 0x7fffffff, myRow = -1;
+    for (int i = wid; i < N; i += 4) {
+        const uint4 a0 = __ldg(D + 2 * i), a1 = __ldg(D + 2 * i + 1);
+        int lo = 0, hi = 256;  // N > r elements are <= 256: the answer lies in [lo, hi]
+        while (lo < hi) {      // lo, hi are warp-uniform
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = lane; j < N; j += 32) c += hamming256(a0, a1, __ldg(D + 2 * j), __ldg(D + 2 * j + 1)) <= mid;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c > r) hi = mid;
+            else lo = mid + 1;
+        }
+        if (lo < myMed) myMed = lo, myRow = i;  // a warp's rows ascend: strict < keeps the first
+    }
+    if (lane == 0) s_med[wid] = myMed, s_row[wid] = myRow;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int bm = 0x7fffffff, br = -1;
+        for (int w = 0; w < 4; w++)
+            if (s_row[w] >= 0 && (br < 0 || s_med[w] < bm || (s_med[w] == bm && s_row[w] < br))) bm = s_med[w], br = s_row[w];
+        bestIdx[p] = br, bestMedian[p] = bm;
+    }
+}
+
 }  // namespace
 
 struct msl_matcher {
@@ -654,12 +695,14 @@ struct msl_matcher {
     size_t distCap = 0;
     uint8_t *d_scr = nullptr;  // arena for the window-search arrays
     size_t scrCap = 0;
+    uint8_t *d_dd = nullptr;   // msl_distinctive_descriptors: offsets | descriptors | outputs (grown on demand)
+    size_t ddCap = 0;
 };
 
 static void matcher_free(msl_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr};
+    void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr, m->d_dd};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1098,6 +1141,39 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
     MSL_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
     MSL_CUDA(cudaMemcpyAsync(best_dist, A.bestDist, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
     MSL_CUDA(cudaMemcpyAsync(nfused, A.nFused, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    return MSL_OK;
+}
+
+int msl_distinctive_descriptors(msl_matcher *m, int n_points, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,
+                                int32_t *best_median) {
+    if (!m || n_points < 0 || (n_points > 0 && (!offsets || !best_idx))) return fail(MSL_ERR_INVALID, "msl_distinctive_descriptors: bad argument");
+    if (n_points == 0) return MSL_OK;
+    if (offsets[0] != 0) return fail(MSL_ERR_INVALID, "msl_distinctive_descriptors: offsets must start at 0");
+    for (int k = 0; k < n_points; k++)
+        if (offsets[k + 1] < offsets[k]) return fail(MSL_ERR_INVALID, "msl_distinctive_descriptors: offsets must be monotone");
+    const size_t total = (size_t)offsets[n_points];
+    if (total && !desc) return fail(MSL_ERR_INVALID, "msl_distinctive_descriptors: null descriptors");
+    MSL_CUDA(cudaSetDevice(m->device));
+    const size_t offBytes = align_up(sizeof(int32_t) * ((size_t)n_points + 1), 256), descBytes = align_up(total * 32 + 32, 256);
+    const size_t outBytes = align_up(sizeof(int32_t) * (size_t)n_points, 256);
+    const size_t need = offBytes + descBytes + 2 * outBytes;
+    if (need > m->ddCap) {
+        MSL_CUDA(cudaStreamSynchronize(m->stream));
+        if (m->d_dd) cudaFree(m->d_dd);
+        m->d_dd = nullptr, m->ddCap = 0;
+        MSL_CUDA(cudaMalloc((void **)&m->d_dd, need));
+        m->ddCap = need;
+    }
+    int32_t *d_off = (int32_t *)m->d_dd;
+    uint8_t *d_desc = m->d_dd + offBytes;
+    int32_t *d_bi = (int32_t *)(m->d_dd + offBytes + descBytes), *d_bm = (int32_t *)(m->d_dd + offBytes + descBytes + outBytes);
+    MSL_CUDA(cudaMemcpyAsync(d_off, offsets, sizeof(int32_t) * ((size_t)n_points + 1), cudaMemcpyHostToDevice, m->stream));
+    if (total) MSL_CUDA(cudaMemcpyAsync(d_desc, desc, total * 32, cudaMemcpyHostToDevice, m->stream));
+    k_distinctive<<<n_points, 128, 0, m->stream>>>(d_off, d_desc, d_bi, d_bm);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaMemcpyAsync(best_idx, d_bi, sizeof(int32_t) * (size_t)n_points, cudaMemcpyDeviceToHost, m->stream));
+    if (best_median) MSL_CUDA(cudaMemcpyAsync(best_median, d_bm, sizeof(int32_t) * (size_t)n_points, cudaMemcpyDeviceToHost, m->stream));
     MSL_CUDA(cudaStreamSynchronize(m->stream));
     return MSL_OK;
 }

@@ -196,3 +196,17 @@ class ORBmatcher:
                                       ptr(ils), len(margs[0]), *[ptr(x) for x in margs], len(kargs[1]), *[ptr(x) for x in kargs],
                                       ptr(bi), ptr(bd), C.byref(nf)))
         return nf.value, bi, bd
+
+    def ComputeDistinctiveDescriptors(self, desc_lists):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263) for a batch of map points.
+        desc_lists: list of (N_k, 32) uint8 arrays (a point's observed descriptors).  Returns (best_idx, best_median)."""
+        n = len(desc_lists)
+        off = np.zeros(n + 1, np.int32)
+        for k, d in enumerate(desc_lists):
+            off[k + 1] = off[k] + len(d)
+        desc = np.ascontiguousarray(np.concatenate([np.asarray(d, np.uint8).reshape(-1, 32) for d in desc_lists] +
+                                                   [np.zeros((0, 32), np.uint8)]))
+        bi = np.zeros(n, np.int32)
+        bm = np.zeros(n, np.int32)
+        check(self._L.msl_distinctive_descriptors(self._h, n, ptr(off), ptr(desc), ptr(bi), ptr(bm)))
+        return bi, bm

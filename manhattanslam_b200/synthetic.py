@@ -368,3 +368,25 @@ def fuse_scene(seed, n_mp=1200, n_kf=1000, K=K_DEFAULT, w=640, h=480):
            "dist": np.stack([mind, maxd], 1).astype(np.float32), "desc": _noisy_desc(r, kf["desc"][tgt], 80)}
     inv_sigma2 = (1.0 / (sf * sf)).astype(np.float32)
     return mps, kf, Tcw.astype(np.float32), inv_sigma2
+
+
+def observation_sets(seed, n_points=400, max_obs=40):
+    """Descriptor sets of map points for MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263): every point has
+    1..max_obs observations that are noisy copies of one descriptor (a few outliers), some points have none, a few have
+    many (more than a warp / more than a tile), some consist of identical descriptors (all medians tie: the first wins)."""
+    r = np.random.default_rng(seed + 7171)
+    out = []
+    for k in range(n_points):
+        n = int(r.integers(1, max_obs + 1))
+        if k % 37 == 5:
+            n = 0
+        elif k % 53 == 7:
+            n = int(r.integers(100, 260))
+        base = r.integers(0, 256, (1, 32), dtype=np.uint8)
+        d = _noisy_desc(r, np.repeat(base, n, 0), 60) if n else np.zeros((0, 32), np.uint8)
+        if n and k % 11 == 3:
+            d[:] = base                      # every row identical
+        if n > 3 and k % 5 == 0:
+            d[r.integers(0, n)] = r.integers(0, 256, 32, dtype=np.uint8)   # an outlier observation
+        out.append(d)
+    return out

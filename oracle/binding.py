@@ -496,6 +496,20 @@ def fuse_search(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf):
     return n, bi, bd
 
 
+def distinctive_descriptors(desc_lists):
+    """desc_lists: list of (N_k, 32) uint8 arrays -> (best_idx, best_median) per map point"""
+    L = lib()
+    off = np.zeros(len(desc_lists) + 1, np.int32)
+    for k, d in enumerate(desc_lists):
+        off[k + 1] = off[k] + len(d)
+    desc = np.ascontiguousarray(np.concatenate([np.asarray(d, np.uint8).reshape(-1, 32) for d in desc_lists] +
+                                               [np.zeros((0, 32), np.uint8)]))
+    bi = np.zeros(len(desc_lists), np.int32)
+    bm = np.zeros(len(desc_lists), np.int32)
+    L.orc_distinctive_descriptors(len(desc_lists), _p(off), _p(desc), _p(bi), _p(bm))
+    return bi, bm
+
+
 class SurfelMappingOracle:
     """The part of SurfelMapping that moveAddSurfels touches (src/SurfelMapping.cpp:194-304)."""
 

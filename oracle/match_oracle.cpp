@@ -13,6 +13,7 @@
 //   * cv::norm of a 3-vector: double accumulation of squares, sqrt in double.
 #include "msl_oracle.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -642,6 +643,40 @@ int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, floa
         if (bestDist <= TH_LOW) nFused++;
     }
     return nFused;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263) for a batch of map points: point k owns the
+// descriptors desc[off[k] .. off[k+1]) (the observations in non-bad KeyFrames, in std::map order).  best_idx[k] = BestIdx
+// (index inside the point's list; -1 for a point without descriptors, which the reference leaves untouched),
+// best_median[k] = BestMedian.
+void orc_distinctive_descriptors(int n_points, const int32_t *off, const uint8_t *desc, int32_t *best_idx,
+                                 int32_t *best_median) {
+    for (int p = 0; p < n_points; p++) {
+        const size_t N = (size_t)(off[p + 1] - off[p]);
+        best_idx[p] = -1, best_median[p] = 0x7fffffff;
+        if (N == 0) continue;
+        const uint8_t *D = desc + 32 * (size_t)off[p];
+        std::vector<float> Distances(N * N);  // float Distances[N][N] in the reference
+        for (size_t i = 0; i < N; i++) {
+            Distances[i * N + i] = 0;
+            for (size_t j = i + 1; j < N; j++) {
+                const int distij = descriptor_distance(D + 32 * i, D + 32 * j);
+                Distances[i * N + j] = (float)distij;
+                Distances[j * N + i] = (float)distij;
+            }
+        }
+        int BestMedian = 0x7fffffff, BestIdx = 0;
+        for (size_t i = 0; i < N; i++) {
+            std::vector<int> vDists(Distances.begin() + i * N, Distances.begin() + (i + 1) * N);
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) {
+                BestMedian = median;
+                BestIdx = (int)i;
+            }
+        }
+        best_idx[p] = BestIdx, best_median[p] = BestMedian;
+    }
 }
 
 }  // extern "C"

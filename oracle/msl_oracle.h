@@ -178,6 +178,12 @@ int orc_fuse_search(const orc_frame_geom *g, const float Tcw[16], float th, floa
                     const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
                     int32_t *best_dist);
 
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:210-263, for a batch of map points: point k owns
+ * desc[off[k] .. off[k+1]).  best_idx[k] = BestIdx inside the point's list (-1 if it has no descriptor),
+ * best_median[k] = BestMedian. */
+void orc_distinctive_descriptors(int n_points, const int32_t *off, const uint8_t *desc, int32_t *best_idx,
+                                 int32_t *best_median);
+
 /* ---------------------------------------------------- plane pre-stage --- */
 
 typedef struct {

@@ -90,8 +90,9 @@ def node_searches():
     nt, m12 = ob.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2)
     mps, kfs, Tcw, ils = S.fuse_scene(3)
     nf, bi, bd = ob.fuse_search(frame_geom(), Tcw, 3.0, lsf, ils, mps, kfs)
+    ddi, ddm = ob.distinctive_descriptors(S.observation_sets(3))
     np.savez_compressed(os.path.join(HERE, "node_searches.npz"), bow_n=nb, bow_match=fm, tri_n=nt, tri_match=m12, fuse_n=nf,
-                        fuse_idx=bi, fuse_dist=bd)
+                        fuse_idx=bi, fuse_dist=bd, dd_idx=ddi, dd_median=ddm)
     print("node search golden written", nb, nt, nf)
 
 

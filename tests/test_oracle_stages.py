@@ -463,6 +463,22 @@ def test_fuse_search_vs_python(oracle):
         assert (bi[mps["valid"] == 0] == -1).all()
 
 
+def test_distinctive_descriptors_vs_numpy(oracle):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263): the oracle against a numpy restatement
+    (full distance matrix, row sort, element int(0.5 (N-1)), first row with the least median)"""
+    sets = S.observation_sets(61, n_points=150)
+    bi, bm = oracle.distinctive_descriptors(sets)
+    for k, d in enumerate(sets):
+        if len(d) == 0:
+            assert bi[k] == -1
+            continue
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (len(d) - 1))]
+        assert bi[k] == int(np.argmin(med)) and bm[k] == med.min(), k
+    identical = [k for k, d in enumerate(sets) if len(d) > 1 and (d == d[0]).all()]
+    assert identical and all(bi[k] == 0 and bm[k] == 0 for k in identical)
+
+
 def test_golden_node_searches(oracle):
     gold = np.load(os.path.join(GOLD, "node_searches.npz"))
     lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
@@ -475,3 +491,5 @@ def test_golden_node_searches(oracle):
     mps, kfs, Tcw, ils = S.fuse_scene(3)
     n, bi, bd = oracle.fuse_search(frame_geom(), Tcw, 3.0, lsf, ils, mps, kfs)
     assert n == int(gold["fuse_n"]) and np.array_equal(bi, gold["fuse_idx"]) and np.array_equal(bd, gold["fuse_dist"])
+    ddi, ddm = oracle.distinctive_descriptors(S.observation_sets(3))
+    assert np.array_equal(ddi, gold["dd_idx"]) and np.array_equal(ddm, gold["dd_median"])
