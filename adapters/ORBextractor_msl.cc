@@ -1,6 +1,7 @@
 // ORBextractor_msl.cc -- ORB_SLAM2::ORBextractor on the B200 front-end (drop-in for src/ORBextractor.cc).
 // Compiles against the reference's unmodified include/ORBextractor.h; Frame.cc / Tracking.cc are untouched:
 // Frame::ExtractORB still calls (*mpORBextractorLeft)(im, cv::Mat(), mvKeys, mDescriptors) (src/Frame.cc:175-177).
+#include <cstring>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>

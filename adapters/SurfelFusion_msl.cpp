@@ -24,8 +24,8 @@ msl_surfel_fusion *msl_handle_of(const SurfelFusion *f) {
 }
 
 SurfelFusion::SurfelFusion(int width, int height, float _fx, float _fy, float _cx, float _cy, float _fuseFar, float _fuseNear)
-    : imageWidth(width), imageHeight(height), spWidth(width / SP_SIZE), spHeight(height / SP_SIZE), fx(_fx), fy(_fy),
-      cx(_cx), cy(_cy), fuseFar(_fuseFar), fuseNear(_fuseNear) {
+    : fx(_fx), fy(_fy), cx(_cx), cy(_cy), imageWidth(width), imageHeight(height), spWidth(width / SP_SIZE),
+      spHeight(height / SP_SIZE), fuseFar(_fuseFar), fuseNear(_fuseNear) {  // declaration order of include/SurfelFusion.h:60-63
     msl_surfel_fusion *h = nullptr;
     if (msl_surfel_create(width, height, _fx, _fy, _cx, _cy, _fuseFar, _fuseNear, 32ll << 20, 0, &h) != MSL_OK)
         throw std::runtime_error(msl_last_error());

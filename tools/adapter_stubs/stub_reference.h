@@ -6,7 +6,9 @@
 #include <set>
 #include <utility>
 #include <vector>
+#include <list>
 #include <opencv2/core/core.hpp>
+#include <Eigen/Eigen>
 namespace DBoW2 {
 typedef unsigned int NodeId;
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
@@ -16,6 +18,8 @@ class MapPoint;
 class KeyFrame;
 class Frame {  // include/Frame.h
 public:
+    void ComputeStereoFromRGBD(const cv::Mat &imDepth);
+    cv::Mat mDistCoef;
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvDepth;
@@ -31,6 +35,28 @@ public:
     float mfScaleFactor, mfLogScaleFactor;
     std::vector<float> mvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+private:
+    void UndistortKeyPoints();
+};
+class ORBextractor {  // include/ORBextractor.h
+public:
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+    ~ORBextractor() {}
+    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);
+    std::vector<cv::Mat> mvImagePyramid;
+protected:
+    std::vector<cv::Point> pattern;
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<int> umax;
+    std::vector<float> mvScaleFactor;
+    std::vector<float> mvInvScaleFactor;
+    std::vector<float> mvLevelSigma2;
+    std::vector<float> mvInvLevelSigma2;
 };
 class KeyFrame {  // include/KeyFrame.h
 public:
@@ -89,5 +115,65 @@ public:
 protected:
     float mfNNratio;
     bool mbCheckOrientation;
+};
+class Map;
+}  // namespace ORB_SLAM2
+
+// ---- global-namespace classes of the reference
+struct Surfel {  // include/Surfel.h
+    float px, py, pz;
+    float nx, ny, nz;
+    float size;
+    float color;
+    int r, g, b;
+    float weight;
+    int updateTimes;
+    int lastUpdate;
+};
+#define SP_SIZE 8
+class SurfelFusion {  // include/SurfelFusion.h (member order as declared there)
+private:
+    float fx, fy, cx, cy;
+    int imageWidth, imageHeight;
+    int spWidth, spHeight;
+    float fuseFar, fuseNear;
+public:
+    SurfelFusion(int width, int height, float _fx, float _fy, float _cx, float _cy, float _fuseFar, float _fuseNear);
+    void fuseInitializeMap(const int referenceFrameIndex, const cv::Mat &inputImage, const cv::Mat &inputDepth,
+                           const cv::Mat &inputPlaneMembershipImg, const Eigen::Matrix4f &pose,
+                           std::vector<Surfel> &localSurfels, std::vector<Surfel> &newSurfels);
+};
+typedef Eigen::Vector3d VertexType;  // include/PlaneExtractor.h
+typedef cv::Vec3d VertexColour;
+struct ImagePointCloud {
+    std::vector<VertexType> vertices;
+    std::vector<VertexColour> verticesColour;
+    int w, h;
+};
+class PlaneDetection {
+public:
+    ImagePointCloud cloud;
+    std::vector<std::vector<int> > plane_vertices_;
+    cv::Mat seg_img_;
+    cv::Mat color_img_;
+    int plane_num_;
+    bool readColorImage(cv::Mat RGBImg);
+    bool readDepthImage(const cv::Mat depthImg, const cv::Mat &K, const float &depthMapFactor);
+    void runPlaneDetection();
+};
+namespace ORB_SLAM2 {
+class Map {  // include/Map.h
+public:
+    std::vector<Surfel> mvLocalSurfels;
+    std::vector<Surfel> mvInactiveSurfels;
+};
+class SurfelMapping {  // include/SurfelMapping.h
+protected:
+    void moveAddSurfels(int referenceIndex);
+    void getAddRemovePoses(int rootIndex, std::vector<int> &poseToAdd, std::vector<int> &poseToRemove);
+    void fuseMap(cv::Mat image, cv::Mat depth, cv::Mat planeMembershipImg, Eigen::Matrix4f poseInput, int referenceIndex);
+    Map *mMap;
+    SurfelFusion *mSurfelFusion;
+    std::set<int> localSurfelsIndexs;
 };
 }  // namespace ORB_SLAM2

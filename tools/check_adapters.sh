@@ -1,10 +1,11 @@
 #!/bin/bash
-# Syntax / type check of the ORBmatcher and MapPoint bindings against stand-ins of the reference headers (the build image has
-# no OpenCV, so adapters/ is not compiled by __graft_entry__.build()).  The stand-ins copy names, types, constness and
-# access levels of the members the bindings use from /root/reference/include/*.h.
-set -e
+# Syntax / type check of every binding in adapters/ against stand-ins of the reference headers (the build image has
+# no OpenCV / Eigen, so adapters/ is not compiled by __graft_entry__.build()).  The stand-ins (tools/adapter_stubs/) copy
+# names, types, constness, declaration order and access levels of the members the bindings use from
+# /root/reference/include/*.h.
 cd "$(dirname "$0")/.."
-for f in adapters/ORBmatcher_msl.cc adapters/MapPoint_msl.cc; do
-  g++ -std=c++14 -fsyntax-only -Wall -Wextra -Itools/adapter_stubs -Iinclude "$f"
-  echo "ok  $f"
+rc=0
+for f in adapters/*.cc adapters/*.cpp; do
+  if g++ -std=c++14 -fsyntax-only -Wall -Wextra -DMSL_SURFEL_RESIDENT -Itools/adapter_stubs -Iinclude "$f"; then echo "ok  $f"; else echo "FAILED  $f"; rc=1; fi
 done
+exit $rc
