@@ -111,3 +111,20 @@ def test_adapter_bindings_typecheck():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run(["bash", os.path.join(root, "tools", "check_adapters.sh")], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.count("ok ") == 7 and "warning" not in out.stderr, out.stdout + out.stderr
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/msl_frontend.h is the drop-in boundary: it must compile as C99 (plain pointers and sizes, no C++ types)
+    and as C++11 (the reference's language) without warnings."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "msl_frontend.h"\nint main(void) { return MSL_OK; }\n')
+    inc = os.path.join(root, "include")
+    for cmd in (["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Wextra", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0 and not out.stderr.strip(), out.stderr
