@@ -128,3 +128,21 @@ def test_header_is_plain_c(tmp_path):
                 ["g++", "-std=c++11", "-Wall", "-Wextra", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
         out = subprocess.run(cmd, capture_output=True, text=True)
         assert out.returncode == 0 and not out.stderr.strip(), out.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the keys the driver reads;
+    run here on a tiny configuration."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--batch", "4", "--surfels", "60000", "--cpu-frames", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "rgbd_frontend_frames_per_s" and j["unit"] == "frames/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["config"]["workload"].startswith("frontend_640x480_b4")
