@@ -275,3 +275,23 @@ def test_fuse_stream_with_panning_camera(oracle, msl):
                 # the NaNs must sit in the same records
                 assert np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6, equal_nan=True), (k, f)
         lo = got.copy()
+
+
+def test_membership_values_other_than_minus_one(oracle, msl):
+    """planeMembershipImg comes out of peac's refineDetails with plane ids >= 0 AND with values <= -2 (floodFill's
+    bookkeeping `trail -= 1`, include/peac/AHCPlaneFitter.hpp:463-467); SurfelFusion only tests `!= -1`
+    (src/SurfelFusion.cpp:366, 543), so every value but -1 means "in a plane"."""
+    g, d, m = _frame(5, 0.4)
+    r = np.random.default_rng(5)
+    m = np.where(m == 0, r.choice(np.array([-9, -2, 0, 3, 17], np.int32), m.shape), m).astype(np.int32)
+    assert (m <= -2).any() and (m > 0).any() and (m == -1).any()
+    o = oracle.SurfelOracle()
+    o.fuse(0, g, d, m, np.eye(4, dtype=np.float32), np.zeros(0, oracle.SURFEL_DTYPE))
+    sf = msl.SurfelFusion(max_surfels=1024)
+    seeds, index = sf.superpixels(g, d, m)
+    assert np.array_equal(index[0], o.index())
+    assert _cmp(o.seeds(), seeds[0], FLOAT_SEED, INT_SEED, "seed") == 0.0
+    # the same frame with every plane pixel set to 0 gives the same superpixels: only `!= -1` matters
+    m0 = np.where(m != -1, 0, -1).astype(np.int32)
+    seeds0, index0 = sf.superpixels(g, d, m0)
+    assert np.array_equal(index0, index) and np.array_equal(seeds0.view(np.uint8), seeds.view(np.uint8))
