@@ -510,6 +510,72 @@ def distinctive_descriptors(desc_lists):
     return bi, bm
 
 
+REFERENCE_ROOT = "/root/reference"
+
+
+def build_ref(force=False):
+    """oracle/_ref/libsurfel_ref.so: the reference's own src/SurfelFusion.cpp compiled against the stand-in headers of
+    oracle/ref_shim/ (see oracle/ref_wrap.cpp).  Built only where /root/reference exists; returns the path or None."""
+    so = os.path.join(_HERE, "_ref", "libsurfel_ref.so")
+    src = os.path.join(REFERENCE_ROOT, "src", "SurfelFusion.cpp")
+    if os.path.exists(src):
+        deps = [src, os.path.join(REFERENCE_ROOT, "include", "SurfelFusion.h"), os.path.join(_HERE, "ref_wrap.cpp"),
+                os.path.join(_HERE, "ref_shim", "Eigen", "Eigen"), os.path.join(_HERE, "ref_shim", "opencv2", "opencv.hpp"),
+                os.path.join(_HERE, "ref_shim", "thread")]
+        if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["make", "-B", "-C", _HERE, "_ref/libsurfel_ref.so"], stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
+class RefSurfelFusion:
+    """The reference's SurfelFusion class itself (oracle/_ref, see build_ref): fuseInitializeMap + read-back of the
+    private superpixel buffers.  Used by tests/test_oracle_ref.py to check the oracle restatement, nowhere else."""
+
+    def __init__(self, w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, fuseFar=30.0, fuseNear=0.5):
+        so = build_ref()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libsurfel_ref.so is not built and /root/reference is absent")
+        self.L = C.CDLL(so)
+        self.L.ref_surfel_create.restype = C.c_void_p
+        self.L.ref_surfel_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6
+        self.L.ref_surfel_destroy.argtypes = [C.c_void_p]
+        self.L.ref_surfel_fuse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        self.L.ref_surfel_index.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_surfel_seeds.argtypes = [C.c_void_p, C.c_void_p]
+        self.w, self.h = w, h
+        self.hd = self.L.ref_surfel_create(w, h, fx, fy, cx, cy, fuseFar, fuseNear)
+
+    def __del__(self):
+        if getattr(self, "hd", None):
+            self.L.ref_surfel_destroy(self.hd)
+            self.hd = None
+
+    def fuse(self, ref, gray, depth, membership, Twc, local):
+        """fuseInitializeMap: mutates `local` in place, returns the new surfels."""
+        h, w = self.h, self.w
+        buf = np.zeros(h * w + 3 * w + 16, np.uint8)  # zero bytes behind the image: the reference reads cv::Vec3b on it
+        buf[:h * w] = np.ascontiguousarray(gray, np.uint8).ravel()
+        d = np.ascontiguousarray(depth, np.float32)
+        m = np.ascontiguousarray(membership, np.int32)
+        T = np.ascontiguousarray(Twc, np.float32)
+        new = np.zeros((w // 8) * (h // 8), SURFEL_DTYPE)
+        n = self.L.ref_surfel_fuse(self.hd, int(ref), _p(buf), w, _p(d), _p(m), _p(T), _p(local), len(local), _p(new), len(new))
+        if n < 0:
+            raise RuntimeError("the reference resized localSurfels")
+        return new[:n].copy()
+
+    def index(self):
+        out = np.zeros((self.h, self.w), np.int32)
+        self.L.ref_surfel_index(self.hd, _p(out))
+        return out
+
+    def seeds(self):
+        out = np.zeros((self.w // 8) * (self.h // 8), SEED_DTYPE)
+        self.L.ref_surfel_seeds(self.hd, _p(out))
+        return out
+
+
 class SurfelMappingOracle:
     """The part of SurfelMapping that moveAddSurfels touches (src/SurfelMapping.cpp:194-304)."""
 
