@@ -513,18 +513,73 @@ def distinctive_descriptors(desc_lists):
 REFERENCE_ROOT = "/root/reference"
 
 
-def build_ref(force=False):
-    """oracle/_ref/libsurfel_ref.so: the reference's own src/SurfelFusion.cpp compiled against the stand-in headers of
-    oracle/ref_shim/ (see oracle/ref_wrap.cpp).  Built only where /root/reference exists; returns the path or None."""
-    so = os.path.join(_HERE, "_ref", "libsurfel_ref.so")
-    src = os.path.join(REFERENCE_ROOT, "src", "SurfelFusion.cpp")
-    if os.path.exists(src):
-        deps = [src, os.path.join(REFERENCE_ROOT, "include", "SurfelFusion.h"), os.path.join(_HERE, "ref_wrap.cpp"),
-                os.path.join(_HERE, "ref_shim", "Eigen", "Eigen"), os.path.join(_HERE, "ref_shim", "opencv2", "opencv.hpp"),
-                os.path.join(_HERE, "ref_shim", "thread")]
+_REF_DEPS = {
+    "libsurfel_ref.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
+                         ["ref_wrap.cpp", "ref_shim/Eigen/Eigen", "ref_shim/opencv2/opencv.hpp", "ref_shim/thread"]),
+    "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
+                      ["ref_orb_wrap.cpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
+}
+
+
+def build_ref(force=False, name="libsurfel_ref.so"):
+    """oracle/_ref/<name>: one of the reference's own source files compiled where it lies, unmodified, against stand-in
+    headers (libsurfel_ref.so: src/SurfelFusion.cpp, see oracle/ref_wrap.cpp; liborb_ref.so: src/ORBextractor.cc, see
+    oracle/ref_orb_wrap.cpp).  Built only where /root/reference exists; returns the path or None."""
+    so = os.path.join(_HERE, "_ref", name)
+    ref_deps, own_deps = _REF_DEPS[name]
+    if os.path.exists(os.path.join(REFERENCE_ROOT, ref_deps[0])):
+        deps = [os.path.join(REFERENCE_ROOT, d) for d in ref_deps] + [os.path.join(_HERE, d) for d in own_deps]
         if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["make", "-B", "-C", _HERE, "_ref/libsurfel_ref.so"], stdout=subprocess.DEVNULL)
+            subprocess.check_call(["make", "-B", "-C", _HERE, "_ref/" + name], stdout=subprocess.DEVNULL)
     return so if os.path.exists(so) else None
+
+
+class RefOrbExtractor:
+    """The reference's ORBextractor class itself (oracle/_ref/liborb_ref.so, see build_ref and oracle/ref_orb_wrap.cpp):
+    one extractor built, called and destroyed per frame.  `arena=True` (default) serves every allocation of the call
+    from a bump arena so that the heap-address tie-break of DistributeOctTree's sort (src/ORBextractor.cc:654) is the
+    node creation order; `arena=False` leaves it to glibc.  Used by tests/test_oracle_ref.py and
+    tools/ref_octree_tiebreak.py, nowhere else."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, arena=True):
+        so = build_ref(name="liborb_ref.so")
+        if so is None:
+            raise RuntimeError("oracle/_ref/liborb_ref.so is not built and /root/reference is absent")
+        self.L = C.CDLL(so)
+        sig = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        for f in (self.L.ref_orb_extract, self.L.ref_orb_extract_malloc):
+            f.argtypes = sig + [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.L.ref_orb_tables.argtypes = sig + [C.c_void_p] * 6
+        self.params = (nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.nfeatures, self.nlevels, self.arena = nfeatures, nlevels, arena
+        self._levels = None
+
+    def tables(self):
+        """(scale, inv_scale, sigma2, inv_sigma2, features_per_level, umax) of the reference's constructor"""
+        f = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        n, u = np.zeros(self.nlevels, np.int32), np.zeros(16, np.int32)
+        self.L.ref_orb_tables(*self.params, *[_p(a) for a in f], _p(n), _p(u))
+        return f + [n, u]
+
+    def __call__(self, gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        h, w = gray.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps, desc = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+        wh = np.zeros((self.nlevels, 2), np.int32)
+        pyr = np.zeros(w * h * 4 + 64, np.uint8)
+        fn = self.L.ref_orb_extract if self.arena else self.L.ref_orb_extract_malloc
+        n = fn(*self.params, _p(gray), w, h, gray.strides[0], _p(kps), _p(desc), cap, _p(wh), _p(pyr))
+        if n < 0 or n > cap:
+            raise RuntimeError("reference ORB extraction failed (%d)" % n)
+        self._levels, off = [], 0
+        for lw, lh in wh:
+            self._levels.append(pyr[off:off + lw * lh].reshape(lh, lw).copy())
+            off += lw * lh
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_image(self, level):
+        return self._levels[level]
 
 
 class RefSurfelFusion:

@@ -94,3 +94,106 @@ def test_small_and_odd_image_sizes_match_reference_source(ref):
         new_r = r.fuse(10, g, d, m, T, lr)
         assert np.array_equal(o.index(), r.index()) and _same(o.seeds(), r.seeds())
         assert _same(lo, lr) and _same(new_o, new_r)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ORBextractor: the oracle restatement against the reference's own src/ORBextractor.cc (oracle/_ref/liborb_ref.so,
+# oracle/ref_orb_wrap.cpp).  OpenCV's five algorithms are the oracle's cv2-pinned primitives on both sides; the
+# constructor tables, the cell loop, DistributeOctTree / DivideNode, IC_Angle, computeOrbDescriptor and the level
+# bookkeeping are the reference's own code.  Everything is compared bit for bit.
+
+@pytest.fixture(scope="module")
+def ref_orb(oracle):
+    if oracle.build_ref(name="liborb_ref.so") is None:
+        pytest.skip("oracle/_ref/liborb_ref.so not built and /root/reference absent")
+    return oracle
+
+
+def _orb_same(o, r, img, nlevels):
+    ko, do = o(img)
+    kr, dr = r(img)
+    assert len(ko) == len(kr), (len(ko), len(kr))
+    for f in ko.dtype.names:
+        a, b = ko[f], kr[f]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f
+    assert np.array_equal(do, dr)
+    for l in range(nlevels):
+        assert np.array_equal(o.level_image(l), r.level_image(l)), "pyramid level %d" % l
+    return ko
+
+
+@pytest.mark.parametrize("nf,sf,nl,ini,mn", [(1000, 1.2, 8, 20, 7), (500, 1.2, 6, 20, 7), (2000, 1.2, 8, 20, 7),
+                                             (1000, 1.5, 4, 20, 7), (1500, 1.1, 12, 15, 5), (300, 2.0, 3, 30, 10)])
+def test_orb_constructor_tables_match_reference_source(ref_orb, nf, sf, nl, ini, mn):
+    """mvScaleFactor (float x double member), sigma^2, inverses, mnFeaturesPerLevel (cvRound), umax
+    (src/ORBextractor.cc:412-468)"""
+    o = ref_orb.OrbOracle(nf, sf, nl, ini, mn)
+    r = ref_orb.RefOrbExtractor(nf, sf, nl, ini, mn)
+    got = o.scale_factors() + [o.features_per_level(), o.umax()]
+    for a, b in zip(got, r.tables()):
+        assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_orb_frame_matches_reference_source(ref_orb, seed):
+    k = _orb_same(ref_orb.OrbOracle(), ref_orb.RefOrbExtractor(), S.gray_frame(seed), 8)
+    assert len(k) > 900 and len(set(k["octave"].tolist())) == 8
+
+
+@pytest.mark.parametrize("kind", ["flat", "noise", "sparse", "gradient"])
+def test_orb_edge_images_match_reference_source(ref_orb, kind):
+    """the same edge images as tests/test_orb_gpu.py::test_orb_edge_images"""
+    r = np.random.default_rng(5)
+    if kind == "flat":
+        img = np.full((480, 640), 77, np.uint8)
+    elif kind == "noise":
+        img = r.integers(0, 256, (480, 640), dtype=np.uint8)
+    elif kind == "sparse":
+        img = np.full((480, 640), 100, np.uint8)
+        for _ in range(12):
+            x, y = r.integers(40, 600), r.integers(40, 440)
+            img[y:y + 5, x:x + 5] += np.uint8(r.integers(9, 18))
+    else:
+        img = (np.add.outer(np.arange(480), np.arange(640)) % 256).astype(np.uint8)
+    k = _orb_same(ref_orb.OrbOracle(), ref_orb.RefOrbExtractor(), img, 8)
+    if kind == "flat":
+        assert len(k) == 0
+
+
+@pytest.mark.parametrize("w,h,nf,nl,sf", [(752, 480, 1200, 8, 1.2), (320, 240, 500, 6, 1.2), (1280, 960, 2000, 8, 1.2),
+                                           (640, 480, 1000, 4, 1.5), (161, 123, 200, 3, 1.2)])
+def test_orb_other_sizes_match_reference_source(ref_orb, w, h, nf, nl, sf):
+    img = S.gray_frame(40 + w % 7, w, h)
+    _orb_same(ref_orb.OrbOracle(nf, sf, nl), ref_orb.RefOrbExtractor(nf, sf, nl), img, nl)
+
+
+def test_orb_strided_input_matches_reference_source(ref_orb):
+    """a view into a wider buffer (cv::Mat step > cols)"""
+    big = S.gray_frame(9, 800, 600)
+    view = big[50:530, 70:710]
+    assert not view.flags["C_CONTIGUOUS"]
+    o, r = ref_orb.OrbOracle(), ref_orb.RefOrbExtractor()
+    ko, do = o(np.ascontiguousarray(view))
+    buf = big.copy()
+    sub = buf[50:530, 70:710]
+    n_cap = 1000 + 64 + 64
+    kps, desc = np.zeros(n_cap, ref_orb.KP_DTYPE), np.zeros((n_cap, 32), np.uint8)
+    n = r.L.ref_orb_extract(*r.params, sub.ctypes.data, 640, 480, buf.strides[0], kps.ctypes.data, desc.ctypes.data, n_cap,
+                            None, None)
+    assert n == len(ko) and kps[:n].tobytes() == ko.tobytes() and np.array_equal(desc[:n], do)
+
+
+def test_orb_heap_address_tiebreak_is_the_only_freedom(ref_orb):
+    """DistributeOctTree sorts (key count, node pointer) pairs (src/ORBextractor.cc:654): equal counts are ordered by heap
+    address.  On the process allocator the reference therefore picks a few different keypoints than on the bump arena
+    (= creation order, what the oracle restates) -- but only there: pyramid, per-level counts of the levels that never
+    reach the largest-first phase, and every keypoint both runs share are identical."""
+    img = S.gray_frame(2)
+    ka, da = ref_orb.RefOrbExtractor(arena=True)(img)
+    km, dm = ref_orb.RefOrbExtractor(arena=False)(img)
+    sa = {bytes(k) + bytes(d) for k, d in zip(ka, da)}
+    sm = {bytes(k) + bytes(d) for k, d in zip(km, dm)}
+    # the bulk of the selection does not depend on the allocator ...
+    assert len(sa & sm) > 0.95 * len(sa)
+    # ... and when it does, only whole keypoints are swapped (a keypoint present in both has identical fields)
+    assert abs(len(ka) - len(km)) <= 16
