@@ -517,14 +517,18 @@ _REF_DEPS = {
     "libsurfel_ref.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
                          ["ref_wrap.cpp", "ref_shim/Eigen/Eigen", "ref_shim/opencv2/opencv.hpp", "ref_shim/thread"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
-                      ["ref_orb_wrap.cpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
+                      ["ref_orb_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
+    "libplane_ref.so": (["src/PlaneExtractor.cpp", "include/PlaneExtractor.h", "include/peac/AHCPlaneFitter.hpp",
+                         "include/peac/AHCPlaneSeg.hpp", "include/peac/AHCParamSet.hpp", "include/peac/eig33sym.hpp"],
+                        ["ref_plane_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "ref_shim_cv/eigenshim.hpp",
+                         "plane_oracle.cpp", "orb_oracle.cpp", "msl_oracle.h"]),
 }
 
 
 def build_ref(force=False, name="libsurfel_ref.so"):
     """oracle/_ref/<name>: one of the reference's own source files compiled where it lies, unmodified, against stand-in
     headers (libsurfel_ref.so: src/SurfelFusion.cpp, see oracle/ref_wrap.cpp; liborb_ref.so: src/ORBextractor.cc, see
-    oracle/ref_orb_wrap.cpp).  Built only where /root/reference exists; returns the path or None."""
+    oracle/ref_orb_wrap.cpp; libplane_ref.so: src/PlaneExtractor.cpp + include/peac/, see oracle/ref_plane_wrap.cpp).  Built only where /root/reference exists; returns the path or None."""
     so = os.path.join(_HERE, "_ref", name)
     ref_deps, own_deps = _REF_DEPS[name]
     if os.path.exists(os.path.join(REFERENCE_ROOT, ref_deps[0])):
@@ -580,6 +584,56 @@ class RefOrbExtractor:
 
     def level_image(self, level):
         return self._levels[level]
+
+
+_PLANE_REF = None
+
+
+def _plane_ref():
+    global _PLANE_REF
+    if _PLANE_REF is None:
+        so = build_ref(name="libplane_ref.so")
+        if so is None:
+            raise RuntimeError("oracle/_ref/libplane_ref.so is not built and /root/reference is absent")
+        L = C.CDLL(so)
+        head = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5
+        L.ref_plane_prestage.argtypes = head + [C.c_void_p] * 4
+        L.ref_plane_run.argtypes = head + [C.c_void_p] * 5 + [C.c_int]
+        _PLANE_REF = L
+    return _PLANE_REF
+
+
+def ref_plane_prestage(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0):
+    """plane_prestage() computed by the reference's own src/PlaneExtractor.cpp + include/peac/ (oracle/_ref/libplane_ref.so,
+    see oracle/ref_plane_wrap.cpp): same outputs, center / normal of blocks with N < 4 returned as 0."""
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    h, w = depth_u16.shape
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    nb = (h2 // 10) * (w2 // 10)
+    cloud, blocks = np.zeros((h2, w2, 3), np.float64), np.zeros(nb, BLOCK_DTYPE)
+    seed, edges = np.zeros(nb, np.uint8), np.zeros(nb, np.uint8)
+    rc = _plane_ref().ref_plane_prestage(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor,
+                                         _p(cloud), _p(blocks), _p(seed), _p(edges))
+    if rc != 0:
+        raise RuntimeError("reference plane pre-stage failed (%d)" % rc)
+    return cloud, blocks, seed, edges
+
+
+def ref_plane_run(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0, cap=64):
+    """Frame::ExtractPlanes' readColorImage / readDepthImage / runPlaneDetection (src/Frame.cc:607-609) by the reference's own
+    code -> (membershipImg[h2,w2] i32, dict(normal, center, N, vertices) of the extracted planes)"""
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    h, w = depth_u16.shape
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    mem = np.zeros((h2, w2), np.int32)
+    nrm, cen = np.zeros((cap, 3)), np.zeros((cap, 3))
+    N, nv = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    n = _plane_ref().ref_plane_run(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor,
+                                   _p(mem), _p(nrm), _p(cen), _p(N), _p(nv), cap)
+    if n < 0:
+        raise RuntimeError("reference plane detection failed (%d)" % n)
+    n = min(n, cap)
+    return mem, dict(normal=nrm[:n], center=cen[:n], N=N[:n], vertices=nv[:n])
 
 
 class RefSurfelFusion:

@@ -20,39 +20,7 @@
 #include <new>
 #include <vector>
 
-#include <sys/mman.h>
-
-// ---- bump arena (only while g_arena_on) ----
-static unsigned char *g_arena = nullptr;
-static size_t g_arena_cap = 0, g_arena_top = 0;
-static bool g_arena_on = false, g_arena_overflow = false;
-
-static void *arena_alloc(size_t n) {
-    if (g_arena_on) {
-        size_t at = (g_arena_top + 15) & ~(size_t)15;
-        if (at + n <= g_arena_cap) {
-            g_arena_top = at + n;
-            return g_arena + at;
-        }
-        g_arena_overflow = true;
-    }
-    void *p = malloc(n ? n : 1);
-    if (!p) throw std::bad_alloc();
-    return p;
-}
-static void arena_free(void *p) noexcept {
-    if (!p) return;
-    if (g_arena && (unsigned char *)p >= g_arena && (unsigned char *)p < g_arena + g_arena_cap) return;  // never reused
-    free(p);
-}
-// hidden: these replace operator new/delete for THIS library only (the templates of the reference are instantiated here)
-#define HID __attribute__((visibility("hidden")))
-HID void *operator new(size_t n) { return arena_alloc(n); }
-HID void *operator new[](size_t n) { return arena_alloc(n); }
-HID void operator delete(void *p) noexcept { arena_free(p); }
-HID void operator delete[](void *p) noexcept { arena_free(p); }
-HID void operator delete(void *p, size_t) noexcept { arena_free(p); }
-HID void operator delete[](void *p, size_t) noexcept { arena_free(p); }
+#include "ref_arena.hpp"
 
 #include <opencv2/core/core.hpp>
 
@@ -67,17 +35,7 @@ struct ref_keypoint {  // = orc_keypoint
 
 static int run(int use_arena, int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, const uint8_t *gray,
                int w, int h, int stride, ref_keypoint *kps, uint8_t *desc, int cap, int32_t *level_wh, uint8_t *pyramid) {
-    if (use_arena) {
-        if (!g_arena) {
-            g_arena_cap = (size_t)1 << 31;  // virtual; pages are touched on use
-            void *m = mmap(nullptr, g_arena_cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-            if (m == MAP_FAILED) return -2;
-            g_arena = (unsigned char *)m;
-        }
-        g_arena_top = 0;
-        g_arena_overflow = false;
-        g_arena_on = true;
-    }
+    if (use_arena && ref_arena_begin() != 0) return -2;
     int n = 0;
     {
         ORB_SLAM2::ORBextractor ext(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST);
@@ -99,12 +57,7 @@ static int run(int use_arena, int nfeatures, float scaleFactor, int nlevels, int
                 for (int y = 0; y < m.rows; y++, off += m.cols) memcpy(pyramid + off, m.ptr(y), m.cols);
         }
     }
-    if (use_arena) {
-        g_arena_on = false;
-        if (g_arena_overflow) return -3;
-        // give the touched pages back so that a long test session does not accumulate resident memory
-        madvise(g_arena, (g_arena_top + 4095) & ~(size_t)4095, MADV_DONTNEED);
-    }
+    if (use_arena && ref_arena_end() != 0) return -3;
     return n;
 }
 

@@ -93,13 +93,43 @@ public:
 };
 typedef Rect_<int> Rect;
 
-template <typename T, int n> struct Vec {
+template <typename T, int n> class Vec {
+public:
     T val[n];
+    Vec() {
+        for (int i = 0; i < n; i++) val[i] = T(0);
+    }
+    Vec(T a, T b) : Vec() { val[0] = a, val[1] = b; }
+    Vec(T a, T b, T c) : Vec() { val[0] = a, val[1] = b, val[2] = c; }
+    explicit Vec(const T *p) {
+        for (int i = 0; i < n; i++) val[i] = p[i];
+    }
+    template <typename U> Vec(const Vec<U, n> &o) {
+        for (int i = 0; i < n; i++) val[i] = (T)o.val[i];
+    }
     T &operator[](int i) { return val[i]; }
     const T &operator[](int i) const { return val[i]; }
 };
 typedef Vec<uchar, 3> Vec3b;
 typedef Vec<double, 3> Vec3d;
+typedef Vec<double, 2> Vec2d;
+typedef Vec<double, 4> Scalar;
+
+template <typename T> class Point3_ {
+public:
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T _x, T _y, T _z) : x(_x), y(_y), z(_z) {}
+};
+typedef Point3_<double> Point3d;
+typedef Point3_<float> Point3f;
+
+class Range {
+public:
+    int start, end;
+    Range() : start(0), end(0) {}
+    Range(int s, int e) : start(s), end(e) {}
+};
 
 class KeyPoint {
 public:
@@ -178,6 +208,19 @@ public:
         m.cols = r.width;
         return m;
     }
+    Mat operator()(const Range &rr, const Range &cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
+    bool isContinuous() const { return (size_t)step == (size_t)cols * elemSize() || rows <= 1; }
+    template <typename T> Mat &setTo(const T &v) {  // every element of this header's window (sizeof(T) == elemSize())
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) *(T *)(data + (size_t)i * step + (size_t)j * sizeof(T)) = v;
+        return *this;
+    }
+    // cv::Mat::at(int i0) on a 2-D matrix: flat element index when continuous (or a single row), else (i0 / cols, i0 % cols)
+    template <typename T> T &at(int i0) {
+        if (isContinuous()) return ((T *)data)[i0];
+        return at<T>(i0 / cols, i0 % cols);
+    }
+    template <typename T> const T &at(int i0) const { return const_cast<Mat *>(this)->at<T>(i0); }
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     template <typename T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
@@ -259,5 +302,8 @@ static inline void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double sig
 }
 
 static inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+static inline int64_t getTickCount() { return 0; }
+static inline double getTickFrequency() { return 1.0; }
 
 }  // namespace cv

@@ -1,0 +1,3 @@
+// Stand-in header (TEST INFRASTRUCTURE): see ../cvshim.hpp / ../../cvshim.hpp
+#pragma once
+#include "cvshim.hpp"

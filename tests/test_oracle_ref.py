@@ -197,3 +197,76 @@ def test_orb_heap_address_tiebreak_is_the_only_freedom(ref_orb):
     assert len(sa & sm) > 0.95 * len(sa)
     # ... and when it does, only whole keypoints are swapped (a keypoint present in both has identical fields)
     assert abs(len(ka) - len(km)) <= 16
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Plane pre-stage: the oracle restatement against the reference's own src/PlaneExtractor.cpp + include/peac/
+# (oracle/_ref/libplane_ref.so, oracle/ref_plane_wrap.cpp).  OpenCV is a pixel container there; the one Eigen algorithm
+# (SelfAdjointEigenSolver<Matrix3d>) is the oracle's Jacobi solver on both sides.  Bit for bit.
+
+@pytest.fixture(scope="module")
+def ref_plane(oracle):
+    if oracle.build_ref(name="libplane_ref.so") is None:
+        pytest.skip("oracle/_ref/libplane_ref.so not built and /root/reference absent")
+    return oracle
+
+
+def _plane_same(B, d16, K, fac):
+    co, bo, so, eo = B.plane_prestage(d16, K=K, depth_map_factor=fac)
+    cr, br, sr, er = B.ref_plane_prestage(d16, K=K, depth_map_factor=fac)
+    assert co.tobytes() == cr.tobytes()  # readDepthImage, src/PlaneExtractor.cpp:44-76
+    assert np.array_equal(bo["N"], br["N"]) and np.array_equal(bo["nouse"], br["nouse"])
+    v = br["N"] >= 4  # center / normal of a rejected block are indeterminate in the reference
+    for f in ("center", "normal", "mse", "curvature"):
+        assert np.array_equal(bo[f][v].view(np.uint64), br[f][v].view(np.uint64)), f
+    assert np.isnan(br["mse"][~v]).all() and np.isnan(bo["mse"][~v]).all()
+    assert not (er & 16).any()  # only 4-neighbour edges exist after initGraph
+    assert np.array_equal(so, sr) and np.array_equal(eo, er)
+    return so, eo
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("fac", [1.0 / 5000.0, 1.0])
+def test_plane_prestage_matches_reference_source(ref_plane, seed, fac):
+    """fac = 1/5000 is TUM's DepthMapFactor (metres: every block passes the millimetre-scaled T_mse); fac = 1 keeps the
+    synthetic depth in millimetres, the unit peac's thresholds assume, so that the seed test and T_ang really decide"""
+    d16, _ = S.depth_frame(seed)
+    so, eo = _plane_same(ref_plane, d16, S.K_DEFAULT, fac)
+    assert 100 < so.sum() < 768 and (eo > 0).sum() > 100
+
+
+@pytest.mark.parametrize("w,h", [(320, 240), (646, 486), (1280, 960), (652, 492)])
+def test_plane_prestage_other_sizes_match_reference_source(ref_plane, w, h):
+    """odd half sizes: ceil(cols / 2) columns, blocks only where a whole 10x10 window fits, neighbours in the partial rim"""
+    K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+    d16, _ = S.depth_frame(60 + w % 5, w, h, K=K)
+    _plane_same(ref_plane, d16, K, 1.0)
+
+
+def test_plane_prestage_degenerate_depth_matches_reference_source(ref_plane):
+    """all-zero depth (every block rejected), a constant plane, and a frame with a hole in every block"""
+    z = np.zeros((480, 640), np.uint16)
+    so, _ = _plane_same(ref_plane, z, S.K_DEFAULT, 1.0)
+    assert so.sum() == 0
+    so, eo = _plane_same(ref_plane, np.full((480, 640), 1500, np.uint16), S.K_DEFAULT, 1.0)
+    assert so.all()
+    holes = np.full((480, 640), 1500, np.uint16)
+    holes[::20, ::20] = 0
+    so, _ = _plane_same(ref_plane, holes, S.K_DEFAULT, 1.0)
+    assert so.sum() == 0
+
+
+def test_reference_peac_membership_has_trail_counters(ref_plane):
+    """the reference's own ahCluster + refineDetails on a synthetic room: plane ids >= 0, -1, and floodFill's <= -2
+    trail counters (include/peac/AHCPlaneFitter.hpp:463-467) all occur -- the value set SurfelFusion's `!= -1` test
+    (src/SurfelFusion.cpp:541) has to treat as 'in a plane'"""
+    d16, _ = S.depth_frame(2)
+    mem, planes = ref_plane.ref_plane_run(d16, depth_map_factor=1.0)
+    assert mem.shape == (240, 320) and len(planes["N"]) >= 2
+    assert (np.diff(planes["N"]) <= 0).all()  # sorted by size, descending
+    vals = set(np.unique(mem).tolist())
+    assert -1 in vals and 0 in vals and min(vals) <= -2 and min(vals) >= -5
+    # plane_vertices_[i] = the pixels labelled i
+    for i, n in enumerate(planes["vertices"]):
+        assert (mem == i).sum() == n
+    assert np.allclose(np.linalg.norm(planes["normal"], axis=1), 1.0, atol=1e-9)
