@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--surfels", type=int, default=5_000_000, help="surfels in the local map per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--widened-only", action="store_true", help="internal: print the `widened` object alone (run_ours calls "
+                    "this in a child process so that a fault in a diagnostic can never take the bench line down)")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
     ap.add_argument("--only", default="", help="diagnostic: comma list of stages (orb,match,plane,surfel) the device-resident "
                                                "step runs; the default (empty) is the full front-end -- anything else is not a bench value")
@@ -246,6 +248,28 @@ def widened_ops(msl, reps=20):
         m.close()
         return res
     except Exception as e:  # noqa: BLE001 -- diagnostics only: never take the bench line down
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def widened_in_child(device, timeout_s=180):
+    """widened_ops in a child process with a deadline: the diagnostics exercise kernels outside the timed step, and neither
+    a device fault nor a hang there may cost the bench line."""
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+    if not env["CUDA_VISIBLE_DEVICES"]:
+        env["CUDA_VISIBLE_DEVICES"] = str(device)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--widened-only"], env=env, capture_output=True,
+                           text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after %d s" % timeout_s}
+    except Exception as e:  # noqa: BLE001
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
@@ -516,7 +540,7 @@ def run_ours(a, rank, world, local_rank):
                "sample": "%d frames (%.1f s): oracle ORB + plane pre-stage + Hamming match frame-parallel on %d threads, oracle "
                          "SurfelFusion with 10 scan threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
 
-    widened = widened_ops(msl) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+    widened = widened_in_child(local_rank) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -539,6 +563,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.widened_only:
+        import manhattanslam_b200 as msl
+        print(json.dumps(widened_ops(msl)))
+        return
     if a.impl == "reference":
         run_reference(a, rank, world)
         return
