@@ -65,8 +65,13 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+_LIB_OVERRIDE = None
+
+
 def lib():
     global _LIB
+    if _LIB_OVERRIDE is not None:
+        return _LIB_OVERRIDE
     if _LIB is None:
         L = C.CDLL(build())
         L.orc_orb_create.restype = C.c_void_p
@@ -522,6 +527,10 @@ _REF_DEPS = {
                          "include/peac/AHCPlaneSeg.hpp", "include/peac/AHCParamSet.hpp", "include/peac/eig33sym.hpp"],
                         ["ref_plane_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "ref_shim_cv/eigenshim.hpp",
                          "plane_oracle.cpp", "orb_oracle.cpp", "msl_oracle.h"]),
+    "libmatch_ref.so": (["src/ORBmatcher.cc", "include/ORBmatcher.h", "Thirdparty/DBoW2/DBoW2/FeatureVector.cpp",
+                         "Thirdparty/DBoW2/DBoW2/FeatureVector.h"],
+                        ["ref_match_wrap.cpp", "ref_shim_cv/cvshim.hpp", "ref_shim_match/slam_standins.hpp", "match_oracle.cpp",
+                         "orb_oracle.cpp", "msl_oracle.h"]),
 }
 
 
@@ -584,6 +593,70 @@ class RefOrbExtractor:
 
     def level_image(self, level):
         return self._levels[level]
+
+
+class _RefMatchProxy:
+    """orc_search_* -> ref_search_* of oracle/_ref/libmatch_ref.so (same flat signatures, see oracle/ref_match_wrap.cpp)"""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        if not name.startswith("orc_search_"):
+            raise AttributeError(name)
+        return getattr(self._L, "ref_" + name[4:])
+
+
+_MATCH_REF = None
+
+
+def _match_ref():
+    global _MATCH_REF
+    if _MATCH_REF is None:
+        so = build_ref(name="libmatch_ref.so")
+        if so is None:
+            raise RuntimeError("oracle/_ref/libmatch_ref.so is not built and /root/reference is absent")
+        _MATCH_REF = C.CDLL(so)
+    return _MATCH_REF
+
+
+class reference_matcher:
+    """context manager: inside it search_by_projection_frame / _points / _keyframe, search_by_bow and
+    search_for_triangulation of this module run the REFERENCE's own src/ORBmatcher.cc (oracle/_ref/libmatch_ref.so)
+    instead of the oracle restatement.  Slots the oracle reports as -3 (assigned, then reset by the rotation check) come
+    back as -1 -- the reference stores NULL for both.  Used by tests/test_oracle_ref.py, nowhere else."""
+
+    def __enter__(self):
+        global _LIB_OVERRIDE
+        _LIB_OVERRIDE = _RefMatchProxy(_match_ref())
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB_OVERRIDE
+        _LIB_OVERRIDE = None
+        return False
+
+
+def ref_descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return _match_ref().ref_descriptor_distance(_p(a), _p(b))
+
+
+def ref_fuse(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf):
+    """ORBmatcher::Fuse of the reference's own source on the arguments of fuse_search -> (nFused, fused_idx per map point:
+    the KeyFrame keypoint the map point was added at, -1 if it was not fused)"""
+    L = _match_ref()
+    L.ref_fuse.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int] + [C.c_void_p] * 5 +
+                           [C.c_int] + [C.c_void_p] * 4 + [C.c_void_p])
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    ils = a(inv_level_sigma2, np.float32)
+    margs = [a(mps["valid"], np.uint8), a(mps["world"], np.float32), a(mps["normal"], np.float32), a(mps["dist"], np.float32),
+             a(mps["desc"], np.uint8)]
+    kargs = [a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["uright"], np.float32), a(kf["desc"], np.uint8)]
+    fi = np.zeros(len(margs[0]), np.int32)
+    n = L.ref_fuse(_p(geom), _p(a(Tcw, np.float32)), th, log_scale_factor, _p(ils), len(margs[0]), *[_p(x) for x in margs],
+                   len(kargs[1]), *[_p(x) for x in kargs], _p(fi))
+    return n, fi
 
 
 _PLANE_REF = None

@@ -148,6 +148,10 @@ struct MatStep {
     operator size_t() const { return v; }
 };
 
+class Mat;
+struct MatExprT;    // alpha * A.t()
+struct MatExprMul;  // alpha * op(A) * B
+
 struct MatZeros {  // the MatExpr of Mat::zeros
     int rows, cols, type;
 };
@@ -164,6 +168,11 @@ public:
         step = stepBytes ? stepBytes : (size_t)c * elemSize();
     }
     Mat(const MatZeros &z) : Mat() { *this = z; }
+    Mat(const MatExprMul &e);  // evaluates the product (below)
+    Mat row(int i) const { return (*this)(Rect(0, i, cols, 1)); }
+    Mat col(int j) const { return (*this)(Rect(j, 0, 1, rows)); }
+    MatExprT t() const;
+    double dot(const Mat &o) const;
     static MatZeros zeros(int r, int c, int type) { return MatZeros{r, c, type}; }
     Mat &operator=(const MatZeros &z) {
         create(z.rows, z.cols, z.type);  // keeps a matching buffer, like cv::Mat::create
@@ -234,6 +243,69 @@ private:
     int type_;
     std::shared_ptr<uchar> hold_;
 };
+
+// ---- cv::Mat arithmetic of src/ORBmatcher.cc: CV_32F pose products only (3x3 by 3x1) ----
+// cv::MatExpr folds `A * B + C` into ONE cv::gemm(A, B, 1, C, 1) and `-A.t() * B` into cv::gemm(A, B, -1, noArray(), 0,
+// GEMM_1_T); which arithmetic those take (small-matrix path with float row sums vs the general path with double
+// accumulation) is pinned against cv2.gemm by tests/test_oracle_primitives.py::test_cv_gemm_semantics, and evaluated here
+// by the same oracle primitives (orc_cv_rx_plus_t, orc_cv_neg_rt_times_t).
+struct MatExprT {
+    Mat a;
+    double alpha;
+};
+struct MatExprMul {
+    Mat a, b;
+    double alpha;
+    bool ta;
+};
+inline MatExprT Mat::t() const { return MatExprT{*this, 1.0}; }
+static inline MatExprT operator-(const MatExprT &e) { return MatExprT{e.a, -e.alpha}; }
+static inline MatExprMul operator*(const Mat &a, const Mat &b) { return MatExprMul{a, b, 1.0, false}; }
+static inline MatExprMul operator*(const MatExprT &a, const Mat &b) { return MatExprMul{a.a, b, a.alpha, true}; }
+static inline void mat33_31(const Mat &a, const Mat &b, float R[9], float x[3]) {
+    assert(a.type() == CV_32FC1 && b.type() == CV_32FC1 && a.rows == 3 && a.cols == 3 && b.rows == 3 && b.cols == 1);
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) R[3 * i + j] = a.at<float>(i, j);
+        x[i] = b.at<float>(i, 0);
+    }
+}
+static inline Mat mat31(const float v[3]) {
+    Mat m(3, 1, CV_32FC1);
+    for (int i = 0; i < 3; i++) m.at<float>(i, 0) = v[i];
+    return m;
+}
+static inline Mat operator+(const MatExprMul &e, const Mat &c) {  // A * B + C
+    assert(!e.ta && e.alpha == 1.0 && c.rows == 3 && c.cols == 1);
+    float R[9], x[3], t[3], o[3];
+    mat33_31(e.a, e.b, R, x);
+    for (int i = 0; i < 3; i++) t[i] = c.at<float>(i, 0);
+    orc_cv_rx_plus_t(R, x, t, o);
+    return mat31(o);
+}
+inline Mat::Mat(const MatExprMul &e) : Mat() {  // -A.t() * B (the only bare product the reference forms)
+    assert(e.ta && e.alpha == -1.0);
+    float R[9], x[3], o[3];
+    mat33_31(e.a, e.b, R, x);
+    orc_cv_neg_rt_times_t(R, x, o);
+    *this = mat31(o);
+}
+static inline Mat operator-(const Mat &a, const Mat &b) {  // 3x1 float difference
+    assert(a.rows == 3 && a.cols == 1 && b.rows == 3 && b.cols == 1);
+    float o[3];
+    for (int i = 0; i < 3; i++) o[i] = a.at<float>(i, 0) - b.at<float>(i, 0);
+    return mat31(o);
+}
+static inline double norm(const Mat &a) {  // NORM_L2 of a 3x1 float vector: squares accumulated in double
+    float v[3];
+    for (int i = 0; i < 3; i++) v[i] = a.at<float>(i, 0);
+    return orc_cv_norm3(v);
+}
+// cv::Mat::dot on three floats: double products, double accumulation (no Python binding to pin it; the oracle's convention)
+inline double Mat::dot(const Mat &o) const {
+    double s = 0;
+    for (int i = 0; i < 3; i++) s += (double)at<float>(i, 0) * (double)o.at<float>(i, 0);
+    return s;
+}
 
 class _InputArray {
 public:

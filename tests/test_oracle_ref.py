@@ -270,3 +270,122 @@ def test_reference_peac_membership_has_trail_counters(ref_plane):
     for i, n in enumerate(planes["vertices"]):
         assert (mem == i).sum() == n
     assert np.allclose(np.linalg.norm(planes["normal"], axis=1), 1.0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ORBmatcher: the oracle restatements against the reference's own src/ORBmatcher.cc (oracle/_ref/libmatch_ref.so,
+# oracle/ref_match_wrap.cpp): compiled unmodified on top of data-only MapPoint / KeyFrame / Frame stand-ins
+# (oracle/ref_shim_match/slam_standins.hpp) whose grid query is the oracle's; the cv::Mat pose products are the oracle's
+# cv2-pinned gemm primitives.  Projections, windows, level rules, ratio tests, slot blocking, rotation histograms, the
+# epipolar test and the chi-square gates are the reference's own code.  Match tables and counts must be identical.
+
+@pytest.fixture(scope="module")
+def ref_match(oracle):
+    if oracle.build_ref(name="libmatch_ref.so") is None:
+        pytest.skip("oracle/_ref/libmatch_ref.so not built and /root/reference absent")
+    return oracle
+
+
+def _null(a):
+    """the reference stores NULL where the oracle records -3 (assigned, then reset by the rotation check)"""
+    a = a.copy()
+    a[a == -3] = -1
+    return a
+
+
+_LSF = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+
+
+def test_descriptor_distance_matches_reference_source(ref_match):
+    r = np.random.default_rng(1)
+    d = r.integers(0, 256, (200, 32), dtype=np.uint8)
+    d[0], d[1] = 0, 255
+    for i in range(0, 200, 2):
+        assert ref_match.ref_descriptor_distance(d[i], d[i + 1]) == ref_match.descriptor_distance(d[i], d[i + 1])
+    assert ref_match.ref_descriptor_distance(d[0], d[1]) == 256
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 11])
+def test_search_by_projection_frame_matches_reference_source(ref_match, seed):
+    """src/ORBmatcher.cc:548-678; the seeds cover bForward, bBackward and neither"""
+    from manhattanslam_b200.matcher import frame_geom
+    B = ref_match
+    cur, last, _, Tc, Tl = S.match_scene(seed)
+    for th in (15.0, 7.0):
+        for chk in (False, True):
+            n, cm = B.search_by_projection_frame(frame_geom(), Tc, Tl, th, chk, last, cur)
+            with B.reference_matcher():
+                nr, cr = B.search_by_projection_frame(frame_geom(), Tc, Tl, th, chk, last, cur)
+            assert n == nr and np.array_equal(_null(cm), cr)
+            assert n > 100
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_search_by_projection_points_matches_reference_source(ref_match, seed):
+    """src/ORBmatcher.cc:40-124 (th == 1 takes the bFactor == false branch)"""
+    from manhattanslam_b200.matcher import frame_geom
+    B = ref_match
+    cur, _, mps, _, _ = S.match_scene(seed)
+    for th, ratio in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+        n, cm = B.search_by_projection_points(frame_geom(), th, ratio, mps, cur)
+        with B.reference_matcher():
+            nr, cr = B.search_by_projection_points(frame_geom(), th, ratio, mps, cur)
+        assert n == nr and np.array_equal(_null(cm), cr)
+        assert n > 100
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_search_by_projection_keyframe_matches_reference_source(ref_match, seed):
+    """src/ORBmatcher.cc:680-797 incl. MapPoint::PredictScale and the distance-invariance range"""
+    from manhattanslam_b200.matcher import frame_geom
+    B = ref_match
+    cur, kf, Tc = S.reloc_scene(seed)
+    for th, od in ((15.0, 100), (10.0, 64)):
+        for chk in (False, True):
+            n, cm = B.search_by_projection_keyframe(frame_geom(), Tc, th, od, chk, _LSF, kf, cur)
+            with B.reference_matcher():
+                nr, cr = B.search_by_projection_keyframe(frame_geom(), Tc, th, od, chk, _LSF, kf, cur)
+            assert n == nr and np.array_equal(_null(cm), cr)
+            assert n > 100
+
+
+@pytest.mark.parametrize("seed,shuffle", [(0, False), (1, True), (2, False), (32, True)])
+def test_search_by_bow_matches_reference_source(ref_match, seed, shuffle):
+    """src/ORBmatcher.cc:146-255 with the real DBoW2::FeatureVector (Thirdparty/DBoW2) built from the CSR arrays"""
+    B = ref_match
+    kf, f = S.bow_scene(seed, shuffle=shuffle)
+    for ratio in (0.7, 0.9):
+        for chk in (False, True):
+            n, fm = B.search_by_bow(ratio, chk, kf, f)
+            with B.reference_matcher():
+                nr, fr = B.search_by_bow(ratio, chk, kf, f)
+            assert n == nr and np.array_equal(_null(fm), fr)
+            assert n > 100
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 41])
+def test_search_for_triangulation_matches_reference_source(ref_match, seed):
+    """src/ORBmatcher.cc:257-406 + CheckDistEpipolarLine :127-144"""
+    B = ref_match
+    kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(seed)
+    for only_stereo in (False, True):
+        for chk in (False, True):
+            n, m = B.search_for_triangulation(F12, Cw1, Tcw2, K2, only_stereo, chk, sf, ls, kf1, kf2)
+            with B.reference_matcher():
+                nr, mr = B.search_for_triangulation(F12, Cw1, Tcw2, K2, only_stereo, chk, sf, ls, kf1, kf2)
+            assert n == nr and np.array_equal(_null(m), mr)
+            assert n > 30
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 51])
+def test_fuse_matches_reference_source(ref_match, seed):
+    """src/ORBmatcher.cc:408-519: the reference only exposes which keypoint a map point was fused at (AddObservation) --
+    the oracle's (best_idx if best_dist <= TH_LOW) -- and the count"""
+    from manhattanslam_b200.matcher import frame_geom
+    B = ref_match
+    mps, kf, Tcw, ils = S.fuse_scene(seed)
+    for th in (3.0, 5.0):
+        n, bi, bd = B.fuse_search(frame_geom(), Tcw, th, _LSF, ils, mps, kf)
+        nr, fi = B.ref_fuse(frame_geom(), Tcw, th, _LSF, ils, mps, kf)
+        assert n == nr and np.array_equal(np.where(bd <= 50, bi, -1), fi)
+        assert n > 100
