@@ -8,14 +8,23 @@
  * include/) may include, link or call it.
  *
  * Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
- * section 4) and cannot be compiled here (needs OpenCV/Eigen C++ headers), so
- * the third-party primitives restated here (cv::FAST, cv::resize INTER_LINEAR
- * 8U, cv::GaussianBlur 7x7 8U, cv::fastAtan2) are pinned bit-exactly against
- * Python cv2 4.13.0 in tests/test_oracle_primitives.py and through committed
- * fixtures in tests/golden/.  Everything above the primitives (octree cull,
- * superpixels, surfel fusion, peac block statistics, grid search) follows the
- * reference source line by line; those stages are "parity unpinned" by any
- * reference-side test because none exists.
+ * section 4) and cannot be built as a whole here (no OpenCV / Eigen / PCL).  Two
+ * anchors replace them:
+ *  (1) the third-party primitives restated here (cv::FAST, cv::resize INTER_LINEAR
+ *      8U, cv::GaussianBlur 7x7 8U, cv::fastAtan2, cvRound, cv::gemm / cv::norm on
+ *      3x3 / 3x1 floats, cv::cvtColor, cv::undistortPoints) are pinned bit-exactly
+ *      against Python cv2 4.13.0 in tests/test_oracle_primitives.py and through
+ *      committed fixtures in tests/golden/;
+ *  (2) everything above the primitives is pinned against the REFERENCE'S OWN
+ *      SOURCE: oracle/Makefile compiles src/ORBextractor.cc, src/ORBmatcher.cc,
+ *      src/PlaneExtractor.cpp (+ include/peac/) and src/SurfelFusion.cpp where they
+ *      lie, unmodified, against stand-in headers (oracle/ref_shim, ref_shim_cv, ref_shim_match) into
+ *      oracle/_ref/, and tests/test_oracle_ref.py requires the restatements here to
+ *      equal them bit for bit.  What the stand-ins decide -- and what therefore
+ *      stays "parity unpinned" -- is listed in DESIGN.md section 2: Eigen's
+ *      arithmetic (3x3 eigen-solver, 4x4 inverse, fixed-size products), cv::Mat::dot,
+ *      Mat::convertTo, the thread schedule of the racy `stable` flag, and heap-address
+ *      order (creation order here) where the reference sorts or iterates by pointer.
  *
  * All functions are plain C ABI so that Python ctypes can drive them.
  */
