@@ -1,6 +1,7 @@
 """CPU tests of the non-ORB oracle stages: independent cross-checks (numpy/LAPACK brute force) of the parts
 that restate third-party arithmetic, invariants of the restated reference logic, and golden vectors."""
 import os
+import sys
 
 import numpy as np
 
@@ -493,3 +494,67 @@ def test_golden_node_searches(oracle):
     assert n == int(gold["fuse_n"]) and np.array_equal(bi, gold["fuse_idx"]) and np.array_equal(bd, gold["fuse_dist"])
     ddi, ddm = oracle.distinctive_descriptors(S.observation_sets(3))
     assert np.array_equal(ddi, gold["dd_idx"]) and np.array_equal(ddm, gold["dd_median"])
+
+
+# ---- golden vectors produced by the reference's own source (tests/golden/make_golden_ref.py, oracle/_ref/*.so)
+def _ref_gold():
+    return np.load(os.path.join(GOLD, "reference_source.npz"))
+
+
+def _null3(a):
+    a = a.copy()
+    a[a == -3] = -1  # the reference stores NULL for "assigned, then reset by the rotation check"
+    return a
+
+
+def test_oracle_equals_reference_source_golden(oracle):
+    """The oracle against outputs of /root/reference/src/{ORBextractor.cc, PlaneExtractor.cpp + peac, SurfelFusion.cpp,
+    ORBmatcher.cc} compiled unmodified, committed as a fixture so that the comparison also runs
+    where /root/reference does not exist."""
+    sys.path.insert(0, GOLD)
+    import make_golden_ref as G
+    gold = _ref_gold()
+    k, d = oracle.OrbOracle()(S.gray_frame(G.ORB_SEED))
+    assert np.array_equal(k.view(np.uint8).reshape(len(k), -1), gold["orb_kps"]) and np.array_equal(d, gold["orb_desc"])
+    d16, _ = S.depth_frame(G.PLANE_SEED)
+    _, blocks, seed, edges = oracle.plane_prestage(d16, depth_map_factor=1.0)
+    gb = gold["plane_blocks"].copy().view(oracle.BLOCK_DTYPE).reshape(-1)
+    v = gb["N"] >= 4
+    assert np.array_equal(blocks["N"], gb["N"]) and np.array_equal(blocks["nouse"], gb["nouse"])
+    for f in ("center", "normal", "mse", "curvature"):
+        assert np.array_equal(blocks[f][v].view(np.uint64), gb[f][v].view(np.uint64)), f
+    assert np.array_equal(seed, gold["plane_seed"]) and np.array_equal(edges, gold["plane_edges"])
+    g, dd, m, T, local = G.surfel_inputs()
+    o = oracle.SurfelOracle()
+    lo = local.copy()
+    new = o.fuse(21, g, dd, m, T, lo)
+    assert np.array_equal(o.index(), gold["surfel_index"].astype(np.int32))
+    assert np.array_equal(o.seeds().view(np.uint8).reshape(-1, 72), gold["surfel_seeds"])
+    assert np.array_equal(lo.view(np.uint8).reshape(len(lo), -1), gold["surfel_local_after"])
+    assert np.array_equal(new.view(np.uint8).reshape(len(new), -1), gold["surfel_new"])
+    # the reference's own peac membership image (trail counters <= -2 included) as SurfelFusion's input
+    mem = gold["peac_membership"].astype(np.int32)
+    assert mem.min() <= -2 and mem.max() >= 1
+    lo2 = local.copy()
+    _, d62 = S.depth_frame(G.PLANE_SEED)
+    new2 = o.fuse(21, g, d62, mem, T, lo2)
+    assert np.array_equal(o.index(), gold["surfel_peac_index"].astype(np.int32))
+    assert np.array_equal(new2.view(np.uint8).reshape(len(new2), -1), gold["surfel_peac_new"])
+    geom = frame_geom()
+    cur, last, mps, Tc, Tl = S.match_scene(G.MATCH_SEED)
+    n, cm = oracle.search_by_projection_frame(geom, Tc, Tl, 15.0, True, last, cur)
+    assert n == int(gold["m_frame_n"]) and np.array_equal(_null3(cm), gold["m_frame"])
+    n, cm = oracle.search_by_projection_points(geom, 3.0, 0.8, mps, cur)
+    assert n == int(gold["m_points_n"]) and np.array_equal(_null3(cm), gold["m_points"])
+    cur2, kf, Tc2 = S.reloc_scene(G.MATCH_SEED)
+    n, cm = oracle.search_by_projection_keyframe(geom, Tc2, 15.0, 100, True, G.LSF, kf, cur2)
+    assert n == int(gold["m_reloc_n"]) and np.array_equal(_null3(cm), gold["m_reloc"])
+    kfb, f = S.bow_scene(G.MATCH_SEED)
+    n, fm = oracle.search_by_bow(0.7, True, kfb, f)
+    assert n == int(gold["m_bow_n"]) and np.array_equal(_null3(fm), gold["m_bow"])
+    kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(G.MATCH_SEED)
+    n, mm = oracle.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2)
+    assert n == int(gold["m_tri_n"]) and np.array_equal(_null3(mm), gold["m_tri"])
+    mpf, kfs, Tcw, ils = S.fuse_scene(G.MATCH_SEED)
+    n, bi, bd = oracle.fuse_search(geom, Tcw, 3.0, G.LSF, ils, mpf, kfs)
+    assert n == int(gold["m_fuse_n"]) and np.array_equal(np.where(bd <= 50, bi, -1), gold["m_fuse"])
