@@ -316,6 +316,23 @@ def plane_prestage(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1
     return cloud, blocks, seed, edges
 
 
+def plane_detect(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0, cap=64):
+    """The whole of ahc::PlaneFitter::run (pre-stage + ahCluster + refineDetails, SURVEY.md section 8 f2) ->
+    (membershipImg[h2,w2] i32, dict(normal, center, N, rid, vertices) of the extracted planes)"""
+    L = lib()
+    L.orc_plane_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p] * 6 + [C.c_int]
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    h, w = depth_u16.shape
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    mem = np.zeros((h2, w2), np.int32)
+    nrm, cen = np.zeros((cap, 3)), np.zeros((cap, 3))
+    N, rid, nv = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    n = L.orc_plane_detect(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor,
+                           _p(mem), _p(nrm), _p(cen), _p(N), _p(rid), _p(nv), cap)
+    n = min(n, cap)
+    return mem, dict(normal=nrm[:n], center=cen[:n], N=N[:n], rid=rid[:n], vertices=nv[:n])
+
+
 def eig33sym(K):
     lib().orc_eig33sym.argtypes = [C.c_void_p] * 3
     K = np.ascontiguousarray(K, np.float64).reshape(9)

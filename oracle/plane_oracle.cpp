@@ -12,6 +12,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <queue>
+#include <set>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -78,14 +82,10 @@ void eig33sym(const double K[9], double s[3], double V[9]) {
     }
 }
 
-}  // namespace
 
-extern "C" {
-
-void orc_eig33sym(const double K[9], double s[3], double V[9]) { eig33sym(K, s, V); }
-
-void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px, float fx, float fy, float cx, float cy,
-                        float depthMapFactor, double *cloud_xyz, orc_block_stat *blocks, uint8_t *seed, uint8_t *edges) {
+// P1-P5; sums9 (optional): the nine running sums of Stats per block (sx sy sz sxx syy szz sxy syz sxz), 0 for rejected blocks
+void prestage(const uint16_t *depth, int w, int h, int dstride_px, float fx, float fy, float cx, float cy, float depthMapFactor,
+              double *cloud_xyz, orc_block_stat *blocks, uint8_t *seed, uint8_t *edges, std::vector<double> *sums9) {
     const int W2 = (int)std::ceil(w / 2.0), H2 = (int)std::ceil(h / 2.0);
     std::vector<double> cloudLocal;
     double *cloud = cloud_xyz;
@@ -113,6 +113,7 @@ void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px, flo
     const int Nh = H2 / windowHeight, Nw = W2 / windowWidth;
     std::vector<orc_block_stat> local((size_t)Nh * Nw);
     std::vector<uint8_t> G((size_t)Nh * Nw, 0);
+    if (sums9) sums9->assign((size_t)Nh * Nw * 9, 0.0);
     for (int bi = 0; bi < Nh; ++bi)
         for (int bj = 0; bj < Nw; ++bj) {
             // PlaneSeg ctor, AHCPlaneSeg.hpp:235-312 (INIT_STRICT)
@@ -148,6 +149,10 @@ void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px, flo
             if (windowValid) {
                 B.nouse = 0;
                 B.N = N;
+                if (sums9) {
+                    double *q = sums9->data() + 9 * (size_t)(bi * Nw + bj);
+                    q[0] = sx, q[1] = sy, q[2] = sz, q[3] = sxx, q[4] = syy, q[5] = szz, q[6] = sxy, q[7] = syz, q[8] = sxz;
+                }
             } else {
                 B.N = 0;
                 B.nouse = 1;
@@ -226,6 +231,19 @@ void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px, flo
     if (blocks) std::memcpy(blocks, local.data(), local.size() * sizeof(orc_block_stat));
     if (seed) std::memcpy(seed, G.data(), G.size());
     if (edges) std::memcpy(edges, E.data(), E.size());
+}
+
+}  // namespace
+
+#include "peac_oracle.inc"
+
+extern "C" {
+
+void orc_eig33sym(const double K[9], double s[3], double V[9]) { eig33sym(K, s, V); }
+
+void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px, float fx, float fy, float cx, float cy,
+                        float depthMapFactor, double *cloud_xyz, orc_block_stat *blocks, uint8_t *seed, uint8_t *edges) {
+    prestage(depth, w, h, dstride_px, fx, fy, cx, cy, depthMapFactor, cloud_xyz, blocks, seed, edges, nullptr);
 }
 
 }  // extern "C"

@@ -389,3 +389,55 @@ def test_fuse_matches_reference_source(ref_match, seed):
         nr, fi = B.ref_fuse(frame_geom(), Tcw, th, _LSF, ils, mps, kf)
         assert n == nr and np.array_equal(np.where(bd <= 50, bi, -1), fi)
         assert n > 100
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f2: the oracle's restatement of ahCluster + refineDetails (oracle/peac_oracle.inc) against the
+# reference's own peac (ref_plane_run: src/PlaneExtractor.cpp + include/peac/ compiled unmodified, inside the bump arena).
+
+def _peac_same(B, d16, K=S.K_DEFAULT, fac=1.0):
+    mo, po = B.plane_detect(d16, K=K, depth_map_factor=fac)
+    mr, pr = B.ref_plane_run(d16, K=K, depth_map_factor=fac)
+    assert np.array_equal(mo, mr)                      # PlaneFitter::membershipImg, trail counters included
+    assert np.array_equal(po["N"], pr["N"]) and np.array_equal(po["vertices"], pr["vertices"])
+    assert po["normal"].tobytes() == pr["normal"].tobytes() and po["center"].tobytes() == pr["center"].tobytes()
+    return mo, po
+
+
+@pytest.mark.parametrize("seed0", [0, 10, 20, 30])
+def test_peac_cluster_and_refine_match_reference_source(ref_plane, seed0):
+    nplanes = []
+    for seed in range(seed0, seed0 + 10):
+        d16, _ = S.depth_frame(seed)
+        mem, planes = _peac_same(ref_plane, d16)
+        nplanes.append(len(planes["N"]))
+        assert mem.min() >= -6
+    assert max(nplanes) >= 2  # multi-plane scenes were among them
+
+
+def test_peac_in_metres_and_other_sizes_match_reference_source(ref_plane):
+    """depth in metres (TUM's factor: every block passes the millimetre-scaled thresholds, one huge plane or none) and
+    image sizes whose half resolution is not a multiple of the 10x10 window"""
+    for seed in (1, 2, 3):
+        d16, _ = S.depth_frame(seed)
+        _peac_same(ref_plane, d16, fac=1.0 / 5000.0)
+    for (w, h) in ((320, 240), (646, 486), (1280, 960)):
+        K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+        d16, _ = S.depth_frame(70 + w % 7, w, h, K=K)
+        _peac_same(ref_plane, d16, K=K)
+
+
+def test_peac_degenerate_depth_matches_reference_source(ref_plane):
+    """no valid block at all; one perfect plane (mse == 0 everywhere: the exact-tie rules of the queue and of the merge
+    candidate choice decide); a frame with a hole in every block"""
+    mem, planes = _peac_same(ref_plane, np.zeros((480, 640), np.uint16))
+    assert len(planes["N"]) == 0 and (mem == -1).all()
+    mem, planes = _peac_same(ref_plane, np.full((480, 640), 1500, np.uint16))
+    assert len(planes["N"]) == 1 and planes["N"][0] == 76800
+    holes = np.full((480, 640), 1500, np.uint16)
+    holes[::20, ::20] = 0
+    _peac_same(ref_plane, holes)
+    two = np.full((480, 640), 1500, np.uint16)  # two fronto-parallel planes with a depth step: two components
+    two[:, 320:] = 2500
+    mem, planes = _peac_same(ref_plane, two)
+    assert len(planes["N"]) == 2
