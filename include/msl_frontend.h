@@ -292,6 +292,34 @@ int msl_plane_prestage_dev(msl_plane *, const uint16_t *d_depth, int dstride_px,
 int msl_plane_sync(msl_plane *);
 void *msl_plane_stream(msl_plane *);
 
+/* Plane detection proper: replaces PlaneDetection::runPlaneDetection (src/PlaneExtractor.cpp:78-82), i.e. the whole of
+ * ahc::PlaneFitter<ImagePointCloud>::run (include/peac/AHCPlaneFitter.hpp:207-258): the pre-stage above, ahCluster
+ * (:939-1143) and refineDetails (:294-374) with findBlockMembership (:480-582) and floodFill (:422-471), with the
+ * reference's default parameters (minSupport 3000, 10x10 windows, ERODE_ALL_BORDER, doRefine).
+ * Per frame: membership = PlaneFitter::membershipImg (h2*w2 int32: plane id, -1 = none, <= -2 = floodFill's trail
+ * counters -- what Tracking hands to SurfelFusion, src/Tracking.cc:228,497); plane_count = plane_num_; planes =
+ * plane_cap records per frame, the first min(plane_count, plane_cap) filled in extractedPlanes order (descending N):
+ * normal / center of extractedPlanes[i] (src/Frame.cc:626-632), N, rid, and vertices = plane_vertices_[i].size(); the
+ * members of plane i are the pixels whose membership equals i, in row-major order (src/Frame.cc:612-621).
+ * Frames of at most 768 blocks (640x480) are supported: MSL_ERR_INVALID otherwise.  MSL_ERR_CAPACITY if a frame
+ * exceeds the region-grow queue (4 entries per half-resolution pixel) or 128 planes. */
+typedef struct {
+    double normal[3];
+    double center[3];
+    int32_t N;        /* PlaneSeg::N (points of the merged blocks; not updated by the region grow, as in the reference) */
+    int32_t rid;      /* PlaneSeg::rid (root block id) */
+    int32_t vertices; /* number of member pixels after refinement */
+    int32_t pad;
+} msl_plane_rec;      /* 64 bytes */
+
+int msl_plane_detect(msl_plane *, const uint16_t *depth, int dstride_px, size_t frame_stride_px, int batch, const float K[4],
+                     float depth_map_factor, int32_t *membership, int32_t *plane_count, msl_plane_rec *planes, int plane_cap);
+/* device buffers in, device buffers out (enqueued on the handle's stream; errors of the frames surface at the next
+ * msl_plane_sync) */
+int msl_plane_detect_dev(msl_plane *, const uint16_t *d_depth, int dstride_px, size_t frame_stride_px, int batch,
+                         const float K[4], float depth_map_factor, int32_t *d_membership, int32_t *d_plane_count,
+                         msl_plane_rec *d_planes, int plane_cap);
+
 /* ------------------------------------------------------------------------------------- surfels
  * Replaces SurfelFusion (include/SurfelFusion.h:44-139, src/SurfelFusion.cpp), the compaction tail of
  * SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391) and SurfelMapping::moveAddSurfels (:194-304), so that

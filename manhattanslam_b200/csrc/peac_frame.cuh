@@ -1,0 +1,629 @@
+// peac_frame.cuh -- per-frame agglomerative plane clustering + refinement: the part of ahc::PlaneFitter::run that follows
+// the pre-stage.  Replaces ahCluster (include/peac/AHCPlaneFitter.hpp:939-1143) and
+// refineDetails (:294-374) with findBlockMembership (:480-582) and floodFill (:422-471), on top of PlaneSeg's merge
+// constructor / connect / disconnectAllNbs / mergeNbsFrom (include/peac/AHCPlaneSeg.hpp:321-437), Stats::compute
+// (:148-181) and DisjointSet (include/peac/DisjointSet.hpp).  Output: PlaneFitter::membershipImg and extractedPlanes.
+//
+// One CTA per frame, everything but the region grow in shared memory (196 KB):
+//   * node table: one 144-byte record per 10x10 block slot (the nine running sums, centre, normal, mse, N, rid, creation
+//     sequence).  A merged node REUSES the slot of the node that was popped from the queue (that slot is referenced
+//     nowhere else any more), so 768 slots serve the <= 1535 nodes a frame can create;
+//   * adjacency: one 768-bit mask per slot instead of std::set<PlaneSeg*>.  The reference visits neighbours in
+//     heap-address order; that order only decides EXACT mse ties between merge candidates, which are resolved here by
+//     creation sequence (what the reference does inside a bump arena, oracle/ref_arena.hpp);
+//   * min-MSE queue: a binary heap of slot ids maintained by thread 0 with libstdc++'s push_heap / pop_heap sift
+//     order, so that equal keys leave the queue in the same order as std::priority_queue;
+//   * per merge step the candidate fits (merged sums -> 3x3 scatter -> Jacobi eigen-solve) of ALL neighbours run in
+//     parallel, one thread per neighbour slot; the adjacency update runs one thread per mask row;
+//   * findBlockMembership: one thread per block; the seeds of the region grow are written in the reference's order
+//     through a per-block count + exclusive scan;
+//   * floodFill is an order-dependent FIFO (a pixel keeps the first plane that reaches it with a smaller distance, and
+//     counts failed visits in negative "trail" values): it runs on thread 0 over per-frame queues in global memory.
+//     A parallel-equivalent formulation is open;
+//   * the final merge reuses the cluster loop on the extracted planes; the plane-id remap and the per-plane pixel counts
+//     run one thread per pixel.
+// All arithmetic is fp64 in the reference's operation order (built with -fmad=false).
+//
+// The same source compiles for the host (PEAC_HOST_EMULATION: one "thread", barriers are no-ops) so that the algorithm
+// is checked against the oracle on CPU-only machines by tests/test_peac_host_emulation.py -- a test harness, not a
+// fallback: the product entry points (msl_plane_detect*) only ever launch the kernel.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__) && !defined(PEAC_HOST_EMULATION)
+#define PEAC_HD __host__ __device__ __forceinline__
+#define PEAC_D __device__
+#define PEAC_SYNC() __syncthreads()
+#define PEAC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define PEAC_UNROLL _Pragma("unroll")
+#else
+#define PEAC_HD inline
+#define PEAC_D inline
+#define PEAC_SYNC() ((void)0)
+#define PEAC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PEAC_UNROLL
+#endif
+
+namespace peac {
+
+constexpr int WIN = 10;           // windowWidth / windowHeight, AHCPlaneFitter.hpp:156-160
+constexpr int MAXB = 768;         // block slots (640x480 input: 32 x 24 blocks)
+constexpr int WORDS = MAXB / 32;  // adjacency mask words per slot
+constexpr int MAXPL = 128;        // extracted planes (>= 3000 of <= 76,800 points each: at most 25)
+constexpr int MIN_SUPPORT = 3000, MAX_STEP = 100000;  // :155-156
+#define PEAC_DEPTH_SIGMA 1.6e-6
+#define PEAC_STDTOL_MERGE 8.0
+#define PEAC_DEPTH_ALPHA 0.04
+#define PEAC_DEPTH_CHANGE_TOL 0.02
+
+struct Geo {
+    int W2, H2, Nw, Nh;
+    int dstride;  // depth row stride in pixels (full resolution)
+    float fx, fy, cx, cy, factor;
+    double thMerge, thRefine;  // cos(60 deg), cos(30 deg) evaluated on the host with std::cos (AHCParamSet.hpp:72-73)
+};
+
+struct Node {        // PlaneSeg
+    double s[9];     // Stats: sx sy sz sxx syy szz sxy syz sxz
+    double center[3], normal[3], mse;
+    int N, rid, seq, nouse;
+};
+
+struct PlaneOut {  // = msl_plane_rec
+    double normal[3], center[3];
+    int32_t N, rid, vertices, pad;
+};
+
+struct Shared {
+    Node node[MAXB];
+    uint32_t nbs[MAXB][WORDS];
+    double candMse[MAXB];  // reused as int scratch by the membership pass
+    int16_t parent[MAXB], dsize[MAXB], heap[MAXB], blkMap[MAXB];
+    uint8_t candHas[MAXB];
+    uint32_t tmpMask[WORDS];
+    int16_t extracted[MAXPL], oldPl[MAXPL], plidmap[MAXPL];
+    uint8_t valid[MAXPL];
+    int32_t count[MAXPL];
+    Node tmp;
+    int heapN, nExtracted, nOld, seqNext, step;
+    int curP, curNb, decision;  // broadcast from thread 0
+    int error;
+};
+
+enum { PEAC_OK = 0, PEAC_ERR_QUEUE = 1, PEAC_ERR_PLANES = 2 };
+
+// ---- symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations (the repository's stand-in for Eigen's solver,
+// identical operation order to oracle/plane_oracle.cpp); eigenvalues ascending, V[3 * k + i] = component k of vector i
+PEAC_HD void eig33(const double K[9], double s[3], double V[9]) {
+    double a[3][3] = {{K[0], K[1], K[2]}, {K[3], K[4], K[5]}, {K[6], K[7], K[8]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 32; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-60 || off <= 1e-34 * diag) break;
+        PEAC_UNROLL
+        for (int p = 0; p < 2; p++) {
+            PEAC_UNROLL
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                PEAC_UNROLL
+                for (int k = 0; k < 3; k++) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq;
+                    a[k][q] = sn * akp + c * akq;
+                }
+                PEAC_UNROLL
+                for (int k = 0; k < 3; k++) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk;
+                    a[q][k] = sn * apk + c * aqk;
+                }
+                PEAC_UNROLL
+                for (int k = 0; k < 3; k++) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - sn * vkq;
+                    v[k][q] = sn * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    int o0 = 0, o1 = 1, o2 = 2;
+    const double e[3] = {a[0][0], a[1][1], a[2][2]};
+    // same selection order as the oracle's exchange sort
+    if (e[o1] < e[o0]) { int t = o0; o0 = o1; o1 = t; }
+    if (e[o2] < e[o0]) { int t = o0; o0 = o2; o2 = t; }
+    if (e[o2] < e[o1]) { int t = o1; o1 = o2; o2 = t; }
+    const int ord[3] = {o0, o1, o2};
+    PEAC_UNROLL
+    for (int i = 0; i < 3; i++) {
+        s[i] = e[ord[i]];
+        PEAC_UNROLL
+        for (int k = 0; k < 3; k++) V[k * 3 + i] = v[k][ord[i]];
+    }
+}
+
+// Stats::compute, AHCPlaneSeg.hpp:148-181 (curvature is not consumed downstream)
+PEAC_HD void fit(Node &n) {
+    const double *s = n.s;
+    const double sc = 1.0 / n.N;
+    n.center[0] = s[0] * sc, n.center[1] = s[1] * sc, n.center[2] = s[2] * sc;
+    double K[9] = {s[3] - s[0] * s[0] * sc, s[6] - s[0] * s[1] * sc, s[8] - s[0] * s[2] * sc, 0, s[4] - s[1] * s[1] * sc,
+                   s[7] - s[1] * s[2] * sc, 0, 0, s[5] - s[2] * s[2] * sc};
+    K[3] = K[1], K[6] = K[2], K[7] = K[5];
+    double sv[3], V[9];
+    eig33(K, sv, V);
+    if ((V[0] * n.center[0] + V[3] * n.center[1]) + V[6] * n.center[2] <= 0) {
+        n.normal[0] = V[0], n.normal[1] = V[3], n.normal[2] = V[6];
+    } else {
+        n.normal[0] = -V[0], n.normal[1] = -V[3], n.normal[2] = -V[6];
+    }
+    n.mse = sv[0] * sc;
+}
+
+PEAC_HD double nsim(const Node &a, const Node &b) {  // normalSimilarity :349-353
+    return fabs((a.normal[0] * b.normal[0] + a.normal[1] * b.normal[1]) + a.normal[2] * b.normal[2]);
+}
+PEAC_HD double t_mse_merge(double z) {  // T_mse(P_MERGING | P_REFINE, z), AHCParamSet.hpp:94-97
+    const double v = PEAC_DEPTH_SIGMA * z * z + PEAC_STDTOL_MERGE;
+    return v * v;
+}
+// PlaneSeg(pa, pb), AHCPlaneSeg.hpp:321-343
+PEAC_HD void merged(const Node &a, const Node &b, Node &m) {
+    PEAC_UNROLL
+    for (int k = 0; k < 9; k++) m.s[k] = a.s[k] + b.s[k];
+    m.N = a.N + b.N;
+    m.rid = a.N >= b.N ? a.rid : b.rid;
+    m.nouse = 0;
+    fit(m);
+}
+
+// ImagePointCloud::get (include/PlaneExtractor.h:48-56) on the cloud of readDepthImage (src/PlaneExtractor.cpp:60-74),
+// recomputed from the depth image: row / col are half-resolution coordinates
+PEAC_HD bool point(const Geo &g, const uint16_t *depth, int row, int col, double pt[3]) {
+    const double z = (double)depth[(size_t)(2 * row) * g.dstride + 2 * col] * (double)g.factor;
+    if (z == 0) return false;
+    pt[0] = ((double)(2 * col) - (double)g.cx) * z / (double)g.fx;
+    pt[1] = ((double)(2 * row) - (double)g.cy) * z / (double)g.fy;
+    pt[2] = z;
+    return true;
+}
+
+// the nine running sums of a block in the reference's row-major order (PlaneSeg ctor, AHCPlaneSeg.hpp:235-312); only
+// called for blocks the pre-stage accepted, so the validity tests are not repeated
+PEAC_HD void block_sums(const Geo &g, const uint16_t *depth, int blk, double s[9]) {
+    const int r0 = (blk / g.Nw) * WIN, c0 = (blk % g.Nw) * WIN;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, syy = 0, szz = 0, sxy = 0, syz = 0, sxz = 0;
+    for (int i = r0; i < r0 + WIN; ++i)
+        for (int j = c0; j < c0 + WIN; ++j) {
+            double p[3] = {0, 0, 0};
+            point(g, depth, i, j, p);
+            const double x = p[0], y = p[1], z = p[2];
+            sx += x, sy += y, sz += z;
+            sxx += x * x, syy += y * y, szz += z * z;
+            sxy += x * y, syz += y * z, sxz += x * z;
+        }
+    s[0] = sx, s[1] = sy, s[2] = sz, s[3] = sxx, s[4] = syy, s[5] = szz, s[6] = sxy, s[7] = syz, s[8] = sxz;
+}
+
+// ---- adjacency masks
+PEAC_HD bool bit(const uint32_t *m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
+PEAC_HD void setbit(uint32_t *m, int i) { m[i >> 5] |= 1u << (i & 31); }
+PEAC_HD void clrbit(uint32_t *m, int i) { m[i >> 5] &= ~(1u << (i & 31)); }
+
+// ---- std::priority_queue<.., PlaneSegMinMSECmp> on slot ids: comp(a, b) = mse[b] < mse[a]; libstdc++'s sift order
+PEAC_HD bool heap_comp(const Shared &S, int a, int b) { return S.node[b].mse < S.node[a].mse; }
+PEAC_HD void heap_sift_up(Shared &S, int hole, int top, int value) {  // std::__push_heap
+    int parent = (hole - 1) / 2;
+    while (hole > top && heap_comp(S, S.heap[parent], value)) {
+        S.heap[hole] = S.heap[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    S.heap[hole] = (int16_t)value;
+}
+PEAC_HD void heap_push(Shared &S, int slot) {
+    S.heap[S.heapN] = (int16_t)slot;
+    S.heapN++;
+    heap_sift_up(S, S.heapN - 1, 0, slot);
+}
+PEAC_HD int heap_pop(Shared &S) {  // top(), then std::pop_heap + pop_back
+    const int top = S.heap[0];
+    const int last = S.heapN - 1;
+    if (last > 0) {
+        const int value = S.heap[last];
+        S.heap[last] = S.heap[0];
+        const int len = last;  // std::__adjust_heap(first, 0, len, value)
+        int hole = 0, second = 0;
+        while (second < (len - 1) / 2) {
+            second = 2 * (second + 1);
+            if (heap_comp(S, S.heap[second], S.heap[second - 1])) second--;
+            S.heap[hole] = S.heap[second];
+            hole = second;
+        }
+        if ((len & 1) == 0 && second == (len - 2) / 2) {
+            second = 2 * (second + 1);
+            S.heap[hole] = S.heap[second - 1];
+            hole = second - 1;
+        }
+        heap_sift_up(S, hole, 0, value);
+    }
+    S.heapN = last;
+    return top;
+}
+
+// ---- DisjointSet.hpp (thread 0 mutates; the read-only find is for the parallel passes)
+PEAC_HD int ds_find(Shared &S, int x) {
+    int r = x;
+    while (S.parent[r] != r) r = S.parent[r];
+    while (S.parent[x] != r) {  // path compression (the recursion of the reference leaves the same parents)
+        const int nx = S.parent[x];
+        S.parent[x] = (int16_t)r;
+        x = nx;
+    }
+    return r;
+}
+PEAC_HD int ds_find_ro(const Shared &S, int x) {
+    while (S.parent[x] != x) x = S.parent[x];
+    return x;
+}
+PEAC_HD void ds_union(Shared &S, int x, int y) {
+    const int xr = ds_find(S, x), yr = ds_find(S, y);
+    if (xr == yr) return;
+    if (S.dsize[xr] < S.dsize[yr])
+        S.parent[xr] = (int16_t)yr, S.dsize[yr] = (int16_t)(S.dsize[yr] + S.dsize[xr]);
+    else
+        S.parent[yr] = (int16_t)xr, S.dsize[xr] = (int16_t)(S.dsize[xr] + S.dsize[yr]);
+}
+
+// ---- ahCluster, AHCPlaneFitter.hpp:939-1143.  nslots = number of block slots of the frame.
+PEAC_D void cluster(Shared &S, const Geo &g, int nslots, int tid, int nt) {
+    for (;;) {
+        if (tid == 0) {
+            int p = -1;
+            while (S.heapN > 0 && S.step <= MAX_STEP) {
+                const int x = heap_pop(S);
+                if (S.node[x].nouse) continue;
+                p = x;
+                break;
+            }
+            S.curP = p;
+        }
+        PEAC_SYNC();
+        const int p = S.curP;
+        if (p < 0) break;
+        // candidate merges with every neighbour, in parallel
+        for (int k = tid; k < nslots; k += nt) {
+            S.candHas[k] = 0;
+            if (!bit(S.nbs[p], k)) continue;
+            if (nsim(S.node[p], S.node[k]) < g.thMerge) continue;
+            Node m;
+            merged(S.node[p], S.node[k], m);
+            S.candMse[k] = m.mse;
+            S.candHas[k] = 1;
+        }
+        PEAC_SYNC();
+        if (tid == 0) {
+            // :1064-1072 in neighbour order (creation sequence): the first minimum wins; on an exact tie the reference
+            // replaces the candidate iff cand->N < merge->mse
+            int best = -1;
+            for (int k = 0; k < nslots; k++)
+                if (S.candHas[k] && (best < 0 || S.candMse[k] < S.candMse[best] ||
+                                     (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq)))
+                    best = k;
+            if (best >= 0) {
+                const double mn = S.candMse[best];
+                int lastSeq = S.node[best].seq;
+                for (;;) {  // walk the tie group in creation order
+                    int nx = -1;
+                    for (int k = 0; k < nslots; k++)
+                        if (S.candHas[k] && S.candMse[k] == mn && S.node[k].seq > lastSeq && (nx < 0 || S.node[k].seq < S.node[nx].seq)) nx = k;
+                    if (nx < 0) break;
+                    lastSeq = S.node[nx].seq;
+                    if ((double)(S.node[p].N + S.node[best].N) < mn) best = nx;
+                }
+                merged(S.node[p], S.node[best], S.tmp);
+            }
+            if (best >= 0 && S.tmp.mse < t_mse_merge(S.tmp.center[2])) {
+                S.decision = 1, S.curNb = best;
+                ds_union(S, S.node[p].rid, S.node[best].rid);  // mergeNbsFrom :383
+            } else {
+                S.decision = 0;
+                if (S.node[p].N >= MIN_SUPPORT) {
+                    if (S.nExtracted < MAXPL)
+                        S.extracted[S.nExtracted++] = (int16_t)p;
+                    else
+                        S.error = PEAC_ERR_PLANES;
+                }
+            }
+        }
+        PEAC_SYNC();
+        if (S.decision) {
+            const int nb = S.curNb;
+            for (int w = tid; w < WORDS; w += nt) S.tmpMask[w] = S.nbs[p][w] | S.nbs[nb][w];
+            PEAC_SYNC();
+            if (tid == 0) clrbit(S.tmpMask, p), clrbit(S.tmpMask, nb);
+            PEAC_SYNC();
+            // disconnectAllNbs of both, then the merged node (in p's slot) becomes a neighbour of the union
+            for (int k = tid; k < nslots; k += nt) {
+                if (k == p) {
+                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = S.tmpMask[w];
+                } else if (k == nb) {
+                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = 0;
+                } else {
+                    clrbit(S.nbs[k], nb);
+                    if (bit(S.tmpMask, k))
+                        setbit(S.nbs[k], p);
+                    else
+                        clrbit(S.nbs[k], p);
+                }
+            }
+            PEAC_SYNC();
+            if (tid == 0) {
+                S.node[nb].nouse = 1;
+                S.tmp.seq = S.seqNext++;
+                S.node[p] = S.tmp;
+                heap_push(S, p);
+                S.step++;
+            }
+        } else {
+            for (int k = tid; k < nslots; k += nt) {  // p->disconnectAllNbs()
+                if (k == p) {
+                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = 0;
+                } else {
+                    clrbit(S.nbs[k], p);
+                }
+            }
+            if (tid == 0) S.step++;
+        }
+        PEAC_SYNC();
+    }
+    if (tid == 0) {
+        // std::sort(extractedPlanes, PlaneSegSizeCmp): descending N; libstdc++ insertion-sorts up to 16 elements, which
+        // keeps equal sizes in extraction order (more than 16 planes with equal sizes among them: order unpinned)
+        for (int i = 1; i < S.nExtracted; i++) {
+            const int16_t v = S.extracted[i];
+            int j = i;
+            while (j > 0 && S.node[S.extracted[j - 1]].N < S.node[v].N) {
+                S.extracted[j] = S.extracted[j - 1];
+                j--;
+            }
+            S.extracted[j] = v;
+        }
+    }
+    PEAC_SYNC();
+}
+
+PEAC_HD int nbs4(int i, int j, int Hh, int Ww, int out[4]) {  // getValid4Neighbor :388-400
+    const int id = i * Ww + j;
+    int c = 0;
+    if (j > 0) out[c++] = id - 1;
+    if (j < Ww - 1) out[c++] = id + 1;
+    if (i > 0) out[c++] = id - Ww;
+    if (i < Hh - 1) out[c++] = id + Ww;
+    return c;
+}
+PEAC_HD int block_of(const Geo &g, int px, int py) {  // getBlockIdx :408-415
+    const int by = py / WIN, bx = px / WIN;
+    return (by < g.Nh && bx < g.Nw) ? by * g.Nw + bx : -1;
+}
+
+// region-grow queue entry: pixel | plane id << 20
+PEAC_HD uint32_t rf_pack(int pix, int plid) { return (uint32_t)pix | ((uint32_t)plid << 20); }
+
+// One frame.  blocks / seed / edges: the pre-stage outputs of the frame (centre, normal, mse, N per block; node mask;
+// edge mask bit0=left,1=right,2=up,3=down).  membership: H2*W2 int32 out.  distMap (H2*W2 floats) and rfq (rfqCap
+// entries) are per-frame scratch in global memory.  planes: <= planeCap records out; *planeCount out.
+template <typename BlockStat>
+PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockStat *blocks, const uint8_t *seed, const uint8_t *edges,
+                  int32_t *membership, float *distMap, uint32_t *rfq, int rfqCap, PlaneOut *planes, int planeCap, int32_t *planeCount,
+                  int32_t *errorOut, int tid, int nt) {
+    const int nb = g.Nw * g.Nh, npix = g.W2 * g.H2;
+    // ---- initGraph's nodes and edges from the pre-stage (AHCPlaneFitter.hpp:756-928)
+    for (int b = tid; b < nb; b += nt) {
+        Node &n = S.node[b];
+        n.N = blocks[b].N, n.rid = b, n.seq = b, n.nouse = blocks[b].nouse ? 1 : 0, n.mse = blocks[b].mse;
+        for (int k = 0; k < 3; k++) n.center[k] = blocks[b].center[k], n.normal[k] = blocks[b].normal[k];
+        if (seed[b])
+            block_sums(g, depth, b, n.s);
+        else
+            for (int k = 0; k < 9; k++) n.s[k] = 0;
+        S.parent[b] = (int16_t)b, S.dsize[b] = 1;
+        uint32_t *m = S.nbs[b];
+        for (int w = 0; w < WORDS; w++) m[w] = 0;
+        const int e = edges[b];
+        if (e & 1) setbit(m, b - 1);
+        if (e & 2) setbit(m, b + 1);
+        if (e & 4) setbit(m, b - g.Nw);
+        if (e & 8) setbit(m, b + g.Nw);
+    }
+    if (tid == 0) S.heapN = 0, S.nExtracted = 0, S.seqNext = nb, S.step = 0, S.error = PEAC_OK;
+    PEAC_SYNC();
+    if (tid == 0)
+        for (int b = 0; b < nb; b++)
+            if (seed[b]) heap_push(S, b);  // minQ.push in block order (:779)
+    PEAC_SYNC();
+    cluster(S, g, nb, tid, nt);
+
+    // ---- refineDetails :294-374.  findBlockMembership(isValidExtractedPlane) :480-582, ERODE_ALL_BORDER
+    for (int i = tid; i < MAXPL; i += nt) S.valid[i] = 0, S.count[i] = 0, S.plidmap[i] = -1;
+    PEAC_SYNC();
+    for (int b = tid; b < nb; b += nt) {
+        const int i = b / g.Nw, j = b - i * g.Nw;
+        const int setid = ds_find_ro(S, b);
+        int bm = -1;
+        if ((int)S.dsize[setid] * (WIN * WIN) >= MIN_SUPPORT) {
+            int q[4];
+            const int nn = nbs4(i, j, g.Nh, g.Nw, q);
+            bool same = true;
+            for (int k = 0; k < nn; k++)
+                if (ds_find_ro(S, q[k]) != setid) {
+                    same = false;
+                    break;
+                }
+            int plid = 0;  // rid2plid[setid]: std::map::operator[] yields 0 for a root that is no plane's rid
+            for (int e = 0; e < S.nExtracted; e++)
+                if (S.node[S.extracted[e]].rid == setid) {
+                    plid = e;
+                    break;
+                }
+            if (same) {
+                bm = plid;
+                if (plid < S.nExtracted) S.valid[plid] = 1;  // benign race: every writer stores 1
+            }
+        }
+        S.blkMap[b] = (int16_t)bm;
+    }
+    PEAC_SYNC();
+    int *cnt = (int *)S.candMse;  // per-block number of region-grow seeds, then their exclusive scan
+    for (int b = tid; b < nb; b += nt) {
+        const int i = b / g.Nw, j = b - i * g.Nw, bm = S.blkMap[b];
+        int c = 0;
+        if (bm < 0) {
+            if (i > 0 && S.blkMap[b - g.Nw] >= 0) c += WIN - 1;
+            if (j > 0 && S.blkMap[b - 1] >= 0) c += WIN - 1;
+        } else {
+            if (i > 0 && S.blkMap[b - g.Nw] != bm) c += WIN - 1;
+            if (j > 0 && S.blkMap[b - 1] != bm) c += WIN - 1;
+        }
+        cnt[b] = c;
+    }
+    for (int px = tid; px < npix; px += nt) {  // membershipImg.setTo(-1) + the block fills; distMap = FLT_MAX
+        const int y = px / g.W2, x = px - y * g.W2, b = block_of(g, x, y);
+        membership[px] = (b >= 0 && S.blkMap[b] >= 0) ? S.blkMap[b] : -1;
+        distMap[px] = FLT_MAX;
+    }
+    PEAC_SYNC();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < nb; b++) {
+            const int c = cnt[b];
+            cnt[b] = acc;
+            acc += c;
+        }
+        S.curP = acc;  // queue length so far
+        if (acc > rfqCap) S.error = PEAC_ERR_QUEUE;
+    }
+    PEAC_SYNC();
+    if (S.error == PEAC_OK)
+        for (int b = tid; b < nb; b += nt) {  // the seeds of the region grow, in the reference's order (:537-580)
+            const int i = b / g.Nw, j = b - i * g.Nw, bm = S.blkMap[b];
+            uint32_t *o = rfq + cnt[b];
+            if (bm < 0) {
+                if (i > 0 && S.blkMap[b - g.Nw] >= 0) {
+                    const int s = (i * WIN - 1) * g.W2 + j * WIN, pl = S.blkMap[b - g.Nw];
+                    for (int k = 1; k < WIN; ++k) *o++ = rf_pack(s + k, pl);
+                }
+                if (j > 0 && S.blkMap[b - 1] >= 0) {
+                    const int s = (i * WIN) * g.W2 + j * WIN - 1, pl = S.blkMap[b - 1];
+                    for (int k = 0; k < WIN - 1; ++k) *o++ = rf_pack(s + k * g.W2, pl);
+                }
+            } else {
+                if (i > 0 && S.blkMap[b - g.Nw] != bm) {
+                    const int s = (i * WIN) * g.W2 + j * WIN;
+                    for (int k = 0; k < WIN - 1; ++k) *o++ = rf_pack(s + k, bm);
+                }
+                if (j > 0 && S.blkMap[b - 1] != bm) {
+                    const int s = (i * WIN) * g.W2 + j * WIN;
+                    for (int k = 1; k < WIN; ++k) *o++ = rf_pack(s + k * g.W2, bm);
+                }
+            }
+        }
+    PEAC_SYNC();
+
+    // ---- floodFill :422-471 (order-dependent FIFO: thread 0)
+    if (tid == 0 && S.error == PEAC_OK) {
+        int qn = S.curP;
+        for (int k = 0; k < qn; ++k) {
+            const uint32_t ent = rfq[k];
+            const int sIdx = (int)(ent & 0xfffffu), plid = (int)(ent >> 20);
+            const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
+            const Node &pl = S.node[S.extracted[plid]];
+            int q[4];
+            const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
+            for (int it = 0; it < nn; ++it) {
+                const int cIdx = q[it];
+                int32_t trail = membership[cIdx];
+                if (trail <= -6) continue;
+                if (trail >= 0 && trail == plid) continue;
+                const int cy = cIdx / g.W2, cx = cIdx - cy * g.W2;
+                const int blkid = block_of(g, cx, cy);
+                if (blkid >= 0 && S.blkMap[blkid] >= 0) continue;
+                double pt[3];
+                float cdist = -1;
+                bool near = false;
+                if (point(g, depth, cy, cx, pt)) {
+                    const double sd = (pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1])) +
+                                      pl.normal[2] * (pt[2] - pl.center[2]);  // signedDist :355-359
+                    cdist = (float)fabs(sd);
+                    near = (double)cdist * (double)cdist < 9 * pl.mse + 1e-5;  // std::pow(float, 2): evaluated in double
+                }
+                if (near) {
+                    if (trail >= 0) {
+                        const int a = S.extracted[trail], b = S.extracted[plid];
+                        if (nsim(pl, S.node[a]) >= g.thRefine) setbit(S.nbs[a], b), setbit(S.nbs[b], a);  // n_pl.connect(pl)
+                    }
+                    if (cdist < distMap[cIdx]) {
+                        membership[cIdx] = plid;
+                        distMap[cIdx] = cdist;
+                        if (qn < rfqCap)
+                            rfq[qn++] = rf_pack(cIdx, plid);
+                        else
+                            S.error = PEAC_ERR_QUEUE;
+                    } else if (trail < 0) {
+                        membership[cIdx] = trail - 1;
+                    }
+                } else if (trail < 0) {
+                    membership[cIdx] = trail - 1;
+                }
+            }
+            if (S.error != PEAC_OK) break;
+        }
+    }
+    PEAC_SYNC();
+
+    // ---- "try to merge one last time" :312-320: the valid planes re-enter the queue in plane order
+    if (tid == 0) {
+        S.nOld = S.nExtracted;
+        for (int i = 0; i < S.nOld; i++) S.oldPl[i] = S.extracted[i];
+        S.nExtracted = 0, S.heapN = 0;
+        for (int i = 0; i < S.nOld; i++)
+            if (S.valid[i]) heap_push(S, S.oldPl[i]);
+    }
+    PEAC_SYNC();
+    cluster(S, g, nb, tid, nt);
+    if (tid == 0) {  // plidmap :322-337 (a merged plane lives in the slot of one of its parts; ds roots are unaffected)
+        for (int i = 0; i < S.nOld; i++) {
+            if (!S.valid[i]) continue;
+            const int root = ds_find(S, S.node[S.oldPl[i]].rid);
+            for (int j = 0; j < S.nExtracted; j++)
+                if (root == S.node[S.extracted[j]].rid) {
+                    S.plidmap[i] = (int16_t)j;
+                    break;
+                }
+        }
+    }
+    PEAC_SYNC();
+    for (int px = tid; px < npix; px += nt) {  // :352-366
+        const int plid = membership[px];
+        if (plid >= 0 && plid < MAXPL && S.plidmap[plid] >= 0) {
+            const int np = S.plidmap[plid];
+            membership[px] = np;
+            PEAC_ATOMIC_ADD(&S.count[np], 1);
+        }
+    }
+    PEAC_SYNC();
+    for (int i = tid; i < S.nExtracted && i < planeCap; i += nt) {
+        const Node &n = S.node[S.extracted[i]];
+        PlaneOut &o = planes[i];
+        for (int k = 0; k < 3; k++) o.normal[k] = n.normal[k], o.center[k] = n.center[k];
+        o.N = n.N, o.rid = n.rid, o.vertices = S.count[i], o.pad = 0;
+    }
+    if (tid == 0) *planeCount = S.nExtracted, *errorOut = S.error;
+}
+
+}  // namespace peac

@@ -9,6 +9,7 @@
 //                          cyclic-Jacobi eigen-solve, normal orientation, mse, curvature, seed test
 //   k_plane_edges   P5     one CTA per frame: the row pass then the column pass of initGraph with their
 //                          --j/++j stepping, one thread per row / column
+//   k_peac_frame    f2     one CTA per frame: ahCluster + refineDetails (peac_frame.cuh) -> membershipImg, planes
 // All arithmetic is fp64 in the reference's operation order (file built with -fmad=false).
 #include <cmath>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "msl_common.cuh"
+#include "peac_frame.cuh"
 
 using namespace msl;
 
@@ -221,6 +223,23 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+static_assert(sizeof(msl_plane_rec) == sizeof(peac::PlaneOut) && sizeof(msl_plane_rec) == 64, "plane record layout");
+
+// ahCluster + refineDetails of one frame per CTA (peac_frame.cuh); 196 KB of dynamic shared memory
+__global__ void __launch_bounds__(256)
+    k_peac_frame(peac::Geo g, size_t frameStride, const uint16_t *__restrict__ depth, const msl_block_stat *__restrict__ blocks,
+                 const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership,
+                 float *__restrict__ distMap, uint32_t *__restrict__ rfq, int rfqCap, peac::PlaneOut *__restrict__ planes, int planeCap,
+                 int32_t *__restrict__ planeCount, int32_t *__restrict__ frameError) {
+    extern __shared__ __align__(16) unsigned char peac_smem[];
+    peac::Shared &S = *reinterpret_cast<peac::Shared *>(peac_smem);
+    const int b = blockIdx.x, nb = g.Nw * g.Nh;
+    const size_t npix = (size_t)g.W2 * g.H2;
+    peac::frame(S, g, depth + b * frameStride, blocks + (size_t)b * nb, seed + (size_t)b * nb, edges + (size_t)b * nb,
+                membership + b * npix, distMap + b * npix, rfq + (size_t)b * rfqCap, rfqCap, planes + (size_t)b * planeCap, planeCap,
+                planeCount + b, frameError + b, (int)threadIdx.x, (int)blockDim.x);
+}
+
 }  // namespace
 
 struct msl_plane {
@@ -231,12 +250,20 @@ struct msl_plane {
     double *d_cloud = nullptr;
     msl_block_stat *d_blocks = nullptr;
     uint8_t *d_seed = nullptr, *d_edges = nullptr;
+    // msl_plane_detect*: allocated on first use
+    int32_t *d_mem = nullptr, *d_count = nullptr, *d_ferr = nullptr;
+    float *d_dist = nullptr;
+    uint32_t *d_rfq = nullptr;
+    msl_plane_rec *d_planes = nullptr;
+    int planeCap = 0;
+    int pendingCheck = 0;  // frames of an enqueued detect whose per-frame error words have not been read yet
 };
 
 static void plane_free(msl_plane *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_depth, p->d_cloud, p->d_blocks, p->d_seed, p->d_edges};
+    void *ptrs[] = {p->d_depth, p->d_cloud, p->d_blocks, p->d_seed, p->d_edges, p->d_mem, p->d_count, p->d_ferr,
+                    p->d_dist, p->d_rfq, p->d_planes};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -274,11 +301,24 @@ int msl_plane_create(int w, int h, int max_batch, int device, msl_plane **out) {
 
 void msl_plane_destroy(msl_plane *p) { plane_free(p); }
 void *msl_plane_stream(msl_plane *p) { return p ? (void *)p->stream : nullptr; }
+static int plane_check_frames(msl_plane *p) {  // after a synchronize: did any frame of the last detect overflow?
+    if (!p->pendingCheck) return MSL_OK;
+    const int n = p->pendingCheck;
+    p->pendingCheck = 0;
+    std::vector<int32_t> e(n);
+    MSL_CUDA(cudaMemcpy(e.data(), p->d_ferr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < n; b++)
+        if (e[b] != 0)
+            return fail(MSL_ERR_CAPACITY, e[b] == peac::PEAC_ERR_QUEUE ? "msl_plane_detect: region-grow queue exceeded"
+                                                                      : "msl_plane_detect: more than 128 planes in a frame");
+    return MSL_OK;
+}
+
 int msl_plane_sync(msl_plane *p) {
     if (!p) return fail(MSL_ERR_INVALID, "null handle");
     MSL_CUDA(cudaSetDevice(p->device));
     MSL_CUDA(cudaStreamSynchronize(p->stream));
-    return MSL_OK;
+    return plane_check_frames(p);
 }
 
 int msl_plane_prestage_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, size_t frame_stride_px, int batch,
@@ -306,6 +346,80 @@ int msl_plane_prestage_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px
     MSL_LAUNCH_CHECK();
     k_plane_edges<<<batch, 128, 0, p->stream>>>(P, blocks, seed, edges);
     MSL_LAUNCH_CHECK();
+    return MSL_OK;
+}
+
+constexpr int PLANE_CAP_INTERNAL = 32;  // records per frame of the handle's own buffer (host entry point)
+
+static int plane_detect_alloc(msl_plane *p) {
+    if (p->d_mem) return MSL_OK;
+    const size_t B = p->maxBatch, npix = (size_t)p->W2 * p->H2;
+    cudaError_t e = cudaMalloc((void **)&p->d_mem, B * npix * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_dist, B * npix * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_rfq, B * npix * 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_count, B * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ferr, B * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_planes, B * PLANE_CAP_INTERNAL * sizeof(msl_plane_rec));
+    if (e == cudaSuccess) e = cudaMemset(p->d_ferr, 0, B * sizeof(int32_t));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_peac_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
+    if (e != cudaSuccess) return fail(MSL_ERR_CUDA, std::string("msl_plane_detect: ") + cudaGetErrorString(e));
+    p->planeCap = PLANE_CAP_INTERNAL;
+    return MSL_OK;
+}
+
+int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, size_t frame_stride_px, int batch,
+                         const float K[4], float depth_map_factor, int32_t *d_membership, int32_t *d_plane_count,
+                         msl_plane_rec *d_planes, int plane_cap) {
+    if (!p || !d_depth || !K || !d_membership || !d_plane_count || (plane_cap > 0 && !d_planes) || plane_cap < 0)
+        return fail(MSL_ERR_INVALID, "msl_plane_detect_dev: bad argument");
+    if (p->Nw * p->Nh > peac::MAXB) return fail(MSL_ERR_INVALID, "msl_plane_detect: frames of more than 768 blocks (640x480) are not supported");
+    if ((size_t)p->W2 * p->H2 >= (1u << 20)) return fail(MSL_ERR_INVALID, "msl_plane_detect: frame too large");
+    int rc = plane_detect_alloc(p);
+    if (rc) return rc;
+    // the pre-stage into the handle's own buffers (P1-P5), then one CTA per frame
+    rc = msl_plane_prestage_dev(p, d_depth, dstride_px, frame_stride_px, batch, K, depth_map_factor, nullptr, p->d_blocks, p->d_seed,
+                                p->d_edges);
+    if (rc) return rc;
+    peac::Geo g;
+    g.W2 = p->W2, g.H2 = p->H2, g.Nw = p->Nw, g.Nh = p->Nh, g.dstride = dstride_px;
+    g.fx = K[0], g.fy = K[1], g.cx = K[2], g.cy = K[3], g.factor = depth_map_factor;
+    g.thMerge = std::cos(60.0 * M_PI / 180.0), g.thRefine = std::cos(30.0 * M_PI / 180.0);  // AHCParamSet.hpp:72-73
+    const int rfqCap = 4 * p->W2 * p->H2;
+    k_peac_frame<<<batch, 256, sizeof(peac::Shared), p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
+                                                                 d_membership, p->d_dist, p->d_rfq, rfqCap,
+                                                                 reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count,
+                                                                 p->d_ferr);
+    MSL_LAUNCH_CHECK();
+    p->pendingCheck = batch > p->pendingCheck ? batch : p->pendingCheck;
+    return MSL_OK;
+}
+
+int msl_plane_detect(msl_plane *p, const uint16_t *depth, int dstride_px, size_t frame_stride_px, int batch, const float K[4],
+                     float depth_map_factor, int32_t *membership, int32_t *plane_count, msl_plane_rec *planes, int plane_cap) {
+    if (!p || !depth || !K || !membership || !plane_count || (plane_cap > 0 && !planes) || plane_cap < 0)
+        return fail(MSL_ERR_INVALID, "msl_plane_detect: bad argument");
+    if (batch < 1 || batch > p->maxBatch || dstride_px < p->w) return fail(MSL_ERR_INVALID, "msl_plane_detect: bad batch/stride");
+    MSL_CUDA(cudaSetDevice(p->device));
+    int rc = plane_detect_alloc(p);
+    if (rc) return rc;
+    const size_t fr = (size_t)p->w * p->h, npix = (size_t)p->W2 * p->H2;
+    for (int b = 0; b < batch; b++)
+        MSL_CUDA(cudaMemcpy2DAsync(p->d_depth + b * fr, (size_t)p->w * 2, depth + b * frame_stride_px, (size_t)dstride_px * 2,
+                                   (size_t)p->w * 2, p->h, cudaMemcpyHostToDevice, p->stream));
+    rc = msl_plane_detect_dev(p, p->d_depth, p->w, fr, batch, K, depth_map_factor, p->d_mem, p->d_count, p->d_planes, p->planeCap);
+    if (rc) return rc;
+    MSL_CUDA(cudaMemcpyAsync(membership, p->d_mem, sizeof(int32_t) * npix * batch, cudaMemcpyDeviceToHost, p->stream));
+    MSL_CUDA(cudaMemcpyAsync(plane_count, p->d_count, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, p->stream));
+    std::vector<msl_plane_rec> rec((size_t)batch * p->planeCap);
+    MSL_CUDA(cudaMemcpyAsync(rec.data(), p->d_planes, sizeof(msl_plane_rec) * rec.size(), cudaMemcpyDeviceToHost, p->stream));
+    MSL_CUDA(cudaStreamSynchronize(p->stream));
+    rc = plane_check_frames(p);
+    if (rc) return rc;
+    for (int b = 0; b < batch; b++) {
+        if (plane_count[b] > p->planeCap) return fail(MSL_ERR_CAPACITY, "msl_plane_detect: more planes than the handle's record buffer holds");
+        for (int i = 0; i < plane_count[b] && i < plane_cap; i++) planes[(size_t)b * plane_cap + i] = rec[(size_t)b * p->planeCap + i];
+    }
     return MSL_OK;
 }
 

@@ -1,4 +1,5 @@
-"""PlaneDetection pre-stage mirror (src/PlaneExtractor.cpp:44-76 + peac PlaneSeg/initGraph) over the CUDA C ABI."""
+"""PlaneDetection mirror (src/PlaneExtractor.cpp: readDepthImage :44-76, runPlaneDetection :78-82 = the peac fitter of
+include/peac/) over the CUDA C ABI."""
 import ctypes as C
 
 import numpy as np
@@ -7,6 +8,8 @@ from ._lib import check, lib, ptr
 
 BLOCK_DTYPE = np.dtype([("center", "<f8", 3), ("normal", "<f8", 3), ("mse", "<f8"), ("curvature", "<f8"),
                         ("N", "<i4"), ("nouse", "<i4")])
+PLANE_DTYPE = np.dtype([("normal", "<f8", 3), ("center", "<f8", 3), ("N", "<i4"), ("rid", "<i4"), ("vertices", "<i4"),
+                        ("pad", "<i4")])  # msl_plane_rec
 
 
 class PlaneDetection:
@@ -45,6 +48,23 @@ class PlaneDetection:
                                          C.c_int(B), ptr(Kf), C.c_float(depthMapFactor), ptr(cloud), ptr(blocks),
                                          ptr(seed), ptr(edges)))
         return cloud, blocks, seed, edges
+
+    def detect(self, depth_u16, K=(525.0, 525.0, 319.5, 239.5), depthMapFactor=1.0 / 5000.0, plane_cap=32):
+        """readDepthImage + runPlaneDetection (src/Frame.cc:607-609) for a batch of depth images ->
+        (membershipImg[B, h2, w2] int32, planes: list of PLANE_DTYPE arrays in extractedPlanes order).
+        plane_vertices_[i] of frame b = np.flatnonzero(membership[b] == i)."""
+        d = np.ascontiguousarray(depth_u16, np.uint16)
+        if d.ndim == 2:
+            d = d[None]
+        B = d.shape[0]
+        assert d.shape[1:] == (self.height, self.width) and B <= self.max_batch
+        mem = np.zeros((B, self.h2, self.w2), np.int32)
+        cnt = np.zeros(B, np.int32)
+        rec = np.zeros((B, plane_cap), PLANE_DTYPE)
+        Kf = np.asarray(K, np.float32)
+        check(self._L.msl_plane_detect(self._h, ptr(d), C.c_int(self.width), C.c_size_t(self.width * self.height), C.c_int(B),
+                                       ptr(Kf), C.c_float(depthMapFactor), ptr(mem), ptr(cnt), ptr(rec), C.c_int(plane_cap)))
+        return mem, [rec[b, :min(int(cnt[b]), plane_cap)].copy() for b in range(B)]
 
     def prestage_dev(self, d_depth, batch, K=(525.0, 525.0, 319.5, 239.5), depthMapFactor=1.0 / 5000.0,
                      d_cloud=None, d_blocks=None, d_seed=None, d_edges=None):

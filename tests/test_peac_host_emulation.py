@@ -1,0 +1,97 @@
+"""The f2 device algorithm (manhattanslam_b200/csrc/peac_frame.cuh: what the k_peac_frame kernel runs) compiled for the
+HOST -- one "thread", no-op barriers, tests/host_emul/peac_host.cpp -- against the oracle's restatement of ahCluster +
+refineDetails (which tests/test_oracle_ref.py pins to the reference's own peac).  This checks the algorithmic content of
+the kernel on CPU-only machines: slot reuse, mask adjacency, libstdc++ heap order, tie rules, region-grow seeds, flood
+fill, the final merge and the plane-id remap.  What it cannot check -- the barriers between the parallel phases and the
+launch plumbing -- is what tests/test_x_peac_gpu.py is for.  A test harness: nothing in the product links it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from manhattanslam_b200 import synthetic as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PL = np.dtype([("normal", "<f8", 3), ("center", "<f8", 3), ("N", "<i4"), ("rid", "<i4"), ("vertices", "<i4"), ("pad", "<i4")])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "host_emul", "peac_host.cpp")
+    hdr = os.path.join(HERE, "..", "manhattanslam_b200", "csrc", "peac_frame.cuh")
+    out_dir = os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libpeac_host.so")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.peac_host_frame.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p] * 5 +
+                                  [C.c_int, C.c_void_p, C.c_int])
+    return L
+
+
+def _run(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0):
+    h, w = d16.shape
+    d16 = np.ascontiguousarray(d16, np.uint16)
+    _, blocks, seed, edges = oracle.plane_prestage(d16, K=K, depth_map_factor=fac)
+    mem = np.zeros(((h + 1) // 2, (w + 1) // 2), np.int32)
+    pl, err = np.zeros(64, PL), np.zeros(1, np.int32)
+    n = emu.peac_host_frame(d16.ctypes.data, w, h, w, K[0], K[1], K[2], K[3], fac, blocks.ctypes.data, seed.ctypes.data,
+                            edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 64, err.ctypes.data, 4 * mem.size)
+    assert n >= 0 and err[0] == 0
+    return mem, pl[:n]
+
+
+def _same(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0):
+    mem, pl = _run(emu, oracle, d16, K, fac)
+    mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=fac)
+    assert len(pl) == len(po["N"])
+    assert np.array_equal(mem, mo)
+    for f in ("N", "rid", "vertices"):
+        assert np.array_equal(pl[f], po[f]), f
+    assert pl["normal"].tobytes() == po["normal"].tobytes() and pl["center"].tobytes() == po["center"].tobytes()
+    return mem, pl
+
+
+def test_shared_memory_fits_one_cta(emu):
+    assert emu.peac_host_shared_bytes() <= 227 * 1024
+
+
+@pytest.mark.parametrize("seed0", [0, 20, 40])
+def test_device_algorithm_equals_oracle(emu, oracle, seed0):
+    counts = []
+    for seed in range(seed0, seed0 + 20):
+        d16, _ = S.depth_frame(seed)
+        _, pl = _same(emu, oracle, d16)
+        counts.append(len(pl))
+    assert max(counts) >= 3
+
+
+def test_device_algorithm_metres_sizes_and_degenerate_depth(emu, oracle):
+    for seed in (1, 2, 3):
+        _same(emu, oracle, S.depth_frame(seed)[0], fac=1.0 / 5000.0)
+    for (w, h) in ((320, 240), (646, 486)):
+        K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+        _same(emu, oracle, S.depth_frame(70 + w % 7, w, h, K=K)[0], K=K)
+    mem, pl = _same(emu, oracle, np.zeros((480, 640), np.uint16))
+    assert len(pl) == 0 and (mem == -1).all()
+    # one perfect plane: every block has mse == 0 -- the queue's and the merge choice's exact-tie rules decide everything
+    mem, pl = _same(emu, oracle, np.full((480, 640), 1500, np.uint16))
+    assert len(pl) == 1 and pl["N"][0] == 76800
+    two = np.full((480, 640), 1500, np.uint16)
+    two[:, 320:] = 2500
+    _, pl = _same(emu, oracle, two)
+    assert len(pl) == 2
+    holes = np.full((480, 640), 1500, np.uint16)
+    holes[::20, ::20] = 0
+    _same(emu, oracle, holes)
+
+
+def test_larger_frames_are_refused(emu, oracle):
+    d16 = np.full((960, 1280), 1500, np.uint16)
+    _, blocks, seed, edges = oracle.plane_prestage(d16)
+    mem, pl, err = np.zeros((480, 640), np.int32), np.zeros(4, PL), np.zeros(1, np.int32)
+    assert emu.peac_host_frame(d16.ctypes.data, 1280, 960, 1280, 525.0, 525.0, 319.5, 239.5, 1.0, blocks.ctypes.data,
+                               seed.ctypes.data, edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 4, err.ctypes.data, 16) == -1
