@@ -30,6 +30,7 @@ typedef unsigned char uchar;
 typedef unsigned short ushort;
 
 #define CV_PI 3.1415926535897932384626433832795
+#define CV_Assert(expr) assert(expr)
 #define CV_8U 0
 #define CV_16U 2
 #define CV_32S 4

@@ -14,6 +14,12 @@ template <typename T, int R, int C, int Opt = ColMajor> class Matrix {
 public:
     T m[R * C];  // storage order per Opt
     Matrix() {}
+    template <int Opt2> Matrix(const Matrix<T, R, C, Opt2> &o) {  // between storage orders
+        for (int i = 0; i < R; i++)
+            for (int j = 0; j < C; j++) (*this)(i, j) = o(i, j);
+    }
+    const T *data() const { return m; }
+    T *data() { return m; }
     Matrix(T x, T y, T z) {
         static_assert(R * C == 3, "3-vector constructor");
         m[0] = x, m[1] = y, m[2] = z;

@@ -42,6 +42,7 @@ class Mat {
 public:
     Mat();
     Mat(int rows, int cols, int type);
+    void create(int rows, int cols, int type);
     template <typename T> T &at(int i);
     template <typename T> const T &at(int i) const;
     template <typename T> T &at(int i, int j);

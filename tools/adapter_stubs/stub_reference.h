@@ -1,3 +1,4 @@
+#include <memory>
 // Stand-ins for the reference's include/{Frame,KeyFrame,MapPoint,ORBmatcher}.h, reduced to the members the bindings use
 // (names, types, constness and access levels copied from those headers).  Only for tools/check_adapters.sh.
 #pragma once
@@ -150,9 +151,38 @@ struct ImagePointCloud {
     std::vector<VertexColour> verticesColour;
     int w, h;
 };
+namespace ahc {  // include/peac/AHCTypes.hpp, AHCParamSet.hpp, AHCPlaneSeg.hpp, AHCPlaneFitter.hpp (members the binding uses)
+using std::shared_ptr;
+struct ParamSet {};
+struct NullImage3D {
+    int width() { return 0; }
+    int height() { return 0; }
+    bool get(const int, const int, double &, double &, double &) const { return false; }
+};
+struct PlaneSeg {
+    typedef ahc::shared_ptr<PlaneSeg> shared_ptr;
+    int rid;
+    double mse;
+    double center[3];
+    double normal[3];
+    int N;
+    double curvature;
+    bool nouse;
+    template <class Image3D>
+    PlaneSeg(const Image3D &points, const int root_block_id, const int seed_row, const int seed_col, const int imgWidth,
+             const int imgHeight, const int winWidth, const int winHeight, const ParamSet &params);
+};
+template <class Image3D> struct PlaneFitter {
+    int windowWidth, windowHeight;
+    ParamSet params;
+    std::vector<PlaneSeg::shared_ptr> extractedPlanes;
+    cv::Mat membershipImg;
+};
+}  // namespace ahc
 class PlaneDetection {
 public:
     ImagePointCloud cloud;
+    ahc::PlaneFitter<ImagePointCloud> plane_filter;
     std::vector<std::vector<int> > plane_vertices_;
     cv::Mat seg_img_;
     cv::Mat color_img_;

@@ -8,4 +8,14 @@ rc=0
 for f in adapters/*.cc adapters/*.cpp; do
   if g++ -std=c++14 -fsyntax-only -Wall -Wextra -DMSL_SURFEL_RESIDENT -Itools/adapter_stubs -Iinclude "$f"; then echo "ok  $f"; else echo "FAILED  $f"; rc=1; fi
 done
+# Second pass, where /root/reference exists: the three bindings whose class headers only need OpenCV / Eigen are checked
+# against the REFERENCE'S OWN headers (include/ORBextractor.h, include/SurfelFusion.h, include/PlaneExtractor.h + the peac
+# fitter) on top of the stand-in OpenCV / Eigen of oracle/ref_shim_cv/ -- the headers the reference sources themselves are
+# compiled against for oracle/_ref/.
+REF=${REF:-/root/reference}
+if [ -d "$REF/include" ]; then
+  for f in adapters/ORBextractor_msl.cc adapters/SurfelFusion_msl.cpp adapters/PlaneExtractor_msl.cpp; do
+    if g++ -std=c++14 -fsyntax-only -w -Ioracle/ref_shim_cv -Ioracle -I"$REF/include" -I"$REF" -Iinclude "$f"; then echo "ok  $f (reference headers)"; else echo "FAILED  $f (reference headers)"; rc=1; fi
+  done
+fi
 exit $rc
