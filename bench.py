@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--surfels", type=int, default=5_000_000, help="surfels in the local map per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--widened-only", action="store_true", help="internal: print the `widened` object alone (run_ours calls "
-                    "this in a child process so that a fault in a diagnostic can never take the bench line down)")
+    ap.add_argument("--widened-only", nargs="?", const="matcher", default="", choices=["matcher", "peac"],
+                    help="internal: print one part of the `widened` object alone (run_ours calls this in child processes so "
+                         "that a fault in a diagnostic can never take the bench line down)")
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames in the bounded CPU sample")
     ap.add_argument("--only", default="", help="diagnostic: comma list of stages (orb,match,plane,surfel) the device-resident "
                                                "step runs; the default (empty) is the full front-end -- anything else is not a bench value")
@@ -251,9 +252,41 @@ def widened_ops(msl, reps=20):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
+def widened_peac(msl, frames=8):
+    """readDepthImage + the whole peac fitter (msl_plane_detect: pre-stage, ahCluster,
+    refineDetails) for a batch of depth frames through the host C ABI, next to the CPU oracle (single thread) on the same
+    frames, and whether membership images and planes agree."""
+    try:
+        from manhattanslam_b200 import synthetic as S
+        from oracle import binding as ob
+        d = np.stack([S.depth_frame(100 + b)[0] for b in range(frames)])
+        pd = msl.PlaneDetection(max_batch=frames)
+        pd.detect(d, depthMapFactor=1.0)
+        t0 = time.perf_counter()
+        mem, planes = pd.detect(d, depthMapFactor=1.0)
+        g_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref = [ob.plane_detect(d[b], depth_map_factor=1.0) for b in range(frames)]
+        c_s = time.perf_counter() - t0
+        equal = all(np.array_equal(mem[b], ref[b][0]) and np.array_equal(planes[b]["N"], ref[b][1]["N"]) and
+                    planes[b]["normal"].tobytes() == ref[b][1]["normal"].tobytes() for b in range(frames))
+        return {"plane_detect_640x480": {"frames": frames, "gpu_call_ms_per_batch": 1e3 * g_s, "cpu_oracle_ms_per_batch": 1e3 * c_s,
+                                         "planes_per_frame": [len(p) for p in planes], "equal": bool(equal),
+                                         "note": "one CTA per frame; the region grow (floodFill) is an order-dependent FIFO "
+                                                 "and runs on one thread per frame"}}
+    except Exception as e:  # noqa: BLE001 -- diagnostics only
+        return {"plane_detect_640x480": {"error": "%s: %s" % (type(e).__name__, e)}}
+
+
 def widened_in_child(device, timeout_s=180):
-    """widened_ops in a child process with a deadline: the diagnostics exercise kernels outside the timed step, and neither
-    a device fault nor a hang there may cost the bench line."""
+    """widened_ops / widened_peac in child processes with a deadline: the diagnostics exercise kernels outside the timed step,
+    and neither a device fault nor a hang there may cost the bench line."""
+    res = _widened_child(device, "matcher", timeout_s)
+    res.update(_widened_child(device, "peac", timeout_s))
+    return res
+
+
+def _widened_child(device, which, timeout_s):
     import subprocess
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
     if not env["CUDA_VISIBLE_DEVICES"]:
@@ -261,16 +294,16 @@ def widened_in_child(device, timeout_s=180):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--widened-only"], env=env, capture_output=True,
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--widened-only", which], env=env, capture_output=True,
                            text=True, timeout=timeout_s)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not lines:
-            return {"error": "child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
+            return {which + "_error": "child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
         return json.loads(lines[-1])
     except subprocess.TimeoutExpired:
-        return {"error": "timed out after %d s" % timeout_s}
+        return {which + "_error": "timed out after %d s" % timeout_s}
     except Exception as e:  # noqa: BLE001
-        return {"error": "%s: %s" % (type(e).__name__, e)}
+        return {which + "_error": "%s: %s" % (type(e).__name__, e)}
 
 
 def run_ours(a, rank, world, local_rank):
@@ -565,7 +598,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.widened_only:
         import manhattanslam_b200 as msl
-        print(json.dumps(widened_ops(msl)))
+        print(json.dumps(widened_ops(msl) if a.widened_only == "matcher" else widened_peac(msl)))
         return
     if a.impl == "reference":
         run_reference(a, rank, world)
