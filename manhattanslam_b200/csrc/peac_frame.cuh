@@ -24,8 +24,10 @@
 //     run one thread per pixel.
 // All arithmetic is fp64 in the reference's operation order (built with -fmad=false).
 //
-// The same source compiles for the host (PEAC_HOST_EMULATION: one "thread", barriers are no-ops) so that the algorithm
-// is checked against the oracle on CPU-only machines by tests/test_peac_host_emulation.py -- a test harness, not a
+// The same source compiles for the host so that it can be checked on CPU-only machines by
+// tests/test_peac_host_emulation.py: PEAC_HOST_EMULATION (one "thread", barriers are no-ops) checks the algorithm against
+// the oracle; PEAC_HOST_EMULATION_MT (several real threads, PEAC_SYNC = a pthread barrier, built with ThreadSanitizer)
+// checks that every shared-memory hand-over between the parallel phases is separated by a barrier.  Test harnesses, not a
 // fallback: the product entry points (msl_plane_detect*) only ever launch the kernel.
 #pragma once
 #include <cfloat>
@@ -38,11 +40,21 @@
 #define PEAC_SYNC() __syncthreads()
 #define PEAC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define PEAC_UNROLL _Pragma("unroll")
+#define PEAC_STORE_FLAG(p) (*(p) = 1)  // several threads may store the same 1
+#elif defined(PEAC_HOST_EMULATION_MT)  // tests/host_emul/peac_host_mt.cpp: real threads + a barrier, under ThreadSanitizer
+void peac_emu_sync();
+#define PEAC_HD inline
+#define PEAC_D inline
+#define PEAC_SYNC() peac_emu_sync()
+#define PEAC_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#define PEAC_STORE_FLAG(p) __atomic_store_n((p), (unsigned char)1, __ATOMIC_RELAXED)
+#define PEAC_UNROLL
 #else
 #define PEAC_HD inline
 #define PEAC_D inline
 #define PEAC_SYNC() ((void)0)
 #define PEAC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PEAC_STORE_FLAG(p) (*(p) = 1)
 #define PEAC_UNROLL
 #endif
 
@@ -473,7 +485,7 @@ PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockSta
                 }
             if (same) {
                 bm = plid;
-                if (plid < S.nExtracted) S.valid[plid] = 1;  // benign race: every writer stores 1
+                if (plid < S.nExtracted) PEAC_STORE_FLAG(&S.valid[plid]);  // every writer stores the same 1
             }
         }
         S.blkMap[b] = (int16_t)bm;

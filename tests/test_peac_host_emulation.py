@@ -95,3 +95,44 @@ def test_larger_frames_are_refused(emu, oracle):
     mem, pl, err = np.zeros((480, 640), np.int32), np.zeros(4, PL), np.zeros(1, np.int32)
     assert emu.peac_host_frame(d16.ctypes.data, 1280, 960, 1280, 525.0, 525.0, 319.5, 239.5, 1.0, blocks.ctypes.data,
                                seed.ctypes.data, edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 4, err.ctypes.data, 16) == -1
+
+
+# ---- the CTA's barriers: several real threads + a pthread barrier under ThreadSanitizer (tests/host_emul/peac_host_mt.cpp)
+@pytest.fixture(scope="module")
+def emu_mt():
+    src = os.path.join(HERE, "host_emul", "peac_host_mt.cpp")
+    hdr = os.path.join(HERE, "..", "manhattanslam_b200", "csrc", "peac_frame.cuh")
+    out_dir = os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "peac_host_mt")
+    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
+        r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-ffp-contract=off", "-pthread", "-o", exe, src],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("ThreadSanitizer build not available: " + r.stderr[-200:])
+    return exe
+
+
+@pytest.mark.parametrize("seed,threads", [(2, 8), (4, 5), (33, 16)])
+def test_cta_phases_are_race_free_under_tsan(emu_mt, oracle, tmp_path, seed, threads):
+    """every hand-over through shared memory (queue pop -> candidate fits -> selection -> mask update -> push, membership
+    -> seeds -> flood fill -> final merge -> remap) must be separated by a barrier: ThreadSanitizer reports none missing,
+    and the threaded run equals the oracle.  (Dropping one PEAC_SYNC() makes this test fail with TSAN reports.)"""
+    d16, _ = S.depth_frame(seed)
+    _, blocks, sd, ed = oracle.plane_prestage(d16, depth_map_factor=1.0)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(np.array([640, 480, 64], np.int32).tobytes())
+        f.write(np.array(list(S.K_DEFAULT) + [1.0], np.float32).tobytes())
+        f.write(d16.tobytes() + blocks.tobytes() + sd.tobytes() + ed.tobytes())
+    r = subprocess.run([emu_mt, str(threads), fin, fout], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:3000]
+    raw = open(fout, "rb").read()
+    cnt, err = np.frombuffer(raw[:8], np.int32)
+    mem = np.frombuffer(raw[8:8 + 4 * 240 * 320], np.int32).reshape(240, 320)
+    pl = np.frombuffer(raw[8 + 4 * 240 * 320:], PL)[:cnt]
+    mo, po = oracle.plane_detect(d16, depth_map_factor=1.0)
+    assert err == 0 and cnt == len(po["N"]) and np.array_equal(mem, mo)
+    assert np.array_equal(pl["N"], po["N"]) and np.array_equal(pl["vertices"], po["vertices"])
+    assert pl["normal"].tobytes() == po["normal"].tobytes() and pl["center"].tobytes() == po["center"].tobytes()
