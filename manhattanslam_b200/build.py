@@ -36,7 +36,9 @@ def _source_hash():
     """Content hash of every input of the build (mtimes do not survive the gpurun snapshot)."""
     import hashlib
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "msl_frontend.h")]
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                  if f.endswith((".cu", ".cuh", ".inc", ".h")) and os.path.isfile(os.path.join(CSRC, f)))
+    deps.append(os.path.join(HERE, "..", "include", "msl_frontend.h"))
     for d in deps:
         h.update(os.path.basename(d).encode())
         with open(d, "rb") as f:

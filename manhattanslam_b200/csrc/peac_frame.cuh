@@ -18,8 +18,13 @@
 //   * findBlockMembership: one thread per block; the seeds of the region grow are written in the reference's order
 //     through a per-block count + exclusive scan;
 //   * floodFill is an order-dependent FIFO (a pixel keeps the first plane that reaches it with a smaller distance, and
-//     counts failed visits in negative "trail" values): it runs on thread 0 over per-frame queues in global memory.
-//     A parallel-equivalent formulation is open;
+//     counts failed visits in negative "trail" values).  It is run LEVEL BY LEVEL with the same result: the entries a
+//     level pushes form the next level; a visit (entry, neighbour) only reads and writes the state of its TARGET pixel
+//     (trail value, best distance), so the visits of a level are resolved in parallel across target pixels and in visit
+//     order per pixel (rounds of atomicMin(own[pixel], visit): the earliest pending visit of every pixel resolves);
+//     the geometric part of a visit (point-plane distance, 3-sigma test) is state-independent and precomputed for all
+//     visits at once; the next level is written in visit order through a chunked scan of the push flags.  The plain
+//     FIFO on thread 0 is kept behind Geo::floodSerial (MSL_PEAC_FLOOD_SERIAL=1) as a cross-check;
 //   * the final merge reuses the cluster loop on the extracted planes; the plane-id remap and the per-plane pixel counts
 //     run one thread per pixel.
 // All arithmetic is fp64 in the reference's operation order (built with -fmad=false).
@@ -39,6 +44,10 @@
 #define PEAC_D __device__
 #define PEAC_SYNC() __syncthreads()
 #define PEAC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define PEAC_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define PEAC_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define PEAC_LOAD(p) (*(volatile const int *)(p))
+#define PEAC_STORE(p, v) (*(volatile int *)(p) = (v))
 #define PEAC_UNROLL _Pragma("unroll")
 #define PEAC_STORE_FLAG(p) (*(p) = 1)  // several threads may store the same 1
 #elif defined(PEAC_HOST_EMULATION_MT)  // tests/host_emul/peac_host_mt.cpp: real threads + a barrier, under ThreadSanitizer
@@ -47,6 +56,15 @@ void peac_emu_sync();
 #define PEAC_D inline
 #define PEAC_SYNC() peac_emu_sync()
 #define PEAC_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#define PEAC_ATOMIC_MIN(p, v) peac_emu_atomic_min((p), (v))
+#define PEAC_ATOMIC_OR(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
+#define PEAC_LOAD(p) __atomic_load_n((p), __ATOMIC_RELAXED)
+#define PEAC_STORE(p, v) __atomic_store_n((p), (v), __ATOMIC_RELAXED)
+inline void peac_emu_atomic_min(int *p, int v) {
+    int cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+}
 #define PEAC_STORE_FLAG(p) __atomic_store_n((p), (unsigned char)1, __ATOMIC_RELAXED)
 #define PEAC_UNROLL
 #else
@@ -54,6 +72,10 @@ void peac_emu_sync();
 #define PEAC_D inline
 #define PEAC_SYNC() ((void)0)
 #define PEAC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PEAC_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
+#define PEAC_ATOMIC_OR(p, v) (*(p) |= (v))
+#define PEAC_LOAD(p) (*(p))
+#define PEAC_STORE(p, v) (*(p) = (v))
 #define PEAC_STORE_FLAG(p) (*(p) = 1)
 #define PEAC_UNROLL
 #endif
@@ -75,6 +97,7 @@ struct Geo {
     int dstride;  // depth row stride in pixels (full resolution)
     float fx, fy, cx, cy, factor;
     double thMerge, thRefine;  // cos(60 deg), cos(30 deg) evaluated on the host with std::cos (AHCParamSet.hpp:72-73)
+    int floodSerial;           // 1: the region grow as the reference's FIFO on thread 0 (A/B and cross-check); 0: by levels
 };
 
 struct Node {        // PlaneSeg
@@ -101,7 +124,20 @@ struct Shared {
     Node tmp;
     int heapN, nExtracted, nOld, seqNext, step;
     int curP, curNb, decision;  // broadcast from thread 0
+    int lvlBegin, lvlEnd, pending;  // region grow by levels
     int error;
+};
+
+// per-frame scratch of the region grow in global memory
+struct Flood {
+    float *distMap;   // H2*W2
+    uint32_t *rfq;    // the queue: rfqCap entries
+    int rfqCap;
+    int *own;         // H2*W2: earliest pending visit of a pixel in the current round
+    int *visC;        // visCap: target pixel of a visit (-1: nothing to do)
+    float *visDist;   // visCap
+    uint8_t *visFlag; // visCap: bit0 near, bit1 pending, bit2 pushes
+    int visCap;
 };
 
 enum { PEAC_OK = 0, PEAC_ERR_QUEUE = 1, PEAC_ERR_PLANES = 2 };
@@ -427,13 +463,184 @@ PEAC_HD int block_of(const Geo &g, int px, int py) {  // getBlockIdx :408-415
 // region-grow queue entry: pixel | plane id << 20
 PEAC_HD uint32_t rf_pack(int pix, int plid) { return (uint32_t)pix | ((uint32_t)plid << 20); }
 
+// floodFill :422-471 as the reference's FIFO, on thread 0 (Geo::floodSerial)
+PEAC_D void flood_serial(Shared &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid) {
+    if (tid != 0 || S.error != PEAC_OK) return;
+    int qn = S.curP;
+    for (int k = 0; k < qn; ++k) {
+        const uint32_t ent = F.rfq[k];
+        const int sIdx = (int)(ent & 0xfffffu), plid = (int)(ent >> 20);
+        const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
+        const Node &pl = S.node[S.extracted[plid]];
+        int q[4];
+        const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
+        for (int it = 0; it < nn; ++it) {
+            const int cIdx = q[it];
+            int32_t trail = membership[cIdx];
+            if (trail <= -6) continue;
+            if (trail >= 0 && trail == plid) continue;
+            const int cy = cIdx / g.W2, cx = cIdx - cy * g.W2;
+            const int blkid = block_of(g, cx, cy);
+            if (blkid >= 0 && S.blkMap[blkid] >= 0) continue;
+            double pt[3];
+            float cdist = -1;
+            bool near = false;
+            if (point(g, depth, cy, cx, pt)) {
+                const double sd = (pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1])) +
+                                  pl.normal[2] * (pt[2] - pl.center[2]);  // signedDist :355-359
+                cdist = (float)fabs(sd);
+                near = (double)cdist * (double)cdist < 9 * pl.mse + 1e-5;  // std::pow(float, 2): evaluated in double
+            }
+            if (near) {
+                if (trail >= 0) {
+                    const int a = S.extracted[trail], b = S.extracted[plid];
+                    if (nsim(pl, S.node[a]) >= g.thRefine) setbit(S.nbs[a], b), setbit(S.nbs[b], a);  // n_pl.connect(pl)
+                }
+                if (cdist < F.distMap[cIdx]) {
+                    membership[cIdx] = plid;
+                    F.distMap[cIdx] = cdist;
+                    if (qn < F.rfqCap)
+                        F.rfq[qn++] = rf_pack(cIdx, plid);
+                    else
+                        S.error = PEAC_ERR_QUEUE;
+                } else if (trail < 0) {
+                    membership[cIdx] = trail - 1;
+                }
+            } else if (trail < 0) {
+                membership[cIdx] = trail - 1;
+            }
+        }
+        if (S.error != PEAC_OK) break;
+    }
+}
+
+// floodFill :422-471 level by level (see the header comment); exactly the FIFO's result
+PEAC_D void flood_levels(Shared &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid, int nt) {
+    const int npix = g.W2 * g.H2;
+    for (int px = tid; px < npix; px += nt) F.own[px] = 0x7fffffff;
+    if (tid == 0) S.lvlBegin = 0, S.lvlEnd = S.curP;
+    PEAC_SYNC();
+    int *scan = (int *)S.candMse;  // nt + 1 ints
+    for (;;) {
+        const int begin = S.lvlBegin, L = S.lvlEnd - begin, nv = 4 * L;
+        if (L <= 0 || S.error != PEAC_OK) break;  // uniform: written by thread 0 before the last barrier
+        if (nv > F.visCap) {
+            if (tid == 0) S.error = PEAC_ERR_QUEUE;
+            break;
+        }
+        // (a) the state-independent part of every visit (entry k, neighbour it)
+        for (int v = tid; v < nv; v += nt) {
+            const uint32_t ent = F.rfq[begin + (v >> 2)];
+            const int sIdx = (int)(ent & 0xfffffu), plid = (int)(ent >> 20), it = v & 3;
+            const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
+            int q[4];
+            const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
+            int c = -1;
+            float cdist = -1;
+            uint8_t fl = 0;
+            if (it < nn) {
+                c = q[it];
+                const int cy = c / g.W2, cx = c - cy * g.W2;
+                const int blkid = block_of(g, cx, cy);
+                if (blkid >= 0 && S.blkMap[blkid] >= 0) {
+                    c = -1;  // inside a kept block: never touched
+                } else {
+                    const Node &pl = S.node[S.extracted[plid]];
+                    double pt[3];
+                    fl = 2;
+                    if (point(g, depth, cy, cx, pt)) {
+                        const double sd = (pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1])) +
+                                          pl.normal[2] * (pt[2] - pl.center[2]);
+                        cdist = (float)fabs(sd);
+                        if ((double)cdist * (double)cdist < 9 * pl.mse + 1e-5) fl = 3;
+                    }
+                }
+            }
+            F.visC[v] = c, F.visDist[v] = cdist, F.visFlag[v] = fl;
+        }
+        PEAC_SYNC();
+        // (b) resolve in visit order per target pixel: every round the earliest pending visit of each pixel
+        for (;;) {
+            if (tid == 0) S.pending = 0;
+            for (int v = tid; v < nv; v += nt)
+                if (F.visFlag[v] & 2) PEAC_ATOMIC_MIN(&F.own[F.visC[v]], v);
+            PEAC_SYNC();
+            for (int v = tid; v < nv; v += nt) {
+                const uint8_t fl = F.visFlag[v];
+                if (!(fl & 2)) continue;
+                const int c = F.visC[v];
+                if (PEAC_LOAD(&F.own[c]) != v) {
+                    PEAC_STORE(&S.pending, 1);
+                    continue;
+                }
+                const int plid = (int)(F.rfq[begin + (v >> 2)] >> 20);
+                const int32_t trail = membership[c];
+                uint8_t out = fl & 1;  // pending cleared
+                if (trail <= -6 || (trail >= 0 && trail == plid)) {
+                } else if (fl & 1) {
+                    if (trail >= 0) {
+                        const int a = S.extracted[trail], b = S.extracted[plid];
+                        if (nsim(S.node[b], S.node[a]) >= g.thRefine) {
+                            PEAC_ATOMIC_OR(&S.nbs[a][b >> 5], 1u << (b & 31));
+                            PEAC_ATOMIC_OR(&S.nbs[b][a >> 5], 1u << (a & 31));
+                        }
+                    }
+                    const float cdist = F.visDist[v];
+                    if (cdist < F.distMap[c]) {
+                        membership[c] = plid;
+                        F.distMap[c] = cdist;
+                        out |= 4;
+                    } else if (trail < 0) {
+                        membership[c] = trail - 1;
+                    }
+                } else if (trail < 0) {
+                    membership[c] = trail - 1;
+                }
+                F.visFlag[v] = out;
+                PEAC_STORE(&F.own[c], 0x7fffffff);
+            }
+            PEAC_SYNC();
+            if (!S.pending) break;
+            PEAC_SYNC();  // everyone has read `pending` before thread 0 clears it
+        }
+        // (c) the next level, in visit order: chunked scan of the push flags
+        const int chunk = (nv + nt - 1) / nt, lo = tid * chunk < nv ? tid * chunk : nv, hi = lo + chunk < nv ? lo + chunk : nv;
+        int cnt = 0;
+        for (int v = lo; v < hi; v++) cnt += (F.visFlag[v] >> 2) & 1;
+        scan[tid] = cnt;
+        PEAC_SYNC();
+        if (tid == 0) {
+            int acc = 0;
+            for (int t = 0; t < nt; t++) {
+                const int c = scan[t];
+                scan[t] = acc;
+                acc += c;
+            }
+            if (S.lvlEnd + acc > F.rfqCap) S.error = PEAC_ERR_QUEUE;
+            scan[nt] = acc;
+        }
+        PEAC_SYNC();
+        if (S.error == PEAC_OK) {
+            uint32_t *o = F.rfq + S.lvlEnd + scan[tid];
+            for (int v = lo; v < hi; v++)
+                if (F.visFlag[v] & 4) *o++ = rf_pack(F.visC[v], (int)(F.rfq[begin + (v >> 2)] >> 20));
+        }
+        PEAC_SYNC();
+        if (tid == 0) S.lvlBegin = S.lvlEnd, S.lvlEnd += scan[nt];
+        PEAC_SYNC();
+    }
+}
+
 // One frame.  blocks / seed / edges: the pre-stage outputs of the frame (centre, normal, mse, N per block; node mask;
-// edge mask bit0=left,1=right,2=up,3=down).  membership: H2*W2 int32 out.  distMap (H2*W2 floats) and rfq (rfqCap
-// entries) are per-frame scratch in global memory.  planes: <= planeCap records out; *planeCount out.
+// edge mask bit0=left,1=right,2=up,3=down).  membership: H2*W2 int32 out.  F: per-frame scratch of the region grow in
+// global memory.  planes: <= planeCap records out; *planeCount out.
 template <typename BlockStat>
 PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockStat *blocks, const uint8_t *seed, const uint8_t *edges,
-                  int32_t *membership, float *distMap, uint32_t *rfq, int rfqCap, PlaneOut *planes, int planeCap, int32_t *planeCount,
-                  int32_t *errorOut, int tid, int nt) {
+                  int32_t *membership, const Flood &F, PlaneOut *planes, int planeCap, int32_t *planeCount, int32_t *errorOut, int tid,
+                  int nt) {
+    float *const distMap = F.distMap;
+    uint32_t *const rfq = F.rfq;
+    const int rfqCap = F.rfqCap;
     const int nb = g.Nw * g.Nh, npix = g.W2 * g.H2;
     // ---- initGraph's nodes and edges from the pre-stage (AHCPlaneFitter.hpp:756-928)
     for (int b = tid; b < nb; b += nt) {
@@ -547,55 +754,11 @@ PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockSta
         }
     PEAC_SYNC();
 
-    // ---- floodFill :422-471 (order-dependent FIFO: thread 0)
-    if (tid == 0 && S.error == PEAC_OK) {
-        int qn = S.curP;
-        for (int k = 0; k < qn; ++k) {
-            const uint32_t ent = rfq[k];
-            const int sIdx = (int)(ent & 0xfffffu), plid = (int)(ent >> 20);
-            const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
-            const Node &pl = S.node[S.extracted[plid]];
-            int q[4];
-            const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
-            for (int it = 0; it < nn; ++it) {
-                const int cIdx = q[it];
-                int32_t trail = membership[cIdx];
-                if (trail <= -6) continue;
-                if (trail >= 0 && trail == plid) continue;
-                const int cy = cIdx / g.W2, cx = cIdx - cy * g.W2;
-                const int blkid = block_of(g, cx, cy);
-                if (blkid >= 0 && S.blkMap[blkid] >= 0) continue;
-                double pt[3];
-                float cdist = -1;
-                bool near = false;
-                if (point(g, depth, cy, cx, pt)) {
-                    const double sd = (pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1])) +
-                                      pl.normal[2] * (pt[2] - pl.center[2]);  // signedDist :355-359
-                    cdist = (float)fabs(sd);
-                    near = (double)cdist * (double)cdist < 9 * pl.mse + 1e-5;  // std::pow(float, 2): evaluated in double
-                }
-                if (near) {
-                    if (trail >= 0) {
-                        const int a = S.extracted[trail], b = S.extracted[plid];
-                        if (nsim(pl, S.node[a]) >= g.thRefine) setbit(S.nbs[a], b), setbit(S.nbs[b], a);  // n_pl.connect(pl)
-                    }
-                    if (cdist < distMap[cIdx]) {
-                        membership[cIdx] = plid;
-                        distMap[cIdx] = cdist;
-                        if (qn < rfqCap)
-                            rfq[qn++] = rf_pack(cIdx, plid);
-                        else
-                            S.error = PEAC_ERR_QUEUE;
-                    } else if (trail < 0) {
-                        membership[cIdx] = trail - 1;
-                    }
-                } else if (trail < 0) {
-                    membership[cIdx] = trail - 1;
-                }
-            }
-            if (S.error != PEAC_OK) break;
-        }
-    }
+    // ---- floodFill :422-471
+    if (g.floodSerial)
+        flood_serial(S, g, depth, membership, F, tid);
+    else
+        flood_levels(S, g, depth, membership, F, tid, nt);
     PEAC_SYNC();
 
     // ---- "try to merge one last time" :312-320: the valid planes re-enter the queue in plane order

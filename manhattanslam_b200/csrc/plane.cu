@@ -12,6 +12,7 @@
 //   k_peac_frame    f2     one CTA per frame: ahCluster + refineDetails (peac_frame.cuh) -> membershipImg, planes
 // All arithmetic is fp64 in the reference's operation order (file built with -fmad=false).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -226,18 +227,31 @@ __global__ void __launch_bounds__(128)
 static_assert(sizeof(msl_plane_rec) == sizeof(peac::PlaneOut) && sizeof(msl_plane_rec) == 64, "plane record layout");
 
 // ahCluster + refineDetails of one frame per CTA (peac_frame.cuh); 196 KB of dynamic shared memory
+struct PeacScratch {  // per-frame strides are implied: npix, rfqCap, visCap
+    float *dist;
+    uint32_t *rfq;
+    int *own, *visC;
+    float *visDist;
+    uint8_t *visFlag;
+    int rfqCap, visCap;
+};
+
 __global__ void __launch_bounds__(256)
     k_peac_frame(peac::Geo g, size_t frameStride, const uint16_t *__restrict__ depth, const msl_block_stat *__restrict__ blocks,
-                 const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership,
-                 float *__restrict__ distMap, uint32_t *__restrict__ rfq, int rfqCap, peac::PlaneOut *__restrict__ planes, int planeCap,
-                 int32_t *__restrict__ planeCount, int32_t *__restrict__ frameError) {
+                 const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership, PeacScratch sc,
+                 peac::PlaneOut *__restrict__ planes, int planeCap, int32_t *__restrict__ planeCount, int32_t *__restrict__ frameError) {
     extern __shared__ __align__(16) unsigned char peac_smem[];
     peac::Shared &S = *reinterpret_cast<peac::Shared *>(peac_smem);
     const int b = blockIdx.x, nb = g.Nw * g.Nh;
     const size_t npix = (size_t)g.W2 * g.H2;
+    peac::Flood F;
+    F.distMap = sc.dist + b * npix, F.own = sc.own + b * npix;
+    F.rfq = sc.rfq + (size_t)b * sc.rfqCap, F.rfqCap = sc.rfqCap;
+    F.visC = sc.visC + (size_t)b * sc.visCap, F.visDist = sc.visDist + (size_t)b * sc.visCap, F.visFlag = sc.visFlag + (size_t)b * sc.visCap;
+    F.visCap = sc.visCap;
     peac::frame(S, g, depth + b * frameStride, blocks + (size_t)b * nb, seed + (size_t)b * nb, edges + (size_t)b * nb,
-                membership + b * npix, distMap + b * npix, rfq + (size_t)b * rfqCap, rfqCap, planes + (size_t)b * planeCap, planeCap,
-                planeCount + b, frameError + b, (int)threadIdx.x, (int)blockDim.x);
+                membership + b * npix, F, planes + (size_t)b * planeCap, planeCap, planeCount + b, frameError + b, (int)threadIdx.x,
+                (int)blockDim.x);
 }
 
 }  // namespace
@@ -252,8 +266,10 @@ struct msl_plane {
     uint8_t *d_seed = nullptr, *d_edges = nullptr;
     // msl_plane_detect*: allocated on first use
     int32_t *d_mem = nullptr, *d_count = nullptr, *d_ferr = nullptr;
-    float *d_dist = nullptr;
+    float *d_dist = nullptr, *d_visDist = nullptr;
     uint32_t *d_rfq = nullptr;
+    int *d_own = nullptr, *d_visC = nullptr;
+    uint8_t *d_visFlag = nullptr;
     msl_plane_rec *d_planes = nullptr;
     int planeCap = 0;
     int pendingCheck = 0;  // frames of an enqueued detect whose per-frame error words have not been read yet
@@ -263,7 +279,7 @@ static void plane_free(msl_plane *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_depth, p->d_cloud, p->d_blocks, p->d_seed, p->d_edges, p->d_mem, p->d_count, p->d_ferr,
-                    p->d_dist, p->d_rfq, p->d_planes};
+                    p->d_dist, p->d_rfq, p->d_planes, p->d_own, p->d_visC, p->d_visDist, p->d_visFlag};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -357,6 +373,11 @@ static int plane_detect_alloc(msl_plane *p) {
     cudaError_t e = cudaMalloc((void **)&p->d_mem, B * npix * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_dist, B * npix * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_rfq, B * npix * 4 * sizeof(uint32_t));
+    // region grow by levels: one level holds at most npix entries = 4 * npix visits
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_own, B * npix * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_visC, B * npix * 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_visDist, B * npix * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_visFlag, B * npix * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_count, B * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ferr, B * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_planes, B * PLANE_CAP_INTERNAL * sizeof(msl_plane_rec));
@@ -385,11 +406,14 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     g.W2 = p->W2, g.H2 = p->H2, g.Nw = p->Nw, g.Nh = p->Nh, g.dstride = dstride_px;
     g.fx = K[0], g.fy = K[1], g.cx = K[2], g.cy = K[3], g.factor = depth_map_factor;
     g.thMerge = std::cos(60.0 * M_PI / 180.0), g.thRefine = std::cos(30.0 * M_PI / 180.0);  // AHCParamSet.hpp:72-73
-    const int rfqCap = 4 * p->W2 * p->H2;
+    const char *fs = getenv("MSL_PEAC_FLOOD_SERIAL");  // 1: the region grow as a FIFO on thread 0 (A/B, cross-check)
+    g.floodSerial = (fs && atoi(fs) != 0) ? 1 : 0;
+    PeacScratch sc;
+    sc.dist = p->d_dist, sc.rfq = p->d_rfq, sc.own = p->d_own, sc.visC = p->d_visC, sc.visDist = p->d_visDist, sc.visFlag = p->d_visFlag;
+    sc.rfqCap = 4 * p->W2 * p->H2, sc.visCap = 4 * p->W2 * p->H2;
     k_peac_frame<<<batch, 256, sizeof(peac::Shared), p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
-                                                                 d_membership, p->d_dist, p->d_rfq, rfqCap,
-                                                                 reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count,
-                                                                 p->d_ferr);
+                                                                 d_membership, sc, reinterpret_cast<peac::PlaneOut *>(d_planes),
+                                                                 plane_cap, d_plane_count, p->d_ferr);
     MSL_LAUNCH_CHECK();
     p->pendingCheck = batch > p->pendingCheck ? batch : p->pendingCheck;
     return MSL_OK;

@@ -1,7 +1,7 @@
 // peac_host_mt.cpp -- TEST HARNESS (tests/test_peac_host_emulation.py): manhattanslam_b200/csrc/peac_frame.cuh run by several
 // REAL threads that play the threads of one CTA, PEAC_SYNC() = a pthread barrier, built with -fsanitize=thread.  A missing
 // barrier between two phases of the kernel shows up as a ThreadSanitizer data-race report (and usually as a wrong result).
-// usage: peac_host_mt <threads> <in.bin> <out.bin>; in.bin = header {w, h, cap} as int32, {fx, fy, cx, cy, factor} as float,
+// usage: peac_host_mt <threads> <in.bin> <out.bin> [flood_serial]; in.bin = header {w, h, cap} as int32, {fx, fy, cx, cy, factor} as float,
 // depth u16[w*h], blocks 72 B x nb, seed u8[nb], edges u8[nb]; out.bin = count i32, error i32, membership i32[h2*w2],
 // planes 64 B x cap.  Never linked into the product library.
 #define PEAC_HOST_EMULATION_MT
@@ -23,7 +23,7 @@ struct BlockStat {
 };
 
 int main(int argc, char **argv) {
-    if (argc != 4) return 2;
+    if (argc != 4 && argc != 5) return 2;
     const int nt = atoi(argv[1]);
     FILE *f = fopen(argv[2], "rb");
     if (!f) return 2;
@@ -36,6 +36,7 @@ int main(int argc, char **argv) {
     g.Nw = g.W2 / peac::WIN, g.Nh = g.H2 / peac::WIN;
     g.dstride = w, g.fx = kf[0], g.fy = kf[1], g.cx = kf[2], g.cy = kf[3], g.factor = kf[4];
     g.thMerge = std::cos(60.0 * M_PI / 180.0), g.thRefine = std::cos(30.0 * M_PI / 180.0);
+    g.floodSerial = argc == 5 ? atoi(argv[4]) : 0;
     const int nb = g.Nw * g.Nh, npix = g.W2 * g.H2;
     if (nb > peac::MAXB) return 3;
     std::vector<uint16_t> depth((size_t)w * h);
@@ -49,6 +50,10 @@ int main(int argc, char **argv) {
     std::vector<int32_t> mem(npix);
     std::vector<float> dist(npix);
     std::vector<uint32_t> rfq((size_t)4 * npix);
+    std::vector<int> own(npix), visC((size_t)4 * npix);
+    std::vector<float> visDist((size_t)4 * npix);
+    std::vector<uint8_t> visFlag((size_t)4 * npix);
+    peac::Flood F{dist.data(), rfq.data(), (int)rfq.size(), own.data(), visC.data(), visDist.data(), visFlag.data(), 4 * npix};
     std::vector<peac::PlaneOut> planes(cap);
     memset(planes.data(), 0, sizeof(peac::PlaneOut) * cap);
     int32_t count = 0, error = 0;
@@ -56,8 +61,8 @@ int main(int argc, char **argv) {
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++)
         th.emplace_back([&, t] {
-            peac::frame(S[0], g, depth.data(), blocks.data(), seed.data(), edges.data(), mem.data(), dist.data(), rfq.data(),
-                        (int)rfq.size(), planes.data(), cap, &count, &error, t, nt);
+            peac::frame(S[0], g, depth.data(), blocks.data(), seed.data(), edges.data(), mem.data(), F, planes.data(), cap, &count,
+                        &error, t, nt);
         });
     for (auto &t : th) t.join();
     f = fopen(argv[3], "wb");

@@ -28,24 +28,26 @@ def emu():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.peac_host_frame.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p] * 5 +
-                                  [C.c_int, C.c_void_p, C.c_int])
+                                  [C.c_int, C.c_void_p, C.c_int, C.c_int])
     return L
 
 
-def _run(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0):
+def _run(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0, flood_serial=0):
     h, w = d16.shape
     d16 = np.ascontiguousarray(d16, np.uint16)
     _, blocks, seed, edges = oracle.plane_prestage(d16, K=K, depth_map_factor=fac)
     mem = np.zeros(((h + 1) // 2, (w + 1) // 2), np.int32)
     pl, err = np.zeros(64, PL), np.zeros(1, np.int32)
     n = emu.peac_host_frame(d16.ctypes.data, w, h, w, K[0], K[1], K[2], K[3], fac, blocks.ctypes.data, seed.ctypes.data,
-                            edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 64, err.ctypes.data, 4 * mem.size)
+                            edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 64, err.ctypes.data, 4 * mem.size, flood_serial)
     assert n >= 0 and err[0] == 0
     return mem, pl[:n]
 
 
 def _same(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0):
-    mem, pl = _run(emu, oracle, d16, K, fac)
+    mem, pl = _run(emu, oracle, d16, K, fac)            # region grow by levels (the default)
+    mem_s, pl_s = _run(emu, oracle, d16, K, fac, 1)     # ... and as the FIFO on thread 0
+    assert np.array_equal(mem, mem_s) and pl.tobytes() == pl_s.tobytes()
     mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=fac)
     assert len(pl) == len(po["N"])
     assert np.array_equal(mem, mo)
@@ -94,7 +96,7 @@ def test_larger_frames_are_refused(emu, oracle):
     _, blocks, seed, edges = oracle.plane_prestage(d16)
     mem, pl, err = np.zeros((480, 640), np.int32), np.zeros(4, PL), np.zeros(1, np.int32)
     assert emu.peac_host_frame(d16.ctypes.data, 1280, 960, 1280, 525.0, 525.0, 319.5, 239.5, 1.0, blocks.ctypes.data,
-                               seed.ctypes.data, edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 4, err.ctypes.data, 16) == -1
+                               seed.ctypes.data, edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 4, err.ctypes.data, 16, 0) == -1
 
 
 # ---- the CTA's barriers: several real threads + a pthread barrier under ThreadSanitizer (tests/host_emul/peac_host_mt.cpp)
