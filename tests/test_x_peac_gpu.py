@@ -77,3 +77,18 @@ def test_plane_detect_equals_reference_source_golden(msl):
     mem, planes = msl.PlaneDetection(max_batch=1).detect(d16, depthMapFactor=1.0)
     assert np.array_equal(mem[0], gold["peac_membership"].astype(np.int32))
     assert np.array_equal(planes[0]["N"], gold["peac_plane_N"])
+
+
+def test_plane_detect_fifo_region_grow_equals_level_region_grow(oracle, msl, monkeypatch):
+    """MSL_PEAC_FLOOD_SERIAL=1 runs floodFill as the reference's FIFO on thread 0 instead of level by level: same result"""
+    d = np.stack([S.depth_frame(40 + b)[0] for b in range(3)])
+    pd = msl.PlaneDetection(max_batch=3)
+    mem_l, planes_l = pd.detect(d, depthMapFactor=1.0)
+    monkeypatch.setenv("MSL_PEAC_FLOOD_SERIAL", "1")
+    mem_s, planes_s = pd.detect(d, depthMapFactor=1.0)
+    monkeypatch.delenv("MSL_PEAC_FLOOD_SERIAL")
+    assert np.array_equal(mem_l, mem_s)
+    for a, b in zip(planes_l, planes_s):
+        assert a.tobytes() == b.tobytes()
+    mo, po = oracle.plane_detect(d[0], depth_map_factor=1.0)
+    _check(mem_s[0], planes_s[0], mo, po)
