@@ -117,6 +117,60 @@ def cpu_frontend(gray, depth, mem, poses, surfels, frames, threads):
     return frames / dt, dt
 
 
+def cpu_stage_breakdown(gray, depth, mem, poses, surfels, frames=2):
+    """SURVEY.md section 8(d) 'CPU baseline timing': where the CPU path spends its time -- each stage of the oracle port on ONE
+    thread (ms per frame; the reference runs ORB on one thread per frame), SurfelFusion with its 10 scan threads, and the
+    OpenCV primitives ORB is made of timed through cv2 (SIMD, the 'optimised OpenCV' lower bound for the oracle's scalar
+    FAST / resize / blur).  A few frames only; reported beside the baseline, never part of it."""
+    from oracle import binding as ob
+    out = {}
+    try:
+        def ms(fn, n=frames):
+            t0 = time.perf_counter()
+            for i in range(n):
+                fn(i)
+            return 1e3 * (time.perf_counter() - t0) / n
+        o = ob.OrbOracle()
+        descs = {}
+
+        def orb(i):
+            descs[i] = o(gray[i])[1]
+        out["orb_1_thread_ms_per_frame"] = ms(orb)
+        out["plane_prestage_1_thread_ms_per_frame"] = ms(lambda i: ob.plane_prestage(make_inputs.depth16[i]))
+        out["plane_detect_1_thread_ms_per_frame"] = ms(lambda i: ob.plane_detect(make_inputs.depth16[i], depth_map_factor=1.0))
+        out["hamming_1000x1000_1_thread_ms"] = ms(lambda i: ob.hamming_best2(descs[0], descs[1]), 1)
+        so, local = ob.SurfelOracle(W, H), surfels.copy()
+        out["surfel_fuse_10_threads_ms_per_frame"] = ms(lambda i: so.fuse(100 + i, gray[i], depth[i], mem[i], poses[i], local,
+                                                                          threads=min(10, os.cpu_count() or 1)))
+    except Exception as e:  # noqa: BLE001 -- diagnostics only
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        g = gray[0]
+        det = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True, type=cv2.FastFeatureDetector_TYPE_9_16)
+
+        def best(fn, n=5):
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return 1e3 * min(ts)
+
+        def pyramid():
+            lv = g
+            for l in range(1, 8):
+                s = 1.0 / (1.2 ** l)
+                lv = cv2.resize(lv, (int(round(W * s)), int(round(H * s))), interpolation=cv2.INTER_LINEAR)
+        out["cv2_1_thread_ms"] = {"version": cv2.__version__, "pyramid_7_resizes": best(pyramid),
+                                  "fast20_nms_level0_whole_image": best(lambda: det.detect(g)),
+                                  "gaussian_blur_7x7_level0": best(lambda: cv2.GaussianBlur(g, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101))}
+    except Exception as e:  # noqa: BLE001
+        out["cv2_1_thread_ms"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
 def run_reference(a, rank, world):
     if rank != 0:
         return
@@ -571,7 +625,8 @@ def run_ours(a, rank, world, local_rank):
         fps, dt = cpu_frontend(gray, depth, mem, poses, surfels, frames, threads)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d frames (%.1f s): oracle ORB + plane pre-stage + Hamming match frame-parallel on %d threads, oracle "
-                         "SurfelFusion with 10 scan threads into the %d-surfel map" % (frames, dt, threads, a.surfels)}
+                         "SurfelFusion with 10 scan threads into the %d-surfel map" % (frames, dt, threads, a.surfels),
+               "stages": cpu_stage_breakdown(gray, depth, mem, poses, surfels)}
 
     widened = widened_in_child(local_rank) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
 
