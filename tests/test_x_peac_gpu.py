@@ -92,3 +92,27 @@ def test_plane_detect_fifo_region_grow_equals_level_region_grow(oracle, msl, mon
         assert a.tobytes() == b.tobytes()
     mo, po = oracle.plane_detect(d[0], depth_map_factor=1.0)
     _check(mem_s[0], planes_s[0], mo, po)
+
+
+def test_detected_membership_feeds_surfel_fusion(oracle, msl):
+    """the chain Tracking runs (src/Tracking.cc:227-229): plane detection -> membershipImg -> SurfelFusion, on the device
+    path and on the oracle; superpixel index, new surfels and the fused map must agree"""
+    seed = 5
+    g = S.gray_frame(seed)
+    d16, d = S.depth_frame(seed)
+    T = S.pose_walk(seed, 1)[0]
+    local = S.surfel_map(seed, 20000, d, T, ref_index=30)
+    mem_g, _ = msl.PlaneDetection(max_batch=1).detect(d16, depthMapFactor=1.0)
+    mem_o, _ = oracle.plane_detect(d16, depth_map_factor=1.0)
+    assert np.array_equal(mem_g[0], mem_o) and (mem_o >= 0).any() and (mem_o <= -2).any()
+    sf = msl.SurfelFusion(max_surfels=len(local) + 4800)
+    sf.upload_map(local)
+    new_g, _ = sf.fuseInitializeMap(31, g, d, mem_g[0], T, compact=False)
+    lo = local.copy()
+    o = oracle.SurfelOracle()
+    new_o = o.fuse(31, g, d, mem_o, T, lo)
+    assert np.array_equal(sf.debug_index(), o.index())
+    assert new_g.tobytes() == new_o.tobytes() or np.isnan(new_o["weight"]).any()
+    got = sf.download_map()
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], lo[f]) or (got[f].dtype.kind == "f" and np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6, equal_nan=True)), f
