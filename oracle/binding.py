@@ -155,6 +155,8 @@ class OrbOracle:
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = self.L.orc_orb_extract(self.h, _p(gray), w, h, gray.strides[0], _p(kps), _p(desc), cap)
+        if n == -2:
+            raise ValueError("the reference is undefined for this geometry (a pyramid level more than twice as tall as wide)")
         if n < 0:
             raise RuntimeError("oracle keypoint capacity exceeded")
         return kps[:n].copy(), desc[:n].copy()
@@ -597,7 +599,7 @@ class RefOrbExtractor:
         cap = self.nfeatures + 8 * self.nlevels + 64
         kps, desc = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
         wh = np.zeros((self.nlevels, 2), np.int32)
-        pyr = np.zeros(w * h * 4 + 64, np.uint8)
+        pyr = np.zeros(w * h * self.nlevels + 64, np.uint8)  # every level is at most as large as the input
         fn = self.L.ref_orb_extract if self.arena else self.L.ref_orb_extract_malloc
         n = fn(*self.params, _p(gray), w, h, gray.strides[0], _p(kps), _p(desc), cap, _p(wh), _p(pyr))
         if n < 0 or n > cap:

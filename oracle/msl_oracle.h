@@ -60,7 +60,8 @@ void orc_orb_features_per_level(const orc_orb *, int32_t *n);
 void orc_orb_umax(const orc_orb *, int32_t *umax16);
 
 /* ORBextractor::operator(), src/ORBextractor.cc:813-870.  Returns the number of
- * keypoints (<= cap) or -1 if cap is too small.  desc is n x 32 bytes. */
+ * keypoints (<= cap), -1 if cap is too small, -2 for a geometry on which the reference itself is undefined (a level more
+ * than twice as tall as wide: zero octree roots, division by zero at :535).  desc is n x 32 bytes. */
 int orc_orb_extract(orc_orb *, const uint8_t *gray, int w, int h, int stride,
                     orc_keypoint *kps, uint8_t *desc, int cap);
 

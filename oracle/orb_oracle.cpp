@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <stdexcept>
 #include <utility>
 #include <vector>
 
@@ -364,6 +365,10 @@ struct orc_orb {
     std::vector<XYR> DistributeOctTree(const std::vector<XYR> &vToDistributeKeys, int minX, int maxX, int minY,
                                        int maxY, int N) {
         const int nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
+        // A level more than twice as tall as wide gives nIni == 0: the reference then divides by zero and indexes an empty
+        // vector (undefined behaviour, :535-560).  The oracle reports it instead (orc_orb_extract returns -2); the CUDA path
+        // refuses such geometry at msl_orb_create.
+        if (nIni < 1) throw std::domain_error("DistributeOctTree: zero root nodes");
         const float hX = static_cast<float>(maxX - minX) / nIni;
         std::list<Node> lNodes;
         std::vector<Node *> vpIniNodes(nIni);
@@ -660,7 +665,11 @@ int orc_orb_extract(orc_orb *o, const uint8_t *gray, int w, int h, int stride, o
                     int cap) {
     if (!gray || w <= 0 || h <= 0) return 0;  // _image.empty() => silent return (:815-816)
     o->ComputePyramid(gray, w, h, stride);
-    o->ComputeKeyPointsOctTree();
+    try {
+        o->ComputeKeyPointsOctTree();
+    } catch (const std::domain_error &) {
+        return -2;  // input geometry for which the reference itself is undefined
+    }
     int nkeypoints = 0;
     for (int level = 0; level < o->nlevels; ++level) nkeypoints += (int)o->levelKps[level].size();
     if (nkeypoints > cap) return -1;
