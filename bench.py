@@ -336,7 +336,7 @@ def widened_in_child(device, timeout_s=180):
     """widened_ops / widened_peac in child processes with a deadline: the diagnostics exercise kernels outside the timed step,
     and neither a device fault nor a hang there may cost the bench line."""
     res = _widened_child(device, "matcher", timeout_s)
-    res.update(_widened_child(device, "peac", timeout_s))
+    res.update(_widened_child(device, "peac", min(timeout_s, 90)))
     return res
 
 
