@@ -212,6 +212,13 @@ typedef struct {
 void orc_plane_prestage(const uint16_t *depth, int w, int h, int dstride_px,
                         float fx, float fy, float cx, float cy, float depthMapFactor,
                         double *cloud_xyz, orc_block_stat *blocks, uint8_t *seed, uint8_t *edges);
+/* Frame::ExtractPlanes' readDepthImage + runPlaneDetection (src/Frame.cc:607-609): the whole of ahc::PlaneFitter::run --
+ * the pre-stage above, ahCluster (include/peac/AHCPlaneFitter.hpp:939-1143) and refineDetails (:294-374); restated in
+ * peac_oracle.inc.  membership: h2*w2 int32 (plane id, -1, or floodFill's trail counters <= -2); per extracted plane
+ * (<= cap): normal[3], center[3], N, rid, number of member pixels.  Returns the number of planes. */
+int orc_plane_detect(const uint16_t *depth, int w, int h, int dstride_px, float fx, float fy, float cx, float cy,
+                     float depthMapFactor, int32_t *membership, double *plane_normal, double *plane_center, int32_t *plane_N,
+                     int32_t *plane_rid, int32_t *plane_vertices, int cap);
 /* symmetric 3x3 eigen-decomposition used above (ascending eigenvalues, columns of V) */
 void orc_eig33sym(const double K[9], double s[3], double V[9]);
 
