@@ -548,7 +548,8 @@ _REF_DEPS = {
                          "plane_oracle.cpp", "orb_oracle.cpp", "msl_oracle.h"]),
     "libmatch_ref.so": (["src/ORBmatcher.cc", "include/ORBmatcher.h", "Thirdparty/DBoW2/DBoW2/FeatureVector.cpp",
                          "Thirdparty/DBoW2/DBoW2/FeatureVector.h"],
-                        ["ref_match_wrap.cpp", "ref_shim_cv/cvshim.hpp", "ref_shim_match/slam_standins.hpp", "match_oracle.cpp",
+                        ["ref_match_wrap.cpp", "ref_shim_cv/cvshim.hpp", "ref_shim_match/slam_standins.hpp",
+                         "ref_shim_match/slam_standins.cpp", "match_oracle.cpp",
                          "orb_oracle.cpp", "msl_oracle.h"]),
 }
 
@@ -617,13 +618,13 @@ class RefOrbExtractor:
 class _RefMatchProxy:
     """orc_search_* -> ref_search_* of oracle/_ref/libmatch_ref.so (same flat signatures, see oracle/ref_match_wrap.cpp)"""
 
-    def __init__(self, L):
-        self._L = L
+    def __init__(self, L, prefix="ref_"):
+        self._L, self._prefix = L, prefix
 
     def __getattr__(self, name):
         if not name.startswith("orc_search_"):
             raise AttributeError(name)
-        return getattr(self._L, "ref_" + name[4:])
+        return getattr(self._L, self._prefix + name[4:])
 
 
 _MATCH_REF = None
@@ -645,9 +646,14 @@ class reference_matcher:
     instead of the oracle restatement.  Slots the oracle reports as -3 (assigned, then reset by the rotation check) come
     back as -1 -- the reference stores NULL for both.  Used by tests/test_oracle_ref.py, nowhere else."""
 
+    def __init__(self, library=None, prefix="ref_"):
+        """library / prefix: another ctypes library exporting <prefix>search_* with the same signatures (the adapter harness
+        of tests/test_adapters_on_mock_abi.py)"""
+        self._lib, self._prefix = library, prefix
+
     def __enter__(self):
         global _LIB_OVERRIDE
-        _LIB_OVERRIDE = _RefMatchProxy(_match_ref())
+        _LIB_OVERRIDE = _RefMatchProxy(self._lib if self._lib is not None else _match_ref(), self._prefix)
         return self
 
     def __exit__(self, *exc):
@@ -661,11 +667,12 @@ def ref_descriptor_distance(a, b):
     return _match_ref().ref_descriptor_distance(_p(a), _p(b))
 
 
-def ref_fuse(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf):
+def ref_fuse(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf, library=None, name="ref_fuse"):
     """ORBmatcher::Fuse of the reference's own source on the arguments of fuse_search -> (nFused, fused_idx per map point:
     the KeyFrame keypoint the map point was added at, -1 if it was not fused)"""
-    L = _match_ref()
-    L.ref_fuse.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int] + [C.c_void_p] * 5 +
+    L = library if library is not None else _match_ref()
+    fn = getattr(L, name)
+    fn.argtypes = ([C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int] + [C.c_void_p] * 5 +
                            [C.c_int] + [C.c_void_p] * 4 + [C.c_void_p])
     a = lambda x, dt: np.ascontiguousarray(x, dt)
     ils = a(inv_level_sigma2, np.float32)
@@ -673,8 +680,8 @@ def ref_fuse(geom, Tcw, th, log_scale_factor, inv_level_sigma2, mps, kf):
              a(mps["desc"], np.uint8)]
     kargs = [a(kf["xy"], np.float32), a(kf["octave"], np.int32), a(kf["uright"], np.float32), a(kf["desc"], np.uint8)]
     fi = np.zeros(len(margs[0]), np.int32)
-    n = L.ref_fuse(_p(geom), _p(a(Tcw, np.float32)), th, log_scale_factor, _p(ils), len(margs[0]), *[_p(x) for x in margs],
-                   len(kargs[1]), *[_p(x) for x in kargs], _p(fi))
+    n = fn(_p(geom), _p(a(Tcw, np.float32)), th, log_scale_factor, _p(ils), len(margs[0]), *[_p(x) for x in margs],
+           len(kargs[1]), *[_p(x) for x in kargs], _p(fi))
     return n, fi
 
 

@@ -43,7 +43,8 @@ void fill_grid(GridGeom &G, const orc_frame_geom *g, const float *xy, const int3
 void fill_frame(Frame &F, const orc_frame_geom *g, int n, const float *xy, const int32_t *octave, const float *angle,
                 const float *uright, const uint8_t *desc) {
     F.fx = g->fx, F.fy = g->fy, F.cx = g->cx, F.cy = g->cy, F.mbf = g->mbf, F.mb = g->mb;
-    F.mnMinX = g->mnMinX, F.mnMaxX = g->mnMaxX, F.mnMinY = g->mnMinY, F.mnMaxY = g->mnMaxY;
+    F.mnMinX = g->mnMinX, F.mnMaxX = g->mnMaxX, F.mnMinY = g->mnMinY, F.mnMaxY = g->mnMaxY;  // statics, as in the reference
+    Frame::mfGridElementWidthInv = g->gridWInv, Frame::mfGridElementHeightInv = g->gridHInv;
     F.N = n;
     F.mnScaleLevels = g->nlevels;
     F.mvScaleFactors.assign(g->scaleFactors, g->scaleFactors + 16);

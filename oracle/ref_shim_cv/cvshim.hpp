@@ -170,6 +170,10 @@ public:
     }
     Mat(const MatZeros &z) : Mat() { *this = z; }
     Mat(const MatExprMul &e);  // evaluates the product (below)
+    void convertTo(Mat &m, int rtype) const {  // same-depth conversions only: a copy
+        assert((rtype & 7) == depth());
+        m = clone();
+    }
     Mat row(int i) const { return (*this)(Rect(0, i, cols, 1)); }
     Mat col(int j) const { return (*this)(Rect(j, 0, 1, rows)); }
     MatExprT t() const;

@@ -81,7 +81,7 @@ public:
         return grid.query(x, y, r, minLevel, maxLevel);
     }
     DBoW2::FeatureVector mFeatVec;
-    float fx, fy, cx, cy;  // static members in the reference
+    static float fx, fy, cx, cy;  // static in the reference as well (include/Frame.h:117-122); defined in slam_standins.cpp
     float mbf, mb;
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
@@ -93,12 +93,14 @@ public:
     int mnScaleLevels;
     float mfScaleFactor, mfLogScaleFactor;
     std::vector<float> mvScaleFactors;
-    float mnMinX, mnMaxX, mnMinY, mnMaxY;  // static members in the reference
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;                          // include/Frame.h:228-231
+    static float mfGridElementWidthInv, mfGridElementHeightInv;          // include/Frame.h:202-203
     GridGeom grid;
 };
 
 class KeyFrame {
 public:
+    cv::Mat GetPose() { return Tcw.clone(); }
     cv::Mat GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
     cv::Mat GetCameraCenter() { return Ow.clone(); }
@@ -108,7 +110,8 @@ public:
     std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r) const { return grid.query(x, y, r, -1, -1); }
     bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
 
-    const float fx, fy, cx, cy, mbf;
+    const float fx, fy, cx, cy, mbf, mb;
+    const float mfGridElementWidthInv, mfGridElementHeightInv;
     const int N;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<float> mvuRight;
@@ -123,7 +126,8 @@ public:
     std::vector<MapPoint *> mvpMapPoints;
     GridGeom grid;
     KeyFrame(const orc_frame_geom &g, int n, int nlevels, float logScaleFactor)
-        : fx(g.fx), fy(g.fy), cx(g.cx), cy(g.cy), mbf(g.mbf), N(n), mnScaleLevels(nlevels), mfLogScaleFactor(logScaleFactor),
+        : fx(g.fx), fy(g.fy), cx(g.cx), cy(g.cy), mbf(g.mbf), mb(g.mb), mfGridElementWidthInv(g.gridWInv),
+          mfGridElementHeightInv(g.gridHInv), N(n), mnScaleLevels(nlevels), mfLogScaleFactor(logScaleFactor),
           mnMinX((int)g.mnMinX), mnMinY((int)g.mnMinY), mnMaxX((int)g.mnMaxX), mnMaxY((int)g.mnMaxY) {}
 };
 

@@ -115,3 +115,83 @@ def test_surfelfusion_binding_equals_reference_class(adp, oracle, seed, pf, n):
                 assert ((x.view(np.uint32) == y.view(np.uint32)) | (np.isnan(x) & np.isnan(y))).all(), f
             else:
                 assert np.array_equal(x, y), f
+
+
+# ---- adapters/ORBmatcher_msl.cc: the binding's seven methods and the reference's own seven (src/ORBmatcher.cc, renamed out of
+# the way by -D macros: what INTEGRATION.md's `#ifndef MSL_FRONTEND` does) in ONE library, called on the same stand-in
+# Frame / KeyFrame / MapPoint object graphs (oracle/ref_shim_match/slam_standins.hpp) through the same wrapper
+# (oracle/ref_match_wrap.cpp compiled twice); the C ABI underneath the binding = tests/host_emul/mock_abi_matcher.cpp.
+@pytest.fixture(scope="module")
+def madp(oracle):
+    if not os.path.isdir(os.path.join(REF, "include")):
+        pytest.skip("/root/reference absent")
+    orc, out = os.path.join(ROOT, "oracle"), os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libmatch_adapter_mock.so")
+    deps = [os.path.join(orc, f) for f in ("ref_match_wrap.cpp", "ref_shim_cv/cvshim.hpp", "ref_shim_match/slam_standins.hpp",
+                                            "ref_shim_match/slam_standins.cpp", "match_oracle.cpp", "orb_oracle.cpp", "msl_oracle.h")]
+    deps += [os.path.join(ROOT, "adapters", "ORBmatcher_msl.cc"), os.path.join(HERE, "host_emul", "mock_abi_matcher.cpp"),
+             os.path.join(ROOT, "include", "msl_frontend.h")]
+    if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+        fl = ["-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + os.path.join(orc, "ref_shim_cv"),
+              "-I" + os.path.join(orc, "ref_shim_match"), "-I" + orc, "-I" + os.path.join(REF, "include"), "-I" + REF,
+              "-I" + os.path.join(ROOT, "include")]
+        inc = ["-DMAPPOINT_H", "-DKEYFRAME_H", "-DFRAME_H", "-include", os.path.join(orc, "ref_shim_match", "slam_standins.hpp")]
+        methods = ["SearchByProjection", "SearchByBoW", "SearchForTriangulation", "Fuse", "DescriptorDistance"]
+        ren = ["-D%s=%s_reference" % (m, m) for m in methods]
+        entries = ["descriptor_distance", "search_by_projection_frame", "search_by_projection_points", "search_by_projection_keyframe",
+                   "search_by_bow", "search_for_triangulation", "fuse"]
+        adp = ["-Dref_%s=adp_%s" % (e, e) for e in entries]
+        objs = []
+
+        def cc(name, src, extra):
+            o = os.path.join(out, name)
+            subprocess.check_call(["g++"] + fl + extra + ["-c", "-o", o, src])
+            objs.append(o)
+        cc("m_ref.o", os.path.join(REF, "src", "ORBmatcher.cc"), inc + ren)
+        cc("m_wrap_ref.o", os.path.join(orc, "ref_match_wrap.cpp"), inc + ren)
+        cc("m_wrap_adp.o", os.path.join(orc, "ref_match_wrap.cpp"), inc + adp)
+        cc("m_adp.o", os.path.join(ROOT, "adapters", "ORBmatcher_msl.cc"), inc)
+        cc("m_fv.o", os.path.join(REF, "Thirdparty", "DBoW2", "DBoW2", "FeatureVector.cpp"), [])
+        subprocess.check_call(["g++"] + fl + inc + ["-shared", "-o", so] + objs +
+                              [os.path.join(orc, "ref_shim_match", "slam_standins.cpp"), os.path.join(HERE, "host_emul", "mock_abi_matcher.cpp"),
+                               os.path.join(orc, "match_oracle.cpp"), os.path.join(orc, "orb_oracle.cpp")])
+        for o in objs:
+            os.remove(o)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_orbmatcher_binding_equals_reference_methods(madp, oracle, seed):
+    from manhattanslam_b200.matcher import frame_geom
+    B, g = oracle, frame_geom()
+    lsf = float(np.float32(np.log(np.float64(np.float32(1.2)))))
+
+    def pair(fn, *a):
+        with B.reference_matcher(madp, "ref_"):
+            r = fn(*a)
+        with B.reference_matcher(madp, "adp_"):
+            d = fn(*a)
+        assert r[0] == d[0] and np.array_equal(r[1], d[1]), fn.__name__
+        return r[0]
+
+    cur, last, mps, Tc, Tl = S.match_scene(seed)
+    cur2, kf, Tc2 = S.reloc_scene(seed)
+    kfb, f = S.bow_scene(seed, shuffle=bool(seed & 1))
+    kf1, kf2, F12, Cw1, Tcw2, K2, sf, ls = S.triangulation_scene(seed)
+    mpf, kfs, Tcw, ils = S.fuse_scene(seed)
+    for chk in (False, True):
+        assert pair(B.search_by_projection_frame, g, Tc, Tl, 15.0, chk, last, cur) > 100
+        assert pair(B.search_by_projection_keyframe, g, Tc2, 15.0, 100, chk, lsf, kf, cur2) > 100
+        assert pair(B.search_by_bow, 0.7, chk, kfb, f) > 100
+        for only_stereo in (False, True):
+            assert pair(B.search_for_triangulation, F12, Cw1, Tcw2, K2, only_stereo, chk, sf, ls, kf1, kf2) > 30
+    for th in (1.0, 3.0):
+        assert pair(B.search_by_projection_points, g, th, 0.8, mps, cur) > 100
+    for th in (3.0, 5.0):
+        r = B.ref_fuse(g, Tcw, th, lsf, ils, mpf, kfs, library=madp, name="ref_fuse")
+        d = B.ref_fuse(g, Tcw, th, lsf, ils, mpf, kfs, library=madp, name="adp_fuse")
+        assert r[0] == d[0] > 100 and np.array_equal(r[1], d[1])
+    madp.adp_descriptor_distance.argtypes = madp.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    d = np.random.default_rng(seed).integers(0, 256, (2, 32), dtype=np.uint8)
+    assert madp.adp_descriptor_distance(d[0].ctypes.data, d[1].ctypes.data) == madp.ref_descriptor_distance(d[0].ctypes.data, d[1].ctypes.data)
