@@ -65,6 +65,9 @@ public:
     void Replace(MapPoint *pMP) { replacedBy = pMP; }
     void AddObservation(KeyFrame *, size_t idx) { addedAt = (int)idx; }
 
+    // members adapters/MapPoint_msl.cc reaches through a derived struct (protected in include/MapPoint.h:109-141)
+    std::map<KeyFrame *, size_t> mObservations;
+    std::mutex mMutexFeatures;
     // stand-in state
     int id = -1, nObs = 0, addedAt = -1;
     bool mbBad = false, inKeyFrame = false;
@@ -100,6 +103,8 @@ public:
 
 class KeyFrame {
 public:
+    bool isBad() { return mbBadKF; }
+    bool mbBadKF = false;
     cv::Mat GetPose() { return Tcw.clone(); }
     cv::Mat GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }

@@ -1,6 +1,7 @@
 // mock_abi_matcher.cpp -- TEST HARNESS (tests/test_adapters_on_mock_abi.py): the matcher entry points of
 // include/msl_frontend.h that adapters/ORBmatcher_msl.cc calls, implemented on the CPU ORACLE (see mock_abi.cpp).
 #include <string>
+#include <vector>
 
 #include "msl_frontend.h"
 #include "msl_oracle.h"
@@ -74,3 +75,10 @@ int msl_fuse_search(msl_matcher *, const msl_frame_geom *g, const float Tcw[16],
 }
 
 }  // extern "C"
+
+extern "C" int msl_distinctive_descriptors(msl_matcher *, int n_points, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,
+                                           int32_t *best_median) {
+    std::vector<int32_t> bm(n_points > 0 ? n_points : 1);
+    orc_distinctive_descriptors(n_points, offsets, desc, best_idx, best_median ? best_median : bm.data());
+    return MSL_OK;
+}

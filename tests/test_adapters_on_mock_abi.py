@@ -195,3 +195,61 @@ def test_orbmatcher_binding_equals_reference_methods(madp, oracle, seed):
     madp.adp_descriptor_distance.argtypes = madp.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
     d = np.random.default_rng(seed).integers(0, 256, (2, 32), dtype=np.uint8)
     assert madp.adp_descriptor_distance(d[0].ctypes.data, d[1].ctypes.data) == madp.ref_descriptor_distance(d[0].ctypes.data, d[1].ctypes.data)
+
+
+# ---- adapters/MapPoint_msl.cc: ComputeDistinctiveDescriptorsBatch on stand-in MapPoint / KeyFrame objects
+@pytest.fixture(scope="module")
+def mpadp(oracle):
+    if not os.path.isdir(os.path.join(REF, "include")):
+        pytest.skip("/root/reference absent")
+    orc, out = os.path.join(ROOT, "oracle"), os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libmappoint_adapter_mock.so")
+    srcs = [os.path.join(HERE, "host_emul", "mappoint_wrap.cpp"), os.path.join(ROOT, "adapters", "MapPoint_msl.cc"),
+            os.path.join(HERE, "host_emul", "mock_abi_matcher.cpp"), os.path.join(orc, "ref_shim_match", "slam_standins.cpp"),
+            os.path.join(REF, "Thirdparty", "DBoW2", "DBoW2", "FeatureVector.cpp"), os.path.join(orc, "match_oracle.cpp"),
+            os.path.join(orc, "orb_oracle.cpp")]
+    deps = srcs + [os.path.join(orc, "ref_shim_match", "slam_standins.hpp"), os.path.join(orc, "ref_shim_cv", "cvshim.hpp")]
+    if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(orc, "ref_shim_cv"),
+                               "-I" + os.path.join(orc, "ref_shim_match"), "-I" + orc, "-I" + os.path.join(REF, "include"), "-I" + REF,
+                               "-I" + os.path.join(ROOT, "include"), "-DMAPPOINT_H", "-DKEYFRAME_H", "-DFRAME_H", "-include",
+                               os.path.join(orc, "ref_shim_match", "slam_standins.hpp"), "-shared", "-o", so] + srcs)
+    L = C.CDLL(so)
+    L.adp_distinctive.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    return L
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_mappoint_batch_binding_picks_the_reference_descriptor(mpadp, oracle, seed):
+    """per map point: the observed rows of the non-bad keyframes in mObservations order (keyframe address = index here), the
+    row with the least median distance (src/MapPoint.cc:210-263) copied into mDescriptor; bad points, points without
+    observations and points whose keyframes are all bad keep their descriptor"""
+    r = np.random.default_rng(seed)
+    n_kf, n_mp = 40, 300
+    kf_rows = r.integers(5, 60, n_kf).astype(np.int32)
+    kf_desc = r.integers(0, 256, (int(kf_rows.sum()), 32), dtype=np.uint8)
+    kf_bad = (r.random(n_kf) < 0.15).astype(np.uint8)
+    row0 = np.concatenate([[0], np.cumsum(kf_rows)])
+    mp_bad = (r.random(n_mp) < 0.1).astype(np.uint8)
+    obs_off, obs_kf, obs_row, expect = [0], [], [], []
+    for p in range(n_mp):
+        k = int(r.choice([0, 1, 2, 3, 8, 20, 33]))
+        ks = np.sort(r.choice(n_kf, min(k, n_kf), replace=False))
+        rows = [int(r.integers(0, kf_rows[q])) for q in ks]
+        obs_kf += ks.tolist()
+        obs_row += rows
+        obs_off.append(len(obs_kf))
+        good = [kf_desc[row0[q] + rw] for q, rw in zip(ks, rows) if not kf_bad[q]]
+        if mp_bad[p] or not good:
+            expect.append(np.zeros(32, np.uint8))
+        else:
+            bi, _ = oracle.distinctive_descriptors([np.stack(good)])
+            expect.append(good[int(bi[0])])
+    out = np.zeros((n_mp, 32), np.uint8)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    oo, ok, orw = a(obs_off, np.int32), a(obs_kf, np.int32), a(obs_row, np.int32)
+    assert mpadp.adp_distinctive(n_kf, kf_rows.ctypes.data, kf_desc.ctypes.data, kf_bad.ctypes.data, n_mp, oo.ctypes.data,
+                                 ok.ctypes.data, orw.ctypes.data, mp_bad.ctypes.data, out.ctypes.data) == 0
+    assert np.array_equal(out, np.stack(expect))
+    assert (out.any(axis=1)).sum() > n_mp // 2
