@@ -210,6 +210,7 @@ public:
     size_t step1() const { return step / elemSize1(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     Size size() const { return Size(cols, rows); }
+    size_t total() const { return (size_t)rows * (size_t)cols; }
     Mat clone() const {
         Mat m(rows, cols, type_);
         for (int i = 0; i < rows; i++) memcpy(m.data + (size_t)i * m.step, data + (size_t)i * step, (size_t)cols * elemSize());

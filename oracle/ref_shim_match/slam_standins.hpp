@@ -88,11 +88,13 @@ public:
     float mbf, mb;
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
-    std::vector<float> mvuRight;
+    std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors;
     std::vector<MapPoint *> mvpMapPoints;
     std::vector<bool> mvbOutlier;
-    cv::Mat mTcw;
+    cv::Mat mTcw, mK, mDistCoef;
+    void UndistortKeyPoints();                         // defined by adapters/FrameGlue_msl.cc (src/Frame.cc:437-463 in the reference)
+    void ComputeStereoFromRGBD(const cv::Mat &imDepth);  // (src/Frame.cc:495-513)
     int mnScaleLevels;
     float mfScaleFactor, mfLogScaleFactor;
     std::vector<float> mvScaleFactors;

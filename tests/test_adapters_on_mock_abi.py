@@ -253,3 +253,56 @@ def test_mappoint_batch_binding_picks_the_reference_descriptor(mpadp, oracle, se
                                  ok.ctypes.data, orw.ctypes.data, mp_bad.ctypes.data, out.ctypes.data) == 0
     assert np.array_equal(out, np.stack(expect))
     assert (out.any(axis=1)).sum() > n_mp // 2
+
+
+# ---- adapters/FrameGlue_msl.cc: Frame::UndistortKeyPoints + Frame::ComputeStereoFromRGBD on the stand-in Frame
+@pytest.fixture(scope="module")
+def gadp(oracle):
+    if not os.path.isdir(os.path.join(REF, "include")):
+        pytest.skip("/root/reference absent")
+    orc, out = os.path.join(ROOT, "oracle"), os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libglue_adapter_mock.so")
+    srcs = [os.path.join(HERE, "host_emul", "glue_wrap.cpp"), os.path.join(ROOT, "adapters", "FrameGlue_msl.cc"),
+            os.path.join(orc, "ref_shim_match", "slam_standins.cpp"), os.path.join(REF, "Thirdparty", "DBoW2", "DBoW2", "FeatureVector.cpp"),
+            os.path.join(orc, "glue_oracle.cpp"), os.path.join(orc, "match_oracle.cpp"), os.path.join(orc, "orb_oracle.cpp")]
+    deps = srcs + [os.path.join(orc, "ref_shim_match", "slam_standins.hpp"), os.path.join(orc, "ref_shim_cv", "cvshim.hpp")]
+    if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(orc, "ref_shim_cv"),
+                               "-I" + os.path.join(orc, "ref_shim_match"), "-I" + orc, "-I" + os.path.join(REF, "include"), "-I" + REF,
+                               "-I" + os.path.join(ROOT, "include"), "-DMAPPOINT_H", "-DKEYFRAME_H", "-DFRAME_H", "-include",
+                               os.path.join(orc, "ref_shim_match", "slam_standins.hpp"), "-shared", "-o", so] + srcs)
+    L = C.CDLL(so)
+    L.adp_frame_glue.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("distorted", [True, False])
+def test_frame_glue_binding(gadp, oracle, distorted):
+    """the RGB-D Frame constructor's two calls (src/Frame.cc:105-112): mvKeysUn (all KeyPoint fields kept, pt undistorted by
+    the cv2-pinned cv::undistortPoints restatement -- or copied when k1 == 0), then mvDepth / mvuRight from the depth at the
+    DISTORTED pixel and the UNDISTORTED x (src/Frame.cc:495-513)"""
+    r = np.random.default_rng(5)
+    n = 800
+    kps = np.zeros(n, oracle.KP_DTYPE)
+    kps["x"], kps["y"] = r.uniform(0, 639, n), r.uniform(0, 479, n)
+    kps["size"], kps["angle"], kps["response"] = 31, r.uniform(0, 360, n), r.integers(7, 200, n)
+    kps["octave"], kps["class_id"] = r.integers(0, 8, n), -1
+    K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)  # Example/TUM1.yaml
+    D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314] if distorted else [0, 0, 0, 0, 0], np.float32)
+    _, depth = S.depth_frame(3)
+    depth = np.ascontiguousarray(depth, np.float32)
+    mbf = 40.0
+    un, ur, kd = np.zeros(n, oracle.KP_DTYPE), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    assert gadp.adp_frame_glue(n, kps.ctypes.data, K4.ctypes.data, D.ctypes.data, 5, depth.ctypes.data, 640, 480, mbf, un.ctypes.data,
+                               ur.ctypes.data, kd.ctypes.data) == 0
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    xy_un = oracle.undistort_keypoints(xy, K4, D)
+    for f in ("size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(un[f], kps[f]), f
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1), xy_un)
+    assert (np.abs(xy_un - xy).max() > 0.5) == distorted
+    ur_o, kd_o = oracle.stereo_from_rgbd(xy, xy_un, depth, mbf)
+    assert np.array_equal(kd, kd_o) and np.array_equal(ur, ur_o)
+    assert (kd > 0).sum() > n // 2 and (kd == -1).sum() > 0
