@@ -8,7 +8,9 @@ import pytest
 
 from manhattanslam_b200 import synthetic as S
 
-pytestmark = pytest.mark.gpu
+# never run on hardware before the round end: a hang must end the process instead of holding the GPU box (pytest-timeout's
+# thread method exits the interpreter, which tears the CUDA context down)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
