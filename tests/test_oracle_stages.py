@@ -558,3 +558,46 @@ def test_oracle_equals_reference_source_golden(oracle):
     mpf, kfs, Tcw, ils = S.fuse_scene(G.MATCH_SEED)
     n, bi, bd = oracle.fuse_search(geom, Tcw, 3.0, G.LSF, ils, mpf, kfs)
     assert n == int(gold["m_fuse_n"]) and np.array_equal(np.where(bd <= 50, bi, -1), gold["m_fuse"])
+
+
+def test_distinctive_kernel_algorithm_replay(oracle):
+    """k_distinctive (manhattanslam_b200/csrc/match.cu) replayed step by step in numpy -- four warps take rows i = w, w + 4, ...;
+    the row median of rank (int)(0.5 * (N - 1)) found by bisection on the value with one warp-wide count per step; strict <
+    inside a warp, (median, row) order across warps -- against the oracle's sort-based restatement of
+    MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263).  The kernel itself has not run on a GPU yet."""
+    def replay(desc):
+        n = len(desc)
+        if n == 0:
+            return -1, 0x7fffffff
+        bits = np.unpackbits(desc, axis=1).astype(np.int32)
+        dist = (bits[:, None, :] != bits[None, :, :]).sum(2)  # what hamming256 recomputes per (row, j)
+        r = int(0.5 * (n - 1))
+        per_warp = []
+        for w in range(4):
+            my_med, my_row = 0x7fffffff, -1
+            for i in range(w, n, 4):
+                lo, hi = 0, 256
+                while lo < hi:
+                    mid = (lo + hi) >> 1
+                    c = int((dist[i] <= mid).sum())  # sum over the 32 lanes' strided counts
+                    if c > r:
+                        hi = mid
+                    else:
+                        lo = mid + 1
+                if lo < my_med:
+                    my_med, my_row = lo, i
+            per_warp.append((my_med, my_row))
+        bm, br = 0x7fffffff, -1
+        for med, row in per_warp:
+            if row >= 0 and (br < 0 or med < bm or (med == bm and row < br)):
+                bm, br = med, row
+        return br, bm
+
+    r = np.random.default_rng(3)
+    sets = S.observation_sets(5, n_points=120, max_obs=40)
+    sets += [r.integers(0, 256, (n, 32), dtype=np.uint8) for n in (1, 2, 3, 4, 5, 31, 32, 33, 64, 129)]
+    base = r.integers(0, 256, 32, dtype=np.uint8)
+    sets += [np.tile(base, (7, 1)), np.tile(base, (1, 1))]  # identical descriptors: every median 0, the first row wins
+    bi, bm = oracle.distinctive_descriptors(sets)
+    for k, d in enumerate(sets):
+        assert replay(np.asarray(d, np.uint8).reshape(-1, 32)) == (int(bi[k]), int(bm[k])), k
