@@ -539,7 +539,7 @@ REFERENCE_ROOT = "/root/reference"
 
 _REF_DEPS = {
     "libsurfel_ref.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
-                         ["ref_wrap.cpp", "ref_shim/Eigen/Eigen", "ref_shim/opencv2/opencv.hpp", "ref_shim/thread"]),
+                         ["ref_wrap.cpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/cvshim.hpp", "ref_shim_cv/seq_thread/thread"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
                       ["ref_orb_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
     "libplane_ref.so": (["src/PlaneExtractor.cpp", "include/PlaneExtractor.h", "include/peac/AHCPlaneFitter.hpp",

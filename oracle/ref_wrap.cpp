@@ -1,7 +1,7 @@
 // ref_wrap.cpp -- C entry points around the REFERENCE's own src/SurfelFusion.cpp (TEST INFRASTRUCTURE).
 //
 // oracle/Makefile compiles /root/reference/src/SurfelFusion.cpp where it lies, unmodified, against the stand-in headers of
-// oracle/ref_shim/ (the build image has neither OpenCV nor Eigen) into oracle/_ref/libsurfel_ref.so.  What that library
+// oracle/ref_shim_cv/ (the build image has neither OpenCV nor Eigen) into oracle/_ref/libsurfel_ref.so.  What that library
 // is: the reference's control flow and scalar arithmetic, line for line; what it is not: Eigen's kernels (the stand-in
 // evaluates products left to right and the 4x4 inverse by cofactors) and real threads (the stand-in runs the ten
 // slices in order).  tests/test_oracle_ref.py compares the oracle restatement against it; nothing else uses it.
@@ -31,8 +31,8 @@ int ref_surfel_fuse(void *p, int ref, uint8_t *gray, int gray_stride, float *dep
                     Surfel *local, int64_t n_local, Surfel *new_out, int cap_new) {
     SurfelFusion *f = (SurfelFusion *)p;
     const int w = f->imageWidth, h = f->imageHeight;
-    cv::Mat image(h, w, (size_t)gray_stride, gray), dep(h, w, sizeof(float) * (size_t)w, depth);
-    cv::Mat mem((h + 1) / 2, (w + 1) / 2, sizeof(int32_t) * (size_t)((w + 1) / 2), membership);
+    cv::Mat image(h, w, CV_8UC1, gray, (size_t)gray_stride), dep(h, w, CV_32FC1, depth);
+    cv::Mat mem((h + 1) / 2, (w + 1) / 2, CV_32SC1, membership);
     Eigen::Matrix4f pose;
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++) pose(i, j) = Twc[4 * i + j];

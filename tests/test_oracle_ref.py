@@ -1,7 +1,7 @@
 """The oracle's SurfelFusion restatement against the REFERENCE'S OWN SOURCE.
 
 oracle/_ref/libsurfel_ref.so is /root/reference/src/SurfelFusion.cpp compiled where it lies, unmodified, against stand-in
-headers for OpenCV / Eigen / <thread> (oracle/ref_shim/, see oracle/ref_wrap.cpp): the reference's control flow and scalar
+headers for OpenCV / Eigen / <thread> (oracle/ref_shim_cv/, see oracle/ref_wrap.cpp): the reference's control flow and scalar
 arithmetic line for line; Eigen's products / 4x4 inverse evaluated as this repository assumes; the ten thread slices run in
 order.  Built here (where /root/reference exists); elsewhere the prebuilt library is used if it travelled, else the tests
 skip.  Everything is compared BIT FOR BIT (NaNs as NaNs): superpixel index, every seed field, the local map, the new surfels."""

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """How deterministic is the reference's own SurfelFusion?  Builds /root/reference/src/SurfelFusion.cpp twice against the
-stand-in OpenCV / Eigen headers of oracle/ref_shim/: once with the sequential <thread> stand-in (the serialisation the
+stand-in OpenCV / Eigen headers of oracle/ref_shim_cv/: once with the sequential <thread> stand-in (the serialisation the
 oracle fixes) and once with the REAL std::thread (ten slices racing on the `stable` flag of updatePixelsKernel,
 src/SurfelFusion.cpp:357-415), runs the threaded build several times per input and counts the pixels whose superpixel
 index differs from the sequential result.  Test infrastructure; needs /root/reference.
@@ -24,15 +24,14 @@ from oracle import binding as ob  # noqa: E402
 def main():
     tmp = tempfile.mkdtemp(prefix="msl_race_")
     try:
-        shim = os.path.join(tmp, "shim")
-        shutil.copytree(os.path.join(ROOT, "oracle", "ref_shim"), shim)
-        os.remove(os.path.join(shim, "thread"))  # fall through to the system <thread>
+        # the include path WITHOUT oracle/ref_shim_cv/seq_thread: <thread> falls through to the system header
         so = os.path.join(tmp, "libsurfel_ref_threads.so")
-        subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-w", "-pthread", "-I" + shim,
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-w", "-pthread",
+                               "-I" + os.path.join(ROOT, "oracle", "ref_shim_cv"), "-I" + os.path.join(ROOT, "oracle"),
                                "-I/root/reference/include", "-shared", "-o", so, "/root/reference/src/SurfelFusion.cpp",
                                os.path.join(ROOT, "oracle", "ref_wrap.cpp")])
         ob.build()
-        ob.build_ref = lambda force=False: so
+        ob.build_ref = lambda force=False, name="libsurfel_ref.so": so
         differ = runs = 0
         for seed, pf, n in [(3, 0.0, 30000), (4, 0.4, 50000), (5, 0.2, 10000), (8, 0.1, 20000)]:
             g = S.gray_frame(seed)
