@@ -4,7 +4,8 @@
 // statistics / seeds / edges (msl_prestage_of()); runPlaneDetection runs the whole fitter on the device
 // (msl_plane_detect: ahCluster + refineDetails) and fills what the callers read: plane_filter.membershipImg,
 // plane_filter.extractedPlanes[i]->normal / center / N / rid, plane_vertices_, plane_num_.  seg_img_ (the debug colouring)
-// is not produced.  Frames of more than 768 blocks fall outside msl_plane_detect: keep the reference's definition there.
+// is not produced.  Frames of more than 3072 blocks (beyond 1280x960) fall outside msl_plane_detect: keep the reference's
+// definition there.
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>

@@ -301,8 +301,9 @@ void *msl_plane_stream(msl_plane *);
  * plane_cap records per frame, the first min(plane_count, plane_cap) filled in extractedPlanes order (descending N):
  * normal / center of extractedPlanes[i] (src/Frame.cc:626-632), N, rid, and vertices = plane_vertices_[i].size(); the
  * members of plane i are the pixels whose membership equals i, in row-major order (src/Frame.cc:612-621).
- * Frames of at most 768 blocks (640x480) are supported: MSL_ERR_INVALID otherwise.  MSL_ERR_CAPACITY if a frame
- * exceeds the region-grow queue (4 entries per half-resolution pixel) or 128 planes. */
+ * Frames of up to 768 blocks (640x480) are processed in shared memory, up to 3072 blocks (1280x960) in global memory;
+ * larger ones: MSL_ERR_INVALID.  MSL_ERR_CAPACITY if a frame exceeds the region-grow queue (4 entries per half-resolution
+ * pixel) or 128 planes. */
 typedef struct {
     double normal[3];
     double center[3];

@@ -4,7 +4,8 @@
 // constructor / connect / disconnectAllNbs / mergeNbsFrom (include/peac/AHCPlaneSeg.hpp:321-437), Stats::compute
 // (:148-181) and DisjointSet (include/peac/DisjointSet.hpp).  Output: PlaneFitter::membershipImg and extractedPlanes.
 //
-// One CTA per frame, everything but the region grow in shared memory (196 KB):
+// One CTA per frame, everything but the region grow in shared memory (196 KB; frames of more than 768 blocks: the same
+// working set, SharedT<3072>, in global memory):
 //   * node table: one 144-byte record per 10x10 block slot (the nine running sums, centre, normal, mse, N, rid, creation
 //     sequence).  A merged node REUSES the slot of the node that was popped from the queue (that slot is referenced
 //     nowhere else any more), so 768 slots serve the <= 1535 nodes a frame can create;
@@ -83,8 +84,8 @@ inline void peac_emu_atomic_min(int *p, int v) {
 namespace peac {
 
 constexpr int WIN = 10;           // windowWidth / windowHeight, AHCPlaneFitter.hpp:156-160
-constexpr int MAXB = 768;         // block slots (640x480 input: 32 x 24 blocks)
-constexpr int WORDS = MAXB / 32;  // adjacency mask words per slot
+constexpr int MAXB = 768;         // block slots of the shared-memory instance (640x480 input: 32 x 24 blocks)
+constexpr int MAXB_BIG = 3072;    // block slots of the global-memory instance (1280x960 input: 64 x 48 blocks)
 constexpr int MAXPL = 128;        // extracted planes (>= 3000 of <= 76,800 points each: at most 25)
 constexpr int MIN_SUPPORT = 3000, MAX_STEP = 100000;  // :155-156
 #define PEAC_DEPTH_SIGMA 1.6e-6
@@ -111,12 +112,16 @@ struct PlaneOut {  // = msl_plane_rec
     int32_t N, rid, vertices, pad;
 };
 
-struct Shared {
-    Node node[MAXB];
-    uint32_t nbs[MAXB][WORDS];
-    double candMse[MAXB];  // reused as int scratch by the membership pass
-    int16_t parent[MAXB], dsize[MAXB], heap[MAXB], blkMap[MAXB];
-    uint8_t candHas[MAXB];
+// The working set of one frame.  SharedT<768> (196 KB) lives in the CTA's shared memory; frames with more blocks use
+// SharedT<3072> in global memory (1.7 MB per frame, L2-resident) -- same code, the reference S is all it sees.
+template <int NB> struct SharedT {
+    static constexpr int SLOTS = NB;       // block slots
+    static constexpr int WORDS = NB / 32;  // adjacency mask words per slot
+    Node node[NB];
+    uint32_t nbs[NB][WORDS];
+    double candMse[NB];  // reused as int scratch by the membership pass and the region grow
+    int16_t parent[NB], dsize[NB], heap[NB], blkMap[NB];
+    uint8_t candHas[NB];
     uint32_t tmpMask[WORDS];
     int16_t extracted[MAXPL], oldPl[MAXPL], plidmap[MAXPL];
     uint8_t valid[MAXPL];
@@ -127,6 +132,8 @@ struct Shared {
     int lvlBegin, lvlEnd, pending;  // region grow by levels
     int error;
 };
+typedef SharedT<MAXB> Shared;
+typedef SharedT<MAXB_BIG> SharedBig;
 
 // per-frame scratch of the region grow in global memory
 struct Flood {
@@ -264,8 +271,10 @@ PEAC_HD void setbit(uint32_t *m, int i) { m[i >> 5] |= 1u << (i & 31); }
 PEAC_HD void clrbit(uint32_t *m, int i) { m[i >> 5] &= ~(1u << (i & 31)); }
 
 // ---- std::priority_queue<.., PlaneSegMinMSECmp> on slot ids: comp(a, b) = mse[b] < mse[a]; libstdc++'s sift order
-PEAC_HD bool heap_comp(const Shared &S, int a, int b) { return S.node[b].mse < S.node[a].mse; }
-PEAC_HD void heap_sift_up(Shared &S, int hole, int top, int value) {  // std::__push_heap
+template <class SH>
+PEAC_HD bool heap_comp(const SH &S, int a, int b) { return S.node[b].mse < S.node[a].mse; }
+template <class SH>
+PEAC_HD void heap_sift_up(SH &S, int hole, int top, int value) {  // std::__push_heap
     int parent = (hole - 1) / 2;
     while (hole > top && heap_comp(S, S.heap[parent], value)) {
         S.heap[hole] = S.heap[parent];
@@ -274,12 +283,14 @@ PEAC_HD void heap_sift_up(Shared &S, int hole, int top, int value) {  // std::__
     }
     S.heap[hole] = (int16_t)value;
 }
-PEAC_HD void heap_push(Shared &S, int slot) {
+template <class SH>
+PEAC_HD void heap_push(SH &S, int slot) {
     S.heap[S.heapN] = (int16_t)slot;
     S.heapN++;
     heap_sift_up(S, S.heapN - 1, 0, slot);
 }
-PEAC_HD int heap_pop(Shared &S) {  // top(), then std::pop_heap + pop_back
+template <class SH>
+PEAC_HD int heap_pop(SH &S) {  // top(), then std::pop_heap + pop_back
     const int top = S.heap[0];
     const int last = S.heapN - 1;
     if (last > 0) {
@@ -305,7 +316,8 @@ PEAC_HD int heap_pop(Shared &S) {  // top(), then std::pop_heap + pop_back
 }
 
 // ---- DisjointSet.hpp (thread 0 mutates; the read-only find is for the parallel passes)
-PEAC_HD int ds_find(Shared &S, int x) {
+template <class SH>
+PEAC_HD int ds_find(SH &S, int x) {
     int r = x;
     while (S.parent[r] != r) r = S.parent[r];
     while (S.parent[x] != r) {  // path compression (the recursion of the reference leaves the same parents)
@@ -315,11 +327,13 @@ PEAC_HD int ds_find(Shared &S, int x) {
     }
     return r;
 }
-PEAC_HD int ds_find_ro(const Shared &S, int x) {
+template <class SH>
+PEAC_HD int ds_find_ro(const SH &S, int x) {
     while (S.parent[x] != x) x = S.parent[x];
     return x;
 }
-PEAC_HD void ds_union(Shared &S, int x, int y) {
+template <class SH>
+PEAC_HD void ds_union(SH &S, int x, int y) {
     const int xr = ds_find(S, x), yr = ds_find(S, y);
     if (xr == yr) return;
     if (S.dsize[xr] < S.dsize[yr])
@@ -329,7 +343,8 @@ PEAC_HD void ds_union(Shared &S, int x, int y) {
 }
 
 // ---- ahCluster, AHCPlaneFitter.hpp:939-1143.  nslots = number of block slots of the frame.
-PEAC_D void cluster(Shared &S, const Geo &g, int nslots, int tid, int nt) {
+template <class SH>
+PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
     for (;;) {
         if (tid == 0) {
             int p = -1;
@@ -392,16 +407,16 @@ PEAC_D void cluster(Shared &S, const Geo &g, int nslots, int tid, int nt) {
         PEAC_SYNC();
         if (S.decision) {
             const int nb = S.curNb;
-            for (int w = tid; w < WORDS; w += nt) S.tmpMask[w] = S.nbs[p][w] | S.nbs[nb][w];
+            for (int w = tid; w < SH::WORDS; w += nt) S.tmpMask[w] = S.nbs[p][w] | S.nbs[nb][w];
             PEAC_SYNC();
             if (tid == 0) clrbit(S.tmpMask, p), clrbit(S.tmpMask, nb);
             PEAC_SYNC();
             // disconnectAllNbs of both, then the merged node (in p's slot) becomes a neighbour of the union
             for (int k = tid; k < nslots; k += nt) {
                 if (k == p) {
-                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = S.tmpMask[w];
+                    for (int w = 0; w < SH::WORDS; w++) S.nbs[k][w] = S.tmpMask[w];
                 } else if (k == nb) {
-                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = 0;
+                    for (int w = 0; w < SH::WORDS; w++) S.nbs[k][w] = 0;
                 } else {
                     clrbit(S.nbs[k], nb);
                     if (bit(S.tmpMask, k))
@@ -421,7 +436,7 @@ PEAC_D void cluster(Shared &S, const Geo &g, int nslots, int tid, int nt) {
         } else {
             for (int k = tid; k < nslots; k += nt) {  // p->disconnectAllNbs()
                 if (k == p) {
-                    for (int w = 0; w < WORDS; w++) S.nbs[k][w] = 0;
+                    for (int w = 0; w < SH::WORDS; w++) S.nbs[k][w] = 0;
                 } else {
                     clrbit(S.nbs[k], p);
                 }
@@ -464,7 +479,8 @@ PEAC_HD int block_of(const Geo &g, int px, int py) {  // getBlockIdx :408-415
 PEAC_HD uint32_t rf_pack(int pix, int plid) { return (uint32_t)pix | ((uint32_t)plid << 20); }
 
 // floodFill :422-471 as the reference's FIFO, on thread 0 (Geo::floodSerial)
-PEAC_D void flood_serial(Shared &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid) {
+template <class SH>
+PEAC_D void flood_serial(SH &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid) {
     if (tid != 0 || S.error != PEAC_OK) return;
     int qn = S.curP;
     for (int k = 0; k < qn; ++k) {
@@ -515,7 +531,8 @@ PEAC_D void flood_serial(Shared &S, const Geo &g, const uint16_t *depth, int32_t
 }
 
 // floodFill :422-471 level by level (see the header comment); exactly the FIFO's result
-PEAC_D void flood_levels(Shared &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid, int nt) {
+template <class SH>
+PEAC_D void flood_levels(SH &S, const Geo &g, const uint16_t *depth, int32_t *membership, const Flood &F, int tid, int nt) {
     const int npix = g.W2 * g.H2;
     for (int px = tid; px < npix; px += nt) F.own[px] = 0x7fffffff;
     if (tid == 0) S.lvlBegin = 0, S.lvlEnd = S.curP;
@@ -634,8 +651,8 @@ PEAC_D void flood_levels(Shared &S, const Geo &g, const uint16_t *depth, int32_t
 // One frame.  blocks / seed / edges: the pre-stage outputs of the frame (centre, normal, mse, N per block; node mask;
 // edge mask bit0=left,1=right,2=up,3=down).  membership: H2*W2 int32 out.  F: per-frame scratch of the region grow in
 // global memory.  planes: <= planeCap records out; *planeCount out.
-template <typename BlockStat>
-PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockStat *blocks, const uint8_t *seed, const uint8_t *edges,
+template <class SH, typename BlockStat>
+PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *blocks, const uint8_t *seed, const uint8_t *edges,
                   int32_t *membership, const Flood &F, PlaneOut *planes, int planeCap, int32_t *planeCount, int32_t *errorOut, int tid,
                   int nt) {
     float *const distMap = F.distMap;
@@ -653,7 +670,7 @@ PEAC_D void frame(Shared &S, const Geo &g, const uint16_t *depth, const BlockSta
             for (int k = 0; k < 9; k++) n.s[k] = 0;
         S.parent[b] = (int16_t)b, S.dsize[b] = 1;
         uint32_t *m = S.nbs[b];
-        for (int w = 0; w < WORDS; w++) m[w] = 0;
+        for (int w = 0; w < SH::WORDS; w++) m[w] = 0;
         const int e = edges[b];
         if (e & 1) setbit(m, b - 1);
         if (e & 2) setbit(m, b + 1);

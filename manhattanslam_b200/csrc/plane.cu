@@ -236,13 +236,17 @@ struct PeacScratch {  // per-frame strides are implied: npix, rfqCap, visCap
     int rfqCap, visCap;
 };
 
+// SH = peac::Shared: the working set in the CTA's dynamic shared memory (frames of <= 768 blocks); SH = peac::SharedBig: in
+// global memory, one record per frame (`big`), for frames of up to 3072 blocks (1280x960)
+template <class SH>
 __global__ void __launch_bounds__(256)
     k_peac_frame(peac::Geo g, size_t frameStride, const uint16_t *__restrict__ depth, const msl_block_stat *__restrict__ blocks,
                  const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership, PeacScratch sc,
-                 peac::PlaneOut *__restrict__ planes, int planeCap, int32_t *__restrict__ planeCount, int32_t *__restrict__ frameError) {
+                 SH *big, peac::PlaneOut *__restrict__ planes, int planeCap, int32_t *__restrict__ planeCount,
+                 int32_t *__restrict__ frameError) {
     extern __shared__ __align__(16) unsigned char peac_smem[];
-    peac::Shared &S = *reinterpret_cast<peac::Shared *>(peac_smem);
     const int b = blockIdx.x, nb = g.Nw * g.Nh;
+    SH &S = big ? big[b] : *reinterpret_cast<SH *>(peac_smem);
     const size_t npix = (size_t)g.W2 * g.H2;
     peac::Flood F;
     F.distMap = sc.dist + b * npix, F.own = sc.own + b * npix;
@@ -270,6 +274,7 @@ struct msl_plane {
     uint32_t *d_rfq = nullptr;
     int *d_own = nullptr, *d_visC = nullptr;
     uint8_t *d_visFlag = nullptr;
+    peac::SharedBig *d_big = nullptr;  // frames of more than 768 blocks: the working set in global memory
     msl_plane_rec *d_planes = nullptr;
     int planeCap = 0;
     int pendingCheck = 0;  // frames of an enqueued detect whose per-frame error words have not been read yet
@@ -279,7 +284,7 @@ static void plane_free(msl_plane *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_depth, p->d_cloud, p->d_blocks, p->d_seed, p->d_edges, p->d_mem, p->d_count, p->d_ferr,
-                    p->d_dist, p->d_rfq, p->d_planes, p->d_own, p->d_visC, p->d_visDist, p->d_visFlag};
+                    p->d_dist, p->d_rfq, p->d_planes, p->d_own, p->d_visC, p->d_visDist, p->d_visFlag, p->d_big};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -365,7 +370,7 @@ int msl_plane_prestage_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px
     return MSL_OK;
 }
 
-constexpr int PLANE_CAP_INTERNAL = 32;  // records per frame of the handle's own buffer (host entry point)
+constexpr int PLANE_CAP_INTERNAL = 128;  // records per frame of the handle's own buffer (host entry point) = peac::MAXPL
 
 static int plane_detect_alloc(msl_plane *p) {
     if (p->d_mem) return MSL_OK;
@@ -382,8 +387,9 @@ static int plane_detect_alloc(msl_plane *p) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ferr, B * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_planes, B * PLANE_CAP_INTERNAL * sizeof(msl_plane_rec));
     if (e == cudaSuccess) e = cudaMemset(p->d_ferr, 0, B * sizeof(int32_t));
+    if (e == cudaSuccess && p->Nw * p->Nh > peac::MAXB) e = cudaMalloc((void **)&p->d_big, B * sizeof(peac::SharedBig));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_peac_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
+        e = cudaFuncSetAttribute(k_peac_frame<peac::Shared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
     if (e != cudaSuccess) return fail(MSL_ERR_CUDA, std::string("msl_plane_detect: ") + cudaGetErrorString(e));
     p->planeCap = PLANE_CAP_INTERNAL;
     return MSL_OK;
@@ -394,7 +400,7 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
                          msl_plane_rec *d_planes, int plane_cap) {
     if (!p || !d_depth || !K || !d_membership || !d_plane_count || (plane_cap > 0 && !d_planes) || plane_cap < 0)
         return fail(MSL_ERR_INVALID, "msl_plane_detect_dev: bad argument");
-    if (p->Nw * p->Nh > peac::MAXB) return fail(MSL_ERR_INVALID, "msl_plane_detect: frames of more than 768 blocks (640x480) are not supported");
+    if (p->Nw * p->Nh > peac::MAXB_BIG) return fail(MSL_ERR_INVALID, "msl_plane_detect: frames of more than 3072 blocks (1280x960) are not supported");
     if ((size_t)p->W2 * p->H2 >= (1u << 20)) return fail(MSL_ERR_INVALID, "msl_plane_detect: frame too large");
     int rc = plane_detect_alloc(p);
     if (rc) return rc;
@@ -411,9 +417,14 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     PeacScratch sc;
     sc.dist = p->d_dist, sc.rfq = p->d_rfq, sc.own = p->d_own, sc.visC = p->d_visC, sc.visDist = p->d_visDist, sc.visFlag = p->d_visFlag;
     sc.rfqCap = 4 * p->W2 * p->H2, sc.visCap = 4 * p->W2 * p->H2;
-    k_peac_frame<<<batch, 256, sizeof(peac::Shared), p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
-                                                                 d_membership, sc, reinterpret_cast<peac::PlaneOut *>(d_planes),
-                                                                 plane_cap, d_plane_count, p->d_ferr);
+    if (p->Nw * p->Nh <= peac::MAXB)
+        k_peac_frame<peac::Shared><<<batch, 256, sizeof(peac::Shared), p->stream>>>(
+            g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges, d_membership, sc, (peac::Shared *)nullptr,
+            reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count, p->d_ferr);
+    else
+        k_peac_frame<peac::SharedBig><<<batch, 256, 0, p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
+                                                                   d_membership, sc, p->d_big, reinterpret_cast<peac::PlaneOut *>(d_planes),
+                                                                   plane_cap, d_plane_count, p->d_ferr);
     MSL_LAUNCH_CHECK();
     p->pendingCheck = batch > p->pendingCheck ? batch : p->pendingCheck;
     return MSL_OK;

@@ -19,12 +19,11 @@ extern "C" int peac_host_frame(const uint16_t *depth, int w, int h, int dstride_
     peac::Geo g;
     g.W2 = (int)std::ceil(w / 2.0), g.H2 = (int)std::ceil(h / 2.0);
     g.Nw = g.W2 / peac::WIN, g.Nh = g.H2 / peac::WIN;
-    if (g.Nw * g.Nh > peac::MAXB) return -1;
+    if (g.Nw * g.Nh > peac::MAXB_BIG) return -1;
     g.dstride = dstride_px;
     g.fx = fx, g.fy = fy, g.cx = cx, g.cy = cy, g.factor = factor;
     g.thMerge = std::cos(60.0 * M_PI / 180.0), g.thRefine = std::cos(30.0 * M_PI / 180.0);
     g.floodSerial = flood_serial;
-    std::vector<peac::Shared> S(1);
     const size_t npix = (size_t)g.W2 * g.H2;
     std::vector<float> dist(npix), visDist(4 * npix);
     std::vector<uint32_t> rfq((size_t)rfq_cap);
@@ -32,8 +31,15 @@ extern "C" int peac_host_frame(const uint16_t *depth, int w, int h, int dstride_
     std::vector<uint8_t> visFlag(4 * npix);
     peac::Flood F{dist.data(), rfq.data(), rfq_cap, own.data(), visC.data(), visDist.data(), visFlag.data(), (int)(4 * npix)};
     int32_t count = 0;
-    peac::frame(S[0], g, depth, blocks, seed, edges, membership, F, planes, cap, &count, error, 0, 1);
+    if (g.Nw * g.Nh <= peac::MAXB) {  // the shared-memory instance of the kernel
+        std::vector<peac::Shared> S(1);
+        peac::frame(S[0], g, depth, blocks, seed, edges, membership, F, planes, cap, &count, error, 0, 1);
+    } else {  // the global-memory instance
+        std::vector<peac::SharedBig> S(1);
+        peac::frame(S[0], g, depth, blocks, seed, edges, membership, F, planes, cap, &count, error, 0, 1);
+    }
     return count;
 }
 
 extern "C" int peac_host_shared_bytes() { return (int)sizeof(peac::Shared); }
+extern "C" int peac_host_shared_big_bytes() { return (int)sizeof(peac::SharedBig); }

@@ -38,7 +38,7 @@ int main(int argc, char **argv) {
     g.thMerge = std::cos(60.0 * M_PI / 180.0), g.thRefine = std::cos(30.0 * M_PI / 180.0);
     g.floodSerial = argc == 5 ? atoi(argv[4]) : 0;
     const int nb = g.Nw * g.Nh, npix = g.W2 * g.H2;
-    if (nb > peac::MAXB) return 3;
+    if (nb > peac::MAXB_BIG) return 3;
     std::vector<uint16_t> depth((size_t)w * h);
     std::vector<BlockStat> blocks(nb);
     std::vector<uint8_t> seed(nb), edges(nb);
@@ -46,7 +46,8 @@ int main(int argc, char **argv) {
         fread(seed.data(), 1, nb, f) != (size_t)nb || fread(edges.data(), 1, nb, f) != (size_t)nb)
         return 2;
     fclose(f);
-    std::vector<peac::Shared> S(1);
+    std::vector<peac::Shared> S(nb <= peac::MAXB ? 1 : 0);
+    std::vector<peac::SharedBig> SB(nb <= peac::MAXB ? 0 : 1);
     std::vector<int32_t> mem(npix);
     std::vector<float> dist(npix);
     std::vector<uint32_t> rfq((size_t)4 * npix);
@@ -61,8 +62,12 @@ int main(int argc, char **argv) {
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++)
         th.emplace_back([&, t] {
-            peac::frame(S[0], g, depth.data(), blocks.data(), seed.data(), edges.data(), mem.data(), F, planes.data(), cap, &count,
-                        &error, t, nt);
+            if (nb <= peac::MAXB)
+                peac::frame(S[0], g, depth.data(), blocks.data(), seed.data(), edges.data(), mem.data(), F, planes.data(), cap, &count,
+                            &error, t, nt);
+            else
+                peac::frame(SB[0], g, depth.data(), blocks.data(), seed.data(), edges.data(), mem.data(), F, planes.data(), cap, &count,
+                            &error, t, nt);
         });
     for (auto &t : th) t.join();
     f = fopen(argv[3], "wb");

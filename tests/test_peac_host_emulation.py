@@ -37,9 +37,9 @@ def _run(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0, flood_serial=0):
     d16 = np.ascontiguousarray(d16, np.uint16)
     _, blocks, seed, edges = oracle.plane_prestage(d16, K=K, depth_map_factor=fac)
     mem = np.zeros(((h + 1) // 2, (w + 1) // 2), np.int32)
-    pl, err = np.zeros(64, PL), np.zeros(1, np.int32)
+    pl, err = np.zeros(128, PL), np.zeros(1, np.int32)
     n = emu.peac_host_frame(d16.ctypes.data, w, h, w, K[0], K[1], K[2], K[3], fac, blocks.ctypes.data, seed.ctypes.data,
-                            edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 64, err.ctypes.data, 4 * mem.size, flood_serial)
+                            edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 128, err.ctypes.data, 4 * mem.size, flood_serial)
     assert n >= 0 and err[0] == 0
     return mem, pl[:n]
 
@@ -48,7 +48,7 @@ def _same(emu, oracle, d16, K=S.K_DEFAULT, fac=1.0):
     mem, pl = _run(emu, oracle, d16, K, fac)            # region grow by levels (the default)
     mem_s, pl_s = _run(emu, oracle, d16, K, fac, 1)     # ... and as the FIFO on thread 0
     assert np.array_equal(mem, mem_s) and pl.tobytes() == pl_s.tobytes()
-    mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=fac)
+    mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=fac, cap=128)
     assert len(pl) == len(po["N"])
     assert np.array_equal(mem, mo)
     for f in ("N", "rid", "vertices"):
@@ -91,11 +91,21 @@ def test_device_algorithm_metres_sizes_and_degenerate_depth(emu, oracle):
     _same(emu, oracle, holes)
 
 
-def test_larger_frames_are_refused(emu, oracle):
-    d16 = np.full((960, 1280), 1500, np.uint16)
+def test_global_memory_instance_on_larger_frames(emu, oracle):
+    """more than 768 blocks: the same code on SharedT<3072> (in global memory on the device) -- 800x600 and 1280x960"""
+    assert emu.peac_host_shared_big_bytes() < 2 << 20
+    for (w, h, seed) in ((800, 600, 4), (1280, 960, 2)):
+        K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+        d16, _ = S.depth_frame(seed, w, h, K=K)
+        _, pl = _same(emu, oracle, d16, K=K)
+        assert len(pl) >= 2
+
+
+def test_frames_beyond_3072_blocks_are_refused(emu, oracle):
+    d16 = np.full((1500, 2000), 1500, np.uint16)
     _, blocks, seed, edges = oracle.plane_prestage(d16)
-    mem, pl, err = np.zeros((480, 640), np.int32), np.zeros(4, PL), np.zeros(1, np.int32)
-    assert emu.peac_host_frame(d16.ctypes.data, 1280, 960, 1280, 525.0, 525.0, 319.5, 239.5, 1.0, blocks.ctypes.data,
+    mem, pl, err = np.zeros((750, 1000), np.int32), np.zeros(4, PL), np.zeros(1, np.int32)
+    assert emu.peac_host_frame(d16.ctypes.data, 2000, 1500, 2000, 525.0, 525.0, 319.5, 239.5, 1.0, blocks.ctypes.data,
                                seed.ctypes.data, edges.ctypes.data, mem.ctypes.data, pl.ctypes.data, 4, err.ctypes.data, 16, 0) == -1
 
 
@@ -115,26 +125,28 @@ def emu_mt():
     return exe
 
 
-@pytest.mark.parametrize("seed,threads", [(2, 8), (4, 5), (33, 16)])
-def test_cta_phases_are_race_free_under_tsan(emu_mt, oracle, tmp_path, seed, threads):
+@pytest.mark.parametrize("seed,threads,w,h", [(2, 8, 640, 480), (4, 5, 640, 480), (33, 16, 640, 480), (2, 8, 800, 600)])
+def test_cta_phases_are_race_free_under_tsan(emu_mt, oracle, tmp_path, seed, threads, w, h):
     """every hand-over through shared memory (queue pop -> candidate fits -> selection -> mask update -> push, membership
     -> seeds -> flood fill -> final merge -> remap) must be separated by a barrier: ThreadSanitizer reports none missing,
     and the threaded run equals the oracle.  (Dropping one PEAC_SYNC() makes this test fail with TSAN reports.)"""
-    d16, _ = S.depth_frame(seed)
-    _, blocks, sd, ed = oracle.plane_prestage(d16, depth_map_factor=1.0)
+    K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+    d16, _ = S.depth_frame(seed, w, h, K=K)
+    _, blocks, sd, ed = oracle.plane_prestage(d16, K=K, depth_map_factor=1.0)
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    w2, h2 = (w + 1) // 2, (h + 1) // 2
     with open(fin, "wb") as f:
-        f.write(np.array([640, 480, 64], np.int32).tobytes())
-        f.write(np.array(list(S.K_DEFAULT) + [1.0], np.float32).tobytes())
+        f.write(np.array([w, h, 64], np.int32).tobytes())
+        f.write(np.array(list(K) + [1.0], np.float32).tobytes())
         f.write(d16.tobytes() + blocks.tobytes() + sd.tobytes() + ed.tobytes())
     r = subprocess.run([emu_mt, str(threads), fin, fout], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:3000]
     raw = open(fout, "rb").read()
     cnt, err = np.frombuffer(raw[:8], np.int32)
-    mem = np.frombuffer(raw[8:8 + 4 * 240 * 320], np.int32).reshape(240, 320)
-    pl = np.frombuffer(raw[8 + 4 * 240 * 320:], PL)[:cnt]
-    mo, po = oracle.plane_detect(d16, depth_map_factor=1.0)
+    mem = np.frombuffer(raw[8:8 + 4 * h2 * w2], np.int32).reshape(h2, w2)
+    pl = np.frombuffer(raw[8 + 4 * h2 * w2:], PL)[:cnt]
+    mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=1.0)
     assert err == 0 and cnt == len(po["N"]) and np.array_equal(mem, mo)
     assert np.array_equal(pl["N"], po["N"]) and np.array_equal(pl["vertices"], po["vertices"])
     assert pl["normal"].tobytes() == po["normal"].tobytes() and pl["center"].tobytes() == po["center"].tobytes()

@@ -60,15 +60,18 @@ def test_plane_detect_degenerate_depth(oracle, msl):
         _check(mem[0], planes[0], mo, po)
 
 
-def test_plane_detect_small_frame_and_unsupported_size(oracle, msl):
-    K = tuple(k * 0.5 for k in S.K_DEFAULT)
-    d16, _ = S.depth_frame(71, 320, 240, K=K)
-    mem, planes = msl.PlaneDetection(width=320, height=240, max_batch=1).detect(d16, K=K, depthMapFactor=1.0)
-    mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=1.0)
-    _check(mem[0], planes[0], mo, po)
-    big = msl.PlaneDetection(width=1280, height=960, max_batch=1)
+def test_plane_detect_other_frame_sizes(oracle, msl):
+    """320x240 (192 blocks, shared-memory instance), 800x600 and 1280x960 (1200 / 3072 blocks: the working set in global
+    memory), and a size beyond 3072 blocks, which is refused"""
+    for (w, h, seed) in ((320, 240, 71), (800, 600, 72), (1280, 960, 73)):
+        K = tuple(k * (w / 640.0) for k in S.K_DEFAULT)
+        d16, _ = S.depth_frame(seed, w, h, K=K)
+        mem, planes = msl.PlaneDetection(width=w, height=h, max_batch=1).detect(d16, K=K, depthMapFactor=1.0, plane_cap=128)
+        mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=1.0, cap=128)
+        _check(mem[0], planes[0], mo, po)
+    big = msl.PlaneDetection(width=2000, height=1500, max_batch=1)
     with pytest.raises(Exception):
-        big.detect(np.full((960, 1280), 1500, np.uint16))
+        big.detect(np.full((1500, 2000), 1500, np.uint16))
 
 
 def test_plane_detect_equals_reference_source_golden(msl):
