@@ -19,7 +19,7 @@ class FakeORB:
 class FakePlane:
     def __init__(self, width=640, height=480, max_batch=1):
         self.width, self.height = width, height
-        if (((width+1)//2)//10) * (((height+1)//2)//10) > 768: self.big = True
+        if (((width+1)//2)//10) * (((height+1)//2)//10) > 3072: self.big = True
         else: self.big = False
     def prestage(self, d16, K=(525.0,525.0,319.5,239.5), depthMapFactor=1/5000., want_cloud=True):
         c,b,s,e = B.plane_prestage(d16, K=K, depth_map_factor=depthMapFactor)
@@ -30,7 +30,7 @@ class FakePlane:
         if d.ndim == 2: d = d[None]
         mems, pls = [], []
         for b in range(len(d)):
-            m, p = B.plane_detect(d[b], K=K, depth_map_factor=depthMapFactor)
+            m, p = B.plane_detect(d[b], K=K, depth_map_factor=depthMapFactor, cap=plane_cap)
             rec = np.zeros(len(p["N"]), PLANE_DTYPE)
             for f in ("normal","center","N","rid","vertices"): rec[f] = p[f]
             mems.append(m); pls.append(rec)
