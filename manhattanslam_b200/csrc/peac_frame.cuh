@@ -122,6 +122,7 @@ template <int NB> struct SharedT {
     double candMse[NB];  // reused as int scratch by the membership pass and the region grow
     int16_t parent[NB], dsize[NB], heap[NB], blkMap[NB];
     uint8_t candHas[NB];
+    int16_t red[1024];  // per-thread best candidate of a merge step (blockDim <= 1024)
     uint32_t tmpMask[WORDS];
     int16_t extracted[MAXPL], oldPl[MAXPL], plidmap[MAXPL];
     uint8_t valid[MAXPL];
@@ -359,7 +360,9 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
         PEAC_SYNC();
         const int p = S.curP;
         if (p < 0) break;
-        // candidate merges with every neighbour, in parallel
+        // candidate merges with every neighbour, in parallel; every thread keeps the best of its own slots
+        // (least mse, then earliest creation: the first minimum in the reference's neighbour order)
+        int mine = -1;
         for (int k = tid; k < nslots; k += nt) {
             S.candHas[k] = 0;
             if (!bit(S.nbs[p], k)) continue;
@@ -368,26 +371,33 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             merged(S.node[p], S.node[k], m);
             S.candMse[k] = m.mse;
             S.candHas[k] = 1;
+            if (mine < 0 || m.mse < S.candMse[mine] || (m.mse == S.candMse[mine] && S.node[k].seq < S.node[mine].seq)) mine = k;
         }
+        S.red[tid] = (int16_t)mine;
         PEAC_SYNC();
         if (tid == 0) {
             // :1064-1072 in neighbour order (creation sequence): the first minimum wins; on an exact tie the reference
             // replaces the candidate iff cand->N < merge->mse
             int best = -1;
-            for (int k = 0; k < nslots; k++)
-                if (S.candHas[k] && (best < 0 || S.candMse[k] < S.candMse[best] ||
-                                     (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq)))
+            for (int t = 0; t < nt; t++) {
+                const int k = S.red[t];
+                if (k >= 0 && (best < 0 || S.candMse[k] < S.candMse[best] ||
+                               (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq)))
                     best = k;
+            }
             if (best >= 0) {
                 const double mn = S.candMse[best];
-                int lastSeq = S.node[best].seq;
-                for (;;) {  // walk the tie group in creation order
-                    int nx = -1;
-                    for (int k = 0; k < nslots; k++)
-                        if (S.candHas[k] && S.candMse[k] == mn && S.node[k].seq > lastSeq && (nx < 0 || S.node[k].seq < S.node[nx].seq)) nx = k;
-                    if (nx < 0) break;
-                    lastSeq = S.node[nx].seq;
-                    if ((double)(S.node[p].N + S.node[best].N) < mn) best = nx;
+                // cand->N = N(p) + N(neighbour) > N(p): the tie rule can only fire when the tied mse exceeds N(p)
+                if (mn > (double)S.node[p].N) {
+                    int lastSeq = S.node[best].seq;
+                    for (;;) {  // walk the tie group in creation order
+                        int nx = -1;
+                        for (int k = 0; k < nslots; k++)
+                            if (S.candHas[k] && S.candMse[k] == mn && S.node[k].seq > lastSeq && (nx < 0 || S.node[k].seq < S.node[nx].seq)) nx = k;
+                        if (nx < 0) break;
+                        lastSeq = S.node[nx].seq;
+                        if ((double)(S.node[p].N + S.node[best].N) < mn) best = nx;
+                    }
                 }
                 merged(S.node[p], S.node[best], S.tmp);
             }
