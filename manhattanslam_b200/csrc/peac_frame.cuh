@@ -343,6 +343,87 @@ PEAC_HD void ds_union(SH &S, int x, int y) {
         S.parent[yr] = (int16_t)xr, S.dsize[xr] = (int16_t)(S.dsize[xr] + S.dsize[yr]);
 }
 
+// ---- std::sort(extractedPlanes.begin(), extractedPlanes.end(), PlaneSegSizeCmp()) exactly as libstdc++ performs it
+// (introsort: median-of-three pivot + unguarded partition down to 16 elements, then one insertion sort).  std::sort is not
+// stable and planes of equal size are common (sizes are multiples of 100 points), so the order of equal keys -- and with
+// it the plane ids written into membershipImg -- is whatever this algorithm leaves.  comp(a, b) = N[b] < N[a].
+template <class SH>
+PEAC_HD bool plane_comp(const SH &S, int a, int b) { return S.node[b].N < S.node[a].N; }
+template <class SH>
+PEAC_HD void plane_linear_insert(SH &S, int16_t *v, int last) {  // std::__unguarded_linear_insert
+    const int16_t val = v[last];
+    int next = last - 1;
+    while (plane_comp(S, val, v[next])) {
+        v[last] = v[next];
+        last = next;
+        --next;
+    }
+    v[last] = val;
+}
+template <class SH>
+PEAC_HD void plane_insertion_sort(SH &S, int16_t *v, int first, int last) {  // std::__insertion_sort
+    for (int i = first + 1; i < last; ++i) {
+        if (plane_comp(S, v[i], v[first])) {
+            const int16_t val = v[i];
+            for (int k = i; k > first; --k) v[k] = v[k - 1];
+            v[first] = val;
+        } else {
+            plane_linear_insert(S, v, i);
+        }
+    }
+}
+template <class SH>
+PEAC_HD bool sort_planes(SH &S) {
+    int16_t *v = S.extracted;
+    const int n = S.nExtracted;
+    if (n < 2) return true;
+    // std::__introsort_loop with its recursion on the right part turned into a stack of (first, last, depth) ranges
+    int lg = 0;
+    while ((n >> (lg + 1)) > 0) lg++;
+    int stF[32], stL[32], stD[32], sp = 0;
+    stF[0] = 0, stL[0] = n, stD[0] = 2 * lg, sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stF[sp], last = stL[sp], depth = stD[sp];
+        while (last - first > 16) {
+            if (depth == 0) return false;  // libstdc++ would heap-sort here; not reachable with <= 128 planes in practice
+            --depth;
+            // std::__move_median_to_first(first, first + 1, mid, last - 1)
+            const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+            int pick;
+            if (plane_comp(S, v[a], v[b])) {
+                if (plane_comp(S, v[b], v[c])) pick = b;
+                else if (plane_comp(S, v[a], v[c])) pick = c;
+                else pick = a;
+            } else if (plane_comp(S, v[a], v[c])) pick = a;
+            else if (plane_comp(S, v[b], v[c])) pick = c;
+            else pick = b;
+            { const int16_t t = v[first]; v[first] = v[pick]; v[pick] = t; }
+            // std::__unguarded_partition(first + 1, last, pivot = first)
+            int lo = first + 1, hi = last;
+            for (;;) {
+                while (plane_comp(S, v[lo], v[first])) ++lo;
+                --hi;
+                while (plane_comp(S, v[first], v[hi])) --hi;
+                if (!(lo < hi)) break;
+                { const int16_t t = v[lo]; v[lo] = v[hi]; v[hi] = t; }
+                ++lo;
+            }
+            if (sp >= 32) return false;
+            stF[sp] = lo, stL[sp] = last, stD[sp] = depth, ++sp;  // __introsort_loop(cut, last, depth_limit)
+            last = lo;
+        }
+    }
+    // std::__final_insertion_sort
+    if (n > 16) {
+        plane_insertion_sort(S, v, 0, 16);
+        for (int i = 16; i < n; ++i) plane_linear_insert(S, v, i);
+    } else {
+        plane_insertion_sort(S, v, 0, n);
+    }
+    return true;
+}
+
 // ---- ahCluster, AHCPlaneFitter.hpp:939-1143.  nslots = number of block slots of the frame.
 template <class SH>
 PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
@@ -455,19 +536,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
         }
         PEAC_SYNC();
     }
-    if (tid == 0) {
-        // std::sort(extractedPlanes, PlaneSegSizeCmp): descending N; libstdc++ insertion-sorts up to 16 elements, which
-        // keeps equal sizes in extraction order (more than 16 planes with equal sizes among them: order unpinned)
-        for (int i = 1; i < S.nExtracted; i++) {
-            const int16_t v = S.extracted[i];
-            int j = i;
-            while (j > 0 && S.node[S.extracted[j - 1]].N < S.node[v].N) {
-                S.extracted[j] = S.extracted[j - 1];
-                j--;
-            }
-            S.extracted[j] = v;
-        }
-    }
+    if (tid == 0 && !sort_planes(S)) S.error = PEAC_ERR_PLANES;  // std::sort(extractedPlanes, PlaneSegSizeCmp) :1139-1141
     PEAC_SYNC();
 }
 

@@ -101,6 +101,24 @@ def test_global_memory_instance_on_larger_frames(emu, oracle):
         assert len(pl) >= 2
 
 
+def test_more_than_16_planes_of_equal_size(emu, oracle):
+    """std::sort of extractedPlanes is not stable and libstdc++ only insertion-sorts up to 16 elements: with 22-23 planes, many
+    of equal size, the plane ids in membershipImg are whatever its introsort leaves -- which the kernel source restates"""
+    w, h = 1280, 960
+    K = tuple(k * 2 for k in S.K_DEFAULT)
+    for gx, gy in ((5, 5), (6, 4)):
+        d16 = np.zeros((h, w), np.uint16)
+        for i in range(gy):
+            for j in range(gx):
+                d16[i * h // gy:(i + 1) * h // gy, j * w // gx:(j + 1) * w // gx] = 1000 + (i * gx + j) * 150
+        _, pl = _same(emu, oracle, d16, K=K)
+        assert len(pl) > 16 and len(set(pl["N"].tolist())) < len(pl)
+        if oracle.build_ref(name="libplane_ref.so"):  # ... and the oracle's std::sort agrees with the reference's own
+            mo, po = oracle.plane_detect(d16, K=K, depth_map_factor=1.0, cap=128)
+            mr, pr = oracle.ref_plane_run(d16, K=K, depth_map_factor=1.0, cap=128)
+            assert np.array_equal(mo, mr) and po["center"].tobytes() == pr["center"].tobytes()
+
+
 def test_frames_beyond_3072_blocks_are_refused(emu, oracle):
     d16 = np.full((1500, 2000), 1500, np.uint16)
     _, blocks, seed, edges = oracle.plane_prestage(d16)
