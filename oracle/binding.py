@@ -540,6 +540,8 @@ REFERENCE_ROOT = "/root/reference"
 _REF_DEPS = {
     "libsurfel_ref.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
                          ["ref_wrap.cpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/cvshim.hpp", "ref_shim_cv/seq_thread/thread"]),
+    "libsurfel_ref_threads.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
+                                 ["ref_wrap.cpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/cvshim.hpp"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
                       ["ref_orb_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
     "libplane_ref.so": (["src/PlaneExtractor.cpp", "include/PlaneExtractor.h", "include/peac/AHCPlaneFitter.hpp",
@@ -739,10 +741,11 @@ class RefSurfelFusion:
     """The reference's SurfelFusion class itself (oracle/_ref, see build_ref): fuseInitializeMap + read-back of the
     private superpixel buffers.  Used by tests/test_oracle_ref.py to check the oracle restatement, nowhere else."""
 
-    def __init__(self, w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, fuseFar=30.0, fuseNear=0.5):
-        so = build_ref()
+    def __init__(self, w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, fuseFar=30.0, fuseNear=0.5, real_threads=False):
+        """real_threads: the build with the real <thread> (the reference's ten racing slices) -- for timing only"""
+        so = build_ref(name="libsurfel_ref_threads.so" if real_threads else "libsurfel_ref.so")
         if so is None:
-            raise RuntimeError("oracle/_ref/libsurfel_ref.so is not built and /root/reference is absent")
+            raise RuntimeError("oracle/_ref/libsurfel_ref*.so is not built and /root/reference is absent")
         self.L = C.CDLL(so)
         self.L.ref_surfel_create.restype = C.c_void_p
         self.L.ref_surfel_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6
@@ -772,6 +775,28 @@ class RefSurfelFusion:
         if n < 0:
             raise RuntimeError("the reference resized localSurfels")
         return new[:n].copy()
+
+    def set_map(self, local):
+        """timing form: the local map in a std::vector inside the library (as Map::mvLocalSurfels in the reference)"""
+        self.L.ref_surfel_set_map.argtypes = [C.c_void_p, C.c_int64]
+        local = np.ascontiguousarray(local)
+        self.L.ref_surfel_set_map(_p(local), len(local))
+
+    def fuse_resident(self, ref, gray, depth, membership, Twc):
+        """fuseInitializeMap on the library-owned map (no copy of the map in or out) -> number of new surfels"""
+        self.L.ref_surfel_fuse_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        h, w = self.h, self.w
+        buf = np.zeros(h * w + 3 * w + 16, np.uint8)
+        buf[:h * w] = np.ascontiguousarray(gray, np.uint8).ravel()
+        d = np.ascontiguousarray(depth, np.float32)
+        m = np.ascontiguousarray(membership, np.int32)
+        T = np.ascontiguousarray(Twc, np.float32)
+        return self.L.ref_surfel_fuse_resident(self.hd, int(ref), _p(buf), w, _p(d), _p(m), _p(T))
+
+    def compact_resident(self):
+        """the tail of SurfelMapping::fuseMap on the library-owned map -> new map size"""
+        self.L.ref_surfel_compact_resident.restype = C.c_int64
+        return self.L.ref_surfel_compact_resident()
 
     def index(self):
         out = np.zeros((self.h, self.w), np.int32)

@@ -45,6 +45,46 @@ int ref_surfel_fuse(void *p, int ref, uint8_t *gray, int gray_stride, float *dep
     return n;
 }
 
+// Timing form: the local map lives in a std::vector owned by this library, as Map::mvLocalSurfels does in the reference, so a
+// fuse does not pay for copying the map in and out.  ref_surfel_set_map loads it; ref_surfel_fuse_resident runs
+// fuseInitializeMap on it and returns the number of new surfels.
+static std::vector<Surfel> g_resident, g_new;
+void ref_surfel_set_map(const Surfel *local, int64_t n) { g_resident.assign(local, local + n); }
+int64_t ref_surfel_map_size() { return (int64_t)g_resident.size(); }
+// the tail of SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391; that file does not compile here, so these lines are a
+// restatement): deleted slots refilled from the back of the deleted list with the new surfels, the rest swap-removed
+int64_t ref_surfel_compact_resident() {
+    std::vector<int> deleted;
+    for (int i = 0; i < (int)g_resident.size(); i++)
+        if (g_resident[i].updateTimes == 0) deleted.push_back(i);
+    for (size_t i = 0; i < g_new.size(); i++) {
+        if (g_new[i].updateTimes == 0) continue;
+        if (!deleted.empty()) {
+            g_resident[deleted.back()] = g_new[i];
+            deleted.pop_back();
+        } else {
+            g_resident.push_back(g_new[i]);
+        }
+    }
+    while (!deleted.empty()) {
+        g_resident[deleted.back()] = g_resident.back();
+        deleted.pop_back();
+        g_resident.pop_back();
+    }
+    return (int64_t)g_resident.size();
+}
+int ref_surfel_fuse_resident(void *p, int ref, uint8_t *gray, int gray_stride, float *depth, int32_t *membership, const float *Twc) {
+    SurfelFusion *f = (SurfelFusion *)p;
+    const int w = f->imageWidth, h = f->imageHeight;
+    cv::Mat image(h, w, CV_8UC1, gray, (size_t)gray_stride), dep(h, w, CV_32FC1, depth);
+    cv::Mat mem((h + 1) / 2, (w + 1) / 2, CV_32SC1, membership);
+    Eigen::Matrix4f pose;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) pose(i, j) = Twc[4 * i + j];
+    f->fuseInitializeMap(ref, image, dep, mem, pose, g_resident, g_new);
+    return (int)g_new.size();
+}
+
 int ref_surfel_index(void *p, int32_t *out) {
     SurfelFusion *f = (SurfelFusion *)p;
     memcpy(out, f->superpixelIndex.data(), sizeof(int32_t) * f->superpixelIndex.size());
