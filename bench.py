@@ -365,8 +365,9 @@ def widened_peac(msl, frames=8):
                     planes[b]["normal"].tobytes() == ref[b][1]["normal"].tobytes() for b in range(frames))
         return {"plane_detect_640x480": {"frames": frames, "gpu_call_ms_per_batch": 1e3 * g_s, "cpu_oracle_ms_per_batch": 1e3 * c_s,
                                          "planes_per_frame": [len(p) for p in planes], "equal": bool(equal),
-                                         "note": "one CTA per frame; the region grow (floodFill) is an order-dependent FIFO "
-                                                 "and runs on one thread per frame"}}
+                                         "flood_serial": os.environ.get("MSL_PEAC_FLOOD_SERIAL", "0"),
+                                         "note": "host API incl. H2D / D2H; one CTA per frame; the region grow runs level by level "
+                                                 "(MSL_PEAC_FLOOD_SERIAL=1: as a FIFO on one thread)"}}
     except Exception as e:  # noqa: BLE001 -- diagnostics only
         return {"plane_detect_640x480": {"error": "%s: %s" % (type(e).__name__, e)}}
 
