@@ -542,6 +542,9 @@ _REF_DEPS = {
                          ["ref_wrap.cpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/cvshim.hpp", "ref_shim_cv/seq_thread/thread"]),
     "libsurfel_ref_threads.so": (["src/SurfelFusion.cpp", "include/SurfelFusion.h"],
                                  ["ref_wrap.cpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/cvshim.hpp"]),
+    "libmapping_ref.so": (["src/SurfelMapping.cpp", "src/SurfelFusion.cpp", "include/SurfelMapping.h", "include/SurfelFusion.h"],
+                          ["ref_mapping_wrap.cpp", "ref_shim_map/map_standins.hpp", "ref_shim_map/pcl/point_types.h",
+                           "ref_shim_cv/cvshim.hpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/seq_thread/thread"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
                       ["ref_orb_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
     "libplane_ref.so": (["src/PlaneExtractor.cpp", "include/PlaneExtractor.h", "include/peac/AHCPlaneFitter.hpp",
@@ -807,6 +810,58 @@ class RefSurfelFusion:
         out = np.zeros((self.w // 8) * (self.h // 8), SEED_DTYPE)
         self.L.ref_surfel_seeds(self.hd, _p(out))
         return out
+
+
+class RefSurfelMapping:
+    """The reference's SurfelMapping class itself (oracle/_ref/libmapping_ref.so: src/SurfelMapping.cpp + src/SurfelFusion.cpp
+    compiled unmodified, see oracle/ref_mapping_wrap.cpp): keyframes go through InsertKeyFrame + ProcessNewKeyFrame."""
+
+    def __init__(self, w=640, h=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, far=30.0, near=0.5):
+        so = build_ref(name="libmapping_ref.so")
+        if so is None:
+            raise RuntimeError("oracle/_ref/libmapping_ref.so is not built and /root/reference is absent")
+        L = self.L = C.CDLL(so)
+        L.ref_mapping_create.restype = C.c_void_p
+        L.ref_mapping_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6
+        L.ref_mapping_destroy.argtypes = [C.c_void_p]
+        L.ref_mapping_keyframe.restype = C.c_int64
+        L.ref_mapping_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_mapping_last_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        for f in (L.ref_mapping_local, L.ref_mapping_inactive):
+            f.restype = C.c_int64
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        self.w, self.h = w, h
+        self.hd = L.ref_mapping_create(w, h, fx, fy, cx, cy, far, near)
+
+    def __del__(self):
+        if getattr(self, "hd", None):
+            self.L.ref_mapping_destroy(self.hd)
+            self.hd = None
+
+    def keyframe(self, gray, depth, membership, Twc, reference_index):
+        """-> (posesToAdd, posesToRemove) that getAddRemovePoses handed to moveAddSurfels for this keyframe"""
+        h, w = self.h, self.w
+        buf = np.zeros(h * w + 3 * w + 16, np.uint8)
+        buf[:h * w] = np.ascontiguousarray(gray, np.uint8).ravel()
+        d = np.ascontiguousarray(depth, np.float32)
+        m = np.ascontiguousarray(membership, np.int32)
+        T = np.ascontiguousarray(Twc, np.float32)
+        self.L.ref_mapping_keyframe(self.hd, _p(buf), w, h, _p(d), _p(m), _p(T), int(reference_index))
+        add, rem, nr = np.zeros(4096, np.int32), np.zeros(4096, np.int32), np.zeros(1, np.int32)
+        na = self.L.ref_mapping_last_lists(self.hd, _p(add), _p(rem), 4096, _p(nr))
+        return add[:na].copy(), rem[:int(nr[0])].copy()
+
+    def _get(self, fn):
+        n = fn(self.hd, None, 0)
+        out = np.zeros(n, SURFEL_DTYPE)
+        fn(self.hd, _p(out), n)
+        return out
+
+    def local(self):
+        return self._get(self.L.ref_mapping_local)
+
+    def inactive(self):
+        return self._get(self.L.ref_mapping_inactive)
 
 
 class SurfelMappingOracle:

@@ -441,3 +441,39 @@ def test_peac_degenerate_depth_matches_reference_source(ref_plane):
     two[:, 320:] = 2500
     mem, planes = _peac_same(ref_plane, two)
     assert len(planes["N"]) == 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f1: SurfelMapping::moveAddSurfels + fuseMap.  oracle/_ref/libmapping_ref.so is the reference's own
+# src/SurfelMapping.cpp + src/SurfelFusion.cpp compiled unmodified (oracle/ref_mapping_wrap.cpp; Map / pcl / cv::FileStorage
+# stand-ins in oracle/ref_shim_map/).  Keyframes go through InsertKeyFrame + ProcessNewKeyFrame as in SurfelMapping::Run; the
+# oracle is driven next to it with the pose lists the reference's getAddRemovePoses produced.
+
+def test_surfel_mapping_stream_matches_reference_source(oracle):
+    """a chain of 26 keyframes (poses fall out of the 10-level drift-free window: their surfels move to mvInactiveSurfels),
+    then links back into the old part of the graph (poses and their surfels move back in, the inactive vector is spliced):
+    Map::mvLocalSurfels and Map::mvInactiveSurfels record for record after every keyframe"""
+    B = oracle
+    if B.build_ref(name="libmapping_ref.so") is None:
+        pytest.skip("oracle/_ref/libmapping_ref.so not built and /root/reference absent")
+    w, h = 320, 240
+    K = tuple(k * 0.5 for k in S.K_DEFAULT)
+    r = B.RefSurfelMapping(w, h, *K)
+    o, mo = B.SurfelOracle(w, h, *K), B.SurfelMappingOracle()
+    local = np.zeros(0, B.SURFEL_DTYPE)
+    refs = [0] + [i - 1 for i in range(1, 26)] + [3, 26, 4, 28, 27, 2, 30, 31]
+    poses = S.pose_walk(5, len(refs))
+    g = S.gray_frame(5, w, h)
+    mem = S.membership(5, w, h, plane_fraction=0.2)
+    moved_out = moved_in = 0
+    for i, ref_index in enumerate(refs):
+        _, d = S.depth_frame(300 + i % 4, w, h, K=K, scene=300)
+        add, rem = r.keyframe(g, d, mem, poses[i], ref_index)
+        moved_out, moved_in = moved_out + len(rem), moved_in + len(add)
+        if len(rem) or len(add):
+            local = mo.move_add(local, rem, add)                 # moveAddSurfels :194-304
+        new = o.fuse(ref_index, g, d, mem, poses[i], local)      # fuseMap :353-392 = fuseInitializeMap + the tail
+        local = B.surfel_compact(local, new)
+        assert _same(local, r.local()), i
+        assert _same(mo.inactive(), r.inactive()), i
+    assert moved_out > 20 and moved_in > 10 and len(local) > 500 and mo.inactive_size() > 1000
