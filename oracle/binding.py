@@ -545,6 +545,9 @@ _REF_DEPS = {
     "libmapping_ref.so": (["src/SurfelMapping.cpp", "src/SurfelFusion.cpp", "include/SurfelMapping.h", "include/SurfelFusion.h"],
                           ["ref_mapping_wrap.cpp", "ref_shim_map/map_standins.hpp", "ref_shim_map/pcl/point_types.h",
                            "ref_shim_cv/cvshim.hpp", "ref_shim_cv/eigenshim.hpp", "ref_shim_cv/seq_thread/thread"]),
+    "libmappoint_ref.so": (["src/MapPoint.cc", "include/MapPoint.h"],
+                           ["ref_mappoint_wrap.cpp", "ref_shim_mp/mp_standins.hpp", "ref_shim_cv/cvshim.hpp", "match_oracle.cpp",
+                            "orb_oracle.cpp", "msl_oracle.h"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],
                       ["ref_orb_wrap.cpp", "ref_arena.hpp", "ref_shim_cv/cvshim.hpp", "orb_oracle.cpp", "msl_oracle.h"]),
     "libplane_ref.so": (["src/PlaneExtractor.cpp", "include/PlaneExtractor.h", "include/peac/AHCPlaneFitter.hpp",

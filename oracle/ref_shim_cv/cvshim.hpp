@@ -170,6 +170,7 @@ public:
     }
     Mat(const MatZeros &z) : Mat() { *this = z; }
     Mat(const MatExprMul &e);  // evaluates the product (below)
+    void copyTo(Mat &m) const { m = clone(); }
     void convertTo(Mat &m, int rtype) const {  // same-depth conversions only: a copy
         assert((rtype & 7) == depth());
         m = clone();
@@ -299,6 +300,17 @@ static inline Mat operator-(const Mat &a, const Mat &b) {  // 3x1 float differen
     assert(a.rows == 3 && a.cols == 1 && b.rows == 3 && b.cols == 1);
     float o[3];
     for (int i = 0; i < 3; i++) o[i] = a.at<float>(i, 0) - b.at<float>(i, 0);
+    return mat31(o);
+}
+// element-wise helpers that only src/MapPoint.cc's normal bookkeeping uses (compiled, not part of any comparison)
+static inline Mat operator+(const Mat &a, const Mat &b) {
+    float o[3];
+    for (int i = 0; i < 3; i++) o[i] = a.at<float>(i, 0) + b.at<float>(i, 0);
+    return mat31(o);
+}
+static inline Mat operator/(const Mat &a, double s) {
+    float o[3];
+    for (int i = 0; i < 3; i++) o[i] = (float)(a.at<float>(i, 0) * (1.0 / s));
     return mat31(o);
 }
 static inline double norm(const Mat &a) {  // NORM_L2 of a 3x1 float vector: squares accumulated in double

@@ -477,3 +477,75 @@ def test_surfel_mapping_stream_matches_reference_source(oracle):
         assert _same(local, r.local()), i
         assert _same(mo.inactive(), r.inactive()), i
     assert moved_out > 20 and moved_in > 10 and len(local) > 500 and mo.inactive_size() > 1000
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MapPoint: oracle/_ref/libmappoint_ref.so is the reference's own src/MapPoint.cc compiled unmodified on KeyFrame / Frame /
+# Map stand-ins (oracle/ref_shim_mp/, oracle/ref_mappoint_wrap.cpp).
+
+@pytest.fixture(scope="module")
+def ref_mp(oracle):
+    import ctypes as C
+    so = oracle.build_ref(name="libmappoint_ref.so")
+    if so is None:
+        pytest.skip("oracle/_ref/libmappoint_ref.so not built and /root/reference absent")
+    L = C.CDLL(so)
+    L.ref_distinctive.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.ref_predict_scale.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_distinctive_descriptors_match_reference_source(ref_mp, oracle, seed):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263) of the reference itself -- observations in
+    std::map<KeyFrame*, size_t> order, bad keyframes skipped, float distance matrix, sorted-row median, first least median --
+    against the oracle's batched restatement"""
+    r = np.random.default_rng(seed)
+    n_kf, n_mp = 40, 300
+    kf_rows = r.integers(5, 60, n_kf).astype(np.int32)
+    kf_desc = r.integers(0, 256, (int(kf_rows.sum()), 32), dtype=np.uint8)
+    # near-duplicate descriptors make medians tie: the first-least-median rule decides
+    kf_desc[::3] = kf_desc[0] ^ (r.integers(0, 256, (len(kf_desc[::3]), 32), dtype=np.uint8) & r.integers(0, 2, (len(kf_desc[::3]), 32), dtype=np.uint8))
+    kf_bad = (r.random(n_kf) < 0.15).astype(np.uint8)
+    row0 = np.concatenate([[0], np.cumsum(kf_rows)])
+    obs_off, obs_kf, obs_row, lists = [0], [], [], []
+    for p in range(n_mp):
+        k = int(r.choice([0, 1, 2, 3, 8, 20, 33]))
+        ks = np.sort(r.choice(n_kf, min(k, n_kf), replace=False))
+        rows = [int(r.integers(0, kf_rows[q])) for q in ks]
+        obs_kf += ks.tolist()
+        obs_row += rows
+        obs_off.append(len(obs_kf))
+        lists.append([kf_desc[row0[q] + rw] for q, rw in zip(ks, rows) if not kf_bad[q]])
+    out = np.zeros((n_mp, 32), np.uint8)
+    a = lambda x: np.ascontiguousarray(x, np.int32)
+    oo, ok, orw = a(obs_off), a(obs_kf), a(obs_row)
+    assert ref_mp.ref_distinctive(n_kf, kf_rows.ctypes.data, kf_desc.ctypes.data, kf_bad.ctypes.data, n_mp, oo.ctypes.data,
+                                  ok.ctypes.data, orw.ctypes.data, out.ctypes.data) == 0
+    bi, _ = oracle.distinctive_descriptors([np.stack(l) if l else np.zeros((0, 32), np.uint8) for l in lists])
+    for p in range(n_mp):
+        expect = lists[p][int(bi[p])] if lists[p] else np.zeros(32, np.uint8)
+        assert np.array_equal(out[p], expect), p
+
+
+def test_predict_scale_matches_reference_source(ref_mp):
+    """MapPoint::PredictScale (src/MapPoint.cc:334-364): ceil(log(mfMaxDistance / dist) / mfLogScaleFactor) with float operands
+    (std::log(float) = logf), clamped to [0, nLevels - 1] -- against the rule the matcher oracles and the stand-in MapPoint
+    restate; plus the 0.8 / 1.2 distance-invariance getters (:324-332)"""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype, libm.logf.argtypes = C.c_float, [C.c_float]
+    r = np.random.default_rng(4)
+    lsf = np.float32(np.log(np.float64(np.float32(1.2))))
+    for max_dist in (np.float32(3.7), np.float32(0.91), np.float32(12.25)):
+        dist = np.concatenate([r.uniform(0.05, 40.0, 4000), max_dist / np.float32(1.2) ** np.arange(-2, 11)]).astype(np.float32)
+        out, inv, top = np.zeros((len(dist), 2), np.int32), np.zeros(2, np.float32), np.array([3.5831808], np.float32)
+        ref_mp.ref_predict_scale(float(max_dist), float(lsf), 8, top.ctypes.data, len(dist), dist.ctypes.data, out.ctypes.data, inv.ctypes.data)
+        expect = np.zeros(len(dist), np.int32)
+        for i, d in enumerate(dist):
+            ratio = np.float32(max_dist / d)
+            n = int(np.ceil(np.float32(libm.logf(float(ratio))) / lsf))
+            expect[i] = min(max(n, 0), 7)
+        assert np.array_equal(out[:, 0], expect) and np.array_equal(out[:, 1], expect)
+        assert len(set(expect.tolist())) == 8
+        assert inv[1] == np.float32(1.2) * max_dist and inv[0] == np.float32(0.8) * np.float32(max_dist / top[0])
