@@ -29,6 +29,7 @@ struct msl_surfel_fusion {
     orc_surfel_fusion *o;
     int w, h;
     std::vector<orc_surfel> map;
+    orc_surfel_mapping *mp;  // the inactive store behind msl_surfel_move_add
 };
 
 extern "C" {
@@ -95,11 +96,29 @@ int msl_plane_detect(msl_plane *p, const uint16_t *depth, int dstride_px, size_t
 int msl_surfel_create(int w, int h, float fx, float fy, float cx, float cy, float fuse_far, float fuse_near, int64_t, int,
                       msl_surfel_fusion **out) {
     if (!out) return fail(MSL_ERR_INVALID, "msl_surfel_create: null out");
-    *out = new msl_surfel_fusion{orc_surfel_create(w, h, fx, fy, cx, cy, fuse_far, fuse_near), w, h, {}};
+    *out = new msl_surfel_fusion{orc_surfel_create(w, h, fx, fy, cx, cy, fuse_far, fuse_near), w, h, {}, orc_mapping_create()};
     return MSL_OK;
 }
 void msl_surfel_destroy(msl_surfel_fusion *h) {
-    if (h) orc_surfel_destroy(h->o), delete h;
+    if (h) orc_surfel_destroy(h->o), orc_mapping_destroy(h->mp), delete h;
+}
+int msl_surfel_move_add(msl_surfel_fusion *h, const int32_t *rem, int n_rem, const int32_t *add, int n_add, int64_t stats[3]) {
+    const int64_t n0 = (int64_t)h->map.size(), cap = n0 + orc_mapping_inactive(h->mp, nullptr, 0);
+    h->map.resize((size_t)cap);
+    const int64_t n = orc_move_add_surfels(h->mp, h->map.data(), n0, cap, rem, n_rem, add, n_add);
+    if (n < 0) return fail(MSL_ERR_STATE, "msl_surfel_move_add: pose state");
+    h->map.resize((size_t)n);
+    if (stats) stats[0] = stats[1] = 0, stats[2] = n;
+    return MSL_OK;
+}
+int64_t msl_surfel_inactive_size(const msl_surfel_fusion *h) { return orc_mapping_inactive(h->mp, nullptr, 0); }
+int msl_surfel_download_inactive(msl_surfel_fusion *h, msl_surfel *out, int64_t cap, int64_t *n) {
+    const int64_t sz = orc_mapping_inactive(h->mp, nullptr, 0);
+    if (n) *n = sz;
+    if (!out) return MSL_OK;
+    if (sz > cap) return fail(MSL_ERR_CAPACITY, "msl_surfel_download_inactive: capacity");
+    orc_mapping_inactive(h->mp, (orc_surfel *)out, cap);
+    return MSL_OK;
 }
 int msl_surfel_upload_map(msl_surfel_fusion *h, const msl_surfel *local, int64_t n) {
     static_assert(sizeof(msl_surfel) == sizeof(orc_surfel), "surfel layout");
@@ -107,18 +126,28 @@ int msl_surfel_upload_map(msl_surfel_fusion *h, const msl_surfel *local, int64_t
     return MSL_OK;
 }
 int msl_surfel_download_map(msl_surfel_fusion *h, msl_surfel *local, int64_t cap, int64_t *n) {
+    if (n) *n = (int64_t)h->map.size();
+    if (!local) return MSL_OK;  // size query
     if ((int64_t)h->map.size() > cap) return fail(MSL_ERR_CAPACITY, "msl_surfel_download_map: capacity");
     memcpy(local, h->map.data(), sizeof(orc_surfel) * h->map.size());
-    if (n) *n = (int64_t)h->map.size();
     return MSL_OK;
 }
 int msl_surfel_fuse(msl_surfel_fusion *h, int ref, const uint8_t *gray, int gray_stride, const float *depth,
                     const int32_t *membership, const float Twc[16], msl_surfel *new_surfels, int cap_new, int compact, int64_t stats[4]) {
-    if (compact) return fail(MSL_ERR_INVALID, "mock: compact not modelled");
+    std::vector<orc_surfel> own;
+    if (!new_surfels) {  // the caller does not want the new surfels back (device-resident mode)
+        own.resize((size_t)(h->w / 8) * (h->h / 8));
+        new_surfels = (msl_surfel *)own.data(), cap_new = (int)own.size();
+    }
     const int n = orc_surfel_fuse(h->o, ref, gray, gray_stride, depth, membership, Twc, h->map.data(), (int64_t)h->map.size(),
                                   (orc_surfel *)new_surfels, cap_new, 1);
-    if (n < 0) return fail(MSL_ERR_CAPACITY, "msl_surfel_fuse: capacity");
-    stats[0] = n, stats[1] = stats[2] = 0, stats[3] = (int64_t)h->map.size();
+    if (n < 0 || n > cap_new) return fail(MSL_ERR_CAPACITY, "msl_surfel_fuse: capacity");
+    if (compact) {  // the tail of SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391)
+        const int64_t n0 = (int64_t)h->map.size();
+        h->map.resize((size_t)(n0 + n));
+        h->map.resize((size_t)orc_surfel_compact(h->map.data(), n0, (const orc_surfel *)new_surfels, n));
+    }
+    if (stats) stats[0] = n, stats[1] = stats[2] = 0, stats[3] = (int64_t)h->map.size();
     return MSL_OK;
 }
 

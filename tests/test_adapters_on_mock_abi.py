@@ -306,3 +306,73 @@ def test_frame_glue_binding(gadp, oracle, distorted):
     ur_o, kd_o = oracle.stereo_from_rgbd(xy, xy_un, depth, mbf)
     assert np.array_equal(kd, kd_o) and np.array_equal(ur, ur_o)
     assert (kd > 0).sum() > n // 2 and (kd == -1).sum() > 0
+
+
+# ---- adapters/SurfelMapping_msl.cpp (device-resident mode) inside the reference's own SurfelMapping class
+@pytest.fixture(scope="module")
+def smadp(oracle):
+    if not os.path.isdir(os.path.join(REF, "include")):
+        pytest.skip("/root/reference absent")
+    assert oracle.build_ref(name="libmapping_ref.so")
+    orc, out = os.path.join(ROOT, "oracle"), os.path.join(HERE, "host_emul", "build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libmapping_adapter_mock.so")
+    srcs = [os.path.join(HERE, "host_emul", "mapping_adapter_wrap.cpp"), os.path.join(ROOT, "adapters", "SurfelMapping_msl.cpp"),
+            os.path.join(ROOT, "adapters", "SurfelFusion_msl.cpp"), os.path.join(HERE, "host_emul", "mock_abi.cpp"),
+            os.path.join(orc, "surfel_oracle.cpp"), os.path.join(orc, "orb_oracle.cpp"), os.path.join(orc, "plane_oracle.cpp")]
+    deps = srcs + [os.path.join(orc, "ref_shim_map", "map_standins.hpp"), os.path.join(orc, "ref_shim_cv", "cvshim.hpp"),
+                   os.path.join(orc, "ref_shim_cv", "eigenshim.hpp"), os.path.join(orc, "peac_oracle.inc")]
+    if not os.path.exists(so) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(so):
+        fl = ["-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-w", "-DMSL_SURFEL_RESIDENT", "-I" + os.path.join(orc, "ref_shim_cv"),
+              "-I" + os.path.join(orc, "ref_shim_map"), "-I" + orc, "-I" + os.path.join(REF, "include"), "-I" + os.path.join(ROOT, "include"),
+              "-DSYSTEM_H", "-DMAP_H", "-include", os.path.join(orc, "ref_shim_map", "map_standins.hpp")]
+        obj = os.path.join(out, "sm_ref.o")
+        # the reference's two definitions renamed out of the way: what `#ifndef MSL_SURFEL_RESIDENT` does in a checkout
+        subprocess.check_call(["g++"] + fl + ["-DmoveAddSurfels=moveAddSurfels_reference", "-DfuseMap=fuseMap_reference", "-c", "-o", obj,
+                                              os.path.join(REF, "src", "SurfelMapping.cpp")])
+        subprocess.check_call(["g++"] + fl + ["-shared", "-o", so, obj] + srcs)
+        os.remove(obj)
+    L = C.CDLL(so)
+    L.adp_mapping_create.restype = C.c_void_p
+    L.adp_mapping_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 6
+    L.adp_mapping_keyframe.restype = C.c_int64
+    L.adp_mapping_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    for f in (L.adp_mapping_local, L.adp_mapping_inactive):
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    return L
+
+
+def test_surfelmapping_binding_equals_reference_class(smadp, oracle):
+    """moveAddSurfels + fuseMap of the binding (surfel maps behind the C ABI, host vectors as mirrors) against the reference's
+    own SurfelMapping over a 34-keyframe pose graph: Map::mvLocalSurfels and Map::mvInactiveSurfels after every keyframe"""
+    w, h = 320, 240
+    K = tuple(k * 0.5 for k in S.K_DEFAULT)
+    r = oracle.RefSurfelMapping(w, h, *K)
+    a = smadp.adp_mapping_create(w, h, *K, 30.0, 0.5)
+
+    def get(fn):
+        n = fn(a, None, 0)
+        out = np.zeros(n, oracle.SURFEL_DTYPE)
+        fn(a, out.ctypes.data, n)
+        return out
+
+    refs = [0] + [i - 1 for i in range(1, 26)] + [3, 26, 4, 28, 27, 2, 30, 31]
+    poses, g, mem = S.pose_walk(5, len(refs)), S.gray_frame(5, w, h), np.ascontiguousarray(S.membership(5, w, h, plane_fraction=0.2), np.int32)
+    moved = 0
+    for i, ri in enumerate(refs):
+        _, d = S.depth_frame(300 + i % 4, w, h, K=K, scene=300)
+        add, rem = r.keyframe(g, d, mem, poses[i], ri)
+        moved += len(add) + len(rem)
+        buf = np.zeros(h * w + 3 * w + 16, np.uint8)
+        buf[:h * w] = g.ravel()
+        dd, T = np.ascontiguousarray(d, np.float32), np.ascontiguousarray(poses[i], np.float32)
+        smadp.adp_mapping_keyframe(a, buf.ctypes.data, w, h, dd.ctypes.data, mem.ctypes.data, T.ctypes.data, ri)
+        for x, y in ((get(smadp.adp_mapping_local), r.local()), (get(smadp.adp_mapping_inactive), r.inactive())):
+            assert x.shape == y.shape, i
+            for f in x.dtype.names:
+                if x[f].dtype.kind == "f":
+                    assert ((x[f].view(np.uint32) == y[f].view(np.uint32)) | (np.isnan(x[f]) & np.isnan(y[f]))).all(), (i, f)
+                else:
+                    assert np.array_equal(x[f], y[f]), (i, f)
+    assert moved > 40 and len(r.inactive()) > 1000
