@@ -17,8 +17,8 @@
  *      committed fixtures in tests/golden/;
  *  (2) everything above the primitives is pinned against the REFERENCE'S OWN
  *      SOURCE: oracle/Makefile compiles src/ORBextractor.cc, src/ORBmatcher.cc,
- *      src/PlaneExtractor.cpp (+ include/peac/) and src/SurfelFusion.cpp where they
- *      lie, unmodified, against stand-in headers (oracle/ref_shim_cv, ref_shim_match) into
+ *      src/PlaneExtractor.cpp (+ include/peac/), src/SurfelFusion.cpp,
+ *      src/SurfelMapping.cpp and src/MapPoint.cc where they lie, unmodified, against stand-in headers (oracle/ref_shim_cv, ref_shim_match, ref_shim_map, ref_shim_mp) into
  *      oracle/_ref/, and tests/test_oracle_ref.py requires the restatements here to
  *      equal them bit for bit.  What the stand-ins decide -- and what therefore
  *      stays "parity unpinned" -- is listed in DESIGN.md section 2: Eigen's
