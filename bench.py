@@ -80,14 +80,22 @@ def make_inputs(rank, batch, n_surfels):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+_REF_SURFEL = None
+
+
 def ref_surfel_available():
     """the reference's own src/SurfelFusion.cpp compiled unmodified with the real <thread> (oracle/_ref/libsurfel_ref_threads.so:
-    built where /root/reference exists, travels to the GPU box prebuilt)"""
-    try:
-        from oracle import binding as ob
-        return ob.build_ref(name="libsurfel_ref_threads.so") is not None
-    except Exception:  # noqa: BLE001
-        return False
+    built where /root/reference exists, travels to the GPU box prebuilt) -- present AND loadable"""
+    global _REF_SURFEL
+    if _REF_SURFEL is None:
+        try:
+            from oracle import binding as ob
+            _REF_SURFEL = ob.build_ref(name="libsurfel_ref_threads.so") is not None
+            if _REF_SURFEL:
+                ob.RefSurfelFusion(W, H, real_threads=True)  # loads the library, builds and destroys one SurfelFusion
+        except Exception:  # noqa: BLE001 -- fall back to the oracle port
+            _REF_SURFEL = False
+    return _REF_SURFEL
 
 
 def baseline_kind():
