@@ -41,7 +41,7 @@
 #include <cstdint>
 
 #if defined(__CUDACC__) && !defined(PEAC_HOST_EMULATION)
-#define PEAC_HD __host__ __device__ __forceinline__
+#define PEAC_HD __device__ __forceinline__
 #define PEAC_D __device__
 #define PEAC_SYNC() __syncthreads()
 #define PEAC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
