@@ -239,7 +239,7 @@ struct PeacScratch {  // per-frame strides are implied: npix, rfqCap, visCap
 // SH = peac::Shared: the working set in the CTA's dynamic shared memory (frames of <= 768 blocks); SH = peac::SharedBig: in
 // global memory, one record per frame (`big`), for frames of up to 3072 blocks (1280x960)
 template <class SH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
     k_peac_frame(peac::Geo g, size_t frameStride, const uint16_t *__restrict__ depth, const msl_block_stat *__restrict__ blocks,
                  const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership, PeacScratch sc,
                  SH *big, peac::PlaneOut *__restrict__ planes, int planeCap, int32_t *__restrict__ planeCount,
@@ -417,12 +417,17 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     PeacScratch sc;
     sc.dist = p->d_dist, sc.rfq = p->d_rfq, sc.own = p->d_own, sc.visC = p->d_visC, sc.visDist = p->d_visDist, sc.visFlag = p->d_visFlag;
     sc.rfqCap = 4 * p->W2 * p->H2, sc.visCap = 4 * p->W2 * p->H2;
+    int threads = 256;  // MSL_PEAC_THREADS = 64 | 128 | 256 | 512: CTA size of k_peac_frame (A/B knob)
+    if (const char *e = getenv("MSL_PEAC_THREADS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256 || v == 512) threads = v;
+    }
     if (p->Nw * p->Nh <= peac::MAXB)
-        k_peac_frame<peac::Shared><<<batch, 256, sizeof(peac::Shared), p->stream>>>(
+        k_peac_frame<peac::Shared><<<batch, threads, sizeof(peac::Shared), p->stream>>>(
             g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges, d_membership, sc, (peac::Shared *)nullptr,
             reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count, p->d_ferr);
     else
-        k_peac_frame<peac::SharedBig><<<batch, 256, 0, p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
+        k_peac_frame<peac::SharedBig><<<batch, threads, 0, p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
                                                                    d_membership, sc, p->d_big, reinterpret_cast<peac::PlaneOut *>(d_planes),
                                                                    plane_cap, d_plane_count, p->d_ferr);
     MSL_LAUNCH_CHECK();

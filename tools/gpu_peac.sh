@@ -15,6 +15,7 @@ for b in 16 148 256; do
   timeout 300 python tools/peac_time.py $b 5 | tee $OUT/${TAG}_peac_levels_b$b.json
 done
 MSL_PEAC_FLOOD_SERIAL=1 timeout 600 python tools/peac_time.py 16 3 | tee $OUT/${TAG}_peac_fifo_b16.json
+for t in 128 512; do MSL_PEAC_THREADS=$t timeout 300 python tools/peac_time.py 148 5 | tee $OUT/${TAG}_peac_levels_b148_t$t.json; done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_peac_frame -c 1 -f -o $OUT/${TAG}_k_peac_frame \
   python tools/peac_time.py 16 1 > $OUT/${TAG}_ncu_peac.log 2>&1
 python tools/ncu_brief.py $OUT/${TAG}_k_peac_frame.ncu-rep > $OUT/${TAG}_k_peac_frame_brief.txt 2>&1
