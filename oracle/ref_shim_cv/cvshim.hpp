@@ -171,6 +171,14 @@ public:
     Mat(const MatZeros &z) : Mat() { *this = z; }
     Mat(const MatExprMul &e);  // evaluates the product (below)
     void copyTo(Mat &m) const { m = clone(); }
+    Mat reshape(int cn) const {  // same bytes, other channel count (continuous matrices only)
+        assert(isContinuous() && ((size_t)cols * channels()) % (size_t)cn == 0);
+        Mat m(*this);
+        m.cols = cols * channels() / cn;
+        m.type_ = CV_MAKETYPE(depth(), cn);
+        m.step = (size_t)m.cols * m.elemSize();
+        return m;
+    }
     void convertTo(Mat &m, int rtype) const {  // same-depth conversions only: a copy
         assert((rtype & 7) == depth());
         m = clone();
@@ -392,6 +400,20 @@ static inline void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double sig
 }
 
 static inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+// cv::undistortPoints(src, dst, K, D, R = noArray(), P = K) on N x 1 two-channel float points: the oracle's cv2-pinned
+// restatement (tests/test_oracle_primitives.py, tests/golden/glue.npz)
+static inline void undistortPoints(const Mat &src, Mat &dst, const Mat &K, const Mat &D, const Mat &, const Mat &) {
+    const int n = src.rows * src.cols * src.channels() / 2;
+    std::vector<float> in((size_t)2 * n), out((size_t)2 * n);
+    memcpy(in.data(), src.data, sizeof(float) * in.size());
+    const float K4[4] = {K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2)};
+    float D5[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < (int)D.total() && i < 5; i++) D5[i] = D.at<float>(i);
+    orc_undistort_points(n, in.data(), K4, D5, out.data());
+    dst.create(src.rows, src.cols, src.type());
+    memcpy(dst.data, out.data(), sizeof(float) * out.size());
+}
 
 static inline int64_t getTickCount() { return 0; }
 static inline double getTickFrequency() { return 1.0; }

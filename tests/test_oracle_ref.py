@@ -549,3 +549,88 @@ def test_predict_scale_matches_reference_source(ref_mp):
         assert np.array_equal(out[:, 0], expect) and np.array_equal(out[:, 1], expect)
         assert len(set(expect.tolist())) == 8
         assert inv[1] == np.float32(1.2) * max_dist and inv[0] == np.float32(0.8) * np.float32(max_dist / top[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Frame: oracle/_ref/libframe_ref.so holds six member functions of the reference's src/Frame.cc -- AssignFeaturesToGrid,
+# GetFeaturesInArea, PosInGrid (the grid), UndistortKeyPoints, ComputeImageBounds,
+# ComputeStereoFromRGBD (the frame glue, row f4) -- cut out of the file at build time and compiled unmodified inside a
+# stand-in class (oracle/ref_frame_wrap.cpp); cv::undistortPoints is the oracle's cv2-pinned restatement.
+
+@pytest.fixture(scope="module")
+def ref_frame(oracle):
+    import ctypes as C
+    so = oracle.build_ref(name="libframe_ref.so")
+    if so is None:
+        pytest.skip("oracle/_ref/libframe_ref.so not built and /root/reference absent")
+    L = C.CDLL(so)
+    L.ref_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int]
+    L.ref_frame_glue.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_image_bounds.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return L
+
+
+def test_frame_grid_matches_reference_source(ref_frame, oracle):
+    """PosInGrid rounds (so keypoints near the right / bottom edge never enter the grid), the query floors / ceils, candidates
+    come back in (cell column, cell row, insertion) order -- which decides ties in every window search"""
+    from manhattanslam_b200.matcher import frame_geom
+    g = frame_geom()
+    r = np.random.default_rng(8)
+    for n in (0, 1, 300, 1000, 3000):
+        xy = np.stack([r.uniform(-5, 645, n), r.uniform(-5, 485, n)], 1).astype(np.float32)
+        octv = r.integers(0, 8, n).astype(np.int32)
+        for _ in range(120):
+            x, y = float(r.uniform(-30, 670)), float(r.uniform(-30, 510))
+            rad = float(r.choice([0.5, 3.0, 7.0, 15.0, 40.0, 200.0, 900.0]))
+            lo, hi = [(-1, -1), (0, 3), (2, 2), (-1, 4), (3, -1), (1, 0)][int(r.integers(0, 6))]
+            got = oracle.features_in_area(g, xy, octv, x, y, rad, lo, hi)
+            out = np.zeros(n + 1, np.int32)
+            k = ref_frame.ref_features_in_area(g.ctypes.data, xy.ctypes.data, octv.ctypes.data, n, x, y, rad, lo, hi, out.ctypes.data, n + 1)
+            assert k == len(got) and np.array_equal(out[:k], got), (n, x, y, rad, lo, hi)
+
+
+@pytest.mark.parametrize("nd,distorted", [(5, True), (4, True), (5, False)])
+def test_frame_glue_matches_reference_source(ref_frame, oracle, nd, distorted):
+    """UndistortKeyPoints + ComputeStereoFromRGBD of the reference against the oracle's orc_undistort_keypoints /
+    orc_stereo_from_rgbd (k1 == 0 copies the keypoints; 4 or 5 distortion coefficients)"""
+    r = np.random.default_rng(6)
+    n = 900
+    kps = np.zeros(n, oracle.KP_DTYPE)
+    kps["x"], kps["y"] = r.uniform(0, 639, n), r.uniform(0, 479, n)
+    kps["size"], kps["angle"], kps["response"] = 31, r.uniform(0, 360, n), r.integers(7, 200, n)
+    kps["octave"], kps["class_id"] = r.integers(0, 8, n), -1
+    K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+    D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314][:nd] if distorted else [0.0] * nd, np.float32)
+    D5 = np.zeros(5, np.float32)
+    D5[:nd] = D
+    depth = np.ascontiguousarray(S.depth_frame(3)[1], np.float32)
+    un, ur, kd = np.zeros(n, oracle.KP_DTYPE), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    assert ref_frame.ref_frame_glue(n, kps.ctypes.data, K4.ctypes.data, D.ctypes.data, nd, depth.ctypes.data, 640, 480, 40.0,
+                                    un.ctypes.data, ur.ctypes.data, kd.ctypes.data) == 0
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    xy_un = oracle.undistort_keypoints(xy, K4, D5)
+    assert np.array_equal(np.stack([un["x"], un["y"]], 1), xy_un)
+    for f in ("size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(un[f], kps[f]), f
+    ur_o, kd_o = oracle.stereo_from_rgbd(xy, xy_un, depth, 40.0)
+    assert np.array_equal(kd, kd_o) and np.array_equal(ur, ur_o)
+    assert (np.abs(xy_un - xy).max() > 0.5) == distorted
+
+
+def test_image_bounds_of_reference_source(ref_frame):
+    """ComputeImageBounds: the geometry every grid query is relative to -- (0, cols, 0, rows) without distortion; with it,
+    the undistorted image corners (cv2-pinned undistortPoints)"""
+    K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+    out = np.zeros(4, np.float32)
+    Z = np.zeros(5, np.float32)
+    ref_frame.ref_image_bounds(640, 480, K4.ctypes.data, Z.ctypes.data, 5, out.ctypes.data)
+    assert out.tolist() == [0.0, 640.0, 0.0, 480.0]
+    D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+    ref_frame.ref_image_bounds(640, 480, K4.ctypes.data, D.ctypes.data, 5, out.ctypes.data)
+    import cv2
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    c = cv2.undistortPoints(np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32).reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    expect = [min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])]
+    assert np.array_equal(out, np.array(expect, np.float32))
