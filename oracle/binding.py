@@ -548,7 +548,7 @@ _REF_DEPS = {
     "libmappoint_ref.so": (["src/MapPoint.cc", "include/MapPoint.h"],
                            ["ref_mappoint_wrap.cpp", "ref_shim_mp/mp_standins.hpp", "ref_shim_cv/cvshim.hpp", "match_oracle.cpp",
                             "orb_oracle.cpp", "msl_oracle.h"]),
-    "libframe_ref.so": (["src/Frame.cc"],
+    "libframe_ref.so": (["src/Frame.cc", "src/KeyFrame.cc"],
                         ["ref_frame_wrap.cpp", "ref_shim_cv/cvshim.hpp", "glue_oracle.cpp", "match_oracle.cpp", "orb_oracle.cpp",
                          "msl_oracle.h"]),
     "liborb_ref.so": (["src/ORBextractor.cc", "include/ORBextractor.h"],

@@ -634,3 +634,28 @@ def test_image_bounds_of_reference_source(ref_frame):
     c = cv2.undistortPoints(np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32).reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
     expect = [min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])]
     assert np.array_equal(out, np.array(expect, np.float32))
+
+
+def test_keyframe_grid_matches_reference_source(ref_frame, oracle):
+    """KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:469-504, no level filter) on the grid a KeyFrame copies from its Frame, and
+    IsInImage (:540-542) -- what ORBmatcher::Fuse searches through"""
+    import ctypes as C
+    from manhattanslam_b200.matcher import frame_geom
+    ref_frame.ref_keyframe_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                                        C.c_int, C.c_void_p]
+    g = frame_geom()
+    gg = {k: g[k][0] for k in g.dtype.names}
+    r = np.random.default_rng(9)
+    for n in (0, 500, 2000):
+        xy = np.stack([r.uniform(-5, 645, n), r.uniform(-5, 485, n)], 1).astype(np.float32)
+        octv = np.zeros(n, np.int32)
+        for _ in range(150):
+            x, y = np.float32(r.uniform(-30, 670)), np.float32(r.uniform(-30, 510))
+            rad = float(r.choice([0.5, 3.0, 7.0, 15.0, 40.0, 200.0]))
+            got = oracle.features_in_area(g, xy, octv, float(x), float(y), rad, -1, -1)
+            out, inimg = np.zeros(n + 1, np.int32), np.zeros(1, np.int32)
+            k = ref_frame.ref_keyframe_features_in_area(g.ctypes.data, xy.ctypes.data, n, float(x), float(y), rad, out.ctypes.data, n + 1,
+                                                        inimg.ctypes.data)
+            assert k == len(got) and np.array_equal(out[:k], got), (n, x, y, rad)
+            expect = (x >= int(gg["mnMinX"])) and (x < int(gg["mnMaxX"])) and (y >= int(gg["mnMinY"])) and (y < int(gg["mnMaxY"]))
+            assert bool(inimg[0]) == bool(expect)
