@@ -5,11 +5,12 @@
 // and src/ORBmatcher.cc compile UNMODIFIED on top of it.
 //
 // What is data here: every member ORBmatcher.cc reads (names, types and constness as in the reference headers).  What is
-// code here, i.e. NOT the reference's: the grid query GetFeaturesInArea (the oracle's orc_features_in_area, the restatement
-// of src/Frame.cc:332-381 / src/KeyFrame.cc:469-504 that tests/test_oracle_stages.py pins on its own), IsInImage
-// (src/KeyFrame.cc:540-542), the two five-line PredictScale (src/MapPoint.cc:334-364) and the 0.8 / 1.2 distance getters
-// (:324-332).  Everything else ORBmatcher does -- projections, windows, level rules, ratio tests, slot blocking,
-// rotation histograms, epipolar test, chi-square gates -- is the reference's own code.
+// code here, i.e. NOT the reference's: the grid query GetFeaturesInArea (the oracle's orc_features_in_area), IsInImage, the
+// two five-line PredictScale and the 0.8 / 1.2 distance getters -- each of which is pinned to the reference's own source on
+// its own: the grid and IsInImage against the functions of src/Frame.cc / src/KeyFrame.cc (oracle/_ref/libframe_ref.so),
+// PredictScale and the getters against src/MapPoint.cc (oracle/_ref/libmappoint_ref.so), tests/test_oracle_ref.py.
+// Everything else ORBmatcher does -- projections, windows, level rules, ratio tests, slot blocking, rotation histograms,
+// epipolar test, chi-square gates -- is the reference's own code.
 #pragma once
 #include <cmath>
 #include <cstdint>
