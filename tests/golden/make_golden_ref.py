@@ -32,6 +32,20 @@ def surfel_inputs():
     return g, d, m, T, local
 
 
+MAP_W, MAP_H = 320, 240
+MAP_K = tuple(k * 0.5 for k in S.K_DEFAULT)
+MAP_REFS = [0] + [i - 1 for i in range(1, 26)] + [3, 26, 4, 28, 27, 2, 30, 31]
+
+
+def mapping_inputs():
+    """the keyframe stream of the SurfelMapping golden: (gray, membership, poses, depth frames by keyframe)"""
+    poses = S.pose_walk(5, len(MAP_REFS))
+    g = S.gray_frame(5, MAP_W, MAP_H)
+    mem = np.ascontiguousarray(S.membership(5, MAP_W, MAP_H, plane_fraction=0.2), np.int32)
+    depths = [S.depth_frame(300 + i % 4, MAP_W, MAP_H, K=MAP_K, scene=300)[1] for i in range(len(MAP_REFS))]
+    return g, mem, poses, depths
+
+
 def main():
     out = {}
     # ORBextractor::operator() (src/ORBextractor.cc) on one frame
@@ -73,6 +87,20 @@ def main():
         out["m_bow_n"], out["m_bow"] = B.search_by_bow(0.7, True, kfb, f)
         out["m_tri_n"], out["m_tri"] = B.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, kf1, kf2)
     out["m_fuse_n"], out["m_fuse"] = B.ref_fuse(geom, Tcw, 3.0, LSF, ils, mpf, kfs)
+    # SurfelMapping (src/SurfelMapping.cpp): a 34-keyframe pose graph through InsertKeyFrame + ProcessNewKeyFrame; the pose lists
+    # getAddRemovePoses handed to moveAddSurfels per keyframe, and both surfel vectors at the end
+    g, mem, poses, depths = mapping_inputs()
+    rm = B.RefSurfelMapping(MAP_W, MAP_H, *MAP_K)
+    adds, rems = [], []
+    for i, ri in enumerate(MAP_REFS):
+        a, r_ = rm.keyframe(g, depths[i], mem, poses[i], ri)
+        adds.append(a), rems.append(r_)
+    out["map_add_off"] = np.cumsum([0] + [len(a) for a in adds]).astype(np.int32)
+    out["map_add"] = np.concatenate(adds + [np.zeros(0, np.int32)]).astype(np.int32)
+    out["map_rem_off"] = np.cumsum([0] + [len(a) for a in rems]).astype(np.int32)
+    out["map_rem"] = np.concatenate(rems + [np.zeros(0, np.int32)]).astype(np.int32)
+    out["map_local"] = rm.local().view(np.uint8).reshape(-1, 56)
+    out["map_inactive"] = rm.inactive().view(np.uint8).reshape(-1, 56)
     np.savez_compressed(os.path.join(HERE, "reference_source.npz"), **out)
     print("written:", {k: (np.asarray(v).shape if np.ndim(v) else int(v)) for k, v in out.items()})
     print("bytes:", os.path.getsize(os.path.join(HERE, "reference_source.npz")))

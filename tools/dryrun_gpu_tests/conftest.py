@@ -37,12 +37,20 @@ class FakePlane:
         return np.stack(mems), pls
 
 class FakeSurfel:
-    def __init__(self, max_surfels=0): self.o = B.SurfelOracle()
+    def __init__(self, width=640, height=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, fuseFar=30.0, fuseNear=0.5, max_surfels=0):
+        self.o = B.SurfelOracle(width, height, fx, fy, cx, cy, fuseFar, fuseNear)
+        self.m = B.SurfelMappingOracle()
+        self.local = np.zeros(0, B.SURFEL_DTYPE)
     def upload_map(self, local): self.local = local.copy()
+    def moveAddSurfels(self, rem, add):
+        self.local = self.m.move_add(self.local, rem, add)
+        return (0, 0, len(self.local))
     def fuseInitializeMap(self, ref, g, d, m, T, compact=False):
         new = self.o.fuse(ref, g, d, m, T, self.local)
+        if compact: self.local = B.surfel_compact(self.local, new)
         return new, (len(new), 0, 0, len(self.local))
     def download_map(self): return self.local.copy()
+    def download_inactive(self): return self.m.inactive()
     def debug_index(self): return self.o.index()
 
 class FakeMatcher:
@@ -59,6 +67,7 @@ class FakeMatcher:
 
 class FakeMsl:
     ORBextractor = FakeORB; PlaneDetection = FakePlane; SurfelFusion = FakeSurfel; ORBmatcher = FakeMatcher
+    SURFEL_DTYPE = B.SURFEL_DTYPE
     frame_geom = staticmethod(frame_geom)
 
 @pytest.fixture(scope="session")
