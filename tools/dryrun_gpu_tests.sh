@@ -4,7 +4,7 @@
 #   bash tools/dryrun_gpu_tests.sh [test files...]
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 TMP=$(mktemp -d)
-FILES=${@:-tests/test_v_reference_golden_gpu.py tests/test_widened_mappoint_gpu.py tests/test_x_peac_gpu.py}
+FILES=${@:-tests/test_v_reference_golden_gpu.py tests/test_widened_mappoint_gpu.py tests/test_x_peac_gpu.py tests/test_y_reference_mapping_gpu.py}
 cp "$ROOT/tools/dryrun_gpu_tests/conftest.py" "$TMP/"
 mkdir -p "$TMP/golden" && cp "$ROOT"/tests/golden/*.npz "$ROOT"/tests/golden/*.py "$TMP/golden/"
 for f in $FILES; do cp "$ROOT/$f" "$TMP/"; done

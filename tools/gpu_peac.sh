@@ -7,7 +7,7 @@ TAG=${1:-run}
 OUT=gpurun_out
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-for t in tests/test_v_reference_golden_gpu.py tests/test_widened_mappoint_gpu.py tests/test_x_peac_gpu.py; do
+for t in tests/test_v_reference_golden_gpu.py tests/test_widened_mappoint_gpu.py tests/test_x_peac_gpu.py tests/test_y_reference_mapping_gpu.py; do
   timeout 600 python -m pytest $t -m gpu -q > $OUT/${TAG}_$(basename $t .py).log 2>&1
   echo "== $t: exit $?"; tail -3 $OUT/${TAG}_$(basename $t .py).log
 done
