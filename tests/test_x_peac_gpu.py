@@ -123,3 +123,17 @@ def test_detected_membership_feeds_surfel_fusion(oracle, msl):
     got = sf.download_map()
     for f in got.dtype.names:
         assert np.array_equal(got[f], lo[f]) or (got[f].dtype.kind == "f" and np.allclose(got[f], lo[f], rtol=1e-4, atol=1e-6, equal_nan=True)), f
+
+
+def test_plane_detect_is_independent_of_the_cta_size(msl, monkeypatch):
+    """MSL_PEAC_THREADS = 64 / 128 / 512 threads per CTA (default 256): identical membership images and planes"""
+    d = np.stack([S.depth_frame(50 + b)[0] for b in range(2)])
+    pd = msl.PlaneDetection(max_batch=2)
+    mem0, planes0 = pd.detect(d, depthMapFactor=1.0)
+    for t in ("64", "128", "512"):
+        monkeypatch.setenv("MSL_PEAC_THREADS", t)
+        mem, planes = pd.detect(d, depthMapFactor=1.0)
+        assert np.array_equal(mem, mem0), t
+        for a, b in zip(planes, planes0):
+            assert a.tobytes() == b.tobytes(), t
+    monkeypatch.delenv("MSL_PEAC_THREADS")
