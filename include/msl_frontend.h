@@ -416,6 +416,9 @@ int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
  * kernel; the "scan" interval of the timing aid is that kernel and "apply" is empty), 2 = k_fuse_scan + k_fuse_apply
  * (environment MSL_FUSE_ONE=0). */
 int msl_surfel_fuse_kernels(const msl_surfel_fusion *);
+/* launch geometry of the last fuseSurfelsKernel launch (test / bench evidence that the persistent multi-draw path ran):
+ * out = {kernels, form (MSL_FUSE_ONE), persistent, grid (CTAs), warps per CTA, 128-surfel segments} */
+int msl_surfel_launch_info(const msl_surfel_fusion *, int32_t out[6]);
 void *msl_surfel_stream(msl_surfel_fusion *);
 
 /* Validation aid: k_fuse_scan divides by the camera-frame depth with a hand-scheduled IEEE sequence that shares one

@@ -130,6 +130,12 @@ class SurfelFusion:
         """1: fuseSurfelsKernel runs as k_fuse_one; 2: as k_fuse_scan + k_fuse_apply (MSL_FUSE_ONE=0)"""
         return int(self._L.msl_surfel_fuse_kernels(self._h))
 
+    def launch_info(self):
+        """launch geometry of the last fuseSurfelsKernel launch (msl_surfel_launch_info)"""
+        out = np.zeros(6, np.int32)
+        check(self._L.msl_surfel_launch_info(self._h, ptr(out)))
+        return dict(zip(("kernels", "form", "persistent", "grid", "warps_per_cta", "segments"), [int(v) for v in out]))
+
     def fuse_kernel_time(self):
         """(total milliseconds, launches) of the projective fuse scan since the last query."""
         ms, n = C.c_double(), C.c_int()
