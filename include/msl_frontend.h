@@ -416,6 +416,11 @@ int msl_surfel_chain_times(msl_surfel_fusion *, double out[5], int *frames);
  * kernel; the "scan" interval of the timing aid is that kernel and "apply" is empty), 2 = k_fuse_scan + k_fuse_apply
  * (environment MSL_FUSE_ONE=0). */
 int msl_surfel_fuse_kernels(const msl_surfel_fusion *);
+/* Per-frame count table of the batched stream API (what the ranks all-gather): after every following
+ * msl_surfel_fuse_batch_dev call d_table[2 b] = new surfels of frame b (initializeSurfels, src/SurfelFusion.cpp:285-331),
+ * d_table[2 b + 1] = surfels frame b updated (fuseSurfelsKernel, :240-279); batch x 2 int32 in device memory, written on the
+ * handle's stream.  NULL switches it off. */
+int msl_surfel_set_count_table(msl_surfel_fusion *, int32_t *d_table);
 /* launch geometry of the last fuseSurfelsKernel launch (test / bench evidence that the persistent multi-draw path ran):
  * out = {kernels, form (MSL_FUSE_ONE), persistent, grid (CTAs), warps per CTA, 128-surfel segments} */
 int msl_surfel_launch_info(const msl_surfel_fusion *, int32_t out[6]);

@@ -130,6 +130,10 @@ class SurfelFusion:
         """1: fuseSurfelsKernel runs as k_fuse_one; 2: as k_fuse_scan + k_fuse_apply (MSL_FUSE_ONE=0)"""
         return int(self._L.msl_surfel_fuse_kernels(self._h))
 
+    def set_count_table(self, d_table):
+        """device pointer of a (batch, 2) int32 table filled by every following fuse_batch_dev: {new, updated} per frame"""
+        check(self._L.msl_surfel_set_count_table(self._h, ptr(d_table) if d_table else None))
+
     def launch_info(self):
         """launch geometry of the last fuseSurfelsKernel launch (msl_surfel_launch_info)"""
         out = np.zeros(6, np.int32)

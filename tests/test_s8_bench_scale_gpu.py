@@ -24,6 +24,9 @@ VARIANTS = {
     "stream_late_loads": {"MSL_STREAM_EARLY": "0"},
     "stream_64regs_wave2": {"MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "2"},
     "stream_no_prefetch": {"MSL_STREAM_PF": "0"},
+    "stream2": {"MSL_FUSE_ONE": "3"},                               # branch-free scan, carried survivors (full fuse rounds)
+    "stream2_64regs": {"MSL_FUSE_ONE": "3", "MSL_STREAM_REGS": "4"},
+    "stream2_late_wave2": {"MSL_FUSE_ONE": "3", "MSL_STREAM_EARLY": "0", "MSL_STREAM_WAVE": "2"},
     "one": {"MSL_FUSE_ONE": "1"},                                   # round 1's kernel (direct loads)
     "one_early": {"MSL_FUSE_ONE": "1", "MSL_ONE_EARLY": "1"},
     "one_wave4": {"MSL_FUSE_ONE": "1", "MSL_ONE_WAVE": "0"},
