@@ -46,14 +46,24 @@ def main(path, top=40):
             dom = hdr[best][6:]
         print("  %5d %6d %5.1f%% %8s  %-16s %s" % (k, int(r[samp] or 0), 100.0 * int(r[samp] or 0) / max(total, 1), r[execd], dom, r[src].strip()))
     try:
-        _, hdr2, rows2 = page(path, "cuda")
-        c2 = {h: i for i, h in enumerate(hdr2)}
-        if "# Samples" in c2:
-            print("hottest source lines (line, samples, share, instructions executed, text):")
-            ls = sorted(rows2, key=lambda r: -int(r[c2["# Samples"]] or 0))[:top]
-            for r in sorted(ls, key=lambda r: int(r[0]) if r[0].isdigit() else 0):
-                print("  %6s %6s %5.1f%% %9s  %s" % (r[0], r[c2["# Samples"]], 100.0 * int(r[c2["# Samples"]] or 0) / max(total, 1),
-                                                 r[c2["Instructions Executed"]], r[c2["Source"]].strip()[:110]))
+        out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+        lines, fname, hdr2 = [], "", None
+        for r in csv.reader(out.splitlines()):
+            if not r:
+                continue
+            if r[0] == "File Path":
+                fname = r[1].split("/")[-1]
+            elif r[0] == "Line No":
+                hdr2 = r
+            elif hdr2 and r[0].isdigit():
+                ns, ne = hdr2.index("# Samples"), hdr2.index("Instructions Executed")
+                try:
+                    lines.append((int(r[ns] or 0), int(r[ne] or 0), fname, int(r[0]), r[1].strip()))
+                except ValueError:
+                    pass
+        print("hottest source lines (file:line, samples, share, warp instructions executed, text):")
+        for sm, ne, fn, ln, txt in sorted(sorted(lines, reverse=True)[:top], key=lambda x: (x[2], x[3])):
+            print("  %-18s %6d %5.1f%% %10d  %s" % ("%s:%d" % (fn, ln), sm, 100.0 * sm / max(total, 1), ne, txt[:100]))
     except Exception as e:  # noqa: BLE001
         print("(no CUDA source view: %s)" % e)
 

@@ -40,7 +40,7 @@ def main():
     d_bd, d_sd = torch.zeros_like(d_bi), torch.zeros_like(d_bi)
     m.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_counts.data_ptr(), d_counts.data_ptr() + 4,
                                B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr())
-    m.sync()
+    torch.cuda.synchronize()
     # the three window searches (k_search) on synthetic tracking scenes, host API
     geom = msl.frame_geom()
     cur, last, mps, Tc, Tl = S.match_scene(1)
