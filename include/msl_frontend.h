@@ -108,6 +108,10 @@ typedef struct {
 
 typedef struct msl_matcher msl_matcher;
 
+/* max_queries / max_train / max_batch size the Hamming batch buffers and the INITIAL scratch of the searches.  The scratch
+ * grows with the call: the reference hands SearchByProjection the whole of mvpLocalMapPoints (src/Tracking.cc:1693) and Fuse
+ * the map points of every neighbour keyframe (src/LocalMapping.cc:569), so the number of map points / queries of a search
+ * is unbounded; only the keypoints of ONE frame or keyframe are limited (4096: the kernels' shared-memory grid). */
 int msl_matcher_create(int max_queries, int max_train, int max_batch, int device, msl_matcher **out);
 void msl_matcher_destroy(msl_matcher *);
 int msl_matcher_sync(msl_matcher *);

@@ -734,6 +734,22 @@ struct Arena {
     }
 };
 
+// The scratch arena of the searches grows with the call: the reference hands SearchByProjection the whole of
+// mvpLocalMapPoints (src/Tracking.cc:1693) and Fuse the map points of every neighbour keyframe (src/LocalMapping.cc:569) --
+// tens of thousands of points -- so only the per-frame keypoint count (MAXK, the kernels' shared-memory grid) is a hard
+// limit; max_queries / max_train of msl_matcher_create size the initial allocation and the Hamming batch buffers.
+static int ensure_scratch(msl_matcher *m, size_t n_a, size_t n_b) {
+    const size_t need = (n_a + n_b) * 96 + 4096;
+    if (need <= m->scrCap) return MSL_OK;
+    MSL_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->d_scr) cudaFree(m->d_scr);
+    m->d_scr = nullptr, m->scrCap = 0;
+    const size_t cap = need + need / 2;
+    MSL_CUDA(cudaMalloc((void **)&m->d_scr, cap));
+    m->scrCap = cap;
+    return MSL_OK;
+}
+
 static int run_search(msl_matcher *m, SearchArgs &A, int32_t *cur_match, int32_t *nmatches) {
     k_search<<<1, 1024, 0, m->stream>>>(A);
     MSL_LAUNCH_CHECK();
@@ -849,7 +865,7 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
                                    const float *cur_angle, const float *cur_uright, const uint8_t *cur_desc,
                                    const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches) {
     if (!m || !geom || !Tcw_cur || !Tcw_last || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_frame: null argument");
-    if (n_last < 0 || n_cur < 0 || n_last > m->maxQ || n_cur > m->maxT || n_cur > MAXK || n_last > 0x7ffffff)
+    if (n_last < 0 || n_cur < 0 || n_cur > MAXK || n_last > 0x7ffffff)
         return fail(MSL_ERR_INVALID, "msl_search_by_projection_frame: too many keypoints for this handle");
     if (n_cur == 0 || n_last == 0) {
         for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
@@ -879,6 +895,10 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
     A.bBackward = -tlc2 > geom->mb;
     std::vector<uint8_t> valid(n_last);
     for (int i = 0; i < n_last; i++) valid[i] = last_has_mp[i] && !last_outlier[i];
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n_last), (size_t)(n_cur));
+        if (rc_) return rc_;
+    }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(valid.data(), n_last);
     A.q_obs = ar.put(last_mp_obs, n_last);
@@ -907,7 +927,7 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
                                     const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match,
                                     int32_t *nmatches) {
     if (!m || !geom || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_points: null argument");
-    if (n_mp < 0 || n_cur < 0 || n_mp > m->maxQ || n_cur > m->maxT || n_cur > MAXK)
+    if (n_mp < 0 || n_cur < 0 || n_cur > MAXK || n_mp > 0x7ffffff)
         return fail(MSL_ERR_INVALID, "msl_search_by_projection_points: too many keypoints for this handle");
     if (n_cur == 0 || n_mp == 0) {
         for (int j = 0; j < n_cur; j++) cur_match[j] = cur_occupied[j] ? -2 : -1;
@@ -919,6 +939,10 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
     memset(&A, 0, sizeof(A));
     A.g = *geom, A.mode = 1, A.th = th, A.nnratio = nnratio, A.checkOri = 0, A.nq = n_mp, A.nc = n_cur;
     A.distTh = TH_HIGH;
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n_mp), (size_t)(n_cur));
+        if (rc_) return rc_;
+    }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(mp_valid, n_mp);
     A.q_obs = ar.put(mp_obs, n_mp);
@@ -947,7 +971,7 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
                                       const int32_t *cur_octave, const float *cur_angle, const uint8_t *cur_desc,
                                       const uint8_t *cur_occupied, int32_t *cur_match, int32_t *nmatches) {
     if (!m || !geom || !Tcw_cur || !cur_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: null argument");
-    if (n_kf < 0 || n_cur < 0 || n_kf > m->maxQ || n_cur > m->maxT || n_cur > MAXK)
+    if (n_kf < 0 || n_cur < 0 || n_cur > MAXK || n_kf > 0x7ffffff)
         return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: too many keypoints for this handle");
     if (geom->nlevels < 1 || geom->nlevels > 16 || !(log_scale_factor > 0.f) || orb_dist < 0 || orb_dist > 255)
         return fail(MSL_ERR_INVALID, "msl_search_by_projection_keyframe: parameter out of range");
@@ -971,6 +995,10 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
         A.Ow[r] = (float)s;
     }
     std::vector<uint8_t> ones(n_kf, 1);  // every slot assigned by this overload blocks later queries (:741-742)
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n_kf), (size_t)(n_cur));
+        if (rc_) return rc_;
+    }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(kf_valid, n_kf);
     A.q_obs = ar.put(ones.data(), n_kf);
@@ -1022,7 +1050,7 @@ int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int 
                       const uint8_t *kf_desc, const float *kf_angle, int n_f, const uint8_t *f_desc, const float *f_angle,
                       int32_t *f_match, int32_t *nmatches) {
     if (!m || !f_match || !nmatches) return fail(MSL_ERR_INVALID, "msl_search_by_bow: null argument");
-    if (n_kf < 0 || n_f < 0 || n_kf > m->maxQ || n_f > m->maxT) return fail(MSL_ERR_INVALID, "msl_search_by_bow: too many keypoints for this handle");
+    if (n_kf < 0 || n_f < 0 || n_kf > 0x7ffffff || n_f > 0x7ffffff) return fail(MSL_ERR_INVALID, "msl_search_by_bow: too many keypoints for this handle");
     if (!csr_ok(n_nodes_kf, kf_node_id, kf_node_off, kf_node_feat, n_kf) || !csr_ok(n_nodes_f, f_node_id, f_node_off, f_node_feat, n_f))
         return fail(MSL_ERR_INVALID, "msl_search_by_bow: malformed feature vector (ids must ascend, offsets must be monotone, indices in range)");
     if (n_kf == 0 || n_f == 0 || n_nodes_kf == 0 || n_nodes_f == 0) {
@@ -1036,6 +1064,10 @@ int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int 
     memset(&A, 0, sizeof(A));
     A.mode = 0, A.nnratio = nnratio, A.checkOri = check_orientation, A.nNodesA = n_nodes_kf, A.nNodesB = n_nodes_f;
     A.nA = n_kf, A.nB = n_f;
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n_kf + n_nodes_kf + n_nodes_f), (size_t)(n_f));
+        if (rc_) return rc_;
+    }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.idA = ar.put(kf_node_id, n_nodes_kf), A.offA = ar.put(kf_node_off, n_nodes_kf + 1);
     A.featA = ar.put(kf_node_feat, kf_node_off[n_nodes_kf]);
@@ -1059,7 +1091,7 @@ int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float
                                  const float *angle2, const uint8_t *desc2, int32_t *matches12, int32_t *nmatches) {
     if (!m || !F12 || !Cw1 || !Tcw2 || !K2 || !scale_factors2 || !level_sigma2_2 || !matches12 || !nmatches)
         return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: null argument");
-    if (n1 < 0 || n2 < 0 || n1 > m->maxQ || n2 > m->maxT) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: too many keypoints for this handle");
+    if (n1 < 0 || n2 < 0 || n1 > 0x7ffffff || n2 > 0x7ffffff) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: too many keypoints for this handle");
     if (nlevels < 1 || nlevels > 16) return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: nlevels out of range");
     if (!csr_ok(n_nodes1, node_id1, node_off1, node_feat1, n1) || !csr_ok(n_nodes2, node_id2, node_off2, node_feat2, n2))
         return fail(MSL_ERR_INVALID, "msl_search_for_triangulation: malformed feature vector");
@@ -1086,6 +1118,10 @@ int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float
         A.ex = K2[0] * C2[0] * invz + K2[2];
         A.ey = K2[1] * C2[1] * invz + K2[3];
     }
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n1 + n_nodes1 + n_nodes2), (size_t)(n2));
+        if (rc_) return rc_;
+    }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.idA = ar.put(node_id1, n_nodes1), A.offA = ar.put(node_off1, n_nodes1 + 1), A.featA = ar.put(node_feat1, node_off1[n_nodes1]);
     A.idB = ar.put(node_id2, n_nodes2), A.offB = ar.put(node_off2, n_nodes2 + 1), A.featB = ar.put(node_feat2, node_off2[n_nodes2]);
@@ -1104,7 +1140,7 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
                     const int32_t *kf_octave, const float *kf_uright, const uint8_t *kf_desc, int32_t *best_idx,
                     int32_t *best_dist, int32_t *nfused) {
     if (!m || !geom || !Tcw || !inv_level_sigma2 || !best_idx || !best_dist || !nfused) return fail(MSL_ERR_INVALID, "msl_fuse_search: null argument");
-    if (n_mp < 0 || n_kf < 0 || n_mp > m->maxQ || n_kf > m->maxT || n_kf > MAXK) return fail(MSL_ERR_INVALID, "msl_fuse_search: too many keypoints for this handle");
+    if (n_mp < 0 || n_kf < 0 || n_kf > MAXK || n_mp > 0x7ffffff) return fail(MSL_ERR_INVALID, "msl_fuse_search: too many keypoints for this handle");
     if (geom->nlevels < 1 || geom->nlevels > 16 || !(log_scale_factor > 0.f)) return fail(MSL_ERR_INVALID, "msl_fuse_search: parameter out of range");
     if (n_mp == 0 || n_kf == 0) {
         for (int i = 0; i < n_mp; i++) best_idx[i] = -1, best_dist[i] = 256;
@@ -1127,6 +1163,10 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
     for (int r = 0; r < 3; r++) {  // KeyFrame::SetPose (src/KeyFrame.cc:79-80): Rwc = Rcw.t(); Ow = -Rwc * tcw -- flags == 0, alpha = -1
         const float t0 = A.Rcw[0 * 3 + r] * A.tcw[0] + A.Rcw[1 * 3 + r] * A.tcw[1] + A.Rcw[2 * 3 + r] * A.tcw[2];
         A.Ow[r] = (float)((double)t0 * -1.0);
+    }
+    {
+        const int rc_ = ensure_scratch(m, (size_t)(n_mp), (size_t)(n_kf));
+        if (rc_) return rc_;
     }
     Arena ar{m->d_scr, 0, m->scrCap, m->stream};
     A.q_valid = ar.put(mp_valid, n_mp), A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);

@@ -140,4 +140,37 @@ int ref_plane_run(const uint16_t *depth, int w, int h, int stride_px, float fx, 
     return rc;
 }
 
+// Timing form for bench.py's reference arm (no arena: glibc's allocator, so it may run on many threads at once, one frame
+// each, like Frame::ExtractPlanes' per-frame std::thread).  full = 0: readColorImage + readDepthImage and the pre-stage of
+// PlaneFitter::run -- the PlaneSeg constructor of every block and initGraph (AHCPlaneFitter.hpp:216-223, 756-928), the part
+// BASELINE.json's config 3 names; full = 1: runPlaneDetection as Frame::ExtractPlanes calls it (src/Frame.cc:607-609).
+// Returns the number of graph nodes (full = 0) or plane_num_ (full = 1), < 0 on error.
+int ref_plane_timed(const uint16_t *depth, int w, int h, int stride_px, float fx, float fy, float cx, float cy, float factor,
+                    int full) {
+    PlaneDetection pd;
+    cv::Mat color, K;
+    if (!read_frame(pd, depth, w, h, stride_px, fx, fy, cx, cy, factor, color, K)) return -1;
+    if (full) {
+        pd.runPlaneDetection();
+        return pd.plane_num_;
+    }
+    Fitter &f = pd.plane_filter;
+    f.clear();
+    f.points = &pd.cloud;
+    f.height = pd.cloud.height();
+    f.width = pd.cloud.width();
+    f.ds.reset(new DisjointSet((f.height / f.windowHeight) * (f.width / f.windowWidth)));
+    Fitter::PlaneSegMinMSEQueue minQ;
+    f.initGraph(minQ);
+    const int nodes = (int)minQ.size();
+    std::vector<ahc::PlaneSeg::shared_ptr> keep;
+    while (!minQ.empty()) {
+        keep.push_back(minQ.top());
+        minQ.pop();
+    }
+    for (size_t k = 0; k < keep.size(); k++) keep[k]->nbs.clear();
+    f.clear();
+    return nodes;
+}
+
 }  // extern "C"

@@ -176,3 +176,22 @@ def test_hamming_best2_ragged_device(oracle, msl):
         obi, obd, osd = oracle.hamming_best2(desc[b, :nq], desc[b + 1, :nt])
         assert np.array_equal(bi[b, :nq], obi) and np.array_equal(bd[b, :nq], obd) and np.array_equal(sd[b, :nq], osd)
         assert (bi[b, nq:] == -7).all()  # rows beyond the count are not touched
+
+
+def test_searches_with_more_map_points_than_the_handle_was_created_for(oracle, msl):
+    """The reference passes the whole of mvpLocalMapPoints to SearchByProjection (src/Tracking.cc:1693) and the map points of
+    every neighbour keyframe to Fuse (src/LocalMapping.cc:569): far more than a frame's keypoints.  The query side of a
+    search grows the handle's scratch on demand; only the per-frame keypoint count is limited."""
+    g = msl.frame_geom()
+    cur, last, mps, Tc, Tl = S.match_scene(7, n_cur=1200, n_last=9000, collide=0.5)
+    m = msl.ORBmatcher(nnratio=0.8, max_queries=512, max_train=2048)  # deliberately small
+    n_o, cm_o = oracle.search_by_projection_points(g, 3.0, 0.8, mps, cur)
+    n_g, cm_g = m.SearchByProjectionPoints(g, 3.0, mps, cur)
+    assert n_o == n_g and np.array_equal(cm_o, cm_g) and n_o > 100
+    n_o, cm_o = oracle.search_by_projection_frame(g, Tc, Tl, 7.0, True, last, cur)
+    n_g, cm_g = m.SearchByProjectionFrame(g, Tc, Tl, 7.0, last, cur)
+    assert n_o == n_g and np.array_equal(cm_o, cm_g)
+    mpf, kfs, Tcw, ils = S.fuse_scene(3, n_mp=12000, n_kf=1500)
+    n_c, bi_c, bd_c = oracle.fuse_search(g, Tcw, 3.0, LSF, ils, mpf, kfs)
+    n_f, bi_f, bd_f = m.Fuse(g, Tcw, mpf, kfs, ils, th=3.0, log_scale_factor=LSF)
+    assert n_c == n_f and np.array_equal(bi_c, bi_f) and np.array_equal(bd_c, bd_f) and n_c > 100

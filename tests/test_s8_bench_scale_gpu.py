@@ -20,20 +20,16 @@ REF0 = 100
 
 # environment knobs of the fuse kernels (read by msl_surfel_create): every launch form the library can be switched to
 VARIANTS = {
-    "default": {},                                                  # k_fuse_stream, 85-register budget, early loads, 3 CTAs per SM
-    "stream_late_loads": {"MSL_STREAM_EARLY": "0"},
-    "stream_64regs_wave2": {"MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "2"},
-    "stream_no_prefetch": {"MSL_STREAM_PF": "0"},
-    "stream2": {"MSL_FUSE_ONE": "3"},                               # branch-free scan, carried survivors (full fuse rounds)
-    "stream2_64regs": {"MSL_FUSE_ONE": "3", "MSL_STREAM_REGS": "4"},
-    "stream2_late_wave2": {"MSL_FUSE_ONE": "3", "MSL_STREAM_EARLY": "0", "MSL_STREAM_WAVE": "2"},
-    "pipe": {"MSL_FUSE_ONE": "4"},                                  # scan of segment s+1 / fuse of segment s interleaved per warp
-    "pipe_64regs_wave4": {"MSL_FUSE_ONE": "4", "MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "4"},
-    "pipe_late_loads": {"MSL_FUSE_ONE": "4", "MSL_STREAM_EARLY": "0"},
+    "default": {},                                                  # k_fuse_pipe: TMA-staged segments, scan(s+1) / fuse(s) interleaved per warp
+    "pipe_64regs_wave4": {"MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "4"},
+    "pipe_late_loads_wave2": {"MSL_STREAM_EARLY": "0", "MSL_STREAM_WAVE": "2"},
+    "pipe_no_prefetch": {"MSL_STREAM_PF": "0"},
+    "stream": {"MSL_FUSE_ONE": "2"},                                # TMA-staged, phases in sequence
+    "stream_64regs_late": {"MSL_FUSE_ONE": "2", "MSL_STREAM_REGS": "4", "MSL_STREAM_EARLY": "0"},
     "one": {"MSL_FUSE_ONE": "1"},                                   # round 1's kernel (direct loads)
-    "one_early": {"MSL_FUSE_ONE": "1", "MSL_ONE_EARLY": "1"},
-    "one_wave4": {"MSL_FUSE_ONE": "1", "MSL_ONE_WAVE": "0"},
+    "one_early_wave4": {"MSL_FUSE_ONE": "1", "MSL_ONE_EARLY": "1", "MSL_ONE_WAVE": "0"},
     "two_kernel_chain": {"MSL_FUSE_ONE": "0"},
+    "superpixels_v1": {"MSL_SP_V2": "0"},                           # round 1's superpixel kernels (local-memory lists)
 }
 KNOBS = sorted({k for v in VARIANTS.values() for k in v})
 

@@ -295,3 +295,31 @@ def test_membership_values_other_than_minus_one(oracle, msl):
     m0 = np.where(m != -1, 0, -1).astype(np.int32)
     seeds0, index0 = sf.superpixels(g, d, m0)
     assert np.array_equal(index0, index) and np.array_equal(seeds0.view(np.uint8), seeds.view(np.uint8))
+
+
+@pytest.mark.parametrize("w,h", [(1280, 960), (328, 248)])
+def test_fuse_stream_other_frame_sizes(oracle, msl, w, h):
+    """BASELINE.json config 5 runs the front-end at 1280x960 (19,200 seeds per frame, K scaled x2): superpixel index, seeds
+    and the map after a three-keyframe stream with compaction must equal the oracle at that size as well (and at a size
+    whose seed grid is not a multiple of the kernels' seed groups)."""
+    s = w / 640.0
+    K = (525.0 * s, 525.0 * s, 319.5 * s + (s - 1) * 0.5, 239.5 * s + (s - 1) * 0.5)
+    frames = [(S.gray_frame(40 + k, w, h), S.depth_frame(40 + k, w, h, K, scene=40)[1], S.membership(40 + k, w, h, plane_fraction=0.3 * (k == 1)))
+              for k in range(3)]
+    T = S.pose_walk(40, 3)
+    local = S.surfel_map(40, 150001, frames[0][1], T[0], K, ref_index=60, w=w, h=h)
+    so = oracle.SurfelOracle(w, h, *K)
+    sf = msl.SurfelFusion(w, h, *K, max_surfels=len(local) + 4 * (w // 8) * (h // 8))
+    seeds, index = sf.superpixels(frames[0][0], frames[0][1], frames[0][2])
+    lo = local.copy()
+    so.fuse(60, *frames[0], T[0], lo.copy())
+    assert np.array_equal(index[0], so.index()), "superpixelIndex"
+    assert _cmp(so.seeds(), seeds[0], FLOAT_SEED, INT_SEED, "seed") == 0.0
+    sf.upload_map(local)
+    for k in range(3):
+        new = so.fuse(60 + k, *frames[k], T[k], lo)
+        lo = oracle.surfel_compact(lo, new)
+    st = sf.fuse_batch(60, np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]), np.stack([f[2] for f in frames]), T)
+    got = sf.download_map()
+    assert st[3] == len(lo) == len(got)
+    assert np.array_equal(got.view(np.uint8), lo.view(np.uint8)), "map after the stream is not bit-identical"
