@@ -325,6 +325,11 @@ int msl_plane_detect_dev(msl_plane *, const uint16_t *d_depth, int dstride_px, s
                          const float K[4], float depth_map_factor, int32_t *d_membership, int32_t *d_plane_count,
                          msl_plane_rec *d_planes, int plane_cap);
 
+/* Measurement aid: globaltimer stamps (ns) of the phases of every frame of the last msl_plane_detect* call: out[8 f + k],
+ * k = 0 start, 1 graph built, 2 ahCluster done, 3 block membership + region-grow seeds, 4 region grow done, 5 final merge
+ * done, 6 end; out[8 f + 7] = merge steps taken. */
+int msl_plane_debug_profile(msl_plane *, int64_t *out, int frames);
+
 /* ------------------------------------------------------------------------------------- surfels
  * Replaces SurfelFusion (include/SurfelFusion.h:44-139, src/SurfelFusion.cpp), the compaction tail of
  * SurfelMapping::fuseMap (src/SurfelMapping.cpp:366-391) and SurfelMapping::moveAddSurfels (:194-304), so that

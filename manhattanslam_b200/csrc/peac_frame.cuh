@@ -51,6 +51,14 @@
 #define PEAC_STORE(p, v) (*(volatile int *)(p) = (v))
 #define PEAC_UNROLL _Pragma("unroll")
 #define PEAC_STORE_FLAG(p) (*(p) = 1)  // several threads may store the same 1
+#define PEAC_STAMP(F, i, tid)                         \
+    do {                                              \
+        if ((F).prof && (tid) == 0) {                 \
+            unsigned long long t_;                    \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+            (F).prof[i] = (long long)t_;              \
+        }                                             \
+    } while (0)
 #elif defined(PEAC_HOST_EMULATION_MT)  // tests/host_emul/peac_host_mt.cpp: real threads + a barrier, under ThreadSanitizer
 void peac_emu_sync();
 #define PEAC_HD inline
@@ -68,17 +76,19 @@ inline void peac_emu_atomic_min(int *p, int v) {
 }
 #define PEAC_STORE_FLAG(p) __atomic_store_n((p), (unsigned char)1, __ATOMIC_RELAXED)
 #define PEAC_UNROLL
+#define PEAC_STAMP(F, i, tid) ((void)0)
 #else
 #define PEAC_HD inline
 #define PEAC_D inline
 #define PEAC_SYNC() ((void)0)
-#define PEAC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define PEAC_ATOMIC_ADD(p, v) ((*(p) += (v)) - (v))  // returns the old value, like atomicAdd
 #define PEAC_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
 #define PEAC_ATOMIC_OR(p, v) (*(p) |= (v))
 #define PEAC_LOAD(p) (*(p))
 #define PEAC_STORE(p, v) (*(p) = (v))
 #define PEAC_STORE_FLAG(p) (*(p) = 1)
 #define PEAC_UNROLL
+#define PEAC_STAMP(F, i, tid) ((void)0)
 #endif
 
 namespace peac {
@@ -130,6 +140,7 @@ template <int NB> struct SharedT {
     Node tmp;
     int heapN, nExtracted, nOld, seqNext, step;
     int curP, curNb, decision;  // broadcast from thread 0
+    int nCand;                  // threads that hold a merge candidate of the current step (entries of red[])
     int lvlBegin, lvlEnd, pending;  // region grow by levels
     int error;
 };
@@ -146,6 +157,7 @@ struct Flood {
     float *visDist;   // visCap
     uint8_t *visFlag; // visCap: bit0 near, bit1 pending, bit2 pushes
     int visCap;
+    long long *prof;  // optional: 8 globaltimer stamps of the frame's phases (msl_plane_debug_profile), else null
 };
 
 enum { PEAC_OK = 0, PEAC_ERR_QUEUE = 1, PEAC_ERR_PLANES = 2 };
@@ -442,8 +454,11 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
         const int p = S.curP;
         if (p < 0) break;
         // candidate merges with every neighbour, in parallel; every thread keeps the best of its own slots
-        // (least mse, then earliest creation: the first minimum in the reference's neighbour order)
+        // (least mse, then earliest creation: the first minimum in the reference's neighbour order) together with the
+        // merged node itself, and threads that found one append themselves to a compact list (a node has a handful of
+        // neighbours: thread 0 looks at those entries only, and the winner's fit is not computed a second time)
         int mine = -1;
+        Node mineNode;
         for (int k = tid; k < nslots; k += nt) {
             S.candHas[k] = 0;
             if (!bit(S.nbs[p], k)) continue;
@@ -452,20 +467,21 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             merged(S.node[p], S.node[k], m);
             S.candMse[k] = m.mse;
             S.candHas[k] = 1;
-            if (mine < 0 || m.mse < S.candMse[mine] || (m.mse == S.candMse[mine] && S.node[k].seq < S.node[mine].seq)) mine = k;
+            if (mine < 0 || m.mse < S.candMse[mine] || (m.mse == S.candMse[mine] && S.node[k].seq < S.node[mine].seq)) mine = k, mineNode = m;
         }
-        S.red[tid] = (int16_t)mine;
+        if (mine >= 0) S.red[PEAC_ATOMIC_ADD(&S.nCand, 1)] = (int16_t)mine;
         PEAC_SYNC();
         if (tid == 0) {
             // :1064-1072 in neighbour order (creation sequence): the first minimum wins; on an exact tie the reference
             // replaces the candidate iff cand->N < merge->mse
             int best = -1;
-            for (int t = 0; t < nt; t++) {
+            const int nc = S.nCand;
+            for (int t = 0; t < nc; t++) {
                 const int k = S.red[t];
-                if (k >= 0 && (best < 0 || S.candMse[k] < S.candMse[best] ||
-                               (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq)))
+                if (best < 0 || S.candMse[k] < S.candMse[best] || (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq))
                     best = k;
             }
+            S.nCand = 0;
             if (best >= 0) {
                 const double mn = S.candMse[best];
                 // cand->N = N(p) + N(neighbour) > N(p): the tie rule can only fire when the tied mse exceeds N(p)
@@ -480,27 +496,43 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
                         if ((double)(S.node[p].N + S.node[best].N) < mn) best = nx;
                     }
                 }
-                merged(S.node[p], S.node[best], S.tmp);
             }
-            if (best >= 0 && S.tmp.mse < t_mse_merge(S.tmp.center[2])) {
-                S.decision = 1, S.curNb = best;
-                ds_union(S, S.node[p].rid, S.node[best].rid);  // mergeNbsFrom :383
-            } else {
-                S.decision = 0;
-                if (S.node[p].N >= MIN_SUPPORT) {
-                    if (S.nExtracted < MAXPL)
-                        S.extracted[S.nExtracted++] = (int16_t)p;
+            S.curNb = best;
+        }
+        PEAC_SYNC();
+        {   // the thread that evaluated the winning neighbour already holds the merged node (a second fit would repeat the
+            // same arithmetic): it publishes it and takes the merge decision; without a candidate thread 0 decides
+            const int best = S.curNb;
+            if ((best >= 0 && (best % nt) == tid) || (best < 0 && tid == 0)) {
+                if (best >= 0) {
+                    if (mine == best)
+                        S.tmp = mineNode;
                     else
-                        S.error = PEAC_ERR_PLANES;
+                        merged(S.node[p], S.node[best], S.tmp);  // the tie walk picked a slot that was not this thread's best
+                }
+                if (best >= 0 && S.tmp.mse < t_mse_merge(S.tmp.center[2])) {
+                    S.decision = 1;
+                    ds_union(S, S.node[p].rid, S.node[best].rid);  // mergeNbsFrom :383
+                } else {
+                    S.decision = 0;
+                    if (S.node[p].N >= MIN_SUPPORT) {
+                        if (S.nExtracted < MAXPL)
+                            S.extracted[S.nExtracted++] = (int16_t)p;
+                        else
+                            S.error = PEAC_ERR_PLANES;
+                    }
                 }
             }
         }
         PEAC_SYNC();
         if (S.decision) {
             const int nb = S.curNb;
-            for (int w = tid; w < SH::WORDS; w += nt) S.tmpMask[w] = S.nbs[p][w] | S.nbs[nb][w];
-            PEAC_SYNC();
-            if (tid == 0) clrbit(S.tmpMask, p), clrbit(S.tmpMask, nb);
+            for (int w = tid; w < SH::WORDS; w += nt) {  // union of the two neighbour sets without the two nodes themselves
+                uint32_t m = S.nbs[p][w] | S.nbs[nb][w];
+                if ((p >> 5) == w) m &= ~(1u << (p & 31));
+                if ((nb >> 5) == w) m &= ~(1u << (nb & 31));
+                S.tmpMask[w] = m;
+            }
             PEAC_SYNC();
             // disconnectAllNbs of both, then the merged node (in p's slot) becomes a neighbour of the union
             for (int k = tid; k < nslots; k += nt) {
@@ -738,6 +770,7 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
     uint32_t *const rfq = F.rfq;
     const int rfqCap = F.rfqCap;
     const int nb = g.Nw * g.Nh, npix = g.W2 * g.H2;
+    PEAC_STAMP(F, 0, tid);
     // ---- initGraph's nodes and edges from the pre-stage (AHCPlaneFitter.hpp:756-928)
     for (int b = tid; b < nb; b += nt) {
         Node &n = S.node[b];
@@ -756,13 +789,15 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
         if (e & 4) setbit(m, b - g.Nw);
         if (e & 8) setbit(m, b + g.Nw);
     }
-    if (tid == 0) S.heapN = 0, S.nExtracted = 0, S.seqNext = nb, S.step = 0, S.error = PEAC_OK;
+    if (tid == 0) S.heapN = 0, S.nExtracted = 0, S.seqNext = nb, S.step = 0, S.error = PEAC_OK, S.nCand = 0;
     PEAC_SYNC();
     if (tid == 0)
         for (int b = 0; b < nb; b++)
             if (seed[b]) heap_push(S, b);  // minQ.push in block order (:779)
     PEAC_SYNC();
+    PEAC_STAMP(F, 1, tid);
     cluster(S, g, nb, tid, nt);
+    PEAC_STAMP(F, 2, tid);
 
     // ---- refineDetails :294-374.  findBlockMembership(isValidExtractedPlane) :480-582, ERODE_ALL_BORDER
     for (int i = tid; i < MAXPL; i += nt) S.valid[i] = 0, S.count[i] = 0, S.plidmap[i] = -1;
@@ -851,11 +886,13 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
     PEAC_SYNC();
 
     // ---- floodFill :422-471
+    PEAC_STAMP(F, 3, tid);
     if (g.floodSerial)
         flood_serial(S, g, depth, membership, F, tid);
     else
         flood_levels(S, g, depth, membership, F, tid, nt);
     PEAC_SYNC();
+    PEAC_STAMP(F, 4, tid);
 
     // ---- "try to merge one last time" :312-320: the valid planes re-enter the queue in plane order
     if (tid == 0) {
@@ -867,6 +904,7 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
     }
     PEAC_SYNC();
     cluster(S, g, nb, tid, nt);
+    PEAC_STAMP(F, 5, tid);
     if (tid == 0) {  // plidmap :322-337 (a merged plane lives in the slot of one of its parts; ds roots are unaffected)
         for (int i = 0; i < S.nOld; i++) {
             if (!S.valid[i]) continue;
@@ -895,6 +933,8 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
         o.N = n.N, o.rid = n.rid, o.vertices = S.count[i], o.pad = 0;
     }
     if (tid == 0) *planeCount = S.nExtracted, *errorOut = S.error;
+    PEAC_STAMP(F, 6, tid);
+    if (F.prof && tid == 0) F.prof[7] = S.step;
 }
 
 }  // namespace peac

@@ -234,12 +234,13 @@ struct PeacScratch {  // per-frame strides are implied: npix, rfqCap, visCap
     float *visDist;
     uint8_t *visFlag;
     int rfqCap, visCap;
+    long long *prof;  // 8 per frame, or null
 };
 
 // SH = peac::Shared: the working set in the CTA's dynamic shared memory (frames of <= 768 blocks); SH = peac::SharedBig: in
 // global memory, one record per frame (`big`), for frames of up to 3072 blocks (1280x960)
-template <class SH>
-__global__ void __launch_bounds__(512)
+template <class SH, int MAXT>
+__global__ void __launch_bounds__(MAXT)
     k_peac_frame(peac::Geo g, size_t frameStride, const uint16_t *__restrict__ depth, const msl_block_stat *__restrict__ blocks,
                  const uint8_t *__restrict__ seed, const uint8_t *__restrict__ edges, int32_t *__restrict__ membership, PeacScratch sc,
                  SH *big, peac::PlaneOut *__restrict__ planes, int planeCap, int32_t *__restrict__ planeCount,
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(512)
     F.rfq = sc.rfq + (size_t)b * sc.rfqCap, F.rfqCap = sc.rfqCap;
     F.visC = sc.visC + (size_t)b * sc.visCap, F.visDist = sc.visDist + (size_t)b * sc.visCap, F.visFlag = sc.visFlag + (size_t)b * sc.visCap;
     F.visCap = sc.visCap;
+    F.prof = sc.prof ? sc.prof + 8 * (size_t)b : nullptr;
     peac::frame(S, g, depth + b * frameStride, blocks + (size_t)b * nb, seed + (size_t)b * nb, edges + (size_t)b * nb,
                 membership + b * npix, F, planes + (size_t)b * planeCap, planeCap, planeCount + b, frameError + b, (int)threadIdx.x,
                 (int)blockDim.x);
@@ -277,6 +279,8 @@ struct msl_plane {
     peac::SharedBig *d_big = nullptr;  // frames of more than 768 blocks: the working set in global memory
     msl_plane_rec *d_planes = nullptr;
     int planeCap = 0;
+    long long *d_prof = nullptr;  // msl_plane_debug_profile: 8 stamps per frame of the last detect call
+    int profFrames = 0;
     int pendingCheck = 0;  // frames of an enqueued detect whose per-frame error words have not been read yet
 };
 
@@ -284,7 +288,7 @@ static void plane_free(msl_plane *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_depth, p->d_cloud, p->d_blocks, p->d_seed, p->d_edges, p->d_mem, p->d_count, p->d_ferr,
-                    p->d_dist, p->d_rfq, p->d_planes, p->d_own, p->d_visC, p->d_visDist, p->d_visFlag, p->d_big};
+                    p->d_dist, p->d_rfq, p->d_planes, p->d_own, p->d_visC, p->d_visDist, p->d_visFlag, p->d_big, p->d_prof};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -387,9 +391,12 @@ static int plane_detect_alloc(msl_plane *p) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ferr, B * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_planes, B * PLANE_CAP_INTERNAL * sizeof(msl_plane_rec));
     if (e == cudaSuccess) e = cudaMemset(p->d_ferr, 0, B * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_prof, B * 8 * sizeof(long long));
     if (e == cudaSuccess && p->Nw * p->Nh > peac::MAXB) e = cudaMalloc((void **)&p->d_big, B * sizeof(peac::SharedBig));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_peac_frame<peac::Shared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
+        e = cudaFuncSetAttribute(k_peac_frame<peac::Shared, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_peac_frame<peac::Shared, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
     if (e != cudaSuccess) return fail(MSL_ERR_CUDA, std::string("msl_plane_detect: ") + cudaGetErrorString(e));
     p->planeCap = PLANE_CAP_INTERNAL;
     return MSL_OK;
@@ -417,21 +424,41 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     PeacScratch sc;
     sc.dist = p->d_dist, sc.rfq = p->d_rfq, sc.own = p->d_own, sc.visC = p->d_visC, sc.visDist = p->d_visDist, sc.visFlag = p->d_visFlag;
     sc.rfqCap = 4 * p->W2 * p->H2, sc.visCap = 4 * p->W2 * p->H2;
-    int threads = 256;  // MSL_PEAC_THREADS = 64 | 128 | 256 | 512: CTA size of k_peac_frame (A/B knob)
+    sc.prof = p->d_prof, p->profFrames = batch;
+    int threads = 256;  // MSL_PEAC_THREADS = 64 | 128 | 256 | 512 | 1024: CTA size of k_peac_frame (A/B knob)
     if (const char *e = getenv("MSL_PEAC_THREADS")) {
         const int v = atoi(e);
-        if (v == 64 || v == 128 || v == 256 || v == 512) threads = v;
+        if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) threads = v;
     }
-    if (p->Nw * p->Nh <= peac::MAXB)
-        k_peac_frame<peac::Shared><<<batch, threads, sizeof(peac::Shared), p->stream>>>(
-            g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges, d_membership, sc, (peac::Shared *)nullptr,
-            reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count, p->d_ferr);
-    else
-        k_peac_frame<peac::SharedBig><<<batch, threads, 0, p->stream>>>(g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges,
-                                                                   d_membership, sc, p->d_big, reinterpret_cast<peac::PlaneOut *>(d_planes),
-                                                                   plane_cap, d_plane_count, p->d_ferr);
+#define PEAC_ARGS g, frame_stride_px, d_depth, p->d_blocks, p->d_seed, p->d_edges, d_membership, sc
+#define PEAC_TAIL reinterpret_cast<peac::PlaneOut *>(d_planes), plane_cap, d_plane_count, p->d_ferr
+    // two register budgets: up to 512 threads per CTA at 110 registers (no spills in the fp64 eigen-solver), 1024 at 64
+    if (p->Nw * p->Nh <= peac::MAXB) {
+        if (threads <= 512)
+            k_peac_frame<peac::Shared, 512><<<batch, threads, sizeof(peac::Shared), p->stream>>>(PEAC_ARGS, (peac::Shared *)nullptr, PEAC_TAIL);
+        else
+            k_peac_frame<peac::Shared, 1024><<<batch, threads, sizeof(peac::Shared), p->stream>>>(PEAC_ARGS, (peac::Shared *)nullptr, PEAC_TAIL);
+    } else {
+        if (threads <= 512)
+            k_peac_frame<peac::SharedBig, 512><<<batch, threads, 0, p->stream>>>(PEAC_ARGS, p->d_big, PEAC_TAIL);
+        else
+            k_peac_frame<peac::SharedBig, 1024><<<batch, threads, 0, p->stream>>>(PEAC_ARGS, p->d_big, PEAC_TAIL);
+    }
+#undef PEAC_ARGS
+#undef PEAC_TAIL
     MSL_LAUNCH_CHECK();
     p->pendingCheck = batch > p->pendingCheck ? batch : p->pendingCheck;
+    return MSL_OK;
+}
+
+// Measurement aid: globaltimer stamps (ns) of the phases of every frame of the last detect call -- out[8 f + k], k = 0 start,
+// 1 graph built, 2 ahCluster done, 3 block membership + region-grow seeds done, 4 region grow done, 5 final merge done,
+// 6 end; out[8 f + 7] = merge steps taken.
+int msl_plane_debug_profile(msl_plane *p, int64_t *out, int frames) {
+    if (!p || !out || frames < 1 || !p->d_prof || frames > p->profFrames) return fail(MSL_ERR_INVALID, "msl_plane_debug_profile: bad argument");
+    MSL_CUDA(cudaSetDevice(p->device));
+    MSL_CUDA(cudaStreamSynchronize(p->stream));
+    MSL_CUDA(cudaMemcpy(out, p->d_prof, sizeof(long long) * 8 * (size_t)frames, cudaMemcpyDeviceToHost));
     return MSL_OK;
 }
 

@@ -74,6 +74,12 @@ class PlaneDetection:
                                              C.c_float(depthMapFactor), ptr(d_cloud), ptr(d_blocks), ptr(d_seed),
                                              ptr(d_edges)))
 
+    def debug_profile(self, frames):
+        """phase stamps of the last detect call (msl_plane_debug_profile): (frames, 8) int64, ns; column 7 = merge steps"""
+        out = np.zeros((frames, 8), np.int64)
+        check(self._L.msl_plane_debug_profile(self._h, ptr(out), C.c_int(frames)))
+        return out
+
     def sync(self):
         check(self._L.msl_plane_sync(self._h))
 

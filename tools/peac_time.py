@@ -25,6 +25,16 @@ def main():
         t0 = time.perf_counter()
         mem, planes = pd.detect(d, depthMapFactor=1.0)
         ts.append(time.perf_counter() - t0)
+    prof = None
+    try:
+        pr = pd.debug_profile(batch).astype(np.float64)
+        names = ["graph", "ahCluster", "membership+seeds", "region_grow", "final_merge", "remap"]
+        d = np.diff(pr[:, :7], axis=1) / 1e3
+        prof = {"phase_us_median_over_frames": {n: float(np.median(d[:, i])) for i, n in enumerate(names)},
+                "frame_us_median": float(np.median((pr[:, 6] - pr[:, 0]) / 1e3)), "frame_us_max": float(np.max((pr[:, 6] - pr[:, 0]) / 1e3)),
+                "batch_span_us": float((pr[:, 6].max() - pr[:, 0].min()) / 1e3), "merge_steps_median": float(np.median(pr[:, 7]))}
+    except Exception as e:  # noqa: BLE001
+        prof = "unavailable: %s" % e
     ok = None
     try:
         from oracle import binding as ob
@@ -33,7 +43,7 @@ def main():
         ok = "oracle unavailable: %s" % e
     print(json.dumps({"batch": batch, "flood_serial": os.environ.get("MSL_PEAC_FLOOD_SERIAL", "0"), "ms_per_batch_min": 1e3 * min(ts),
                       "ms_per_batch_median": 1e3 * float(np.median(ts)), "frames_per_s": batch / float(np.median(ts)),
-                      "planes_first_frames": [len(p) for p in planes[:8]], "equals_oracle_first_frames": ok,
+                      "threads": os.environ.get("MSL_PEAC_THREADS", "256"), "profile": prof, "planes_first_frames": [len(p) for p in planes[:8]], "equals_oracle_first_frames": ok,
                       "note": "host API: H2D of the depth frames, pre-stage, k_peac_frame, D2H of membership + planes, sync"}))
 
 
