@@ -3,7 +3,8 @@
 
 One step = one pass of the front-end over one batch of synthetic RGB-D frames per GPU.  The default workload is the
 configuration the metric is quoted on (BASELINE.json configs 2-4 in one step, 640x480, batch 64, 5 M-surfel map):
-ORB extraction, brute-force Hamming match of every frame's descriptors against the next frame's, the plane pre-stage on the
+ORB extraction, brute-force Hamming match of every frame's descriptors against the next frame's, ORBmatcher::SearchByProjection
+of every frame against its predecessor (the frame glue + Tracking::UpdateLastFrame on the device), the plane pre-stage on the
 u16 depth and the projective surfel fusion of the 64-frame stream into a device-resident map (superpixels batched,
 fuse / initialise / compact frame by frame in order).  --workload selects BASELINE.json's other configurations
 (orb_match_640x480_b64, plane_640x480_b256, surfel_640x480_b64_map5M, frontend_1280x960_b64_map5M).
@@ -33,11 +34,12 @@ UNIT = "frames/s"
 MAP_STEADY_FRACTION = 0.89  # measured with the oracle on this generator (see make_inputs)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
-ALL_STAGES = ["orb", "hamming_match", "plane_prestage", "surfel_fuse"]
+ALL_STAGES = ["orb", "hamming_match", "search_by_projection", "plane_prestage", "surfel_fuse"]
+MBF, TH_DEPTH_FACTOR, TH_PROJ = 40.0, 40.0, 15.0  # Camera.bf / ThDepth of Example/TUM3.yaml; th of TrackWithMotionModel (src/Tracking.cc:1249)
 WORKLOADS = {
     # name: (width, height, frames per GPU per step, surfels per GPU, stages)
     "frontend_640x480_b64_map5M": (640, 480, 64, 5_000_000, ALL_STAGES),          # the headline (configs 2 + 3 + 4 in one step)
-    "orb_match_640x480_b64": (640, 480, 64, 0, ["orb", "hamming_match"]),           # BASELINE.json config 2
+    "orb_match_640x480_b64": (640, 480, 64, 0, ["orb", "hamming_match", "search_by_projection"]),  # BASELINE.json config 2
     "plane_640x480_b256": (640, 480, 256, 0, ["plane_prestage"]),                   # config 3
     "surfel_640x480_b64_map5M": (640, 480, 64, 5_000_000, ["surfel_fuse"]),         # config 4
     "frontend_1280x960_b64_map5M": (1280, 960, 64, 5_000_000, ALL_STAGES),          # config 5: one rank's 64 of the 512 frames
@@ -69,7 +71,7 @@ def parse():
     a.batch = a.batch if a.batch > 0 else batch
     a.surfels = a.surfels if a.surfels >= 0 else surfels
     if a.only:
-        alias = {"match": "hamming_match", "plane": "plane_prestage", "surfel": "surfel_fuse"}
+        alias = {"match": "hamming_match", "plane": "plane_prestage", "surfel": "surfel_fuse", "track": "search_by_projection"}
         want = {alias.get(x, x) for x in a.only.split(",") if x}
         a.stages = [s for s in a.stages if s in want]
     if "surfel_fuse" not in a.stages:
@@ -143,6 +145,10 @@ def ref_parts(stages):
         # the reference has no brute-force matcher (DescriptorDistance, src/ORBmatcher.cc:835-849, is called from the window
         # searches); the all-pairs best-2 loop around that bit trick is the oracle's
         parts["hamming_match"] = "oracle port (all-pairs loop over the reference's DescriptorDistance bit trick)"
+    if "search_by_projection" in stages:
+        parts["search_by_projection"] = ("reference src/ORBmatcher.cc (SearchByProjection) on Last-frame map points built as "
+                                         "Tracking::UpdateLastFrame / Frame::UnprojectStereo do (numpy restatement)"
+                                         if _ref_lib("libmatch_ref.so") else "oracle port")
     if "plane_prestage" in stages:
         parts["plane_prestage"] = ("reference src/PlaneExtractor.cpp + include/peac (readDepthImage, PlaneSeg, initGraph)"
                                    if _ref_lib("libplane_ref.so") else "oracle port")
@@ -156,10 +162,42 @@ def baseline_kind(stages):
     """"reference" when the stage that dominates the CPU time of the workload is the reference's own source from
     oracle/_ref; "port" when it is the oracle port"""
     parts = ref_parts(stages)
-    for s in ("surfel_fuse", "orb", "plane_prestage", "hamming_match"):  # by CPU cost
+    for s in ("surfel_fuse", "orb", "search_by_projection", "plane_prestage", "hamming_match"):  # by CPU cost
         if s in parts:
             return "reference" if parts[s].startswith("reference") else "port"
     return "port"
+
+
+def last_frame_side(kps, desc, xy_un, kdepth, Tcw, K, th_depth):
+    """The Last-frame side of Tracking::TrackWithMotionModel as the reference builds it: Tracking::UpdateLastFrame
+    (src/Tracking.cc:1052-1104) gives the keypoints with depth > 0 -- in (depth, index) order, all up to mThDepth, at least the
+    100 closest -- "visual odometry" MapPoints at Frame::UnprojectStereo (src/Frame.cc:515-526): x3Dw = mRwc * x3Dc + mOw in
+    cv::Mat arithmetic (CV_32F row sums a0*b0 + a1*b1 + a2*b2 in float, then (float)(t0 + c) in double; mOw = -mRcw.t() * mtcw
+    with double accumulation).  Vectorised numpy; tests/test_track_batch_gpu.py checks it against the oracle's cv2-pinned
+    primitives point by point."""
+    f32 = np.float32
+    fx, fy, cx, cy = (f32(v) for v in K)
+    invfx, invfy = f32(1.0) / fx, f32(1.0) / fy
+    Rcw, tcw = Tcw[:3, :3].astype(f32), Tcw[:3, 3].astype(f32)
+    Ow = np.array([f32(sum((-np.float64(Rcw[k, r])) * np.float64(tcw[k]) for k in range(3))) for r in range(3)], f32)
+    n = len(kps)
+    z = np.asarray(kdepth, f32)
+    pos = np.flatnonzero(z > 0)
+    order = pos[np.lexsort((pos, z[pos]))]  # std::sort of (z, index) pairs
+    zs = z[order]
+    stop = np.flatnonzero((zs > f32(th_depth)) & (np.arange(1, len(order) + 1) > 100))
+    sel = order[:(stop[0] + 1) if len(stop) else len(order)]
+    has = np.zeros(n, np.uint8)
+    has[sel] = 1
+    u, v, zz = xy_un[sel, 0].astype(f32), xy_un[sel, 1].astype(f32), z[sel]
+    x3 = np.stack([(u - cx) * zz * invfx, (v - cy) * zz * invfy, zz], 1).astype(f32)
+    Rwc = np.ascontiguousarray(Rcw.T)
+    world = np.zeros((n, 3), f32)
+    for r in range(3):
+        t0 = (Rwc[r, 0] * x3[:, 0] + Rwc[r, 1] * x3[:, 1]) + Rwc[r, 2] * x3[:, 2]  # float32 at every step
+        world[sel, r] = (t0.astype(np.float64) + np.float64(Ow[r])).astype(f32)
+    return {"has_mp": has, "outlier": np.zeros(n, np.uint8), "mp_obs": np.zeros(n, np.uint8), "mp_world": world,
+            "mp_desc": desc, "octave": kps["octave"].astype(np.int32), "angle": kps["angle"].astype(np.float32)}
 
 
 class CpuFrontend:
@@ -175,6 +213,9 @@ class CpuFrontend:
         self.depth16 = make_inputs.depth16
         self.K = camera(a)
         self.parts = ref_parts(a.stages)
+        from manhattanslam_b200.matcher import frame_geom
+        self.geom = frame_geom(a.W, a.H, *self.K, bf=MBF)
+        self.Tcw = np.stack([np.linalg.inv(p.astype(np.float64)) for p in self.poses]).astype(np.float32)
         self.tl = threading.local()
         self.ref = 100
         self.rs = self.so = self.local = None
@@ -191,7 +232,7 @@ class CpuFrontend:
         if not hasattr(self.tl, "o"):
             self.tl.o = ob.RefOrbExtractor(arena=False) if self.parts.get("orb", "").startswith("reference") else ob.OrbOracle()
         k, d = self.tl.o(self.gray[i])
-        self.descs[i] = d
+        self.descs[i], self.kps[i] = d, k
         return len(k)
 
     def _plane(self, i):
@@ -204,12 +245,24 @@ class CpuFrontend:
     def _match(self, i):  # brute-force Hamming best-2 of frame i against frame i+1
         return int(self.ob.hamming_best2(self.descs[i], self.descs[i + 1])[1].sum())
 
+    def _track(self, i):
+        """ORBmatcher::SearchByProjection(frame i+1, frame i, 15) as Tracking::TrackWithMotionModel calls it"""
+        ob = self.ob
+        kl, kc = self.kps[i], self.kps[i + 1]
+        xy_l, xy_c = np.stack([kl["x"], kl["y"]], 1), np.stack([kc["x"], kc["y"]], 1)
+        _, kd_l = ob.stereo_from_rgbd(xy_l, xy_l, self.depth[i], MBF)
+        ur_c, _ = ob.stereo_from_rgbd(xy_c, xy_c, self.depth[i + 1], MBF)
+        last = last_frame_side(kl, self.descs[i], xy_l, kd_l, self.Tcw[i], self.K, MBF * TH_DEPTH_FACTOR / self.K[0])
+        cur = {"xy": xy_c, "octave": kc["octave"].astype(np.int32), "angle": kc["angle"].astype(np.float32), "uright": ur_c,
+               "desc": self.descs[i + 1], "occupied": np.zeros(len(kc), np.uint8)}
+        return ob.search_by_projection_frame(self.geom, self.Tcw[i + 1], self.Tcw[i], TH_PROJ, True, last, cur)[0]
+
     def step(self, frames):
         """one bounded step over the first `frames` frames of the batch -> seconds"""
         from concurrent.futures import ThreadPoolExecutor
         st = self.a.stages
         frames = min(frames, len(self.gray))
-        self.descs = [None] * frames
+        self.descs, self.kps = [None] * frames, [None] * frames
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=self.threads) as ex:
             if "orb" in st:
@@ -218,6 +271,12 @@ class CpuFrontend:
                 list(ex.map(self._plane, range(frames)))
             if "hamming_match" in st and "orb" in st:
                 list(ex.map(self._match, range(frames - 1)))
+            if "search_by_projection" in st and "orb" in st:
+                if self.parts["search_by_projection"].startswith("reference"):
+                    with self.ob.reference_matcher():
+                        list(ex.map(self._track, range(frames - 1)))
+                else:
+                    list(ex.map(self._track, range(frames - 1)))
         if "surfel_fuse" in st:
             for i in range(frames):
                 if self.rs is not None:
@@ -515,6 +574,9 @@ def kernel_alg_bytes(W, H, B, n_map, upd, killed, kp_rows):
         "k_blur": B * 2.0 * pyr,
         "k_describe": B * (kp_rows * (749 + 31 * 31) + kp_rows * 60.0),
         "k_hamming_best2": (B - 1) * (2 * kp_rows * 32.0 + kp_rows * 12.0),
+        "k_keypoint_glue": B * kp_rows * (28.0 + 4.0 + 16.0),
+        "k_track_last": B * kp_rows * (28.0 + 8.0 + 4.0 + 1.0 + 12.0 + 8.0),
+        "k_search_batch": (B - 1) * kp_rows * (2 * 32.0 + 13.0 + 8.0 + 12.0 + 4.0),
         "k_plane_blocks": B * (npx * 1.0 + nblk * 72.0),  # u16 depth at even rows / columns, sector-granular = W*H bytes
         "k_plane_edges": B * nblk * (72.0 + 2.0),
         "k_sp_init": B * (nseeds * (72.0 + 40.0) + nseeds * 8.0),
@@ -546,6 +608,8 @@ BOUND_NOTE = {  # what each kernel is bound by in practice
     "k_fast_cells": "integer ALU (FAST-9 segment test, ~200 ops per pixel); tiles staged by TMA, data from L2",
     "k_octree": "latency (a few thousand keys per level, sequential rounds)", "k_describe": "L2 gather + shuffle",
     "k_hamming_best2": "integer ALU (xor + popc)", "k_plane_blocks": "fp64 latency (per-block Jacobi)",
+    "k_search_batch": "latency (one CTA per frame pair: sorted grid in shared memory, fixed point of the slot blocking)",
+    "k_track_last": "latency (depth ranks by counting, one CTA per frame)",
     "k_plane_edges": "latency", "k_sp_pixels": "fp64 issue (the reference's float/double cost)", "k_sp_fix": "latency",
     "k_sp_seeds2": "shared-memory latency (sequential float sums per seed)", "k_sp_fit2": "fp64 latency (sequential sums per seed)",
     "k_resize": "L2", "k_blur": "L2", "k_load_level0": "hbm", "k_sp_norms": "hbm", "k_sp_records": "hbm",
@@ -612,13 +676,18 @@ def run_ours(a, rank, world, local_rank):
     depth16 = make_inputs.depth16
 
     do_orb, do_match, do_plane, do_surfel = "orb" in st, "hamming_match" in st and "orb" in st, "plane_prestage" in st, "surfel_fuse" in st
+    do_track = "search_by_projection" in st and "orb" in st
     orb = msl.ORBextractor(width=W, height=H, max_batch=B, device=local_rank) if do_orb else None
     cap = orb.capacity if orb else 0
     sf = None
     if do_surfel:
         sf = msl.SurfelFusion(W, H, *K4, max_surfels=len(surfels) + 4 * B * (W // 8) * (H // 8), device=local_rank)
         sf.upload_map(surfels)
-    matcher = msl.ORBmatcher(max_queries=cap, max_train=cap, max_batch=B, device=local_rank) if do_match else None
+    matcher = msl.ORBmatcher(nnratio=0.9, max_queries=cap, max_train=cap, max_batch=B, device=local_rank) if (do_match or do_track) else None
+    glue = msl.FrameGlue(W, H, max_batch=B, device=local_rank) if do_track else None
+    geom = msl.frame_geom(W, H, *K4, bf=MBF)
+    th_depth = MBF * TH_DEPTH_FACTOR / K4[0]  # Tracking::mThDepth (src/Tracking.cc:130)
+    Tcw = np.stack([np.linalg.inv(p.astype(np.float64)) for p in poses]).astype(np.float32)
     plane = msl.PlaneDetection(W, H, max_batch=B, device=local_rank) if do_plane else None
     nblk = plane.nblocks if plane else 0
 
@@ -641,6 +710,12 @@ def run_ours(a, rank, world, local_rank):
     h_kps = torch.empty((B, max(cap, 1), 28), dtype=torch.uint8).pin_memory()
     h_desc = torch.empty((B, max(cap, 1), 32), dtype=torch.uint8).pin_memory()
     h_counts = torch.zeros(B, dtype=torch.int32).pin_memory()
+    d_xy = torch.zeros((B, max(cap, 1), 2), dtype=torch.float32, device=dev)
+    d_ur, d_kd = torch.zeros((B, max(cap, 1)), dtype=torch.float32, device=dev), torch.zeros((B, max(cap, 1)), dtype=torch.float32, device=dev)
+    d_cm = torch.zeros((B, max(cap, 1)), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(B, dtype=torch.int32, device=dev)
+    h_cm = torch.zeros((B, max(cap, 1)), dtype=torch.int32).pin_memory()
+    h_nm = torch.zeros(B, dtype=torch.int32).pin_memory()
     # the count table of SURVEY.md section 8(e), double-buffered so that the all-gather of step k (own stream) never holds up
     # the kernels of step k+1: per frame {keypoints, new surfels, updated surfels}
     d_kpc = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
@@ -671,6 +746,12 @@ def run_ours(a, rank, world, local_rank):
             matcher.hamming_best2_counts_dev(d_desc.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_kpc[k].data_ptr(),
                                              d_kpc[k].data_ptr() + 4, B - 1, d_bi.data_ptr(), d_bd.data_ptr(), d_sd.data_ptr(),
                                              stream=orb.stream)
+        if do_track:  # frame glue + UpdateLastFrame + SearchByProjection(frame b+1, frame b), still on the ORB stream
+            glue.keypoints_dev(d_kps.data_ptr(), cap, d_kpc[k].data_ptr(), B, K4, None, d_depth.data_ptr(), MBF, d_xy.data_ptr(),
+                               d_ur.data_ptr(), d_kd.data_ptr(), stream=orb.stream)
+            matcher.SearchByProjectionFrames_dev(geom, TH_PROJ, th_depth, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_kpc[k].data_ptr(),
+                                                 B, d_xy.data_ptr(), d_ur.data_ptr(), d_kd.data_ptr(), Tcw, d_cm.data_ptr(),
+                                                 d_nm.data_ptr(), stream=orb.stream)
         if do_plane:
             plane.prestage_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, None, d_blocks.data_ptr(), d_seedm.data_ptr(),
                                d_edges.data_ptr())
@@ -873,6 +954,12 @@ def run_ours(a, rank, world, local_rank):
                                                C.c_void_p(h_desc.data_ptr() + cap * 32), C.c_int(cap), C.c_int(B - 1),
                                                C.c_void_p(h_match[0].data_ptr()), C.c_void_p(h_match[1].data_ptr()),
                                                C.c_void_p(h_match[2].data_ptr())))
+        if do_track:
+            check(matcher._L.msl_search_by_projection_frames(
+                matcher._h, glue._h, ptr(geom), C.c_float(TH_PROJ), 1, C.c_float(th_depth), C.c_void_p(h_kps.data_ptr()),
+                C.c_void_p(h_desc.data_ptr()), C.c_int(cap), C.c_void_p(h_counts.data_ptr()), C.c_int(B),
+                C.c_void_p(h_depth.data_ptr()), C.c_int(W), C.c_int(H), ptr(Tcw), C.c_void_p(h_cm.data_ptr()),
+                C.c_void_p(h_nm.data_ptr())))
 
     def e2e_plane():
         torch.cuda.set_device(local_rank)
@@ -920,6 +1007,9 @@ def run_ours(a, rank, world, local_rank):
     if do_match:
         h2d += 2 * (B - 1) * cap * 32
         d2h += 3 * (B - 1) * cap * 4
+    if do_track:
+        h2d += B * cap * (28 + 32) + B * 4 + h_depth.numel() * 4 + B * 64
+        d2h += (B - 1) * cap * 4 + (B - 1) * 4
     if do_plane:
         h2d += h_d16.numel() * 2
         d2h += h_blocks.numel() + 2 * B * nblk

@@ -107,6 +107,7 @@ typedef struct {
 } msl_frame_geom;
 
 typedef struct msl_matcher msl_matcher;
+typedef struct msl_glue msl_glue; /* frame glue handle, declared below */
 
 /* max_queries / max_train / max_batch size the Hamming batch buffers and the INITIAL scratch of the searches.  The scratch
  * grows with the call: the reference hands SearchByProjection the whole of mvpLocalMapPoints (src/Tracking.cc:1693) and Fuse
@@ -152,6 +153,28 @@ int msl_search_by_projection_frame(msl_matcher *, const msl_frame_geom *geom, co
                                    const int32_t *cur_octave, const float *cur_angle, const float *cur_uright,
                                    const uint8_t *cur_desc, const uint8_t *cur_occupied, int32_t *cur_match,
                                    int32_t *nmatches);
+
+/* The same search for a BATCH of consecutive frames straight from device-resident extractor / glue output (no host round
+ * trip): pair p has Last = frame p and Current = frame p + 1, p < n_frames - 1.  The Last side is built on the device as
+ * Tracking::TrackWithMotionModel finds it after Tracking::UpdateLastFrame (src/Tracking.cc:1052-1104): every keypoint with
+ * depth > 0 in (depth, index) order up to th_depth (Tracking::mThDepth), at least the 100 closest, carries a MapPoint at
+ * Frame::UnprojectStereo (src/Frame.cc:515-526) with no observations; no slot of the Current frame is occupied.
+ * d_kps / d_desc / d_counts: msl_orb_extract_dev's output (`rows` rows per frame, rows <= 4096); d_xy_un / d_uright /
+ * d_kdepth: msl_glue_keypoints_dev's output; Tcw: n_frames x 16 floats on the host (pose of every frame).
+ * d_cur_match: (n_frames - 1) x rows int32, row p = cur_match of pair p as above; d_nmatches: n_frames - 1 int32.
+ * Asynchronous on `stream` (NULL = the handle's stream). */
+int msl_search_by_projection_frames_dev(msl_matcher *, const msl_frame_geom *geom, float th, int check_orientation, float th_depth,
+                                        const msl_keypoint *d_kps, const uint8_t *d_desc, int rows, const int32_t *d_counts,
+                                        int n_frames, const float *d_xy_un, const float *d_uright, const float *d_kdepth,
+                                        const float *Tcw, int32_t *d_cur_match, int32_t *d_nmatches, void *stream);
+
+/* Host form: extractor output (kps / desc / counts, `rows` rows per frame), the CV_32F depth frames (dense w x h) and the poses
+ * in host memory; uploads, runs msl_glue_keypoints_dev (undistortion-free camera) + the search, downloads cur_match
+ * ((n_frames - 1) x rows) and nmatches.  `glue`: any glue handle of this frame size (supplies the kernels). */
+int msl_search_by_projection_frames(msl_matcher *, msl_glue *glue, const msl_frame_geom *geom, float th, int check_orientation,
+                                    float th_depth, const msl_keypoint *kps, const uint8_t *desc, int rows, const int32_t *counts,
+                                    int n_frames, const float *depth, int w, int h, const float *Tcw, int32_t *cur_match,
+                                    int32_t *nmatches);
 
 /* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &, th) (src/ORBmatcher.cc:40-117).
  * Per map point k: mp_valid (mbTrackInView && !isBad()), mp_obs (Observations()>0), mp_proj_xyr
@@ -237,8 +260,6 @@ int msl_distinctive_descriptors(msl_matcher *, int n_points, const int32_t *offs
  * The per-frame steps either side of the ORB extractor, so that a frame can stay on the device from decode to the
  * feature grid: Tracking::GrabImage's cvtColor and depth conversion (src/Tracking.cc:184-211),
  * Frame::UndistortKeyPoints (src/Frame.cc:437-463) and Frame::ComputeStereoFromRGBD (src/Frame.cc:495-513). */
-
-typedef struct msl_glue msl_glue;
 
 int msl_glue_create(int w, int h, int max_batch, int device, msl_glue **out);
 void msl_glue_destroy(msl_glue *);

@@ -149,7 +149,7 @@ __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int n2) {  // n2 =
         }
 }
 
-__global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
+__device__ void search_body(const SearchArgs &A) {
     __shared__ uint32_t keys[MAXK];          // (cell << 12 | index), sorted; 0xffffffff = not in grid
     __shared__ unsigned short cellStart[NCELLS + 1];
     __shared__ int blockedAt[MAXK];           // first query index holding the slot (INF = free)
@@ -369,6 +369,99 @@ __global__ void __launch_bounds__(1024) k_search(SearchArgs A) {
     }
     __syncthreads();
     if (tid == 0) *A.nmatches = s_n;
+}
+
+__global__ void __launch_bounds__(1024) k_search(SearchArgs A) { search_body(A); }
+
+// ---- SearchByProjection(CurrentFrame, LastFrame, th) for a BATCH of consecutive frame pairs straight from the device-resident
+// output of the extractor and the frame glue (pair p: Last = frame p, Current = frame p + 1).
+// k_track_last is the Last-frame side of Tracking::TrackWithMotionModel: Tracking::UpdateLastFrame (src/Tracking.cc:1052-1104)
+// gives the RGB-D keypoints of the last frame "visual odometry" MapPoints -- sorted by depth, all with z <= mThDepth, at
+// least the 100 closest -- at Frame::UnprojectStereo (src/Frame.cc:515-526), x3Dw = mRwc * x3Dc + mOw as cv::Mat
+// arithmetic (gemm_row).  Such points have no observations, so they never block a slot (q_obs = 0), and a fresh current
+// frame has no occupied slot.
+struct TrackPose {      // per frame: Rwc (= Rcw^T), Ow, and for the pair whose CURRENT frame this is: Rcw, tcw, direction flags
+    float Rwc[9], Ow[3], Rcw[9], tcw[3];
+    int bForward, bBackward;
+};
+
+__global__ void __launch_bounds__(256)
+    k_track_last(const msl_keypoint *__restrict__ kps, int rows, const int32_t *__restrict__ counts, const float *__restrict__ xyUn,
+                 const float *__restrict__ kdepth, const TrackPose *__restrict__ poses, float cx, float cy, float invfx, float invfy,
+                 float thDepth, uint8_t *__restrict__ valid, float *__restrict__ world, int32_t *__restrict__ octave,
+                 float *__restrict__ angle) {
+    __shared__ float sz[MAXK];
+    __shared__ int s_cut;
+    const int f = blockIdx.x, tid = threadIdx.x, n = min(counts[f], min(rows, MAXK));
+    const size_t o = (size_t)f * rows;
+    for (int i = tid; i < n; i += blockDim.x) sz[i] = kdepth[o + i];
+    if (tid == 0) s_cut = 0x7fffffff;
+    __syncthreads();
+    // rank of every keypoint with z > 0 in std::sort order of (z, index) pairs (:1064-1073)
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float z = sz[i];
+        int rank = -1;
+        if (z > 0) {
+            rank = 0;
+            for (int j = 0; j < n; j++) {
+                const float zj = sz[j];
+                rank += (zj > 0) && (zj < z || (zj == z && j < i));
+            }
+            // the loop over the sorted list stops after the first point with z > mThDepth once more than 100 were taken (:1102)
+            if (z > thDepth && rank + 1 > 100) atomicMin(&s_cut, rank);
+        }
+        octave[o + i] = kps[o + i].octave;
+        angle[o + i] = kps[o + i].angle;
+        world[3 * (o + i)] = __int_as_float(rank);  // parked until the cut is known
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    const TrackPose &T = poses[f];
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int rank = __float_as_int(world[3 * (o + i)]);
+        const bool sel = rank >= 0 && rank <= cut;
+        valid[o + i] = sel ? 1 : 0;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (sel) {
+            const float z = sz[i], u = xyUn[2 * (o + i)], v = xyUn[2 * (o + i) + 1];
+            const float x3[3] = {(u - cx) * z * invfx, (v - cy) * z * invfy, z};
+            w0 = gemm_row(T.Rwc, x3, T.Ow[0]), w1 = gemm_row(T.Rwc + 3, x3, T.Ow[1]), w2 = gemm_row(T.Rwc + 6, x3, T.Ow[2]);
+        }
+        world[3 * (o + i)] = w0, world[3 * (o + i) + 1] = w1, world[3 * (o + i) + 2] = w2;
+    }
+}
+
+struct SearchBatch {
+    msl_frame_geom g;
+    float th;
+    int checkOri, rows;
+    const int32_t *counts;
+    const TrackPose *poses;
+    const uint8_t *valid, *zeros, *desc;
+    const float *world, *xyUn, *angle, *uright;
+    const int32_t *octave;
+    int32_t *match, *nmatches, *assign, *bin;
+};
+
+__global__ void __launch_bounds__(1024) k_search_batch(SearchBatch Bt) {
+    __shared__ SearchArgs A;
+    const int pr = blockIdx.x;  // Last = frame pr, Current = frame pr + 1
+    if (threadIdx.x == 0) {
+        const size_t l = (size_t)pr * Bt.rows, c = l + Bt.rows;
+        const TrackPose &T = Bt.poses[pr + 1];
+        A.g = Bt.g, A.mode = 0, A.th = Bt.th, A.nnratio = 0, A.checkOri = Bt.checkOri, A.distTh = TH_HIGH;
+        for (int k = 0; k < 9; k++) A.Rcw[k] = T.Rcw[k];
+        for (int k = 0; k < 3; k++) A.tcw[k] = T.tcw[k], A.Ow[k] = 0.f;
+        A.logScale = 0.f, A.bForward = T.bForward, A.bBackward = T.bBackward;
+        A.nq = min(Bt.counts[pr], min(Bt.rows, MAXK)), A.nc = min(Bt.counts[pr + 1], min(Bt.rows, MAXK));
+        A.q_valid = Bt.valid + l, A.q_obs = Bt.zeros, A.q_desc = Bt.desc + 32 * l, A.q_f3 = Bt.world + 3 * l, A.q_f2 = nullptr;
+        A.q_level = Bt.octave + l, A.q_aux = Bt.angle + l;
+        A.c_xy = Bt.xyUn + 2 * c, A.c_angle = Bt.angle + c, A.c_uright = Bt.uright + c, A.c_octave = Bt.octave + c;
+        A.c_desc = Bt.desc + 32 * c, A.c_occ = Bt.zeros;
+        A.c_match = Bt.match + l, A.nmatches = Bt.nmatches + pr, A.assign = Bt.assign + l, A.bin = Bt.bin + l;
+    }
+    __syncthreads();
+    search_body(A);
 }
 
 // ------------------------------------------------------------- vocabulary-node searches (SearchByBoW, SearchForTriangulation)
@@ -697,12 +790,14 @@ struct msl_matcher {
     size_t scrCap = 0;
     uint8_t *d_dd = nullptr;   // msl_distinctive_descriptors: offsets | descriptors | outputs (grown on demand)
     size_t ddCap = 0;
+    uint8_t *d_trk = nullptr;  // msl_search_by_projection_frames_dev: per-frame scratch (grown on demand)
+    size_t trkCap = 0;
 };
 
 static void matcher_free(msl_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr, m->d_dd};
+    void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr, m->d_dd, m->d_trk};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -918,6 +1013,112 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
     A.bin = ar.get<int32_t>(n_last);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_frame: scratch arena / copy failure");
     return run_search(m, A, cur_match, nmatches);
+}
+
+int msl_search_by_projection_frames_dev(msl_matcher *m, const msl_frame_geom *geom, float th, int check_orientation, float th_depth,
+                                        const msl_keypoint *d_kps, const uint8_t *d_desc, int rows, const int32_t *d_counts,
+                                        int n_frames, const float *d_xy_un, const float *d_uright, const float *d_kdepth,
+                                        const float *Tcw, int32_t *d_cur_match, int32_t *d_nmatches, void *stream) {
+    if (!m || !geom || !d_kps || !d_desc || !d_counts || !d_xy_un || !d_uright || !d_kdepth || !Tcw || !d_cur_match || !d_nmatches)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_frames_dev: null argument");
+    if (n_frames < 2 || rows < 1 || rows > MAXK) return fail(MSL_ERR_INVALID, "msl_search_by_projection_frames_dev: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    const size_t F = (size_t)n_frames, R = (size_t)rows;
+    // scratch: poses | valid | zeros | world | octave | angle | assign | bin
+    const size_t oPose = 0, oValid = align_up(oPose + F * sizeof(TrackPose), 256), oZero = align_up(oValid + F * R, 256),
+                 oWorld = align_up(oZero + R, 256), oOct = align_up(oWorld + F * R * 12, 256), oAng = align_up(oOct + F * R * 4, 256),
+                 oAsg = align_up(oAng + F * R * 4, 256), oBin = align_up(oAsg + F * R * 4, 256), total = oBin + F * R * 4;
+    if (total > m->trkCap) {
+        MSL_CUDA(cudaStreamSynchronize(st));
+        if (m->d_trk) cudaFree(m->d_trk);
+        m->d_trk = nullptr, m->trkCap = 0;
+        MSL_CUDA(cudaMalloc((void **)&m->d_trk, total));
+        m->trkCap = total;
+    }
+    // per-frame pose blocks as the reference forms them: Rwc = Rcw.t(), Ow = -Rcw.t() * tcw (transposed operand: cv::gemm's
+    // general path, double accumulation, one rounding; src/Frame.cc:305-311); per pair tlc = Rlw * twc + tlw (:554-568)
+    std::vector<TrackPose> tp(F);
+    for (size_t f = 0; f < F; f++) {
+        const float *T = Tcw + 16 * f;
+        TrackPose &P = tp[f];
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) P.Rcw[r * 3 + c] = T[r * 4 + c], P.Rwc[c * 3 + r] = T[r * 4 + c];
+            P.tcw[r] = T[r * 4 + 3];
+        }
+        for (int r = 0; r < 3; r++) {
+            double sum = 0;
+            for (int k = 0; k < 3; k++) sum += (double)(-P.Rcw[k * 3 + r]) * (double)P.tcw[k];
+            P.Ow[r] = (float)sum;
+        }
+        P.bForward = P.bBackward = 0;
+        if (f > 0) {  // this frame is the Current frame of pair f - 1
+            const float *Tl = Tcw + 16 * (f - 1);
+            const float Rlw2[3] = {Tl[8], Tl[9], Tl[10]};
+            const float tlc2 = gemm_row(Rlw2, P.Ow, Tl[11]);
+            P.bForward = tlc2 > geom->mb, P.bBackward = -tlc2 > geom->mb;
+        }
+    }
+    MSL_CUDA(cudaMemcpyAsync(m->d_trk + oPose, tp.data(), F * sizeof(TrackPose), cudaMemcpyHostToDevice, st));
+    MSL_CUDA(cudaMemsetAsync(m->d_trk + oZero, 0, R, st));
+    uint8_t *valid = m->d_trk + oValid;
+    float *world = (float *)(m->d_trk + oWorld), *angle = (float *)(m->d_trk + oAng);
+    int32_t *octave = (int32_t *)(m->d_trk + oOct);
+    const float invfx = 1.0f / geom->fx, invfy = 1.0f / geom->fy;  // Frame::invfx / invfy (src/Frame.cc:123-124)
+    k_track_last<<<n_frames, 256, 0, st>>>(d_kps, rows, d_counts, d_xy_un, d_kdepth, (const TrackPose *)(m->d_trk + oPose), geom->cx,
+                                           geom->cy, invfx, invfy, th_depth, valid, world, octave, angle);
+    MSL_LAUNCH_CHECK();
+    SearchBatch Bt;
+    Bt.g = *geom, Bt.th = th, Bt.checkOri = check_orientation, Bt.rows = rows, Bt.counts = d_counts;
+    Bt.poses = (const TrackPose *)(m->d_trk + oPose), Bt.valid = valid, Bt.zeros = m->d_trk + oZero, Bt.desc = d_desc;
+    Bt.world = world, Bt.xyUn = d_xy_un, Bt.angle = angle, Bt.uright = d_uright, Bt.octave = octave;
+    Bt.match = d_cur_match, Bt.nmatches = d_nmatches, Bt.assign = (int32_t *)(m->d_trk + oAsg), Bt.bin = (int32_t *)(m->d_trk + oBin);
+    k_search_batch<<<n_frames - 1, 1024, 0, st>>>(Bt);
+    MSL_LAUNCH_CHECK();
+    return MSL_OK;
+}
+
+// Host form of the batched search: extractor output, depth frames and poses in host memory.  Uploads them, runs the frame
+// glue (Frame::ComputeStereoFromRGBD, undistortion-free camera: mvKeysUn = mvKeys), the Last-frame side and the search on
+// the matcher's stream, downloads the match tables.  `glue` supplies the glue kernels (any handle created for this frame size).
+int msl_search_by_projection_frames(msl_matcher *m, msl_glue *glue, const msl_frame_geom *geom, float th, int check_orientation,
+                                    float th_depth, const msl_keypoint *kps, const uint8_t *desc, int rows, const int32_t *counts,
+                                    int n_frames, const float *depth, int w, int h, const float *Tcw, int32_t *cur_match,
+                                    int32_t *nmatches) {
+    if (!m || !glue || !geom || !kps || !desc || !counts || !depth || !Tcw || !cur_match || !nmatches)
+        return fail(MSL_ERR_INVALID, "msl_search_by_projection_frames: null argument");
+    if (n_frames < 2 || rows < 1 || rows > MAXK || w < 1 || h < 1) return fail(MSL_ERR_INVALID, "msl_search_by_projection_frames: bad size");
+    MSL_CUDA(cudaSetDevice(m->device));
+    const size_t F = (size_t)n_frames, R = (size_t)rows, npx = (size_t)w * h;
+    const size_t oK = 0, oD = align_up(oK + F * R * sizeof(msl_keypoint), 256), oC = align_up(oD + F * R * 32, 256),
+                 oZ = align_up(oC + F * 4, 256), oXY = align_up(oZ + F * npx * 4, 256), oUR = align_up(oXY + F * R * 8, 256),
+                 oKD = align_up(oUR + F * R * 4, 256), oCM = align_up(oKD + F * R * 4, 256), oNM = align_up(oCM + F * R * 4, 256),
+                 total = oNM + F * 4;
+    if (total > m->ddCap) {  // (shares the grow-on-demand staging buffer of msl_distinctive_descriptors)
+        MSL_CUDA(cudaStreamSynchronize(m->stream));
+        if (m->d_dd) cudaFree(m->d_dd);
+        m->d_dd = nullptr, m->ddCap = 0;
+        MSL_CUDA(cudaMalloc((void **)&m->d_dd, total));
+        m->ddCap = total;
+    }
+    uint8_t *b = m->d_dd;
+    cudaStream_t st = m->stream;
+    MSL_CUDA(cudaMemcpyAsync(b + oK, kps, F * R * sizeof(msl_keypoint), cudaMemcpyHostToDevice, st));
+    MSL_CUDA(cudaMemcpyAsync(b + oD, desc, F * R * 32, cudaMemcpyHostToDevice, st));
+    MSL_CUDA(cudaMemcpyAsync(b + oC, counts, F * 4, cudaMemcpyHostToDevice, st));
+    MSL_CUDA(cudaMemcpyAsync(b + oZ, depth, F * npx * 4, cudaMemcpyHostToDevice, st));
+    const float K4[4] = {geom->fx, geom->fy, geom->cx, geom->cy};
+    int rc = msl_glue_keypoints_dev(glue, (const msl_keypoint *)(b + oK), rows, (const int32_t *)(b + oC), n_frames, K4, nullptr,
+                                    (const float *)(b + oZ), geom->mbf, (float *)(b + oXY), (float *)(b + oUR), (float *)(b + oKD), st);
+    if (rc) return rc;
+    rc = msl_search_by_projection_frames_dev(m, geom, th, check_orientation, th_depth, (const msl_keypoint *)(b + oK), b + oD, rows,
+                                             (const int32_t *)(b + oC), n_frames, (const float *)(b + oXY), (const float *)(b + oUR),
+                                             (const float *)(b + oKD), Tcw, (int32_t *)(b + oCM), (int32_t *)(b + oNM), st);
+    if (rc) return rc;
+    MSL_CUDA(cudaMemcpyAsync(cur_match, b + oCM, (F - 1) * R * 4, cudaMemcpyDeviceToHost, st));
+    MSL_CUDA(cudaMemcpyAsync(nmatches, b + oNM, (F - 1) * 4, cudaMemcpyDeviceToHost, st));
+    MSL_CUDA(cudaStreamSynchronize(st));
+    return MSL_OK;
 }
 
 int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, float th, float nnratio, int n_mp,

@@ -56,3 +56,16 @@ class FrameGlue:
         check(self._L.msl_glue_keypoints(self._h, ptr(kps), C.c_int(n), ptr(K4), ptr(D5), ptr(dep), C.c_float(mbf), ptr(xy),
                                          ptr(ur), ptr(kd)))
         return xy, ur, kd
+
+    def keypoints_dev(self, d_kps, rows, d_counts, batch, K4, D5, d_depth, mbf, d_xy_un, d_uright, d_kdepth, stream=None):
+        """batched device form on msl_orb_extract_dev's ragged output (msl_glue_keypoints_dev)"""
+        K4 = np.ascontiguousarray(K4, np.float32)
+        D5 = None if D5 is None else np.ascontiguousarray(D5, np.float32)
+        check(self._L.msl_glue_keypoints_dev(self._h, ptr(d_kps), C.c_int(rows), ptr(d_counts), C.c_int(batch), ptr(K4), ptr(D5),
+                                             ptr(d_depth), C.c_float(mbf), ptr(d_xy_un), ptr(d_uright), ptr(d_kdepth),
+                                             C.c_void_p(stream or 0)))
+
+    @property
+    def stream(self):
+        return self._L.msl_glue_stream(self._h)
+

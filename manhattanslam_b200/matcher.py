@@ -96,6 +96,17 @@ class ORBmatcher:
             C.byref(nm)))
         return nm.value, cm
 
+    def SearchByProjectionFrames_dev(self, geom, th, th_depth, d_kps, d_desc, rows, d_counts, n_frames, d_xy_un, d_uright, d_kdepth,
+                                     Tcw, d_cur_match, d_nmatches, stream=None):
+        """SearchByProjection(Cur, Last, th) for the n_frames - 1 consecutive pairs of a device-resident batch
+        (msl_search_by_projection_frames_dev): Tracking::UpdateLastFrame + Frame::UnprojectStereo on the device."""
+        Tcw = np.ascontiguousarray(Tcw, np.float32)
+        assert Tcw.shape == (n_frames, 4, 4) or Tcw.shape == (n_frames, 16)
+        check(self._L.msl_search_by_projection_frames_dev(
+            self._h, ptr(geom), C.c_float(th), int(self.mbCheckOrientation), C.c_float(th_depth), ptr(d_kps), ptr(d_desc),
+            C.c_int(rows), ptr(d_counts), C.c_int(n_frames), ptr(d_xy_un), ptr(d_uright), ptr(d_kdepth), ptr(Tcw),
+            ptr(d_cur_match), ptr(d_nmatches), C.c_void_p(stream or 0)))
+
     def SearchByProjectionPoints(self, geom, th, mps, cur):
         """SearchByProjection(Frame &F, const vector<MapPoint*> &, th).  Returns (nmatches, cur_match)."""
         n_mp, n_cur = len(mps["level"]), len(cur["octave"])

@@ -633,8 +633,13 @@ class _RefMatchProxy:
         self._L, self._prefix = L, prefix
 
     def __getattr__(self, name):
-        if not name.startswith("orc_search_"):
-            raise AttributeError(name)
+        if not name.startswith("orc_search_"):  # everything but the searches stays with the oracle library
+            global _LIB_OVERRIDE
+            saved, _LIB_OVERRIDE = _LIB_OVERRIDE, None
+            try:
+                return getattr(lib(), name)
+            finally:
+                _LIB_OVERRIDE = saved
         return getattr(self._L, self._prefix + name[4:])
 
 

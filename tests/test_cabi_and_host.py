@@ -151,7 +151,7 @@ def test_bench_reference_arm_contract():
     assert (j["cpu_baseline"]["kind"] == "reference") == os.path.exists(os.path.join(root, "oracle", "_ref", "libsurfel_ref_threads.so"))
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["config"]["workload"] == "frontend_640x480_b64_map5M_DIAGNOSTIC" and j["config"]["batch_per_gpu"] == 4
-    assert j["config"]["surfels_per_gpu"] == 60000 and j["config"]["stages"] == ["orb", "hamming_match", "plane_prestage", "surfel_fuse"]
+    assert j["config"]["surfels_per_gpu"] == 60000 and j["config"]["stages"] == ["orb", "hamming_match", "search_by_projection", "plane_prestage", "surfel_fuse"]
     # both arms print the same `config` dict (the driver compares them): it is built by one function from the arguments alone
     import bench
     sys_argv = sys.argv

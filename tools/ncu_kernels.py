@@ -45,6 +45,20 @@ def main():
     geom = msl.frame_geom()
     cur, last, mps, Tc, Tl = S.match_scene(1)
     m.SearchByProjectionFrame(geom, Tc, Tl, 7.0, last, cur)
+    # the batched SearchByProjection(frame b+1, frame b): frame glue, UpdateLastFrame on the device, k_search_batch
+    glue = msl.FrameGlue(W, H, max_batch=B)
+    d_xy = torch.zeros((B, cap, 2), dtype=torch.float32, device=dev)
+    d_ur, d_kd = torch.zeros((B, cap), dtype=torch.float32, device=dev), torch.zeros((B, cap), dtype=torch.float32, device=dev)
+    d_cm, d_nm = torch.zeros((B, cap), dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+    K4 = (525.0, 525.0, 319.5, 239.5)
+    glue.keypoints_dev(d_kps.data_ptr(), cap, d_counts.data_ptr(), B, K4, None, d_depth.data_ptr(), 40.0, d_xy.data_ptr(),
+                       d_ur.data_ptr(), d_kd.data_ptr())
+    torch.cuda.synchronize()
+    Tcw = np.stack([np.linalg.inv(p.astype(np.float64)) for p in poses]).astype(np.float32)
+    m.SearchByProjectionFrames_dev(msl.frame_geom(W, H, *K4, bf=40.0), 15.0, 3.05, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                   d_counts.data_ptr(), B, d_xy.data_ptr(), d_ur.data_ptr(), d_kd.data_ptr(), Tcw, d_cm.data_ptr(),
+                                   d_nm.data_ptr())
+    torch.cuda.synchronize()
     pl = msl.PlaneDetection(W, H, max_batch=B)
     nblk = pl.nblocks
     d_blocks = torch.zeros((B, nblk, 72), dtype=torch.uint8, device=dev)
