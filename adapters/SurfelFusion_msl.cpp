@@ -1,11 +1,13 @@
 // SurfelFusion_msl.cpp -- SurfelFusion on the B200 front-end (drop-in for src/SurfelFusion.cpp).
 // SurfelMapping::fuseMap (src/SurfelMapping.cpp:353-364) is unchanged.  This is the exact drop-in: the host
 // vector Map::mvLocalSurfels stays authoritative, so every call uploads it, fuses on the device and downloads it
-// again (one PCIe round trip of 56 B/surfel per keyframe).  INTEGRATION.md describes the device-resident mode
+// again -- the upload whole (the host mutates the vector between calls: the fuseMap tail, moveAddSurfels), the download only for
+// the surfels the call changed (msl_surfel_download_changed: ~30 % of the map).  INTEGRATION.md describes the device-resident mode
 // (compaction and SurfelMapping::moveAddSurfels on the device, no round trip): adapters/SurfelMapping_msl.cpp.
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
+#include <vector>
 
 #include "SurfelFusion.h"
 #include "msl_frontend.h"
@@ -53,7 +55,15 @@ void SurfelFusion::fuseInitializeMap(const int referenceFrameIndex, const cv::Ma
                         (int)newSurfels.size(), /*compact=*/0, stats) != MSL_OK)
         throw std::runtime_error(msl_last_error());
     newSurfels.resize((size_t)stats[0]);
+    // dirty download: only the surfels this call updated (lastUpdate == referenceFrameIndex) or deleted (updateTimes == 0)
+    // differ from what was uploaded -- about 30 % of the map (msl_surfel_download_changed); patched into the host vector
+    static thread_local std::vector<int32_t> idx;
+    static thread_local std::vector<msl_surfel> rec;
+    if (idx.size() < localSurfels.size()) idx.resize(localSurfels.size()), rec.resize(localSurfels.size());
     int64_t n = 0;
-    if (msl_surfel_download_map(h, reinterpret_cast<msl_surfel *>(localSurfels.data()), (int64_t)localSurfels.size(), &n) != MSL_OK)
+    if (msl_surfel_download_changed(h, referenceFrameIndex, idx.data(), rec.data(), (int64_t)idx.size(), &n) != MSL_OK)
         throw std::runtime_error(msl_last_error());
+    Surfel *dst = localSurfels.data();
+    const Surfel *src = reinterpret_cast<const Surfel *>(rec.data());
+    for (int64_t k = 0; k < n; k++) dst[idx[k]] = src[k];
 }

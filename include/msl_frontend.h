@@ -346,9 +346,10 @@ int msl_plane_detect_dev(msl_plane *, const uint16_t *d_depth, int dstride_px, s
                          const float K[4], float depth_map_factor, int32_t *d_membership, int32_t *d_plane_count,
                          msl_plane_rec *d_planes, int plane_cap);
 
-/* Measurement aid: globaltimer stamps (ns) of the phases of every frame of the last msl_plane_detect* call: out[8 f + k],
- * k = 0 start, 1 graph built, 2 ahCluster done, 3 block membership + region-grow seeds, 4 region grow done, 5 final merge
- * done, 6 end; out[8 f + 7] = merge steps taken. */
+/* Measurement aid: 16 values per frame of the last msl_plane_detect* call: out[16 f + k], k = 0..6 globaltimer stamps (ns) --
+ * start, graph built, ahCluster done, block membership + region-grow seeds, region grow done, final merge done, end;
+ * k = 7 merge steps taken; k = 8..13 SM cycles of ahCluster's sub-phases summed over its steps (queue pop, candidate fits,
+ * selection, publish + decision, adjacency update, node copy + queue push). */
 int msl_plane_debug_profile(msl_plane *, int64_t *out, int frames);
 
 /* ------------------------------------------------------------------------------------- surfels
@@ -392,6 +393,11 @@ void msl_surfel_destroy(msl_surfel_fusion *);
 int msl_surfel_upload_map(msl_surfel_fusion *, const msl_surfel *local, int64_t n);
 int msl_surfel_download_map(msl_surfel_fusion *, msl_surfel *local, int64_t cap, int64_t *n);
 int64_t msl_surfel_map_size(const msl_surfel_fusion *);
+/* Dirty download for the exact drop-in (adapters/SurfelFusion_msl.cpp, host vector authoritative): the surfels the last
+ * NON-compacting msl_surfel_fuse call with reference index `ref` changed -- updated (lastUpdate == ref,
+ * src/SurfelFusion.cpp:275) or deleted (updateTimes == 0, :182 / :210 / :237) -- as (index, record) pairs in ascending index
+ * order.  idx / rec NULL: only *n.  About 30 % of the map instead of all of it over PCIe per keyframe. */
+int msl_surfel_download_changed(msl_surfel_fusion *, int ref, int32_t *idx, msl_surfel *rec, int64_t cap, int64_t *n);
 
 /* SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304) on the device-resident maps.  poses_to_remove /
  * poses_to_add are what SurfelMapping::getAddRemovePoses (:306-326) returned (that walk over the pose graph stays on

@@ -59,7 +59,9 @@
             (F).prof[i] = (long long)t_;              \
         }                                             \
     } while (0)
+#define PEAC_CLOCK() clock64()
 #elif defined(PEAC_HOST_EMULATION_MT)  // tests/host_emul/peac_host_mt.cpp: real threads + a barrier, under ThreadSanitizer
+#define PEAC_CLOCK() 0LL
 void peac_emu_sync();
 #define PEAC_HD inline
 #define PEAC_D inline
@@ -89,6 +91,7 @@ inline void peac_emu_atomic_min(int *p, int v) {
 #define PEAC_STORE_FLAG(p) (*(p) = 1)
 #define PEAC_UNROLL
 #define PEAC_STAMP(F, i, tid) ((void)0)
+#define PEAC_CLOCK() 0LL
 #endif
 
 namespace peac {
@@ -157,7 +160,7 @@ struct Flood {
     float *visDist;   // visCap
     uint8_t *visFlag; // visCap: bit0 near, bit1 pending, bit2 pushes
     int visCap;
-    long long *prof;  // optional: 8 globaltimer stamps of the frame's phases (msl_plane_debug_profile), else null
+    long long *prof;  // optional: 8 globaltimer stamps of the frame's phases + 8 cycle counters of ahCluster's sub-phases (msl_plane_debug_profile), else null
 };
 
 enum { PEAC_OK = 0, PEAC_ERR_QUEUE = 1, PEAC_ERR_PLANES = 2 };
@@ -437,8 +440,19 @@ PEAC_HD bool sort_planes(SH &S) {
 }
 
 // ---- ahCluster, AHCPlaneFitter.hpp:939-1143.  nslots = number of block slots of the frame.
+// prof (optional, thread 0): cycles accumulated per sub-phase of a merge step -- [0] queue pop, [1] candidate fits,
+// [2] selection, [3] publish + decision, [4] adjacency update, [5] node copy + queue push
 template <class SH>
-PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
+PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long *prof = nullptr) {
+    long long tc = PEAC_CLOCK(), acc[6] = {0, 0, 0, 0, 0, 0};
+#define PEAC_LAP(i)                          \
+    do {                                     \
+        if (prof && tid == 0) {              \
+            const long long t_ = PEAC_CLOCK(); \
+            acc[i] += t_ - tc;               \
+            tc = t_;                         \
+        }                                    \
+    } while (0)
     for (;;) {
         if (tid == 0) {
             int p = -1;
@@ -451,6 +465,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             S.curP = p;
         }
         PEAC_SYNC();
+        PEAC_LAP(0);
         const int p = S.curP;
         if (p < 0) break;
         // candidate merges with every neighbour, in parallel; every thread keeps the best of its own slots
@@ -471,6 +486,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
         }
         if (mine >= 0) S.red[PEAC_ATOMIC_ADD(&S.nCand, 1)] = (int16_t)mine;
         PEAC_SYNC();
+        PEAC_LAP(1);
         if (tid == 0) {
             // :1064-1072 in neighbour order (creation sequence): the first minimum wins; on an exact tie the reference
             // replaces the candidate iff cand->N < merge->mse
@@ -500,6 +516,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             S.curNb = best;
         }
         PEAC_SYNC();
+        PEAC_LAP(2);
         {   // the thread that evaluated the winning neighbour already holds the merged node (a second fit would repeat the
             // same arithmetic): it publishes it and takes the merge decision; without a candidate thread 0 decides
             const int best = S.curNb;
@@ -525,6 +542,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             }
         }
         PEAC_SYNC();
+        PEAC_LAP(3);
         if (S.decision) {
             const int nb = S.curNb;
             for (int w = tid; w < SH::WORDS; w += nt) {  // union of the two neighbour sets without the two nodes themselves
@@ -549,6 +567,7 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
                 }
             }
             PEAC_SYNC();
+            PEAC_LAP(4);
             if (tid == 0) {
                 S.node[nb].nouse = 1;
                 S.tmp.seq = S.seqNext++;
@@ -567,9 +586,13 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt) {
             if (tid == 0) S.step++;
         }
         PEAC_SYNC();
+        PEAC_LAP(5);
     }
     if (tid == 0 && !sort_planes(S)) S.error = PEAC_ERR_PLANES;  // std::sort(extractedPlanes, PlaneSegSizeCmp) :1139-1141
     PEAC_SYNC();
+    if (prof && tid == 0)
+        for (int i = 0; i < 6; i++) prof[i] += acc[i];
+#undef PEAC_LAP
 }
 
 PEAC_HD int nbs4(int i, int j, int Hh, int Ww, int out[4]) {  // getValid4Neighbor :388-400
@@ -796,7 +819,9 @@ PEAC_D void frame(SH &S, const Geo &g, const uint16_t *depth, const BlockStat *b
             if (seed[b]) heap_push(S, b);  // minQ.push in block order (:779)
     PEAC_SYNC();
     PEAC_STAMP(F, 1, tid);
-    cluster(S, g, nb, tid, nt);
+    if (F.prof && tid == 0)
+        for (int i = 8; i < 16; i++) F.prof[i] = 0;
+    cluster(S, g, nb, tid, nt, F.prof ? F.prof + 8 : nullptr);
     PEAC_STAMP(F, 2, tid);
 
     // ---- refineDetails :294-374.  findBlockMembership(isValidExtractedPlane) :480-582, ERODE_ALL_BORDER

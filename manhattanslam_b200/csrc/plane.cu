@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(MAXT)
     F.rfq = sc.rfq + (size_t)b * sc.rfqCap, F.rfqCap = sc.rfqCap;
     F.visC = sc.visC + (size_t)b * sc.visCap, F.visDist = sc.visDist + (size_t)b * sc.visCap, F.visFlag = sc.visFlag + (size_t)b * sc.visCap;
     F.visCap = sc.visCap;
-    F.prof = sc.prof ? sc.prof + 8 * (size_t)b : nullptr;
+    F.prof = sc.prof ? sc.prof + 16 * (size_t)b : nullptr;
     peac::frame(S, g, depth + b * frameStride, blocks + (size_t)b * nb, seed + (size_t)b * nb, edges + (size_t)b * nb,
                 membership + b * npix, F, planes + (size_t)b * planeCap, planeCap, planeCount + b, frameError + b, (int)threadIdx.x,
                 (int)blockDim.x);
@@ -391,7 +391,7 @@ static int plane_detect_alloc(msl_plane *p) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_ferr, B * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_planes, B * PLANE_CAP_INTERNAL * sizeof(msl_plane_rec));
     if (e == cudaSuccess) e = cudaMemset(p->d_ferr, 0, B * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_prof, B * 8 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_prof, B * 16 * sizeof(long long));
     if (e == cudaSuccess && p->Nw * p->Nh > peac::MAXB) e = cudaMalloc((void **)&p->d_big, B * sizeof(peac::SharedBig));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_peac_frame<peac::Shared, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(peac::Shared));
@@ -451,14 +451,15 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     return MSL_OK;
 }
 
-// Measurement aid: globaltimer stamps (ns) of the phases of every frame of the last detect call -- out[8 f + k], k = 0 start,
-// 1 graph built, 2 ahCluster done, 3 block membership + region-grow seeds done, 4 region grow done, 5 final merge done,
-// 6 end; out[8 f + 7] = merge steps taken.
+// Measurement aid: per frame of the last detect call 16 values -- out[16 f + k], k = 0..6 globaltimer stamps (ns): start, graph
+// built, ahCluster done, block membership + region-grow seeds done, region grow done, final merge done, end; k = 7 merge
+// steps taken; k = 8..13 SM cycles of ahCluster's sub-phases summed over its steps: queue pop, candidate fits, selection,
+// publish + decision, adjacency update, node copy + queue push.
 int msl_plane_debug_profile(msl_plane *p, int64_t *out, int frames) {
     if (!p || !out || frames < 1 || !p->d_prof || frames > p->profFrames) return fail(MSL_ERR_INVALID, "msl_plane_debug_profile: bad argument");
     MSL_CUDA(cudaSetDevice(p->device));
     MSL_CUDA(cudaStreamSynchronize(p->stream));
-    MSL_CUDA(cudaMemcpy(out, p->d_prof, sizeof(long long) * 8 * (size_t)frames, cudaMemcpyDeviceToHost));
+    MSL_CUDA(cudaMemcpy(out, p->d_prof, sizeof(long long) * 16 * (size_t)frames, cudaMemcpyDeviceToHost));
     return MSL_OK;
 }
 

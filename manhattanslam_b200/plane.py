@@ -75,8 +75,9 @@ class PlaneDetection:
                                              ptr(d_edges)))
 
     def debug_profile(self, frames):
-        """phase stamps of the last detect call (msl_plane_debug_profile): (frames, 8) int64, ns; column 7 = merge steps"""
-        out = np.zeros((frames, 8), np.int64)
+        """profile of the last detect call (msl_plane_debug_profile): (frames, 16) int64 -- columns 0..6 phase stamps in ns,
+        7 merge steps, 8..13 cycles of ahCluster's sub-phases"""
+        out = np.zeros((frames, 16), np.int64)
         check(self._L.msl_plane_debug_profile(self._h, ptr(out), C.c_int(frames)))
         return out
 

@@ -60,6 +60,15 @@ class SurfelFusion:
         check(self._L.msl_surfel_download_map(self._h, ptr(out), C.c_int64(len(out)), C.byref(n)))
         return out
 
+    def download_changed(self, ref):
+        """(indices, records) of the surfels the last non-compacting fuse call with reference index `ref` updated or deleted"""
+        n = C.c_int64()
+        check(self._L.msl_surfel_download_changed(self._h, int(ref), None, None, C.c_int64(0), C.byref(n)))
+        idx, rec = np.zeros(n.value, np.int32), np.zeros(n.value, SURFEL_DTYPE)
+        if n.value:
+            check(self._L.msl_surfel_download_changed(self._h, int(ref), ptr(idx), ptr(rec), C.c_int64(n.value), C.byref(n)))
+        return idx, rec
+
     def moveAddSurfels(self, poses_to_remove, poses_to_add):
         """SurfelMapping::moveAddSurfels (src/SurfelMapping.cpp:194-304) on the device-resident maps; the two lists
         are getAddRemovePoses' outputs.  Returns (moved_out, moved_in, local_size)."""

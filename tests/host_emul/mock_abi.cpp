@@ -132,6 +132,21 @@ int msl_surfel_download_map(msl_surfel_fusion *h, msl_surfel *local, int64_t cap
     memcpy(local, h->map.data(), sizeof(orc_surfel) * h->map.size());
     return MSL_OK;
 }
+int msl_surfel_download_changed(msl_surfel_fusion *h, int ref, int32_t *idx, msl_surfel *rec, int64_t cap, int64_t *n) {
+    int64_t c = 0;
+    for (size_t i = 0; i < h->map.size(); i++) {
+        const orc_surfel &e = h->map[i];
+        if (e.updateTimes != 0 && e.lastUpdate != ref) continue;
+        if (idx && rec) {
+            if (c >= cap) return fail(MSL_ERR_CAPACITY, "msl_surfel_download_changed: capacity");
+            idx[c] = (int32_t)i;
+            memcpy(rec + c, &e, sizeof(e));
+        }
+        c++;
+    }
+    if (n) *n = c;
+    return MSL_OK;
+}
 int msl_surfel_fuse(msl_surfel_fusion *h, int ref, const uint8_t *gray, int gray_stride, const float *depth,
                     const int32_t *membership, const float Twc[16], msl_surfel *new_surfels, int cap_new, int compact, int64_t stats[4]) {
     std::vector<orc_surfel> own;

@@ -323,3 +323,26 @@ def test_fuse_stream_other_frame_sizes(oracle, msl, w, h):
     got = sf.download_map()
     assert st[3] == len(lo) == len(got)
     assert np.array_equal(got.view(np.uint8), lo.view(np.uint8)), "map after the stream is not bit-identical"
+
+
+@pytest.mark.parametrize("n", [0, 7, 150003])
+def test_dirty_download_equals_full_download(oracle, msl, n):
+    """The exact drop-in keeps the host vector authoritative: after a fuseInitializeMap call (no compaction tail) the host copy
+    patched with msl_surfel_download_changed must equal the full download -- and the oracle's map."""
+    g, d, m = _frame(9)
+    T = S.pose_walk(9, 1)[0]
+    local = S.surfel_map(9, n, d, T, ref_index=77)
+    sf = msl.SurfelFusion(max_surfels=max(n, 16))
+    sf.upload_map(local)
+    sf.fuseInitializeMap(77, g, d, m, T, compact=False)
+    idx, rec = sf.download_changed(77)
+    full = sf.download_map()
+    host = local.copy()
+    host[idx] = rec
+    assert np.array_equal(host.view(np.uint8), full.view(np.uint8))
+    assert np.all(np.diff(idx) > 0)
+    lo = local.copy()
+    oracle.SurfelOracle().fuse(77, g, d, m, T, lo)
+    assert np.array_equal(lo.view(np.uint8), host.view(np.uint8))
+    if n > 1000:
+        assert 0.05 * n < len(idx) < 0.7 * n

@@ -29,10 +29,12 @@ def main():
     try:
         pr = pd.debug_profile(batch).astype(np.float64)
         names = ["graph", "ahCluster", "membership+seeds", "region_grow", "final_merge", "remap"]
-        d = np.diff(pr[:, :7], axis=1) / 1e3
-        prof = {"phase_us_median_over_frames": {n: float(np.median(d[:, i])) for i, n in enumerate(names)},
+        dd = np.diff(pr[:, :7], axis=1) / 1e3
+        prof = {"phase_us_median_over_frames": {n: float(np.median(dd[:, i])) for i, n in enumerate(names)},
                 "frame_us_median": float(np.median((pr[:, 6] - pr[:, 0]) / 1e3)), "frame_us_max": float(np.max((pr[:, 6] - pr[:, 0]) / 1e3)),
-                "batch_span_us": float((pr[:, 6].max() - pr[:, 0].min()) / 1e3), "merge_steps_median": float(np.median(pr[:, 7]))}
+                "batch_span_us": float((pr[:, 6].max() - pr[:, 0].min()) / 1e3), "merge_steps_median": float(np.median(pr[:, 7])),
+                "ahCluster_cycles_per_step_median": {n: float(np.median(pr[:, 8 + i] / np.maximum(pr[:, 7], 1))) for i, n in enumerate(
+                    ["pop", "candidate_fits", "select", "publish_decide", "adjacency", "copy_push"])}}
     except Exception as e:  # noqa: BLE001
         prof = "unavailable: %s" % e
     ok = None
