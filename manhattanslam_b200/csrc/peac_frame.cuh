@@ -134,8 +134,9 @@ template <int NB> struct SharedT {
     uint32_t nbs[NB][WORDS];
     double candMse[NB];  // reused as int scratch by the membership pass and the region grow
     int16_t parent[NB], dsize[NB], heap[NB], blkMap[NB];
-    uint8_t candHas[NB];
-    int16_t red[1024];  // per-thread best candidate of a merge step (blockDim <= 1024)
+    double heapKey[NB];  // mse of heap[i]: a queued node's mse never changes, and the sift loops compare keys without the
+                         // dependent load heap[i] -> node[heap[i]].mse
+    int16_t red[NB];    // the candidates (neighbour slots that pass the normal test) of the current merge step
     uint32_t tmpMask[WORDS];
     int16_t extracted[MAXPL], oldPl[MAXPL], plidmap[MAXPL];
     uint8_t valid[MAXPL];
@@ -286,24 +287,23 @@ PEAC_HD bool bit(const uint32_t *m, int i) { return (m[i >> 5] >> (i & 31)) & 1u
 PEAC_HD void setbit(uint32_t *m, int i) { m[i >> 5] |= 1u << (i & 31); }
 PEAC_HD void clrbit(uint32_t *m, int i) { m[i >> 5] &= ~(1u << (i & 31)); }
 
-// ---- std::priority_queue<.., PlaneSegMinMSECmp> on slot ids: comp(a, b) = mse[b] < mse[a]; libstdc++'s sift order
+// ---- std::priority_queue<.., PlaneSegMinMSECmp> on slot ids: comp(a, b) = mse[b] < mse[a]; libstdc++'s sift order.
+// The key (mse) of every entry is kept beside its slot id.
 template <class SH>
-PEAC_HD bool heap_comp(const SH &S, int a, int b) { return S.node[b].mse < S.node[a].mse; }
-template <class SH>
-PEAC_HD void heap_sift_up(SH &S, int hole, int top, int value) {  // std::__push_heap
+PEAC_HD void heap_sift_up(SH &S, int hole, int top, int value, double key) {  // std::__push_heap
     int parent = (hole - 1) / 2;
-    while (hole > top && heap_comp(S, S.heap[parent], value)) {
-        S.heap[hole] = S.heap[parent];
+    while (hole > top && key < S.heapKey[parent]) {  // comp(heap[parent], value) = mse[value] < mse[heap[parent]]
+        S.heap[hole] = S.heap[parent], S.heapKey[hole] = S.heapKey[parent];
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    S.heap[hole] = (int16_t)value;
+    S.heap[hole] = (int16_t)value, S.heapKey[hole] = key;
 }
 template <class SH>
 PEAC_HD void heap_push(SH &S, int slot) {
-    S.heap[S.heapN] = (int16_t)slot;
-    S.heapN++;
-    heap_sift_up(S, S.heapN - 1, 0, slot);
+    const int at = S.heapN;
+    S.heapN = at + 1;
+    heap_sift_up(S, at, 0, slot, S.node[slot].mse);
 }
 template <class SH>
 PEAC_HD int heap_pop(SH &S) {  // top(), then std::pop_heap + pop_back
@@ -311,21 +311,21 @@ PEAC_HD int heap_pop(SH &S) {  // top(), then std::pop_heap + pop_back
     const int last = S.heapN - 1;
     if (last > 0) {
         const int value = S.heap[last];
-        S.heap[last] = S.heap[0];
+        const double key = S.heapKey[last];
         const int len = last;  // std::__adjust_heap(first, 0, len, value)
         int hole = 0, second = 0;
         while (second < (len - 1) / 2) {
             second = 2 * (second + 1);
-            if (heap_comp(S, S.heap[second], S.heap[second - 1])) second--;
-            S.heap[hole] = S.heap[second];
+            if (S.heapKey[second - 1] < S.heapKey[second]) second--;  // comp(heap[second], heap[second - 1])
+            S.heap[hole] = S.heap[second], S.heapKey[hole] = S.heapKey[second];
             hole = second;
         }
         if ((len & 1) == 0 && second == (len - 2) / 2) {
             second = 2 * (second + 1);
-            S.heap[hole] = S.heap[second - 1];
+            S.heap[hole] = S.heap[second - 1], S.heapKey[hole] = S.heapKey[second - 1];
             hole = second - 1;
         }
-        heap_sift_up(S, hole, 0, value);
+        heap_sift_up(S, hole, 0, value, key);
     }
     S.heapN = last;
     return top;
@@ -470,21 +470,20 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long 
         if (p < 0) break;
         // candidate merges with every neighbour, in parallel; every thread keeps the best of its own slots
         // (least mse, then earliest creation: the first minimum in the reference's neighbour order) together with the
-        // merged node itself, and threads that found one append themselves to a compact list (a node has a handful of
-        // neighbours: thread 0 looks at those entries only, and the winner's fit is not computed a second time)
+        // merged node itself, and every candidate goes to a compact list (a node has a handful of neighbours: thread 0's
+        // selection and tie walk look at those entries only -- scanning all 768 slots for ties cost more than the fits --
+        // and the winner's fit is not computed a second time)
         int mine = -1;
         Node mineNode;
         for (int k = tid; k < nslots; k += nt) {
-            S.candHas[k] = 0;
             if (!bit(S.nbs[p], k)) continue;
             if (nsim(S.node[p], S.node[k]) < g.thMerge) continue;
             Node m;
             merged(S.node[p], S.node[k], m);
             S.candMse[k] = m.mse;
-            S.candHas[k] = 1;
+            S.red[PEAC_ATOMIC_ADD(&S.nCand, 1)] = (int16_t)k;
             if (mine < 0 || m.mse < S.candMse[mine] || (m.mse == S.candMse[mine] && S.node[k].seq < S.node[mine].seq)) mine = k, mineNode = m;
         }
-        if (mine >= 0) S.red[PEAC_ATOMIC_ADD(&S.nCand, 1)] = (int16_t)mine;
         PEAC_SYNC();
         PEAC_LAP(1);
         if (tid == 0) {
@@ -503,10 +502,12 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long 
                 // cand->N = N(p) + N(neighbour) > N(p): the tie rule can only fire when the tied mse exceeds N(p)
                 if (mn > (double)S.node[p].N) {
                     int lastSeq = S.node[best].seq;
-                    for (;;) {  // walk the tie group in creation order
+                    for (;;) {  // walk the tie group in creation order (over the step's candidates: a handful)
                         int nx = -1;
-                        for (int k = 0; k < nslots; k++)
-                            if (S.candHas[k] && S.candMse[k] == mn && S.node[k].seq > lastSeq && (nx < 0 || S.node[k].seq < S.node[nx].seq)) nx = k;
+                        for (int t = 0; t < nc; t++) {
+                            const int k = S.red[t];
+                            if (S.candMse[k] == mn && S.node[k].seq > lastSeq && (nx < 0 || S.node[k].seq < S.node[nx].seq)) nx = k;
+                        }
                         if (nx < 0) break;
                         lastSeq = S.node[nx].seq;
                         if ((double)(S.node[p].N + S.node[best].N) < mn) best = nx;
@@ -552,13 +553,10 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long 
                 S.tmpMask[w] = m;
             }
             PEAC_SYNC();
-            // disconnectAllNbs of both, then the merged node (in p's slot) becomes a neighbour of the union
+            // disconnectAllNbs of both, then the merged node (in p's slot) becomes a neighbour of the union; the two rows and
+            // the node record are written word by word by as many threads
             for (int k = tid; k < nslots; k += nt) {
-                if (k == p) {
-                    for (int w = 0; w < SH::WORDS; w++) S.nbs[k][w] = S.tmpMask[w];
-                } else if (k == nb) {
-                    for (int w = 0; w < SH::WORDS; w++) S.nbs[k][w] = 0;
-                } else {
+                if (k != p && k != nb) {
                     clrbit(S.nbs[k], nb);
                     if (bit(S.tmpMask, k))
                         setbit(S.nbs[k], p);
@@ -566,15 +564,18 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long 
                         clrbit(S.nbs[k], p);
                 }
             }
+            for (int w = tid; w < SH::WORDS; w += nt) S.nbs[p][w] = S.tmpMask[w], S.nbs[nb][w] = 0;
+            if (tid == nt - 1) S.tmp.seq = S.seqNext++;
             PEAC_SYNC();
             PEAC_LAP(4);
-            if (tid == 0) {
-                S.node[nb].nouse = 1;
-                S.tmp.seq = S.seqNext++;
-                S.node[p] = S.tmp;
-                heap_push(S, p);
-                S.step++;
+            {
+                const double *src = reinterpret_cast<const double *>(&S.tmp);
+                double *dst = reinterpret_cast<double *>(&S.node[p]);
+                for (int w = tid; w < (int)(sizeof(Node) / sizeof(double)); w += nt) dst[w] = src[w];
             }
+            if (tid == 0) S.node[nb].nouse = 1, S.step++;
+            PEAC_SYNC();
+            if (tid == 0) heap_push(S, p);
         } else {
             for (int k = tid; k < nslots; k += nt) {  // p->disconnectAllNbs()
                 if (k == p) {
@@ -679,42 +680,71 @@ PEAC_D void flood_levels(SH &S, const Geo &g, const uint16_t *depth, int32_t *me
             if (tid == 0) S.error = PEAC_ERR_QUEUE;
             break;
         }
-        // (a) the state-independent part of every visit (entry k, neighbour it)
-        for (int v = tid; v < nv; v += nt) {
-            const uint32_t ent = F.rfq[begin + (v >> 2)];
-            const int sIdx = (int)(ent & 0xfffffu), plid = (int)(ent >> 20), it = v & 3;
-            const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
-            int q[4];
-            const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
-            int c = -1;
-            float cdist = -1;
-            uint8_t fl = 0;
-            if (it < nn) {
-                c = q[it];
-                const int cy = c / g.W2, cx = c - cy * g.W2;
-                const int blkid = block_of(g, cx, cy);
-                if (blkid >= 0 && S.blkMap[blkid] >= 0) {
-                    c = -1;  // inside a kept block: never touched
-                } else {
-                    const Node &pl = S.node[S.extracted[plid]];
-                    double pt[3];
+        // (a) the state-independent part of every visit (entry k, neighbour it); four visits per thread at a time so that
+        // their queue and depth loads are in flight together (one CTA per frame: nothing else hides the L2 round trips)
+        for (int v0 = tid; v0 < nv; v0 += 4 * nt) {
+            int cc[4], plid[4];
+            uint16_t raw[4];
+            PEAC_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int v = v0 + u * nt;
+                cc[u] = -1, plid[u] = 0, raw[u] = 0;
+                if (v < nv) {
+                    const uint32_t ent = F.rfq[begin + (v >> 2)];
+                    const int sIdx = (int)(ent & 0xfffffu), it = v & 3;
+                    plid[u] = (int)(ent >> 20);
+                    const int seedy = sIdx / g.W2, seedx = sIdx - seedy * g.W2;
+                    int q[4];
+                    const int nn = nbs4(seedy, seedx, g.H2, g.W2, q);
+                    if (it < nn) {
+                        const int c = q[it];
+                        const int cy = c / g.W2, cx = c - cy * g.W2;
+                        const int blkid = block_of(g, cx, cy);
+                        if (!(blkid >= 0 && S.blkMap[blkid] >= 0)) {  // inside a kept block: never touched
+                            cc[u] = c;
+                            raw[u] = depth[(size_t)(2 * cy) * g.dstride + 2 * cx];
+                        }
+                    }
+                }
+            }
+            PEAC_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int v = v0 + u * nt;
+                if (v >= nv) continue;
+                float cdist = -1;
+                uint8_t fl = 0;
+                if (cc[u] >= 0) {
                     fl = 2;
-                    if (point(g, depth, cy, cx, pt)) {
+                    const double z = (double)raw[u] * (double)g.factor;  // point(): ImagePointCloud::get on readDepthImage's cloud
+                    if (z != 0) {
+                        const int cy = cc[u] / g.W2, cx = cc[u] - cy * g.W2;
+                        const double pt[3] = {((double)(2 * cx) - (double)g.cx) * z / (double)g.fx,
+                                              ((double)(2 * cy) - (double)g.cy) * z / (double)g.fy, z};
+                        const Node &pl = S.node[S.extracted[plid[u]]];
                         const double sd = (pl.normal[0] * (pt[0] - pl.center[0]) + pl.normal[1] * (pt[1] - pl.center[1])) +
                                           pl.normal[2] * (pt[2] - pl.center[2]);
                         cdist = (float)fabs(sd);
                         if ((double)cdist * (double)cdist < 9 * pl.mse + 1e-5) fl = 3;
                     }
                 }
+                F.visC[v] = cc[u], F.visDist[v] = cdist, F.visFlag[v] = fl;
             }
-            F.visC[v] = c, F.visDist[v] = cdist, F.visFlag[v] = fl;
         }
         PEAC_SYNC();
         // (b) resolve in visit order per target pixel: every round the earliest pending visit of each pixel
         for (;;) {
             if (tid == 0) S.pending = 0;
-            for (int v = tid; v < nv; v += nt)
-                if (F.visFlag[v] & 2) PEAC_ATOMIC_MIN(&F.own[F.visC[v]], v);
+            for (int v0 = tid; v0 < nv; v0 += 4 * nt) {  // four at a time: flag and target loads in flight together
+                int tc[4];
+                PEAC_UNROLL
+                for (int u = 0; u < 4; u++) {
+                    const int v = v0 + u * nt;
+                    tc[u] = (v < nv && (F.visFlag[v] & 2)) ? F.visC[v] : -1;
+                }
+                PEAC_UNROLL
+                for (int u = 0; u < 4; u++)
+                    if (tc[u] >= 0) PEAC_ATOMIC_MIN(&F.own[tc[u]], v0 + u * nt);
+            }
             PEAC_SYNC();
             for (int v = tid; v < nv; v += nt) {
                 const uint8_t fl = F.visFlag[v];

@@ -425,7 +425,7 @@ int msl_plane_detect_dev(msl_plane *p, const uint16_t *d_depth, int dstride_px, 
     sc.dist = p->d_dist, sc.rfq = p->d_rfq, sc.own = p->d_own, sc.visC = p->d_visC, sc.visDist = p->d_visDist, sc.visFlag = p->d_visFlag;
     sc.rfqCap = 4 * p->W2 * p->H2, sc.visCap = 4 * p->W2 * p->H2;
     sc.prof = p->d_prof, p->profFrames = batch;
-    int threads = 256;  // MSL_PEAC_THREADS = 64 | 128 | 256 | 512 | 1024: CTA size of k_peac_frame (A/B knob)
+    int threads = 512;  // MSL_PEAC_THREADS = 64 | 128 | 256 | 512 | 1024: CTA size of k_peac_frame (measured r02e: 512 is the fastest -- the region grow scales with the threads, the eigen-solver spills at the 64 registers 1024 threads leave)
     if (const char *e = getenv("MSL_PEAC_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256 || v == 512 || v == 1024) threads = v;
