@@ -43,6 +43,10 @@ WORKLOADS = {
     "plane_640x480_b256": (640, 480, 256, 0, ["plane_prestage"]),                   # config 3
     "surfel_640x480_b64_map5M": (640, 480, 64, 5_000_000, ["surfel_fuse"]),         # config 4
     "frontend_1280x960_b64_map5M": (1280, 960, 64, 5_000_000, ALL_STAGES),          # config 5: one rank's 64 of the 512 frames
+    # SURVEY.md section 8(f) row f2 widened into the step: PlaneDetection::runPlaneDetection (ahCluster + refineDetails) on the
+    # device produces the membership image the surfel stage consumes, as src/Tracking.cc:227-229 hands it over.  (With real
+    # membership most of a piecewise-planar synthetic scene is "in a plane", where ManhattanSLAM builds no surfels.)
+    "frontend_peac_640x480_b64_map5M": (640, 480, 64, 5_000_000, ["orb", "hamming_match", "search_by_projection", "plane_detect", "surfel_fuse"]),
 }
 DEFAULT_WORKLOAD = "frontend_640x480_b64_map5M"
 
@@ -152,6 +156,9 @@ def ref_parts(stages):
     if "plane_prestage" in stages:
         parts["plane_prestage"] = ("reference src/PlaneExtractor.cpp + include/peac (readDepthImage, PlaneSeg, initGraph)"
                                    if _ref_lib("libplane_ref.so") else "oracle port")
+    if "plane_detect" in stages:
+        parts["plane_detect"] = ("reference src/PlaneExtractor.cpp + include/peac (readDepthImage + runPlaneDetection), its "
+                                 "membershipImg feeds SurfelFusion" if _ref_lib("libplane_ref.so") else "oracle port")
     if "surfel_fuse" in stages:
         parts["surfel_fuse"] = ("reference src/SurfelFusion.cpp (its ten std::threads, map resident in the library)"
                                 if _ref_lib("libsurfel_ref_threads.so") else "oracle port (10 scan threads)")
@@ -162,7 +169,7 @@ def baseline_kind(stages):
     """"reference" when the stage that dominates the CPU time of the workload is the reference's own source from
     oracle/_ref; "port" when it is the oracle port"""
     parts = ref_parts(stages)
-    for s in ("surfel_fuse", "orb", "search_by_projection", "plane_prestage", "hamming_match"):  # by CPU cost
+    for s in ("surfel_fuse", "orb", "plane_detect", "search_by_projection", "plane_prestage", "hamming_match"):  # by CPU cost
         if s in parts:
             return "reference" if parts[s].startswith("reference") else "port"
     return "port"
@@ -217,6 +224,7 @@ class CpuFrontend:
         self.geom = frame_geom(a.W, a.H, *self.K, bf=MBF)
         self.Tcw = np.stack([np.linalg.inv(p.astype(np.float64)) for p in self.poses]).astype(np.float32)
         self.tl = threading.local()
+        self.mem_det = np.full_like(self.mem, -1) if "plane_detect" in a.stages else None
         self.ref = 100
         self.rs = self.so = self.local = None
         if "surfel_fuse" in a.stages:
@@ -241,6 +249,14 @@ class CpuFrontend:
             return ob.ref_plane_timed(self.depth16[i], self.K, 1.0 / 5000.0, full=False)
         ob.plane_prestage(self.depth16[i], self.K)
         return 1
+
+    def _detect(self, i):  # readDepthImage + runPlaneDetection; the membership image goes to the surfel stage
+        ob = self.ob
+        if self.parts["plane_detect"].startswith("reference"):
+            return ob.ref_plane_timed(self.depth16[i], self.K, 1.0 / 5000.0, full=True, membership=self.mem_det[i])
+        m, pl = ob.plane_detect(self.depth16[i], self.K, depth_map_factor=1.0 / 5000.0)
+        self.mem_det[i][...] = m
+        return len(pl["N"])
 
     def _match(self, i):  # brute-force Hamming best-2 of frame i against frame i+1
         return int(self.ob.hamming_best2(self.descs[i], self.descs[i + 1])[1].sum())
@@ -269,6 +285,8 @@ class CpuFrontend:
                 assert sum(ex.map(self._orb, range(frames))) > 0
             if "plane_prestage" in st:
                 list(ex.map(self._plane, range(frames)))
+            if "plane_detect" in st:
+                list(ex.map(self._detect, range(frames)))
             if "hamming_match" in st and "orb" in st:
                 list(ex.map(self._match, range(frames - 1)))
             if "search_by_projection" in st and "orb" in st:
@@ -278,12 +296,13 @@ class CpuFrontend:
                 else:
                     list(ex.map(self._track, range(frames - 1)))
         if "surfel_fuse" in st:
+            mem = self.mem_det if self.mem_det is not None else self.mem
             for i in range(frames):
                 if self.rs is not None:
-                    self.rs.fuse_resident(self.ref + i, self.gray[i], self.depth[i], self.mem[i], self.poses[i])
+                    self.rs.fuse_resident(self.ref + i, self.gray[i], self.depth[i], mem[i], self.poses[i])
                     self.rs.compact_resident()
                 else:
-                    new = self.so.fuse(self.ref + i, self.gray[i], self.depth[i], self.mem[i], self.poses[i], self.local,
+                    new = self.so.fuse(self.ref + i, self.gray[i], self.depth[i], mem[i], self.poses[i], self.local,
                                        threads=min(10, self.threads))
                     self.local = self.ob.surfel_compact(self.local, new)
             self.ref += frames
@@ -581,6 +600,7 @@ def kernel_alg_bytes(W, H, B, n_map, upd, killed, kp_rows):
         "k_search_batch": (B - 1) * kp_rows * (2 * 32.0 + 13.0 + 8.0 + 12.0 + 4.0),
         "k_plane_blocks": B * (npx * 1.0 + nblk * 72.0),  # u16 depth at even rows / columns, sector-granular = W*H bytes
         "k_plane_edges": B * nblk * (72.0 + 2.0),
+        "k_peac_frame": B * (npx * 1.0 + w2 * h2 * (4.0 + 4.0)),  # depth in, membership + distance map out; the rest stays on chip
         "k_sp_init": B * (nseeds * (72.0 + 40.0) + nseeds * 8.0),
         "k_sp_pixels": B * (npx * (1 + 4 + 1) + npx * 8.0),           # gray + depth + membership(1/4 res, 4 B) R; target + index W
         "k_sp_fix": B * npx * 8.0 * 0.25,                                # pending pixels only (a quarter, typically)
@@ -612,6 +632,7 @@ BOUND_NOTE = {  # what each kernel is bound by in practice
     "k_hamming_best2": "integer ALU (xor + popc)", "k_plane_blocks": "fp64 latency (per-block Jacobi)",
     "k_search_batch": "latency (one CTA per frame pair: sorted grid in shared memory, fixed point of the slot blocking)",
     "k_track_last": "latency (depth ranks by counting, one CTA per frame)",
+    "k_peac_frame": "latency (one CTA per frame: ~600 dependent merge steps with an fp64 eigen-solve each, then a level-synchronous region grow)",
     "k_plane_edges": "latency", "k_sp_pixels": "fp64 issue (the reference's float/double cost)", "k_sp_fix": "latency",
     "k_sp_seeds2": "shared-memory latency (sequential float sums per seed)", "k_sp_fit2": "fp64 latency (sequential sums per seed)",
     "k_resize": "L2", "k_blur": "L2", "k_load_level0": "hbm", "k_sp_norms": "hbm", "k_sp_records": "hbm",
@@ -679,6 +700,7 @@ def run_ours(a, rank, world, local_rank):
 
     do_orb, do_match, do_plane, do_surfel = "orb" in st, "hamming_match" in st and "orb" in st, "plane_prestage" in st, "surfel_fuse" in st
     do_track = "search_by_projection" in st and "orb" in st
+    do_detect = "plane_detect" in st
     orb = msl.ORBextractor(width=W, height=H, max_batch=B, device=local_rank) if do_orb else None
     cap = orb.capacity if orb else 0
     sf = None
@@ -690,7 +712,7 @@ def run_ours(a, rank, world, local_rank):
     geom = msl.frame_geom(W, H, *K4, bf=MBF)
     th_depth = MBF * TH_DEPTH_FACTOR / K4[0]  # Tracking::mThDepth (src/Tracking.cc:130)
     Tcw = np.stack([np.linalg.inv(p.astype(np.float64)) for p in poses]).astype(np.float32)
-    plane = msl.PlaneDetection(W, H, max_batch=B, device=local_rank) if do_plane else None
+    plane = msl.PlaneDetection(W, H, max_batch=B, device=local_rank) if (do_plane or do_detect) else None
     nblk = plane.nblocks if plane else 0
 
     # pinned host staging (e2e leg) and device-resident inputs (kernel leg)
@@ -724,11 +746,19 @@ def run_ours(a, rank, world, local_rank):
     d_sfc = [torch.zeros((B, 2), dtype=torch.int32, device=dev) for _ in range(2)]
     d_table = [torch.zeros((B, 3), dtype=torch.int32, device=dev) for _ in range(2)]
     gathered = [torch.zeros((world * B, 3), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
+    # plane detection on the device: membership image (double-buffered: the detection of step k+1 may run while the superpixel
+    # stage of step k still reads step k's), plane count and records per frame
+    PCAP = 32
+    d_memdet = [torch.full(((B, (H + 1) // 2, (W + 1) // 2)), -1, dtype=torch.int32, device=dev) for _ in range(2)] if do_detect else None
+    d_pcount = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_precs = torch.zeros((B, PCAP, 64), dtype=torch.uint8, device=dev)
+    ev_mem_free = [None, None]
     torch.cuda.synchronize()
 
     s_orb = torch.cuda.ExternalStream(orb.stream, device=dev) if orb else None
     s_sf = torch.cuda.ExternalStream(sf.stream, device=dev) if sf else None
     s_pl = torch.cuda.ExternalStream(plane.stream, device=dev) if plane else None
+    s_sfin = torch.cuda.ExternalStream(sf.input_stream, device=dev) if (sf and do_detect) else None
     lib_streams = [s for s in (s_orb, s_sf, s_pl) if s is not None]
     s_comm = torch.cuda.Stream(device=dev)
     ev_gather = [None, None]
@@ -757,9 +787,23 @@ def run_ours(a, rank, world, local_rank):
         if do_plane:
             plane.prestage_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, None, d_blocks.data_ptr(), d_seedm.data_ptr(),
                                d_edges.data_ptr())
+        mem_ptr = d_mem.data_ptr()
+        if do_detect:  # readDepthImage + runPlaneDetection for the batch; its membership image is the surfel stage's input
+            if ev_mem_free[k] is not None:
+                s_pl.wait_event(ev_mem_free[k])  # the superpixel stage of two steps ago has read this buffer
+            plane.detect_dev(d_d16.data_ptr(), B, K4, 1.0 / 5000.0, d_memdet[k].data_ptr(), d_pcount.data_ptr(), d_precs.data_ptr(), PCAP)
+            mem_ptr = d_memdet[k].data_ptr()
+            if do_surfel:
+                ev = torch.cuda.Event()
+                ev.record(s_pl)
+                s_sfin.wait_event(ev)
         if do_surfel:
             sf.set_count_table(d_sfc[k].data_ptr())
-            sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
+            sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), mem_ptr, poses, B, True)
+            if do_detect:
+                ev = torch.cuda.Event()
+                ev.record(s_sfin)
+                ev_mem_free[k] = ev
         state["ref"] += B
         if world > 1:  # the path's single collective: the per-frame count table to every rank, off the compute streams
             for s in lib_streams:
@@ -832,7 +876,7 @@ def run_ours(a, rank, world, local_rank):
         # chain and no other stream is busy), to separate the kernel's own efficiency from SM sharing in the timed region
         barrier()
         sf.set_timing(2)
-        sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, B, True)
+        sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), (d_memdet[0] if do_detect else d_mem).data_ptr(), poses, B, True)
         state["ref"] += B
         iso_chain, iso_frames = sf.chain_times()
         sf.set_timing(0)
@@ -913,7 +957,8 @@ def run_ours(a, rank, world, local_rank):
             barrier()
             pre = sf.download_map()
             r0 = state["ref"]
-            sf.fuse_batch_dev(r0, d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), d_mem.data_ptr(), poses, NCHK, True)
+            mem_chk = d_memdet[0].cpu().numpy() if do_detect else mem
+            sf.fuse_batch_dev(r0, d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), (d_memdet[0] if do_detect else d_mem).data_ptr(), poses, NCHK, True)
             state["ref"] += NCHK
             post = sf.download_map()
             so = ob.SurfelOracle(W, H, *K4)
@@ -922,7 +967,7 @@ def run_ours(a, rank, world, local_rank):
             n = len(pre)
             L = ob.lib()
             for i in range(NCHK):
-                new = np.ascontiguousarray(so.fuse(r0 + i, gray[i], depth[i], mem[i], poses[i], buf[:n], threads=min(16, os.cpu_count() or 1)))
+                new = np.ascontiguousarray(so.fuse(r0 + i, gray[i], depth[i], mem_chk[i], poses[i], buf[:n], threads=min(16, os.cpu_count() or 1)))
                 n = L.orc_surfel_compact(ob._p(buf), n, ob._p(new), len(new))
             ok = n == len(post) and np.array_equal(buf[:n].view(np.uint8), post.view(np.uint8))
             parity = {"check": "ok" if ok else "MISMATCH", "frames": NCHK, "map_surfels": int(len(pre)),
@@ -1005,6 +1050,16 @@ def run_ours(a, rank, world, local_rank):
                 C.c_void_p(h_depth.data_ptr()), C.c_int(W), C.c_int(H), ptr(Tcw), C.c_void_p(h_cm.data_ptr()),
                 C.c_void_p(h_nm.data_ptr())))
 
+    h_memdet = torch.zeros((B, (H + 1) // 2, (W + 1) // 2), dtype=torch.int32).pin_memory() if do_detect else None
+    h_pcount = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_precs = torch.zeros((B, PCAP, 64), dtype=torch.uint8).pin_memory()
+
+    def e2e_detect():
+        torch.cuda.set_device(local_rank)
+        check(plane._L.msl_plane_detect(plane._h, C.c_void_p(h_d16.data_ptr()), C.c_int(W), C.c_size_t(W * H), C.c_int(B), ptr(Kf),
+                                        C.c_float(1.0 / 5000.0), C.c_void_p(h_memdet.data_ptr()), C.c_void_p(h_pcount.data_ptr()),
+                                        C.c_void_p(h_precs.data_ptr()), C.c_int(PCAP)))
+
     def e2e_plane():
         torch.cuda.set_device(local_rank)
         check(plane._L.msl_plane_prestage(plane._h, C.c_void_p(h_d16.data_ptr()), C.c_int(W), C.c_size_t(W * H), C.c_int(B),
@@ -1014,8 +1069,10 @@ def run_ours(a, rank, world, local_rank):
     def e2e_surfel(ref):
         torch.cuda.set_device(local_rank)
         stats = np.zeros(4, np.int64)
+        if do_detect:
+            e2e_detect()  # the membership image comes back to the host and goes in again with the frame, as in the reference
         check(sf._L.msl_surfel_fuse_batch(sf._h, ref, C.c_void_p(h_gray.data_ptr()), C.c_int(W),
-                                          C.c_void_p(h_depth.data_ptr()), C.c_void_p(h_mem.data_ptr()), ptr(poses),
+                                          C.c_void_p(h_depth.data_ptr()), C.c_void_p((h_memdet if do_detect else h_mem).data_ptr()), ptr(poses),
                                           C.c_int(B), 1, ptr(stats)))
         return stats
 
@@ -1027,6 +1084,8 @@ def run_ours(a, rank, world, local_rank):
             futs.append(pool.submit(e2e_plane))
         if do_surfel:
             futs.append(pool.submit(e2e_surfel, state["ref"]))
+        elif do_detect:
+            futs.append(pool.submit(e2e_detect))
         state["ref"] += B
         for f in futs:
             f.result()
@@ -1057,6 +1116,9 @@ def run_ours(a, rank, world, local_rank):
     if do_plane:
         h2d += h_d16.numel() * 2
         d2h += h_blocks.numel() + 2 * B * nblk
+    if do_detect:
+        h2d += h_d16.numel() * 2
+        d2h += h_memdet.numel() * 4 + B * 4 + h_precs.numel()
     if do_surfel:
         h2d += h_gray.numel() + h_depth.numel() * 4 + h_mem.numel() * 4 + 64 * B
         d2h += 32

@@ -461,6 +461,10 @@ int msl_surfel_set_count_table(msl_surfel_fusion *, int32_t *d_table);
  * out = {kernels, form (MSL_FUSE_ONE), persistent, grid (CTAs), warps per CTA, 128-surfel segments} */
 int msl_surfel_launch_info(const msl_surfel_fusion *, int32_t out[6]);
 void *msl_surfel_stream(msl_surfel_fusion *);
+/* cudaStream_t on which msl_surfel_fuse_batch_dev / msl_surfel_fuse_dev READ their frame inputs (gray, depth, membership): a
+ * producer of device-resident inputs (msl_plane_detect_dev's membership image, src/Tracking.cc:227-229) makes it wait for
+ * its event before the call, and records an event on it after the call to learn when the buffer may be overwritten. */
+void *msl_surfel_input_stream(msl_surfel_fusion *);
 
 /* Validation aid: k_fuse_scan divides by the camera-frame depth with a hand-scheduled IEEE sequence that shares one
  * reciprocal between the two image coordinates; this compares it bit for bit with the compiler's division on n random

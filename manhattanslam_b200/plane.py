@@ -74,6 +74,13 @@ class PlaneDetection:
                                              C.c_float(depthMapFactor), ptr(d_cloud), ptr(d_blocks), ptr(d_seed),
                                              ptr(d_edges)))
 
+    def detect_dev(self, d_depth, batch, K, depthMapFactor, d_membership, d_plane_count, d_planes, plane_cap):
+        """device buffers in, device buffers out, asynchronous on the handle's stream (msl_plane_detect_dev)"""
+        Kf = np.asarray(K, np.float32)
+        check(self._L.msl_plane_detect_dev(self._h, ptr(d_depth), C.c_int(self.width), C.c_size_t(self.width * self.height),
+                                           C.c_int(batch), ptr(Kf), C.c_float(depthMapFactor), ptr(d_membership),
+                                           ptr(d_plane_count), ptr(d_planes), C.c_int(plane_cap)))
+
     def debug_profile(self, frames):
         """profile of the last detect call (msl_plane_debug_profile): (frames, 16) int64 -- columns 0..6 phase stamps in ns,
         7 merge steps, 8..13 cycles of ahCluster's sub-phases"""

@@ -159,6 +159,13 @@ class SurfelFusion:
     def stream(self):
         return self._L.msl_surfel_stream(self._h)
 
+    @property
+    def input_stream(self):
+        """the stream on which the batched API READS its frame inputs (gray, depth, membership): producers of device-resident
+        inputs make it wait for their event, and record on it to learn when a buffer may be overwritten"""
+        self._L.msl_surfel_input_stream.restype = C.c_void_p
+        return self._L.msl_surfel_input_stream(self._h)
+
     def superpixels(self, images, depths, memberships, want_index=True):
         """generateSuperPixels for a batch of independent frames -> (seeds[B, nseeds], index[B, H, W])."""
         images = np.ascontiguousarray(images, np.uint8)

@@ -751,14 +751,15 @@ def ref_plane_run(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.
     return mem, dict(normal=nrm[:n], center=cen[:n], N=N[:n], vertices=nv[:n])
 
 
-def ref_plane_timed(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0, full=False):
+def ref_plane_timed(depth_u16, K=(525.0, 525.0, 319.5, 239.5), depth_map_factor=1.0 / 5000.0, full=False, membership=None):
     """timing form of the reference's own plane code (bench.py's reference arm; thread-safe, no outputs): the pre-stage
     (readDepthImage + PlaneSeg constructors + initGraph) or, full=True, runPlaneDetection -> graph nodes / plane_num_"""
     depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
     h, w = depth_u16.shape
     L = _plane_ref()
-    L.ref_plane_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_int]
-    n = L.ref_plane_timed(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor, int(full))
+    L.ref_plane_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_int, C.c_void_p]
+    n = L.ref_plane_timed(_p(depth_u16), w, h, depth_u16.strides[0] // 2, K[0], K[1], K[2], K[3], depth_map_factor, int(full),
+                          _p(membership))
     if n < 0:
         raise RuntimeError("reference plane code failed (%d)" % n)
     return n

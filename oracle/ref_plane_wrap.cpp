@@ -144,14 +144,19 @@ int ref_plane_run(const uint16_t *depth, int w, int h, int stride_px, float fx, 
 // each, like Frame::ExtractPlanes' per-frame std::thread).  full = 0: readColorImage + readDepthImage and the pre-stage of
 // PlaneFitter::run -- the PlaneSeg constructor of every block and initGraph (AHCPlaneFitter.hpp:216-223, 756-928), the part
 // BASELINE.json's config 3 names; full = 1: runPlaneDetection as Frame::ExtractPlanes calls it (src/Frame.cc:607-609).
-// Returns the number of graph nodes (full = 0) or plane_num_ (full = 1), < 0 on error.
+// membership (optional, full = 1): membershipImg out.  Returns the number of graph nodes (full = 0) or plane_num_ (full = 1),
+// < 0 on error.  With glibc's allocator exact mse ties may resolve differently from the arena build (see ref_arena.hpp).
 int ref_plane_timed(const uint16_t *depth, int w, int h, int stride_px, float fx, float fy, float cx, float cy, float factor,
-                    int full) {
+                    int full, int32_t *membership) {
     PlaneDetection pd;
     cv::Mat color, K;
     if (!read_frame(pd, depth, w, h, stride_px, fx, fy, cx, cy, factor, color, K)) return -1;
     if (full) {
         pd.runPlaneDetection();
+        if (membership) {  // what Tracking hands to SurfelMapping (src/Tracking.cc:227-229)
+            const cv::Mat &m = pd.plane_filter.membershipImg;
+            for (int y = 0; y < m.rows; y++) memcpy(membership + (size_t)y * m.cols, m.ptr(y), sizeof(int32_t) * (size_t)m.cols);
+        }
         return pd.plane_num_;
     }
     Fitter &f = pd.plane_filter;
