@@ -46,23 +46,21 @@ void Frame::UndistortKeyPoints() {
 }
 
 void Frame::ComputeStereoFromRGBD(const cv::Mat &imDepth) {
+    // N depth samples at the (distorted) keypoint positions (:495-513).  Done on the host: going through msl_glue_keypoints
+    // would upload the whole CV_32F image (1.2 MB at 640x480) and block the tracking thread on a PCIe round trip for N
+    // scalar reads.  A frame that is already on the device (msl_glue_upload_frames) uses msl_glue_keypoints_dev instead,
+    // chained on the extractor's stream ("frame sets").
     mvuRight.assign(N, -1);
     mvDepth.assign(N, -1);
-    if (N == 0) return;
-    CV_Assert(imDepth.type() == CV_32F && imDepth.isContinuous());
-    const float K4[4] = {fx, fy, cx, cy};
-    const float D0[5] = {0, 0, 0, 0, 0};  // mvKeysUn is already known: only x_un is needed for uRight
-    const std::vector<msl_keypoint> k = flatten(mvKeys);
-    std::vector<float> xy(2 * (size_t)N), ur(N), kd(N);
-    if (msl_glue_keypoints(glue(imDepth.cols, imDepth.rows), k.data(), N, K4, D0, imDepth.ptr<float>(), mbf, xy.data(), ur.data(),
-                           kd.data()) != MSL_OK)
-        throw std::runtime_error(msl_last_error());
-    // uRight is defined on the UNDISTORTED x (:509): correct the device's (distorted-x) value by the same subtraction
-    for (int i = 0; i < N; i++)
-        if (kd[i] > 0) {
-            mvDepth[i] = kd[i];
-            mvuRight[i] = mvKeysUn[i].pt.x - mbf / kd[i];
+    CV_Assert(imDepth.type() == CV_32F);
+    for (int i = 0; i < N; i++) {
+        const cv::Point2f &p = mvKeys[i].pt;
+        const float d = imDepth.ptr<float>((int)p.y)[(int)p.x];  // Mat::at<float>(float v, float u): both truncate to int
+        if (d > 0) {
+            mvDepth[i] = d;
+            mvuRight[i] = mvKeysUn[i].pt.x - mbf / d;
         }
+    }
 }
 
 }  // namespace ORB_SLAM2

@@ -79,7 +79,7 @@ void PlaneDetection::runPlaneDetection() {
         if (it == g_pre.end() || it->second.depth.empty()) throw std::runtime_error("runPlaneDetection before readDepthImage");
         p = &it->second;
     }
-    const int W2 = cloud.w, H2 = cloud.h, cap = 64;
+    const int W2 = cloud.w, H2 = cloud.h, cap = 128;  // peac::MAXPL, the library's own limit (msl_plane_detect)
     cv::Mat &mem = plane_filter.membershipImg;
     mem.create(H2, W2, CV_32SC1);
     if (!mem.isContinuous()) throw std::runtime_error("membershipImg must be continuous");
@@ -88,7 +88,11 @@ void PlaneDetection::runPlaneDetection() {
     if (msl_plane_detect(p->h, p->depth.ptr<uint16_t>(), (int)(p->depth.step / 2), (size_t)(p->depth.step / 2) * p->depth.rows, 1, p->K,
                          p->factor, mem.ptr<int32_t>(), &n, rec.data(), cap) != MSL_OK)
         throw std::runtime_error(msl_last_error());
-    if (n > cap) n = cap;
+    if (n > cap) {
+        // more planes than the record array holds (never seen below 1280x960): the reference has no limit, so fail loudly rather
+        // than leave labels >= cap in membershipImg without an extractedPlanes / plane_vertices_ entry
+        throw std::runtime_error("runPlaneDetection: more than 128 planes extracted");
+    }
     // extractedPlanes: PlaneSeg has no default constructor; build each on an empty cloud (rejected: N = 0, nouse) and
     // set the fields Frame::ExtractPlanes reads (src/Frame.cc:626-632)
     plane_filter.extractedPlanes.clear();

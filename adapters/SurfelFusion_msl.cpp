@@ -4,6 +4,7 @@
 // again -- the upload whole (the host mutates the vector between calls: the fuseMap tail, moveAddSurfels), the download only for
 // the surfels the call changed (msl_surfel_download_changed: ~30 % of the map).  INTEGRATION.md describes the device-resident mode
 // (compaction and SurfelMapping::moveAddSurfels on the device, no round trip): adapters/SurfelMapping_msl.cpp.
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -25,14 +26,45 @@ msl_surfel_fusion *msl_handle_of(const SurfelFusion *f) {
     return g_h.at(f);
 }
 
+// The reference class has no destructor to hook (include/SurfelFusion.h): the owner releases the device map explicitly --
+// call it from SurfelMapping's destructor / Stop().  Without it a SurfelFusion object that is destroyed
+// leaks its device map, and an object later allocated at the same address would find a stale table entry (its constructor
+// overwrites it).
+void msl_release_of(const SurfelFusion *f) {
+    msl_surfel_fusion *h = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_h.find(f);
+        if (it == g_h.end()) return;
+        h = it->second;
+        g_h.erase(it);
+    }
+    msl_surfel_destroy(h);
+}
+
+// Device map capacity in surfels (56 B each + 8 B of queue / compaction planes): MSL_SURFEL_CAPACITY, default 32 Mi (2.4 GB).
+static long long surfel_capacity() {
+    if (const char *e = std::getenv("MSL_SURFEL_CAPACITY")) {
+        const long long v = std::atoll(e);
+        if (v > 0) return v;
+    }
+    return 32ll << 20;
+}
+
 SurfelFusion::SurfelFusion(int width, int height, float _fx, float _fy, float _cx, float _cy, float _fuseFar, float _fuseNear)
     : fx(_fx), fy(_fy), cx(_cx), cy(_cy), imageWidth(width), imageHeight(height), spWidth(width / SP_SIZE),
       spHeight(height / SP_SIZE), fuseFar(_fuseFar), fuseNear(_fuseNear) {  // declaration order of include/SurfelFusion.h:60-63
     msl_surfel_fusion *h = nullptr;
-    if (msl_surfel_create(width, height, _fx, _fy, _cx, _cy, _fuseFar, _fuseNear, 32ll << 20, 0, &h) != MSL_OK)
+    if (msl_surfel_create(width, height, _fx, _fy, _cx, _cy, _fuseFar, _fuseNear, surfel_capacity(), 0, &h) != MSL_OK)
         throw std::runtime_error(msl_last_error());
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_h[this] = h;
+    msl_surfel_fusion *stale = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_h.find(this);
+        if (it != g_h.end()) stale = it->second;  // an earlier object at this address that was never released
+        g_h[this] = h;
+    }
+    if (stale) msl_surfel_destroy(stale);
 }
 
 void SurfelFusion::fuseInitializeMap(const int referenceFrameIndex, const cv::Mat &inputImage, const cv::Mat &inputDepth,

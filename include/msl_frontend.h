@@ -274,6 +274,21 @@ int msl_glue_cvt_gray_dev(msl_glue *, const uint8_t *d_src, int stride, size_t f
 /* mImDepth.convertTo(mImDepth, CV_32F, mDepthMapFactor) (src/Tracking.cc:205-207) on CV_16U depth */
 int msl_glue_depth_to_float(msl_glue *, const uint16_t *depth16, int batch, float factor, float *depth);
 int msl_glue_depth_to_float_dev(msl_glue *, const uint16_t *d_depth16, int64_t n, float factor, float *d_depth);
+/* The sensor frames of a batch uploaded ONCE for every stage.  The reference's Frame constructor hands the same host images to
+ * every consumer -- ExtractORB(imGray), ComputeStereoFromRGBD(imDepth), ExtractPlanes(imDepth as CV_16U) (src/Frame.cc:90-110,
+ * :604-610) and later SurfelFusion through the KeyFrame (src/SurfelMapping.cpp:353-364) -- so a binding that goes through the
+ * host entry points uploads gray twice and depth three times.  Here gray (CV_8U) and the sensor depth (CV_16U) go up once, on
+ * the handle's own copy stream, into frame set `slot` (0 or 1: double-buffered so that the upload of the next batch overlaps the
+ * work on the current one), and the CV_32F depth of Tracking::GrabImageRGBD (convertTo(CV_32F, mDepthMapFactor),
+ * src/Tracking.cc:205-207) is produced on the device.  `aux` (optional, aux_ints int32 values) rides along, e.g. a
+ * membership image computed on the host.  Returns at once; the device pointers stay valid until the slot's next upload and are
+ * meant for the *_dev entry points after msl_glue_frames_wait(glue, slot, <that handle's stream>).  The caller must not upload
+ * into a slot whose consumers of the previous upload have not been synchronised. */
+int msl_glue_upload_frames(msl_glue *, int slot, const uint8_t *gray, int gray_stride, const uint16_t *depth16,
+                           int depth_stride_px, int batch, float factor, const int32_t *aux, size_t aux_ints,
+                           const uint8_t **d_gray, const uint16_t **d_depth16, const float **d_depth, const int32_t **d_aux);
+/* makes `stream` (cudaStream_t; NULL = block the host) wait for the upload + conversion of frame set `slot` */
+int msl_glue_frames_wait(msl_glue *, int slot, void *stream);
 /* Frame::UndistortKeyPoints + Frame::ComputeStereoFromRGBD for one frame's keypoints (mvKeys as returned by
  * msl_orb_extract): K4 = fx, fy, cx, cy; D5 = k1, k2, p1, p2, k3 (NULL or D5[0] == 0: mvKeysUn = mvKeys);
  * depth = CV_32F metres, dense w*h, or NULL to skip the stereo part; mbf = Frame::mbf.

@@ -133,6 +133,17 @@ struct msl_glue {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_out = nullptr;  // staging for the host entry points
     size_t inCap = 0, outCap = 0;
+    // frame sets (msl_glue_upload_frames): the sensor frames of a batch, uploaded once for every stage
+    cudaStream_t upStream = nullptr;
+    struct FrameSet {
+        uint8_t *gray = nullptr;
+        uint16_t *d16 = nullptr;
+        float *depth = nullptr;
+        int32_t *aux = nullptr;
+        size_t auxCap = 0;
+        cudaEvent_t ready = nullptr;
+        bool used = false;
+    } fs[2];
 };
 
 static int glue_reserve(msl_glue *g, size_t in, size_t out) {
@@ -185,6 +196,14 @@ void msl_glue_destroy(msl_glue *g) {
     cudaSetDevice(g->device);
     if (g->d_in) cudaFree(g->d_in);
     if (g->d_out) cudaFree(g->d_out);
+    for (auto &f : g->fs) {
+        if (f.gray) cudaFree(f.gray);
+        if (f.d16) cudaFree(f.d16);
+        if (f.depth) cudaFree(f.depth);
+        if (f.aux) cudaFree(f.aux);
+        if (f.ready) cudaEventDestroy(f.ready);
+    }
+    if (g->upStream) cudaStreamDestroy(g->upStream);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -243,6 +262,58 @@ int msl_glue_depth_to_float(msl_glue *g, const uint16_t *depth16, int batch, flo
     if (rc) return rc;
     MSL_CUDA(cudaMemcpyAsync(depth, g->d_out, n * 4, cudaMemcpyDeviceToHost, g->stream));
     MSL_CUDA(cudaStreamSynchronize(g->stream));
+    return MSL_OK;
+}
+
+// The sensor frames of a batch uploaded ONCE for every stage of the front-end (the reference's Frame constructor hands the same
+// mImGray / imDepth to ExtractORB, ComputeStereoFromRGBD, ExtractPlanes and, through the KeyFrame, to SurfelFusion --
+// src/Frame.cc:90-110, src/Tracking.cc:184-211): gray and the sensor's CV_16U depth go up on the handle's copy stream, the
+// CV_32F depth of Tracking::GrabImageRGBD (imDepth.convertTo(CV_32F, mDepthMapFactor)) is produced on the device.
+int msl_glue_upload_frames(msl_glue *g, int slot, const uint8_t *gray, int gray_stride, const uint16_t *depth16, int depth_stride_px,
+                           int batch, float factor, const int32_t *aux, size_t aux_ints, const uint8_t **d_gray,
+                           const uint16_t **d_depth16, const float **d_depth, const int32_t **d_aux) {
+    if (!g || !gray || !depth16 || slot < 0 || slot > 1) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad argument");
+    if (batch < 1 || batch > g->maxBatch) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad batch");
+    if (gray_stride < g->w || depth_stride_px < g->w) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad stride");
+    MSL_CUDA(cudaSetDevice(g->device));
+    msl_glue::FrameSet &f = g->fs[slot];
+    const size_t npx = (size_t)g->w * g->h, cap = npx * g->maxBatch;
+    if (!g->upStream) MSL_CUDA(cudaStreamCreateWithFlags(&g->upStream, cudaStreamNonBlocking));
+    if (!f.gray) {
+        MSL_CUDA(cudaMalloc((void **)&f.gray, cap));
+        MSL_CUDA(cudaMalloc((void **)&f.d16, cap * 2));
+        MSL_CUDA(cudaMalloc((void **)&f.depth, cap * 4));
+        MSL_CUDA(cudaEventCreateWithFlags(&f.ready, cudaEventDisableTiming));
+    }
+    if (aux && aux_ints > f.auxCap) {
+        if (f.aux) cudaFree(f.aux);
+        f.aux = nullptr, f.auxCap = 0;
+        MSL_CUDA(cudaMalloc((void **)&f.aux, aux_ints * 4));
+        f.auxCap = aux_ints;
+    }
+    cudaStream_t st = g->upStream;
+    if (gray_stride == g->w) MSL_CUDA(cudaMemcpyAsync(f.gray, gray, npx * batch, cudaMemcpyHostToDevice, st));
+    else MSL_CUDA(cudaMemcpy2DAsync(f.gray, g->w, gray, gray_stride, g->w, (size_t)g->h * batch, cudaMemcpyHostToDevice, st));
+    if (depth_stride_px == g->w) MSL_CUDA(cudaMemcpyAsync(f.d16, depth16, npx * batch * 2, cudaMemcpyHostToDevice, st));
+    else MSL_CUDA(cudaMemcpy2DAsync(f.d16, (size_t)g->w * 2, depth16, (size_t)depth_stride_px * 2, (size_t)g->w * 2, (size_t)g->h * batch, cudaMemcpyHostToDevice, st));
+    if (aux && aux_ints) MSL_CUDA(cudaMemcpyAsync(f.aux, aux, aux_ints * 4, cudaMemcpyHostToDevice, st));
+    const int64_t n = (int64_t)(npx * batch);
+    k_depth_to_float<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(f.d16, n, factor, f.depth);
+    MSL_LAUNCH_CHECK();
+    MSL_CUDA(cudaEventRecord(f.ready, st));
+    f.used = true;
+    if (d_gray) *d_gray = f.gray;
+    if (d_depth16) *d_depth16 = f.d16;
+    if (d_depth) *d_depth = f.depth;
+    if (d_aux) *d_aux = aux ? f.aux : nullptr;
+    return MSL_OK;
+}
+
+int msl_glue_frames_wait(msl_glue *g, int slot, void *stream) {
+    if (!g || slot < 0 || slot > 1 || !g->fs[slot].used) return fail(MSL_ERR_INVALID, "msl_glue_frames_wait: no upload in this slot");
+    MSL_CUDA(cudaSetDevice(g->device));
+    if (stream) MSL_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g->fs[slot].ready, 0));
+    else MSL_CUDA(cudaEventSynchronize(g->fs[slot].ready));
     return MSL_OK;
 }
 

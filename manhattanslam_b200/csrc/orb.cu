@@ -127,14 +127,18 @@ __global__ void __launch_bounds__(256) k_resize(const LevelInfo *__restrict__ lv
 // against neighbours whose true score is below its own when they are <= minTh), so they are returned as 0 after a
 // cheap test: any 9-arc of the 16-ring contains two of the four compass pixels (0, 4, 8, 12) that are 4 apart or
 // three of them, so S_max > minTh needs >= 2 compass pixels beyond the threshold on the same side.
-__device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch, int minTh) {
+__device__ __forceinline__ bool fast_quick(const uint8_t *c, int pitch, int minTh) {
     const int v = c[0];
-    {
-        const int c0 = v - c[3 * pitch], c4 = v - c[3], c8 = v - c[-3 * pitch], c12 = v - c[-3];
-        const int pos = (c0 > minTh) + (c4 > minTh) + (c8 > minTh) + (c12 > minTh);
-        const int neg = (c0 < -minTh) + (c4 < -minTh) + (c8 < -minTh) + (c12 < -minTh);
-        if (pos < 2 && neg < 2) return 0;
-    }
+    const int c0 = v - c[3 * pitch], c4 = v - c[3], c8 = v - c[-3 * pitch], c12 = v - c[-3];
+    const int pos = (c0 > minTh) + (c4 > minTh) + (c8 > minTh) + (c12 > minTh);
+    const int neg = (c0 < -minTh) + (c4 < -minTh) + (c8 < -minTh) + (c12 < -minTh);
+    return pos >= 2 || neg >= 2;
+}
+// the full score of a pixel that passed fast_quick (the two are separate passes in k_fast_cells: about one pixel in ten
+// passes the compass test on natural texture, but six warps in ten hold at least one that does -- the survivors are
+// compacted into a list first so that the 200-instruction arc reduction runs on full warps)
+__device__ __forceinline__ int fast_smax(const uint8_t *c, int pitch) {
+    const int v = c[0];
     int d[16];
     d[0] = v - c[3 * pitch];
     d[1] = v - c[3 * pitch + 1];
@@ -217,8 +221,9 @@ __global__ void __launch_bounds__(128)
     __shared__ uint8_t sc[CELL_TILE * CELL_TILE];
     __shared__ uint8_t sv[CELL_TILE * CELL_TILE];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint16_t cand[CELL_TILE * CELL_TILE];  // pixels that passed the compass test (any order)
     __shared__ int wsum[4];
-    __shared__ int s_any;
+    __shared__ int s_any, s_ncand;
     const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
     const Cell C = cells[cell];
     const int level = cellLevel[cell];
@@ -246,12 +251,35 @@ __global__ void __launch_bounds__(128)
         }
     }
     const uint8_t *roi = tile + (C.x0 & 15);  // ROI origin inside the 16-byte aligned box
-    if (tid == 0) s_any = 0;
+    if (tid == 0) s_any = 0, s_ncand = 0;
     __syncthreads();
     const int np = cw * ch;
-    for (int p = tid; p < np; p += 128) {
-        int cy = p / cw, cx = p - cy * cw;
-        sc[cy * CELL_TILE + cx] = (uint8_t)fast_smax(roi + (cy + 3) * tileW + cx + 3, tileW, min(minTh, iniTh));
+    const int lane = tid & 31, wid = tid >> 5;
+    {
+        const int thq = min(minTh, iniTh);
+        for (int p0 = 0; p0 < np; p0 += 128) {
+            const int p = p0 + tid;
+            bool pass = false;
+            int q = 0;
+            if (p < np) {
+                const int cy = p / cw, cx = p - cy * cw;
+                q = cy * CELL_TILE + cx;
+                pass = fast_quick(roi + (cy + 3) * tileW + cx + 3, tileW, thq);
+                if (!pass) sc[q] = 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_ncand, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) cand[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)q;
+        }
+        __syncthreads();
+        const int nc = s_ncand;
+        for (int i = tid; i < nc; i += 128) {
+            const int q = cand[i];
+            const int cy = q / CELL_TILE, cx = q - cy * CELL_TILE;
+            sc[q] = (uint8_t)fast_smax(roi + (cy + 3) * tileW + cx + 3, tileW);
+        }
     }
     __syncthreads();
     // in-cell NMS: strict maximum over the 8 neighbours; neighbours outside the cell's ring count as 0
@@ -281,7 +309,6 @@ __global__ void __launch_bounds__(128)
     uint32_t *out = staging + ((size_t)frame * totalCells + cell) * capCell;
     const int offX = C.x0 + 3 - MIN_BORDER, offY = C.y0 + 3 - MIN_BORDER;
     int base = 0;
-    const int lane = tid & 31, wid = tid >> 5;
     for (int p0 = 0; p0 < np; p0 += 128) {
         int p = p0 + tid;
         int s = 0, cx = 0, cy = 0;

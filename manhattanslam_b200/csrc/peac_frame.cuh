@@ -486,18 +486,51 @@ PEAC_D void cluster(SH &S, const Geo &g, int nslots, int tid, int nt, long long 
         }
         PEAC_SYNC();
         PEAC_LAP(1);
+#if defined(__CUDA_ARCH__) && !defined(PEAC_HOST_EMULATION) && defined(PEAC_WARP_SELECT)
+        // merged planes collect dozens of neighbours: the first minimum (least mse, then earliest creation -- a total order,
+        // creation sequences are unique) is found by the first warp with shuffles; thread 0 then only handles exact ties
+        int warpBest = -1, warpTies = 0;
+        if (tid < 32) {
+            const int nc = S.nCand;
+            int best = -1;
+            double bm = 0;
+            int bs = 0;
+            for (int t = tid; t < nc; t += 32) {
+                const int k = S.red[t];
+                const double m = S.candMse[k];
+                const int sq = S.node[k].seq;
+                if (best < 0 || m < bm || (m == bm && sq < bs)) best = k, bm = m, bs = sq;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const double om = __shfl_xor_sync(0xffffffffu, bm, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (ob >= 0 && (best < 0 || om < bm || (om == bm && os < bs))) best = ob, bm = om, bs = os;
+            }
+            int ties = 0;  // candidates sharing the minimal mse (the winner included)
+            for (int t = tid; t < nc; t += 32) ties += S.candMse[S.red[t]] == bm;
+            for (int o = 16; o > 0; o >>= 1) ties += __shfl_xor_sync(0xffffffffu, ties, o);
+            warpBest = best, warpTies = ties;
+        }
+#endif
         if (tid == 0) {
             // :1064-1072 in neighbour order (creation sequence): the first minimum wins; on an exact tie the reference
             // replaces the candidate iff cand->N < merge->mse
             int best = -1;
             const int nc = S.nCand;
+#if defined(__CUDA_ARCH__) && !defined(PEAC_HOST_EMULATION) && defined(PEAC_WARP_SELECT)
+            best = warpBest;
+            const bool mayTie = warpTies > 1;
+#else
+            const bool mayTie = true;
             for (int t = 0; t < nc; t++) {
                 const int k = S.red[t];
                 if (best < 0 || S.candMse[k] < S.candMse[best] || (S.candMse[k] == S.candMse[best] && S.node[k].seq < S.node[best].seq))
                     best = k;
             }
+#endif
             S.nCand = 0;
-            if (best >= 0) {
+            if (best >= 0 && mayTie) {
                 const double mn = S.candMse[best];
                 // cand->N = N(p) + N(neighbour) > N(p): the tie rule can only fire when the tied mse exceeds N(p)
                 if (mn > (double)S.node[p].N) {
@@ -746,16 +779,41 @@ PEAC_D void flood_levels(SH &S, const Geo &g, const uint16_t *depth, int32_t *me
                     if (tc[u] >= 0) PEAC_ATOMIC_MIN(&F.own[tc[u]], v0 + u * nt);
             }
             PEAC_SYNC();
-            for (int v = tid; v < nv; v += nt) {
-                const uint8_t fl = F.visFlag[v];
+            for (int v0 = tid; v0 < nv; v0 += 4 * nt) {
+              // four visits at a time: flags and targets, then the owners, then the state of the resolved targets are loaded
+              // together (the visits a round resolves have distinct target pixels, so they do not see each other's writes)
+              uint8_t flb[4];
+              int cb[4], ownb[4], plidb[4];
+              int32_t trailb[4];
+              float distb[4];
+              PEAC_UNROLL
+              for (int u = 0; u < 4; u++) {
+                  const int v = v0 + u * nt;
+                  flb[u] = v < nv ? F.visFlag[v] : 0;
+                  cb[u] = (flb[u] & 2) ? F.visC[v] : -1;
+              }
+              PEAC_UNROLL
+              for (int u = 0; u < 4; u++) ownb[u] = cb[u] >= 0 ? PEAC_LOAD(&F.own[cb[u]]) : -1;
+              PEAC_UNROLL
+              for (int u = 0; u < 4; u++) {
+                  const int v = v0 + u * nt;
+                  const bool mineNow = cb[u] >= 0 && ownb[u] == v;
+                  plidb[u] = mineNow ? (int)(F.rfq[begin + (v >> 2)] >> 20) : 0;
+                  trailb[u] = mineNow ? membership[cb[u]] : 0;
+                  distb[u] = mineNow ? F.distMap[cb[u]] : 0.f;
+              }
+              PEAC_UNROLL
+              for (int u = 0; u < 4; u++) {
+                const int v = v0 + u * nt;
+                const uint8_t fl = flb[u];
                 if (!(fl & 2)) continue;
-                const int c = F.visC[v];
-                if (PEAC_LOAD(&F.own[c]) != v) {
+                const int c = cb[u];
+                if (ownb[u] != v) {
                     PEAC_STORE(&S.pending, 1);
                     continue;
                 }
-                const int plid = (int)(F.rfq[begin + (v >> 2)] >> 20);
-                const int32_t trail = membership[c];
+                const int plid = plidb[u];
+                const int32_t trail = trailb[u];
                 uint8_t out = fl & 1;  // pending cleared
                 if (trail <= -6 || (trail >= 0 && trail == plid)) {
                 } else if (fl & 1) {
@@ -767,7 +825,7 @@ PEAC_D void flood_levels(SH &S, const Geo &g, const uint16_t *depth, int32_t *me
                         }
                     }
                     const float cdist = F.visDist[v];
-                    if (cdist < F.distMap[c]) {
+                    if (cdist < distb[u]) {
                         membership[c] = plid;
                         F.distMap[c] = cdist;
                         out |= 4;
@@ -779,6 +837,7 @@ PEAC_D void flood_levels(SH &S, const Geo &g, const uint16_t *depth, int32_t *me
                 }
                 F.visFlag[v] = out;
                 PEAC_STORE(&F.own[c], 0x7fffffff);
+              }
             }
             PEAC_SYNC();
             if (!S.pending) break;

@@ -65,6 +65,21 @@ class FrameGlue:
                                              ptr(d_depth), C.c_float(mbf), ptr(d_xy_un), ptr(d_uright), ptr(d_kdepth),
                                              C.c_void_p(stream or 0)))
 
+    def upload_frames(self, slot, gray_ptr, d16_ptr, batch, factor, aux_ptr=None, aux_ints=0, gray_stride=None, depth_stride_px=None):
+        """msl_glue_upload_frames: the sensor frames (host pointers: gray u8, depth u16) of a batch uploaded once for every
+        stage, CV_32F depth produced on the device (src/Tracking.cc:205-207).  Returns the device pointers
+        (gray, depth16, depth_f32, aux) as ints; asynchronous -- order consumers with frames_wait."""
+        dg, d16, dd, da = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._L.msl_glue_upload_frames(self._h, C.c_int(slot), C.c_void_p(gray_ptr), C.c_int(gray_stride or self.width),
+                                             C.c_void_p(d16_ptr), C.c_int(depth_stride_px or self.width), C.c_int(batch),
+                                             C.c_float(factor), C.c_void_p(aux_ptr or 0), C.c_size_t(aux_ints), C.byref(dg),
+                                             C.byref(d16), C.byref(dd), C.byref(da)))
+        return dg.value, d16.value, dd.value, da.value
+
+    def frames_wait(self, slot, stream=None):
+        """makes `stream` (a cudaStream_t as int; None blocks the host) wait for frame set `slot`"""
+        check(self._L.msl_glue_frames_wait(self._h, C.c_int(slot), C.c_void_p(stream or 0)))
+
     @property
     def stream(self):
         return self._L.msl_glue_stream(self._h)
