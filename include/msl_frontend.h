@@ -117,6 +117,18 @@ int msl_matcher_create(int max_queries, int max_train, int max_batch, int device
 void msl_matcher_destroy(msl_matcher *);
 int msl_matcher_sync(msl_matcher *);
 void *msl_matcher_stream(msl_matcher *); /* cudaStream_t */
+/* Deferred batches.  The reference calls the searches in loops over keyframes -- Tracking::Relocalization runs SearchByBoW
+ * against every candidate keyframe (src/Tracking.cc:1930-1950), LocalMapping::CreateNewMapPoints runs SearchForTriangulation
+ * against every neighbour (src/LocalMapping.cc:330-351), SearchInNeighbors runs Fuse against every target keyframe
+ * (src/LocalMapping.cc:540-570) -- and one call is a few tens of microseconds of kernel behind a PCIe round trip.  Between
+ * msl_matcher_batch_begin and msl_matcher_batch_end the six window / vocabulary searches (msl_search_by_projection_frame /
+ * _points / _keyframe, msl_search_by_bow, msl_search_for_triangulation, msl_fuse_search) only pack their inputs (the input
+ * arrays may be reused as soon as the call returns); msl_matcher_batch_end uploads everything in one copy, runs one CTA per
+ * recorded call and then fills every call's output arrays, which must stay valid until then.  Calls with an empty side
+ * return their (empty) result at once.  If the recorded calls outgrow the handle's scratch arena the recorded part is
+ * executed early -- results are only promised at batch_end.  Outside a batch every search is a batch of one. */
+int msl_matcher_batch_begin(msl_matcher *);
+int msl_matcher_batch_end(msl_matcher *);
 
 /* All-pairs Hamming distance of 256-bit descriptors: dist[b][i][j] = popcount(q[b][i] ^ t[b][j]),
  * batch pairs; q: batch x nq x 32, t: batch x nt x 32, dist: batch x nq x nt uint16. */

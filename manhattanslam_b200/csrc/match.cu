@@ -372,6 +372,13 @@ __device__ void search_body(const SearchArgs &A) {
 }
 
 __global__ void __launch_bounds__(1024) k_search(SearchArgs A) { search_body(A); }
+// one CTA per recorded call of a deferred batch (msl_matcher_batch_begin / _end)
+__global__ void __launch_bounds__(1024) k_search_many(const SearchArgs *__restrict__ args) {
+    __shared__ SearchArgs A;
+    if (threadIdx.x < sizeof(SearchArgs) / 4) reinterpret_cast<uint32_t *>(&A)[threadIdx.x] = reinterpret_cast<const uint32_t *>(args + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    search_body(A);
+}
 
 // ---- SearchByProjection(CurrentFrame, LastFrame, th) for a BATCH of consecutive frame pairs straight from the device-resident
 // output of the extractor and the frame glue (pair p: Last = frame p, Current = frame p + 1).
@@ -500,7 +507,7 @@ struct NodeArgs {
     int32_t *out, *bin, *nmatches;
 };
 
-__global__ void __launch_bounds__(1024) k_node_search(NodeArgs A) {
+__device__ __forceinline__ void node_search_body(const NodeArgs &A) {
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_n, s_ind[3];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -617,6 +624,12 @@ __global__ void __launch_bounds__(1024) k_node_search(NodeArgs A) {
     }
     if (tid == 0) *A.nmatches = s_n;
 }
+__global__ void __launch_bounds__(1024) k_node_search(const NodeArgs *__restrict__ args) {  // one CTA per recorded call
+    __shared__ NodeArgs A;
+    if (threadIdx.x < sizeof(NodeArgs) / 4) reinterpret_cast<uint32_t *>(&A)[threadIdx.x] = reinterpret_cast<const uint32_t *>(args + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    node_search_body(A);
+}
 
 // ------------------------------------------------------------------------------- Fuse (search part)
 struct FuseArgs {
@@ -632,7 +645,7 @@ struct FuseArgs {
     int32_t *bestIdx, *bestDist, *nFused;
 };
 
-__global__ void __launch_bounds__(1024) k_fuse_search(FuseArgs A) {
+__device__ __forceinline__ void fuse_search_body(const FuseArgs &A) {
     __shared__ uint32_t keys[MAXK];  // (cell << 12 | index), sorted; 0xffffffff = not in grid
     __shared__ unsigned short cellStart[NCELLS + 1];
     __shared__ int s_n;
@@ -735,6 +748,12 @@ __global__ void __launch_bounds__(1024) k_fuse_search(FuseArgs A) {
     __syncthreads();
     if (tid == 0) *A.nFused = s_n;
 }
+__global__ void __launch_bounds__(1024) k_fuse_search(const FuseArgs *__restrict__ args) {  // one CTA per recorded call
+    __shared__ FuseArgs A;
+    if (threadIdx.x < sizeof(FuseArgs) / 4) reinterpret_cast<uint32_t *>(&A)[threadIdx.x] = reinterpret_cast<const uint32_t *>(args + blockIdx.x)[threadIdx.x];
+    __syncthreads();
+    fuse_search_body(A);
+}
 
 // --------------------------------------------------- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263), batched
 // One CTA (4 warps) per map point, one warp per row i of the point's N x N distance matrix.  The row's median -- the
@@ -787,11 +806,29 @@ struct msl_matcher {
     uint16_t *d_dist = nullptr;
     size_t distCap = 0;
     uint8_t *d_scr = nullptr;  // arena for the window-search arrays
+    uint8_t *h_scr = nullptr;  // its pinned host mirror: a call's inputs are packed here and go up in ONE copy
     size_t scrCap = 0;
     uint8_t *d_dd = nullptr;   // msl_distinctive_descriptors: offsets | descriptors | outputs (grown on demand)
     size_t ddCap = 0;
     uint8_t *d_trk = nullptr;  // msl_search_by_projection_frames_dev: per-frame scratch (grown on demand)
     size_t trkCap = 0;
+    // deferred execution (msl_matcher_batch_begin / _end; a single call is a batch of one): the calls recorded so far
+    bool batching = false;
+    size_t batchOff = 0;  // arena bytes taken by the recorded calls
+    std::vector<SearchArgs> bSearch;
+    std::vector<NodeArgs> bNode;
+    std::vector<FuseArgs> bFuse;
+    struct Out {
+        void *host;
+        const void *dev;
+        size_t bytes;
+    };
+    struct Pending {
+        const void *first;  // the call's outputs are contiguous in the arena: [first, first + bytes)
+        size_t bytes;
+        Out out[3];
+    };
+    std::vector<Pending> pending;
 };
 
 static void matcher_free(msl_matcher *m) {
@@ -800,23 +837,31 @@ static void matcher_free(msl_matcher *m) {
     void *ptrs[] = {m->d_q, m->d_t, m->d_bi, m->d_bd, m->d_sd, m->d_dist, m->d_scr, m->d_dd, m->d_trk};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (m->h_scr) cudaFreeHost(m->h_scr);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
 
-// bump allocator over the scratch arena + H2D copy
+// Bump allocator over the scratch arena.  A search takes a dozen small host arrays: copied one by one from pageable memory
+// they cost more than the kernel (each cudaMemcpyAsync of a pageable buffer is a staged, effectively synchronous copy), so
+// put() packs them into the arena's pinned host mirror at the offsets they will have on the device and flush() sends the
+// packed range up in ONE copy; the outputs (allocated with get() after the inputs, so they are contiguous) come back in
+// one copy into the mirror (fetch) and are handed out from there.
 struct Arena {
     uint8_t *base;
     size_t off, cap;
     cudaStream_t st;
+    uint8_t *hbase;
     bool ok = true;
+    size_t inEnd = 0;
     template <typename T>
     const T *put(const T *h, size_t n) {
         off = align_up(off, 16);
         if (off + n * sizeof(T) > cap) { ok = false; return nullptr; }
         T *d = (T *)(base + off);
+        if (n) memcpy(hbase + off, h, n * sizeof(T));
         off += n * sizeof(T);
-        if (n && cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        inEnd = off;
         return d;
     }
     template <typename T>
@@ -827,31 +872,107 @@ struct Arena {
         off += n * sizeof(T);
         return d;
     }
+    bool flush() {  // every put() so far -> device
+        if (!ok) return false;
+        if (inEnd && cudaMemcpyAsync(base, hbase, inEnd, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        return ok;
+    }
+    // [first, first + bytes) of the arena -> the mirror, then wait; host(p) is the mirror address of device address p
+    bool fetch(const void *first, size_t bytes) {
+        const size_t o = (const uint8_t *)first - base;
+        if (cudaMemcpyAsync(hbase + o, first, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+        return cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    template <typename T>
+    const T *host(const T *d) const { return (const T *)(hbase + ((const uint8_t *)d - base)); }
 };
 
 // The scratch arena of the searches grows with the call: the reference hands SearchByProjection the whole of
 // mvpLocalMapPoints (src/Tracking.cc:1693) and Fuse the map points of every neighbour keyframe (src/LocalMapping.cc:569) --
 // tens of thousands of points -- so only the per-frame keypoint count (MAXK, the kernels' shared-memory grid) is a hard
 // limit; max_queries / max_train of msl_matcher_create size the initial allocation and the Hamming batch buffers.
+static int matcher_execute(msl_matcher *m);
 static int ensure_scratch(msl_matcher *m, size_t n_a, size_t n_b) {
     const size_t need = (n_a + n_b) * 96 + 4096;
+    if (m->batchOff + need <= m->scrCap) return MSL_OK;
+    if (!m->pending.empty()) {  // a deferred batch has filled the arena: run what is recorded, then start over at offset 0
+        const int rc = matcher_execute(m);
+        if (rc) return rc;
+    }
     if (need <= m->scrCap) return MSL_OK;
     MSL_CUDA(cudaStreamSynchronize(m->stream));
     if (m->d_scr) cudaFree(m->d_scr);
-    m->d_scr = nullptr, m->scrCap = 0;
+    if (m->h_scr) cudaFreeHost(m->h_scr);
+    m->d_scr = nullptr, m->h_scr = nullptr, m->scrCap = 0;
     const size_t cap = need + need / 2;
     MSL_CUDA(cudaMalloc((void **)&m->d_scr, cap));
+    MSL_CUDA(cudaMallocHost((void **)&m->h_scr, cap));
     m->scrCap = cap;
     return MSL_OK;
 }
 
-static int run_search(msl_matcher *m, SearchArgs &A, int32_t *cur_match, int32_t *nmatches) {
-    k_search<<<1, 1024, 0, m->stream>>>(A);
-    MSL_LAUNCH_CHECK();
-    MSL_CUDA(cudaMemcpyAsync(cur_match, A.c_match, sizeof(int32_t) * A.nc, cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+static_assert(sizeof(SearchArgs) <= 1024 && sizeof(NodeArgs) <= 1024 && sizeof(FuseArgs) <= 1024 && sizeof(SearchArgs) % 4 == 0 &&
+                  sizeof(NodeArgs) % 4 == 0 && sizeof(FuseArgs) % 4 == 0,
+              "argument records: loaded by one CTA pass, and the 4096 spare bytes per call of ensure_scratch cover them");
+// Runs every recorded call: the packed inputs and the argument records go up in one copy, one launch per kind of search with
+// one CTA per call, the outputs come back with one copy per call into the pinned mirror and are handed to the callers'
+// arrays after a single synchronisation.
+static int matcher_execute(msl_matcher *m) {
+    if (m->pending.empty()) {
+        m->batchOff = 0;
+        return MSL_OK;
+    }
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
+    ar.inEnd = m->batchOff;
+    const SearchArgs *dS = m->bSearch.empty() ? nullptr : ar.put(m->bSearch.data(), m->bSearch.size());
+    const NodeArgs *dN = m->bNode.empty() ? nullptr : ar.put(m->bNode.data(), m->bNode.size());
+    const FuseArgs *dF = m->bFuse.empty() ? nullptr : ar.put(m->bFuse.data(), m->bFuse.size());
+    const size_t nS = m->bSearch.size(), nN = m->bNode.size(), nF = m->bFuse.size();
+    std::vector<msl_matcher::Pending> pend;
+    pend.swap(m->pending);
+    m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear();
+    m->batchOff = 0;
+    if (!ar.flush()) return fail(MSL_ERR_CUDA, "matcher: scratch arena / input copy failure");
+    if (nS) {
+        k_search_many<<<(unsigned)nS, 1024, 0, m->stream>>>(dS);
+        MSL_LAUNCH_CHECK();
+    }
+    if (nN) {
+        k_node_search<<<(unsigned)nN, 1024, 0, m->stream>>>(dN);
+        MSL_LAUNCH_CHECK();
+    }
+    if (nF) {
+        k_fuse_search<<<(unsigned)nF, 1024, 0, m->stream>>>(dF);
+        MSL_LAUNCH_CHECK();
+    }
+    for (const auto &p : pend)
+        MSL_CUDA(cudaMemcpyAsync(m->h_scr + ((const uint8_t *)p.first - m->d_scr), p.first, p.bytes, cudaMemcpyDeviceToHost, m->stream));
     MSL_CUDA(cudaStreamSynchronize(m->stream));
+    for (const auto &p : pend)
+        for (const auto &o : p.out)
+            if (o.host && o.bytes) memcpy(o.host, m->h_scr + ((const uint8_t *)o.dev - m->d_scr), o.bytes);
     return MSL_OK;
+}
+
+// records a call (its inputs are packed, its outputs allocated); executes at once unless a deferred batch is open.
+// The three arrays of `outs` are adjacent in the arena, in this order.
+static int matcher_record(msl_matcher *m, const Arena &ar, msl_matcher::Out o0, msl_matcher::Out o1, msl_matcher::Out o2) {
+    if (!ar.ok) return fail(MSL_ERR_CUDA, "matcher: scratch arena overflow");
+    msl_matcher::Pending p;
+    p.first = o0.dev;
+    p.bytes = (const uint8_t *)o2.dev + o2.bytes - (const uint8_t *)o0.dev;
+    p.out[0] = o0, p.out[1] = o1, p.out[2] = o2;
+    m->pending.push_back(p);
+    m->batchOff = align_up(ar.off, 256);
+    return m->batching ? MSL_OK : matcher_execute(m);
+}
+
+// c_match and nmatches are adjacent in the arena (allocated in that order by every caller)
+static int run_search(msl_matcher *m, Arena &ar, SearchArgs &A, int32_t *cur_match, int32_t *nmatches) {
+    m->bSearch.push_back(A);
+    const int rc = matcher_record(m, ar, {cur_match, A.c_match, sizeof(int32_t) * A.nc}, {nmatches, A.nmatches, sizeof(int32_t)}, {nullptr, A.nmatches, sizeof(int32_t)});
+    if (rc) m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear(), m->pending.clear(), m->batchOff = 0;
+    return rc;
 }
 
 extern "C" {
@@ -874,6 +995,7 @@ int msl_matcher_create(int max_queries, int max_train, int max_batch, int device
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_sd, B * max_queries * 4);
     m->scrCap = (size_t)(max_queries + max_train) * 96 + 4096;
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_scr, m->scrCap);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_scr, m->scrCap);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         matcher_free(m);
@@ -890,6 +1012,22 @@ int msl_matcher_sync(msl_matcher *m) {
     MSL_CUDA(cudaSetDevice(m->device));
     MSL_CUDA(cudaStreamSynchronize(m->stream));
     return MSL_OK;
+}
+
+int msl_matcher_batch_begin(msl_matcher *m) {
+    if (!m) return fail(MSL_ERR_INVALID, "null handle");
+    if (m->batching) return fail(MSL_ERR_STATE, "msl_matcher_batch_begin: a batch is already open");
+    m->batching = true;
+    return MSL_OK;
+}
+int msl_matcher_batch_end(msl_matcher *m) {
+    if (!m) return fail(MSL_ERR_INVALID, "null handle");
+    if (!m->batching) return fail(MSL_ERR_STATE, "msl_matcher_batch_end: no open batch");
+    m->batching = false;
+    MSL_CUDA(cudaSetDevice(m->device));
+    const int rc = matcher_execute(m);
+    if (rc) m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear(), m->pending.clear(), m->batchOff = 0;
+    return rc;
 }
 
 int msl_hamming_best2_dev(msl_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int batch,
@@ -994,7 +1132,7 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
         const int rc_ = ensure_scratch(m, (size_t)(n_last), (size_t)(n_cur));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.q_valid = ar.put(valid.data(), n_last);
     A.q_obs = ar.put(last_mp_obs, n_last);
     A.q_desc = ar.put(last_mp_desc, (size_t)n_last * 32);
@@ -1012,7 +1150,7 @@ int msl_search_by_projection_frame(msl_matcher *m, const msl_frame_geom *geom, c
     A.assign = ar.get<int32_t>(n_last);
     A.bin = ar.get<int32_t>(n_last);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_frame: scratch arena / copy failure");
-    return run_search(m, A, cur_match, nmatches);
+    return run_search(m, ar, A, cur_match, nmatches);
 }
 
 int msl_search_by_projection_frames_dev(msl_matcher *m, const msl_frame_geom *geom, float th, int check_orientation, float th_depth,
@@ -1144,7 +1282,7 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
         const int rc_ = ensure_scratch(m, (size_t)(n_mp), (size_t)(n_cur));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.q_valid = ar.put(mp_valid, n_mp);
     A.q_obs = ar.put(mp_obs, n_mp);
     A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);
@@ -1162,7 +1300,7 @@ int msl_search_by_projection_points(msl_matcher *m, const msl_frame_geom *geom, 
     A.assign = ar.get<int32_t>(n_mp);
     A.bin = ar.get<int32_t>(n_mp);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_points: scratch arena / copy failure");
-    return run_search(m, A, cur_match, nmatches);
+    return run_search(m, ar, A, cur_match, nmatches);
 }
 
 int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom, const float Tcw_cur[16], float th,
@@ -1200,7 +1338,7 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
         const int rc_ = ensure_scratch(m, (size_t)(n_kf), (size_t)(n_cur));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.q_valid = ar.put(kf_valid, n_kf);
     A.q_obs = ar.put(ones.data(), n_kf);
     A.q_desc = ar.put(kf_mp_desc, (size_t)n_kf * 32);
@@ -1219,7 +1357,7 @@ int msl_search_by_projection_keyframe(msl_matcher *m, const msl_frame_geom *geom
     A.assign = ar.get<int32_t>(n_kf);
     A.bin = ar.get<int32_t>(n_kf);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_projection_keyframe: scratch arena / copy failure");
-    return run_search(m, A, cur_match, nmatches);
+    return run_search(m, ar, A, cur_match, nmatches);
 }
 
 static bool csr_ok(int nNodes, const uint32_t *id, const int32_t *off, const int32_t *feat, int nFeat) {
@@ -1236,13 +1374,12 @@ static bool csr_ok(int nNodes, const uint32_t *id, const int32_t *off, const int
     return true;
 }
 
-static int run_node_search(msl_matcher *m, NodeArgs &A, int nOut, int32_t *out, int32_t *nmatches) {
-    k_node_search<<<1, 1024, 0, m->stream>>>(A);
-    MSL_LAUNCH_CHECK();
-    MSL_CUDA(cudaMemcpyAsync(out, A.out, sizeof(int32_t) * nOut, cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaStreamSynchronize(m->stream));
-    return MSL_OK;
+// out, bin and nmatches are adjacent in the arena (allocated in that order by both callers)
+static int run_node_search(msl_matcher *m, Arena &ar, NodeArgs &A, int nOut, int32_t *out, int32_t *nmatches) {
+    m->bNode.push_back(A);
+    const int rc = matcher_record(m, ar, {out, A.out, sizeof(int32_t) * nOut}, {nullptr, A.bin, 0}, {nmatches, A.nmatches, sizeof(int32_t)});
+    if (rc) m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear(), m->pending.clear(), m->batchOff = 0;
+    return rc;
 }
 
 int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int n_nodes_kf, const uint32_t *kf_node_id,
@@ -1269,7 +1406,7 @@ int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int 
         const int rc_ = ensure_scratch(m, (size_t)(n_kf + n_nodes_kf + n_nodes_f), (size_t)(n_f));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.idA = ar.put(kf_node_id, n_nodes_kf), A.offA = ar.put(kf_node_off, n_nodes_kf + 1);
     A.featA = ar.put(kf_node_feat, kf_node_off[n_nodes_kf]);
     A.idB = ar.put(f_node_id, n_nodes_f), A.offB = ar.put(f_node_off, n_nodes_f + 1);
@@ -1278,7 +1415,7 @@ int msl_search_by_bow(msl_matcher *m, float nnratio, int check_orientation, int 
     A.b_desc = ar.put(f_desc, (size_t)n_f * 32), A.b_angle = ar.put(f_angle, n_f);
     A.out = ar.get<int32_t>(n_f), A.bin = ar.get<int32_t>(n_f), A.nmatches = ar.get<int32_t>(1);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_by_bow: scratch arena / copy failure");
-    return run_node_search(m, A, n_f, f_match, nmatches);
+    return run_node_search(m, ar, A, n_f, f_match, nmatches);
 }
 
 int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float Cw1[3], const float Tcw2[16],
@@ -1323,7 +1460,7 @@ int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float
         const int rc_ = ensure_scratch(m, (size_t)(n1 + n_nodes1 + n_nodes2), (size_t)(n2));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.idA = ar.put(node_id1, n_nodes1), A.offA = ar.put(node_off1, n_nodes1 + 1), A.featA = ar.put(node_feat1, node_off1[n_nodes1]);
     A.idB = ar.put(node_id2, n_nodes2), A.offB = ar.put(node_off2, n_nodes2 + 1), A.featB = ar.put(node_feat2, node_off2[n_nodes2]);
     A.a_flag = ar.put(has_mp1, n1), A.a_desc = ar.put(desc1, (size_t)n1 * 32), A.a_angle = ar.put(angle1, n1);
@@ -1332,7 +1469,7 @@ int msl_search_for_triangulation(msl_matcher *m, const float F12[9], const float
     A.b_xy = ar.put(xy2, (size_t)n2 * 2), A.b_uright = ar.put(uright2, n2), A.b_octave = ar.put(octave2, n2);
     A.out = ar.get<int32_t>(n1), A.bin = ar.get<int32_t>(n1), A.nmatches = ar.get<int32_t>(1);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_search_for_triangulation: scratch arena / copy failure");
-    return run_node_search(m, A, n1, matches12, nmatches);
+    return run_node_search(m, ar, A, n1, matches12, nmatches);
 }
 
 int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[16], float th, float log_scale_factor,
@@ -1369,7 +1506,7 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
         const int rc_ = ensure_scratch(m, (size_t)(n_mp), (size_t)(n_kf));
         if (rc_) return rc_;
     }
-    Arena ar{m->d_scr, 0, m->scrCap, m->stream};
+    Arena ar{m->d_scr, m->batchOff, m->scrCap, m->stream, m->h_scr};
     A.q_valid = ar.put(mp_valid, n_mp), A.q_desc = ar.put(mp_desc, (size_t)n_mp * 32);
     A.q_world = ar.put(mp_world, (size_t)n_mp * 3), A.q_normal = ar.put(mp_normal, (size_t)n_mp * 3);
     A.q_dist = ar.put(mp_dist, (size_t)n_mp * 2);
@@ -1377,13 +1514,11 @@ int msl_fuse_search(msl_matcher *m, const msl_frame_geom *geom, const float Tcw[
     A.c_desc = ar.put(kf_desc, (size_t)n_kf * 32);
     A.bestIdx = ar.get<int32_t>(n_mp), A.bestDist = ar.get<int32_t>(n_mp), A.nFused = ar.get<int32_t>(1);
     if (!ar.ok) return fail(MSL_ERR_CUDA, "msl_fuse_search: scratch arena / copy failure");
-    k_fuse_search<<<1, 1024, 0, m->stream>>>(A);
-    MSL_LAUNCH_CHECK();
-    MSL_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaMemcpyAsync(best_dist, A.bestDist, sizeof(int32_t) * n_mp, cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaMemcpyAsync(nfused, A.nFused, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
-    MSL_CUDA(cudaStreamSynchronize(m->stream));
-    return MSL_OK;
+    m->bFuse.push_back(A);
+    const int rc = matcher_record(m, ar, {best_idx, A.bestIdx, sizeof(int32_t) * n_mp}, {best_dist, A.bestDist, sizeof(int32_t) * n_mp},
+                                  {nfused, A.nFused, sizeof(int32_t)});
+    if (rc) m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear(), m->pending.clear(), m->batchOff = 0;
+    return rc;
 }
 
 int msl_distinctive_descriptors(msl_matcher *m, int n_points, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,

@@ -94,7 +94,7 @@ class ORBmatcher:
             self._h, ptr(geom), ptr(a(Tcw_cur, np.float32)), ptr(a(Tcw_last, np.float32)), C.c_float(th),
             int(self.mbCheckOrientation), n_last, *[ptr(x) for x in args], n_cur, *[ptr(x) for x in cargs], ptr(cm),
             C.byref(nm)))
-        return nm.value, cm
+        return self._ret(lambda: (nm.value, cm))
 
     def SearchByProjectionFrames_dev(self, geom, th, th_depth, d_kps, d_desc, rows, d_counts, n_frames, d_xy_un, d_uright, d_kdepth,
                                      Tcw, d_cur_match, d_nmatches, stream=None):
@@ -120,7 +120,7 @@ class ORBmatcher:
         check(self._L.msl_search_by_projection_points(
             self._h, ptr(geom), C.c_float(th), C.c_float(self.mfNNratio), n_mp, *[ptr(x) for x in args], n_cur,
             *[ptr(x) for x in cargs], ptr(cm), C.byref(nm)))
-        return nm.value, cm
+        return self._ret(lambda: (nm.value, cm))
 
     def SearchByProjectionKeyFrame(self, geom, Tcw_cur, th, ORBdist, kf, cur, log_scale_factor=None):
         """SearchByProjection(Frame &Cur, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
@@ -140,11 +140,50 @@ class ORBmatcher:
             self._h, ptr(geom), ptr(a(Tcw_cur, np.float32)), C.c_float(th), int(ORBdist), int(self.mbCheckOrientation),
             C.c_float(log_scale_factor), n_kf, *[ptr(x) for x in args], n_cur, *[ptr(x) for x in cargs], ptr(cm),
             C.byref(nm)))
-        return nm.value, cm
+        return self._ret(lambda: (nm.value, cm))
+
+    # ---- deferred batches (msl_matcher_batch_begin / _end): inside `with matcher.batch():` the six searches return a
+    # Deferred whose .get() yields the usual tuple once the block has ended (one upload, one CTA per call, one sync)
+    class Deferred:
+        def __init__(self, thunk):
+            self._thunk, self._done = thunk, False
+
+        def get(self):
+            if not self._done:
+                raise RuntimeError("the batch is still open")
+            return self._thunk()
+
+    class _Batch:
+        def __init__(self, m):
+            self.m = m
+
+        def __enter__(self):
+            check(self.m._L.msl_matcher_batch_begin(self.m._h))
+            self.m._open = []
+            return self.m
+
+        def __exit__(self, *exc):
+            pend, self.m._open = self.m._open, None
+            check(self.m._L.msl_matcher_batch_end(self.m._h))
+            for d in pend:
+                d._done = True
+            return False
+
+    def batch(self):
+        return ORBmatcher._Batch(self)
+
+    def _ret(self, thunk):
+        if getattr(self, "_open", None) is None:
+            return thunk()
+        d = ORBmatcher.Deferred(thunk)
+        self._open.append(d)
+        return d
 
     @staticmethod
     def _csr(fv):
         """DBoW2::FeatureVector (dict node id -> feature indices) -> (ids u32 ascending, offsets i32, features i32)"""
+        if isinstance(fv, tuple) and len(fv) == 3 and isinstance(fv[0], np.ndarray):
+            return fv  # already packed
         items = sorted(fv.items())
         ids = np.asarray([k for k, _ in items], np.uint32)
         off = np.zeros(len(items) + 1, np.int32)
@@ -166,7 +205,7 @@ class ORBmatcher:
         check(self._L.msl_search_by_bow(self._h, C.c_float(self.mfNNratio), int(self.mbCheckOrientation), len(kid), ptr(kid),
                                         ptr(koff), ptr(kfeat), len(fid), ptr(fid), ptr(foff), ptr(ffeat), len(ka), ptr(kv),
                                         ptr(kd), ptr(ka), len(fa), ptr(fd), ptr(fa), ptr(fm), C.byref(nm)))
-        return nm.value, fm
+        return self._ret(lambda: (nm.value, fm))
 
     def SearchForTriangulation(self, kf1, kf2, F12, Cw1, Tcw2, K2, scale_factors2, level_sigma2_2, bOnlyStereo=False):
         """SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vMatchedPairs, bOnlyStereo)
@@ -187,7 +226,7 @@ class ORBmatcher:
             int(bOnlyStereo), int(self.mbCheckOrientation), len(sf), ptr(sf), ptr(ls), len(id1), ptr(id1), ptr(off1), ptr(ft1),
             len(id2), ptr(id2), ptr(off2), ptr(ft2), len(a1[0]), *[ptr(x) for x in a1], len(a2[0]), *[ptr(x) for x in a2],
             ptr(m12), C.byref(nm)))
-        return nm.value, m12
+        return self._ret(lambda: (nm.value, m12))
 
     def Fuse(self, geom, Tcw, mps, kf, inv_level_sigma2, th=3.0, log_scale_factor=None):
         """The search part of Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) (src/ORBmatcher.cc:408-519).
@@ -206,7 +245,7 @@ class ORBmatcher:
         check(self._L.msl_fuse_search(self._h, ptr(geom), ptr(a(Tcw, np.float32)), C.c_float(th), C.c_float(log_scale_factor),
                                       ptr(ils), len(margs[0]), *[ptr(x) for x in margs], len(kargs[1]), *[ptr(x) for x in kargs],
                                       ptr(bi), ptr(bd), C.byref(nf)))
-        return nf.value, bi, bd
+        return self._ret(lambda: (nf.value, bi, bd))
 
     def ComputeDistinctiveDescriptors(self, desc_lists):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:210-263) for a batch of map points.

@@ -456,6 +456,8 @@ def search_by_projection_keyframe(geom, Tcw_cur, th, orb_dist, check_ori, log_sc
 
 def _csr(fv):
     """FeatureVector dict/list of (node id, [feature indices]) -> (ids u32, offsets i32, features i32), ascending ids."""
+    if isinstance(fv, tuple) and len(fv) == 3 and isinstance(fv[0], np.ndarray):
+        return fv  # already packed (bench.py packs once so that neither arm is timed on Python list handling)
     items = sorted(fv.items()) if isinstance(fv, dict) else sorted(fv)
     ids = np.asarray([k for k, _ in items], np.uint32)
     off = np.zeros(len(items) + 1, np.int32)

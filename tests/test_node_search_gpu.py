@@ -139,3 +139,42 @@ def test_golden_node_searches_gpu(msl):
     mps, kfs, Tcw, ils = S.fuse_scene(3)
     n, bi, bd = m.Fuse(msl.frame_geom(), Tcw, mps, kfs, ils, th=3.0, log_scale_factor=LSF)
     assert n == int(gold["fuse_n"]) and np.array_equal(bi, gold["fuse_idx"]) and np.array_equal(bd, gold["fuse_dist"])
+
+
+def test_deferred_batch_of_mixed_searches(oracle, msl):
+    """msl_matcher_batch_begin / _end: eight SearchByBoW, SearchForTriangulation, Fuse and SearchByProjection calls recorded,
+    one upload, one CTA per call -- every call's result equals the oracle's (and the immediate call's); a small handle whose
+    arena overflows mid-batch executes the recorded part early and still delivers everything at the end."""
+    geom = msl.frame_geom()
+    for cap in (4096, 64):  # 64: the arena holds about one call -> early execution inside the batch
+        m = msl.ORBmatcher(nnratio=0.7, max_queries=cap, max_train=cap)
+        bows = [S.bow_scene(10 + k, shuffle=bool(k & 1)) for k in range(3)]
+        tris = [S.triangulation_scene(20 + k) for k in range(3)]
+        fus = [S.fuse_scene(30 + k) for k in range(2)]
+        cur, last, mps2, Tc, Tl = S.match_scene(41)
+        with m.batch():
+            rb = [m.SearchByBoW(kf, f) for kf, f in bows]
+            rt = [m.SearchForTriangulation(k1, k2, F12, Cw1, Tcw2, K2, sf, ls) for k1, k2, F12, Cw1, Tcw2, K2, sf, ls in tris]
+            rf = [m.Fuse(geom, Tcw, mps, kfs, ils, th=3.0, log_scale_factor=LSF) for mps, kfs, Tcw, ils in fus]
+            rp = m.SearchByProjectionFrame(geom, Tc, Tl, 7.0, last, cur)
+            with pytest.raises(RuntimeError):
+                rb[0].get()
+        for (kf, f), r in zip(bows, rb):
+            n_o, fm_o = oracle.search_by_bow(0.7, True, kf, f)
+            n_g, fm_g = r.get()
+            assert n_o == n_g and np.array_equal(fm_o, fm_g)
+        for (k1, k2, F12, Cw1, Tcw2, K2, sf, ls), r in zip(tris, rt):
+            n_o, m_o = oracle.search_for_triangulation(F12, Cw1, Tcw2, K2, False, True, sf, ls, k1, k2)
+            n_g, m_g = r.get()
+            assert n_o == n_g and np.array_equal(m_o, m_g)
+        for (mps, kfs, Tcw, ils), r in zip(fus, rf):
+            n_o, bi_o, bd_o = oracle.fuse_search(geom, Tcw, 3.0, LSF, ils, mps, kfs)
+            n_g, bi_g, bd_g = r.get()
+            assert n_o == n_g and np.array_equal(bi_o, bi_g) and np.array_equal(bd_o, bd_g)
+        n_o, cm_o = oracle.search_by_projection_frame(geom, Tc, Tl, 7.0, True, last, cur)
+        n_g, cm_g = rp.get()
+        assert n_o == n_g and np.array_equal(cm_o, cm_g)
+        # the handle is back in immediate mode
+        n_g, fm_g = m.SearchByBoW(*bows[0])
+        assert (n_g, fm_g.tobytes()) == (rb[0].get()[0], rb[0].get()[1].tobytes())
+        m.close()
