@@ -129,6 +129,11 @@ void *msl_matcher_stream(msl_matcher *); /* cudaStream_t */
  * executed early -- results are only promised at batch_end.  Outside a batch every search is a batch of one. */
 int msl_matcher_batch_begin(msl_matcher *);
 int msl_matcher_batch_end(msl_matcher *);
+/* measurement aid: with timing on, every execution (a batch, or a single search) is bracketed by CUDA events on the handle's
+ * stream; msl_matcher_last_execution returns the device time of the last one -- upload + kernels + download -- and the
+ * number of calls it ran */
+int msl_matcher_set_timing(msl_matcher *, int on);
+int msl_matcher_last_execution(msl_matcher *, double *device_ms, int *calls);
 
 /* All-pairs Hamming distance of 256-bit descriptors: dist[b][i][j] = popcount(q[b][i] ^ t[b][j]),
  * batch pairs; q: batch x nq x 32, t: batch x nt x 32, dist: batch x nq x nt uint16. */

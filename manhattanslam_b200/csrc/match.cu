@@ -829,6 +829,11 @@ struct msl_matcher {
         Out out[3];
     };
     std::vector<Pending> pending;
+    // optional timing of an execution on the stream (msl_matcher_set_timing): upload + kernels + download
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float lastMs = 0.f;
+    int lastCalls = 0;
 };
 
 static void matcher_free(msl_matcher *m) {
@@ -838,6 +843,8 @@ static void matcher_free(msl_matcher *m) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->h_scr) cudaFreeHost(m->h_scr);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -932,6 +939,7 @@ static int matcher_execute(msl_matcher *m) {
     pend.swap(m->pending);
     m->bSearch.clear(), m->bNode.clear(), m->bFuse.clear();
     m->batchOff = 0;
+    if (m->timing) MSL_CUDA(cudaEventRecord(m->ev0, m->stream));
     if (!ar.flush()) return fail(MSL_ERR_CUDA, "matcher: scratch arena / input copy failure");
     if (nS) {
         k_search_many<<<(unsigned)nS, 1024, 0, m->stream>>>(dS);
@@ -947,7 +955,12 @@ static int matcher_execute(msl_matcher *m) {
     }
     for (const auto &p : pend)
         MSL_CUDA(cudaMemcpyAsync(m->h_scr + ((const uint8_t *)p.first - m->d_scr), p.first, p.bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (m->timing) MSL_CUDA(cudaEventRecord(m->ev1, m->stream));
     MSL_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->timing) {
+        MSL_CUDA(cudaEventElapsedTime(&m->lastMs, m->ev0, m->ev1));
+        m->lastCalls = (int)pend.size();
+    }
     for (const auto &p : pend)
         for (const auto &o : p.out)
             if (o.host && o.bytes) memcpy(o.host, m->h_scr + ((const uint8_t *)o.dev - m->d_scr), o.bytes);
@@ -1014,6 +1027,21 @@ int msl_matcher_sync(msl_matcher *m) {
     return MSL_OK;
 }
 
+int msl_matcher_set_timing(msl_matcher *m, int on) {
+    if (!m) return fail(MSL_ERR_INVALID, "null handle");
+    MSL_CUDA(cudaSetDevice(m->device));
+    if (on && !m->ev0) {
+        MSL_CUDA(cudaEventCreate(&m->ev0));
+        MSL_CUDA(cudaEventCreate(&m->ev1));
+    }
+    m->timing = on != 0;
+    return MSL_OK;
+}
+int msl_matcher_last_execution(msl_matcher *m, double *device_ms, int *calls) {
+    if (!m || !device_ms || !calls) return fail(MSL_ERR_INVALID, "msl_matcher_last_execution: null argument");
+    *device_ms = m->lastMs, *calls = m->lastCalls;
+    return MSL_OK;
+}
 int msl_matcher_batch_begin(msl_matcher *m) {
     if (!m) return fail(MSL_ERR_INVALID, "null handle");
     if (m->batching) return fail(MSL_ERR_STATE, "msl_matcher_batch_begin: a batch is already open");

@@ -172,6 +172,15 @@ class ORBmatcher:
     def batch(self):
         return ORBmatcher._Batch(self)
 
+    def set_timing(self, on=True):
+        check(self._L.msl_matcher_set_timing(self._h, int(on)))
+
+    def last_execution(self):
+        """(device ms of the last execution: upload + kernels + download, calls it ran)"""
+        ms, n = C.c_double(), C.c_int()
+        check(self._L.msl_matcher_last_execution(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def _ret(self, thunk):
         if getattr(self, "_open", None) is None:
             return thunk()
