@@ -1167,9 +1167,10 @@ def run_ours(a, rank, world, local_rank):
     # ---- e2e (headline): the sensor frames of a step -- gray (CV_8U) and depth (CV_16U), what System::TrackRGBD receives -- go up
     # ONCE from pinned host memory into a frame set every stage reads (msl_glue_upload_frames; the CV_32F depth of
     # Tracking::GrabImageRGBD is produced on the device), the stages run through their *_dev entry points on their own
-    # streams, and every result comes back to pinned host memory before the step ends.  The upload of step k+1 is issued
-    # behind the launches of step k (double-buffered frame sets), as a streaming front-end does; all K uploads and all K
-    # downloads lie inside the timed region.
+    # streams, and every result comes back to pinned host memory.  Steps are pipelined the way a streaming front-end runs:
+    # the upload and the launches of step k+1 are issued before the host waits for the results of step k (two frame sets,
+    # two sets of result buffers); all K uploads and all K downloads lie inside the timed region, which ends when the last
+    # step's results are on the host.
     glue_up = glue if glue is not None else msl.FrameGlue(W, H, max_batch=B, device=local_rank)
     wait_streams = [x for x in (orb.stream if orb else None, plane.stream if plane else None,
                                 sf.input_stream if sf else None) if x]
@@ -1181,51 +1182,84 @@ def run_ours(a, rank, world, local_rank):
                                                      aux.numel() if aux is not None else 0)
         return {"gray": g_, "depth": dep_, "d16": d16_, "mem": aux_ or resident["mem"]}
 
-    def step_frames(i, sets, last):
+    # results land in two sets of pinned host buffers: step i's launches (and its downloads, enqueued behind them on the
+    # producing streams) are issued BEFORE step i-1's results are awaited, as a streaming consumer does -- otherwise the
+    # host's wait at the end of a step would drain the device and the next step's superpixel stage could not overlap this
+    # step's fuse chain, which is where the device-resident number comes from
+    def pin_like(t_):
+        return torch.empty_like(t_).pin_memory()
+
+    hres = [{"kps": h_kps, "desc": h_desc, "counts": h_counts, "match": h_match, "cm": h_cm, "nm": h_nm, "blocks": h_blocks,
+             "seedm": h_seedm, "memdet": h_memdet, "pcount": h_pcount, "precs": h_precs,
+             "sfc": torch.zeros((B, 2), dtype=torch.int32).pin_memory()}]
+    hres.append({k_: (pin_like(v_) if v_ is not None else None) for k_, v_ in hres[0].items()})
+    done_ev = [None, None]
+
+    def launch_frames(i, sets):
         slot = i & 1
+        H_ = hres[slot]
         for st_ in wait_streams:
             glue_up.frames_wait(slot, st_)
         k = state["k"] & 1
         step_dev(sets[slot])
-        if not last:
-            sets[slot ^ 1] = upload(slot ^ 1)
+        evs = []
         if do_orb:
             with torch.cuda.stream(s_orb):
-                h_kps.copy_(d_kps, non_blocking=True)
-                h_desc.copy_(d_desc, non_blocking=True)
-                h_counts.copy_(d_kpc[k], non_blocking=True)
+                H_["kps"].copy_(d_kps, non_blocking=True)
+                H_["desc"].copy_(d_desc, non_blocking=True)
+                H_["counts"].copy_(d_kpc[k], non_blocking=True)
                 if do_match:
-                    h_match[0].copy_(d_bi, non_blocking=True)
-                    h_match[1].copy_(d_bd, non_blocking=True)
-                    h_match[2].copy_(d_sd, non_blocking=True)
+                    H_["match"][0].copy_(d_bi, non_blocking=True)
+                    H_["match"][1].copy_(d_bd, non_blocking=True)
+                    H_["match"][2].copy_(d_sd, non_blocking=True)
                 if do_track:
-                    h_cm.copy_(d_cm, non_blocking=True)
-                    h_nm.copy_(d_nm, non_blocking=True)
+                    H_["cm"].copy_(d_cm, non_blocking=True)
+                    H_["nm"].copy_(d_nm, non_blocking=True)
+                e_ = torch.cuda.Event()
+                e_.record(s_orb)
+                evs.append(e_)
         if plane is not None:
             with torch.cuda.stream(s_pl):
                 if do_plane:
-                    h_blocks.copy_(d_blocks, non_blocking=True)
-                    h_seedm[0].copy_(d_seedm, non_blocking=True)
-                    h_seedm[1].copy_(d_edges, non_blocking=True)
+                    H_["blocks"].copy_(d_blocks, non_blocking=True)
+                    H_["seedm"][0].copy_(d_seedm, non_blocking=True)
+                    H_["seedm"][1].copy_(d_edges, non_blocking=True)
                 if do_detect:
-                    h_memdet.copy_(d_memdet[k], non_blocking=True)
-                    h_pcount.copy_(d_pcount, non_blocking=True)
-                    h_precs.copy_(d_precs, non_blocking=True)
-        if do_surfel:
-            sf.read_stats()  # synchronises the surfel chain: {updated, deleted, new, map size} of the step on the host
-        for s_ in lib_streams:
-            s_.synchronize()
+                    H_["memdet"].copy_(d_memdet[k], non_blocking=True)
+                    H_["pcount"].copy_(d_pcount, non_blocking=True)
+                    H_["precs"].copy_(d_precs, non_blocking=True)
+                e_ = torch.cuda.Event()
+                e_.record(s_pl)
+                evs.append(e_)
+        if do_surfel:  # the surfel stage's per-frame result: {new surfels, updated surfels} of every frame
+            with torch.cuda.stream(s_sf):
+                H_["sfc"].copy_(d_sfc[k], non_blocking=True)
+                e_ = torch.cuda.Event()
+                e_.record(s_sf)
+                evs.append(e_)
+        done_ev[slot] = evs
+
+    def collect_frames(i):
+        for e_ in done_ev[i & 1] or []:
+            e_.synchronize()
+        done_ev[i & 1] = None
+
+    def run_frames(n_steps):
+        sets = [None, None]
+        sets[0] = upload(0)
+        for i in range(n_steps):
+            launch_frames(i, sets)
+            if i > 0:
+                collect_frames(i - 1)  # step i-1 is complete on the host: its frame set may be overwritten
+            if i + 1 < n_steps:
+                sets[(i + 1) & 1] = upload((i + 1) & 1)
+        collect_frames(n_steps - 1)
 
     barrier()
-    sets = [None, None]
-    sets[0] = upload(0)
-    for i in range(min(a.warmup, 2)):
-        step_frames(i, sets, False)
-    barrier()  # (the frame set the next step reads was uploaded by the last warm-up step: upload it again inside the region)
+    run_frames(min(a.warmup, 2) + 1)
+    barrier()
     t0 = time.perf_counter()
-    sets[0] = upload(0)
-    for i in range(a.steps):
-        step_frames(i, sets, i + 1 == a.steps)
+    run_frames(a.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -1245,7 +1279,7 @@ def run_ours(a, rank, world, local_rank):
     if do_detect:
         fd2h += h_memdet.numel() * 4 + B * 4 + h_precs.numel()
     if do_surfel:
-        fd2h += 32
+        fd2h += B * 8
     h2d = d2h = 0
     if do_orb:
         h2d += h_gray.numel()
@@ -1296,7 +1330,8 @@ def run_ours(a, rank, world, local_rank):
                        "what": "host C ABI, pinned host buffers: the sensor frames (gray CV_8U + depth CV_16U%s) uploaded once per step "
                                "into a frame set every stage reads (msl_glue_upload_frames, CV_32F depth produced on the device), "
                                "stages through their *_dev entry points, every result copied back to the host inside the step; "
-                               "the upload of step k+1 is issued behind the launches of step k" % (
+                               "the upload and the launches of step k+1 are issued before the results of step k are awaited (two frame sets, two "
+                               "sets of host result buffers), every copy inside the timed region" % (
                                    " + the host-computed membership image" if aux is not None else "")},
                "e2e_host_calls": {"value": e2e_calls_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                   "what": "the same step through the per-class host entry points (msl_orb_extract, msl_hamming_best2, "

@@ -255,53 +255,75 @@ __global__ void __launch_bounds__(128)
     __syncthreads();
     const int np = cw * ch;
     const int lane = tid & 31, wid = tid >> 5;
+    // pixel p = tid, tid + 128, ... of the cell in row-major order: (cy, cx) advanced by a fixed step instead of divided out
+    // of p in each of the three passes (the divisions were a fifth of the kernel's instructions)
+    const int cwd = max(cw, 1);  // (an empty cell has np <= 0: no pass runs)
+    const int stepY = 128 / cwd, stepX = 128 - stepY * cwd;
+    const int cy0 = tid / cwd, cx0 = tid - cy0 * cwd;
+#define FAST_ADVANCE(cy, cx) \
+    do {                     \
+        cx += stepX;         \
+        cy += stepY;         \
+        if (cx >= cw) {      \
+            cx -= cw;        \
+            cy++;            \
+        }                    \
+    } while (0)
+    // scores with a one-pixel border of zeros (a neighbour outside the cell counts as 0 in the NMS): no bounds tests
+    uint8_t *const scI = sc + CELL_TILE + 1;  // score of (cy, cx) at scI[cy * CELL_TILE + cx]
+    for (int i = tid; i < 2 * (cw + 2) + 2 * ch; i += 128) {
+        int by, bx;
+        if (i < cw + 2) by = -1, bx = i - 1;
+        else if (i < 2 * (cw + 2)) by = ch, bx = i - (cw + 2) - 1;
+        else if (i < 2 * (cw + 2) + ch) by = i - 2 * (cw + 2), bx = -1;
+        else by = i - 2 * (cw + 2) - ch, bx = cw;
+        scI[by * CELL_TILE + bx] = 0;
+    }
     {
         const int thq = min(minTh, iniTh);
+        int cy = cy0, cx = cx0;
         for (int p0 = 0; p0 < np; p0 += 128) {
             const int p = p0 + tid;
             bool pass = false;
             int q = 0;
             if (p < np) {
-                const int cy = p / cw, cx = p - cy * cw;
                 q = cy * CELL_TILE + cx;
                 pass = fast_quick(roi + (cy + 3) * tileW + cx + 3, tileW, thq);
-                if (!pass) sc[q] = 0;
+                if (!pass) scI[q] = 0;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
             int base = 0;
             if (lane == 0 && bal) base = atomicAdd(&s_ncand, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (pass) cand[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)q;
+            FAST_ADVANCE(cy, cx);
         }
         __syncthreads();
         const int nc = s_ncand;
         for (int i = tid; i < nc; i += 128) {
             const int q = cand[i];
             const int cy = q / CELL_TILE, cx = q - cy * CELL_TILE;
-            sc[q] = (uint8_t)fast_smax(roi + (cy + 3) * tileW + cx + 3, tileW);
+            scI[q] = (uint8_t)fast_smax(roi + (cy + 3) * tileW + cx + 3, tileW);
         }
     }
     __syncthreads();
     // in-cell NMS: strict maximum over the 8 neighbours; neighbours outside the cell's ring count as 0
     int any = 0;
-    for (int p = tid; p < np; p += 128) {
-        int cy = p / cw, cx = p - cy * cw;
-        int s = sc[cy * CELL_TILE + cx];
-        int keep = 0;
-        if (s > minTh) {
-            int m = 0;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dx == 0 && dy == 0) continue;
-                    int nx = cx + dx, ny = cy + dy;
-                    if (nx >= 0 && nx < cw && ny >= 0 && ny < ch) m = max(m, (int)sc[ny * CELL_TILE + nx]);
-                }
-            keep = s > m;
+    {
+        int cy = cy0, cx = cx0;
+        for (int p = tid; p < np; p += 128) {
+            const uint8_t *c = scI + cy * CELL_TILE + cx;
+            const int s = c[0];
+            int keep = 0;
+            if (s > minTh) {
+                const int m0 = max(max((int)c[-CELL_TILE - 1], (int)c[-CELL_TILE]), max((int)c[-CELL_TILE + 1], (int)c[-1]));
+                const int m1 = max(max((int)c[1], (int)c[CELL_TILE - 1]), max((int)c[CELL_TILE], (int)c[CELL_TILE + 1]));
+                keep = s > max(m0, m1);
+            }
+            sv[cy * CELL_TILE + cx] = keep ? (uint8_t)s : 0;
+            any |= (keep && s > iniTh);
+            FAST_ADVANCE(cy, cx);
         }
-        sv[cy * CELL_TILE + cx] = keep ? (uint8_t)s : 0;
-        any |= (keep && s > iniTh);
     }
     if (any) s_any = 1;
     __syncthreads();
@@ -309,30 +331,30 @@ __global__ void __launch_bounds__(128)
     uint32_t *out = staging + ((size_t)frame * totalCells + cell) * capCell;
     const int offX = C.x0 + 3 - MIN_BORDER, offY = C.y0 + 3 - MIN_BORDER;
     int base = 0;
-    for (int p0 = 0; p0 < np; p0 += 128) {
-        int p = p0 + tid;
-        int s = 0, cx = 0, cy = 0;
-        if (p < np) {
-            cy = p / cw;
-            cx = p - cy * cw;
-            s = sv[cy * CELL_TILE + cx];
-        }
-        const bool f = s > thr;
-        const unsigned bal = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) wsum[wid] = __popc(bal);
-        __syncthreads();
-        int pre = 0, tot = 0;
+    {
+        int cy = cy0, cx = cx0;
+        for (int p0 = 0; p0 < np; p0 += 128) {
+            const int p = p0 + tid;
+            const int s = p < np ? (int)sv[cy * CELL_TILE + cx] : 0;
+            const bool f = s > thr;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) wsum[wid] = __popc(bal);
+            __syncthreads();
+            int pre = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            int c = wsum[w];
-            if (w < wid) pre += c;
-            tot += c;
+            for (int w = 0; w < 4; w++) {
+                int c = wsum[w];
+                if (w < wid) pre += c;
+                tot += c;
+            }
+            if (f) out[base + pre + __popc(bal & ((1u << lane) - 1))] =
+                       (uint32_t)(cx + offX) | ((uint32_t)(cy + offY) << 12) | ((uint32_t)s << 24);
+            base += tot;
+            FAST_ADVANCE(cy, cx);
+            __syncthreads();
         }
-        if (f) out[base + pre + __popc(bal & ((1u << lane) - 1))] =
-                   (uint32_t)(cx + offX) | ((uint32_t)(cy + offY) << 12) | ((uint32_t)s << 24);
-        base += tot;
-        __syncthreads();
     }
+#undef FAST_ADVANCE
     if (tid == 0) cellCount[(size_t)frame * totalCells + cell] = base;
 }
 
@@ -625,11 +647,17 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * (len - 1) - p;
     return p;
 }
+// Each thread produces FOUR horizontally adjacent outputs per pass (byte loads, one division per element and 16-bit
+// shared-memory traffic per pixel made the per-pixel form issue-bound at ~170 instructions per pixel): interior tiles are
+// staged with aligned 32-bit loads (rows are padded to 16 bytes and tiles start at multiples of 64), the horizontal pass
+// reads three words and writes four 16-bit sums with one 64-bit store, the vertical pass reads seven 64-bit words and
+// writes four bytes with one store.  Border tiles take the per-byte path with BORDER_REFLECT_101.
 __global__ void __launch_bounds__(256)
     k_blur(const LevelInfo *__restrict__ lv, const int *__restrict__ tileBase, int nlevels,
            const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, size_t frameStride) {
-    __shared__ uint8_t in[(BLUR_TH + 6)][BLUR_TW + 8];
-    __shared__ uint16_t hz[(BLUR_TH + 6)][BLUR_TW];
+    constexpr int INW = (BLUR_TW + 8) / 4;                 // words per staged row: columns tx - 4 .. tx + 67
+    __shared__ __align__(16) uint32_t in32[(BLUR_TH + 6) * INW];
+    __shared__ __align__(16) uint16_t hz[(BLUR_TH + 6)][BLUR_TW];
     int level = 0;
     while (level + 1 < nlevels && (int)blockIdx.x >= tileBase[level + 1]) level++;
     const LevelInfo L = lv[level];
@@ -638,26 +666,64 @@ __global__ void __launch_bounds__(256)
     const int tx = (t % tilesX) * BLUR_TW, ty = (t / tilesX) * BLUR_TH;
     const uint8_t *src = pyr + blockIdx.y * frameStride + L.offset;
     const int tid = threadIdx.x;
-    for (int p = tid; p < (BLUR_TH + 6) * (BLUR_TW + 6); p += 256) {
-        int ry = p / (BLUR_TW + 6), rx = p - ry * (BLUR_TW + 6);
-        int gy = reflect101(ty + ry - 3, L.h), gx = reflect101(tx + rx - 3, L.w);
-        in[ry][rx] = src[(size_t)gy * L.pitch + gx];
+    const bool interior = tx >= 4 && tx + BLUR_TW + 4 <= L.w && ty >= 3 && ty + BLUR_TH + 3 <= L.h;
+    if (interior) {
+        for (int i = tid; i < (BLUR_TH + 6) * INW; i += 256) {
+            const int ry = i / INW, w = i - ry * INW;
+            in32[i] = *reinterpret_cast<const uint32_t *>(src + (size_t)(ty - 3 + ry) * L.pitch + tx - 4 + 4 * w);
+        }
+    } else {
+        uint8_t *in8 = reinterpret_cast<uint8_t *>(in32);
+        for (int p = tid; p < (BLUR_TH + 6) * (BLUR_TW + 6); p += 256) {
+            const int ry = p / (BLUR_TW + 6), rx = p - ry * (BLUR_TW + 6);
+            const int gy = reflect101(ty + ry - 3, L.h), gx = reflect101(tx + rx - 3, L.w);
+            in8[ry * (INW * 4) + rx + 1] = src[(size_t)gy * L.pitch + gx];
+        }
     }
     __syncthreads();
-    for (int p = tid; p < (BLUR_TH + 6) * BLUR_TW; p += 256) {
-        int ry = p / BLUR_TW, rx = p - ry * BLUR_TW;
-        const uint8_t *r = &in[ry][rx];
-        hz[ry][rx] = (uint16_t)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+        const int ry = i / (BLUR_TW / 4), g = i - ry * (BLUR_TW / 4);
+        const uint32_t *row = in32 + ry * INW + g;
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+        // bytes 1 .. 10 of the three words: columns x - 3 .. x + 6 for the outputs x .. x + 3
+        const uint32_t b1 = (w0 >> 8) & 0xff, b2 = (w0 >> 16) & 0xff, b3 = w0 >> 24;
+        const uint32_t b4 = w1 & 0xff, b5 = (w1 >> 8) & 0xff, b6 = (w1 >> 16) & 0xff, b7 = w1 >> 24;
+        const uint32_t b8 = w2 & 0xff, b9 = (w2 >> 8) & 0xff, b10 = (w2 >> 16) & 0xff;
+        const uint32_t h0 = 18 * (b1 + b7) + 34 * (b2 + b6) + 48 * (b3 + b5) + 56 * b4;
+        const uint32_t h1 = 18 * (b2 + b8) + 34 * (b3 + b7) + 48 * (b4 + b6) + 56 * b5;
+        const uint32_t h2 = 18 * (b3 + b9) + 34 * (b4 + b8) + 48 * (b5 + b7) + 56 * b6;
+        const uint32_t h3 = 18 * (b4 + b10) + 34 * (b5 + b9) + 48 * (b6 + b8) + 56 * b7;
+        *reinterpret_cast<uint2 *>(&hz[ry][4 * g]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // each <= 65280
     }
     __syncthreads();
     uint8_t *dst = blur + blockIdx.y * frameStride + L.offset;
-    for (int p = tid; p < BLUR_TH * BLUR_TW; p += 256) {
-        int ry = p / BLUR_TW, rx = p - ry * BLUR_TW;
-        int gx = tx + rx, gy = ty + ry;
+    {
+        const int ry = tid >> 4, g = tid & 15;  // 16 rows x 16 groups of four columns
+        const int gx = tx + 4 * g, gy = ty + ry;
         if (gx < L.w && gy < L.h) {
-            uint32_t acc = 18u * (hz[ry][rx] + hz[ry + 6][rx]) + 34u * (hz[ry + 1][rx] + hz[ry + 5][rx]) +
-                           48u * (hz[ry + 2][rx] + hz[ry + 4][rx]) + 56u * hz[ry + 3][rx];
-            dst[(size_t)gy * L.pitch + gx] = (uint8_t)((acc + (1u << 15)) >> 16);
+            uint2 r[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) r[k] = *reinterpret_cast<const uint2 *>(&hz[ry + k][4 * g]);
+            uint32_t o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[7];
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const uint32_t w = (c < 2) ? r[k].x : r[k].y;
+                    v[k] = (c & 1) ? (w >> 16) : (w & 0xffff);
+                }
+                const uint32_t acc = 18u * (v[0] + v[6]) + 34u * (v[1] + v[5]) + 48u * (v[2] + v[4]) + 56u * v[3];
+                o[c] = (acc + (1u << 15)) >> 16;
+            }
+            uint8_t *out = dst + (size_t)gy * L.pitch + gx;
+            if (gx + 3 < L.w) {
+                *reinterpret_cast<uint32_t *>(out) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (gx + c < L.w) out[c] = (uint8_t)o[c];
+            }
         }
     }
 }
