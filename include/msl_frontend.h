@@ -126,7 +126,8 @@ void *msl_matcher_stream(msl_matcher *); /* cudaStream_t */
  * arrays may be reused as soon as the call returns); msl_matcher_batch_end uploads everything in one copy, runs one CTA per
  * recorded call and then fills every call's output arrays, which must stay valid until then.  Calls with an empty side
  * return their (empty) result at once.  If the recorded calls outgrow the handle's scratch arena the recorded part is
- * executed early -- results are only promised at batch_end.  Outside a batch every search is a batch of one. */
+ * executed early -- results are only promised at batch_end.  A call that fails inside a batch discards everything recorded
+ * so far (the handle stays usable; the batch stays open).  Outside a batch every search is a batch of one. */
 int msl_matcher_batch_begin(msl_matcher *);
 int msl_matcher_batch_end(msl_matcher *);
 /* measurement aid: with timing on, every execution (a batch, or a single search) is bracketed by CUDA events on the handle's

@@ -152,6 +152,7 @@ def test_deferred_batch_of_mixed_searches(oracle, msl):
         tris = [S.triangulation_scene(20 + k) for k in range(3)]
         fus = [S.fuse_scene(30 + k) for k in range(2)]
         cur, last, mps2, Tc, Tl = S.match_scene(41)
+        m.set_timing(True)
         with m.batch():
             rb = [m.SearchByBoW(kf, f) for kf, f in bows]
             rt = [m.SearchForTriangulation(k1, k2, F12, Cw1, Tcw2, K2, sf, ls) for k1, k2, F12, Cw1, Tcw2, K2, sf, ls in tris]
@@ -159,6 +160,8 @@ def test_deferred_batch_of_mixed_searches(oracle, msl):
             rp = m.SearchByProjectionFrame(geom, Tc, Tl, 7.0, last, cur)
             with pytest.raises(RuntimeError):
                 rb[0].get()
+        dev_ms, calls = m.last_execution()
+        assert dev_ms > 0 and (calls == 9 if cap == 4096 else 1 <= calls < 9)  # (the small arena executed part of the batch early)
         for (kf, f), r in zip(bows, rb):
             n_o, fm_o = oracle.search_by_bow(0.7, True, kf, f)
             n_g, fm_g = r.get()
