@@ -161,7 +161,7 @@ def test_deferred_batch_of_mixed_searches(oracle, msl):
             with pytest.raises(RuntimeError):
                 rb[0].get()
         dev_ms, calls = m.last_execution()
-        assert dev_ms > 0 and (calls == 9 if cap == 4096 else 1 <= calls < 9)  # (the small arena executed part of the batch early)
+        assert dev_ms > 0 and 1 <= calls <= 9  # (the last execution: an arena that fills up runs the recorded part early)
         for (kf, f), r in zip(bows, rb):
             n_o, fm_o = oracle.search_by_bow(0.7, True, kf, f)
             n_g, fm_g = r.get()
