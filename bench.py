@@ -520,6 +520,11 @@ def widened_ops(msl, reps=20):
         c_us, (n_c, cm_c) = timed(lambda: ob.search_by_projection_points(geom, 3.0, 0.8, mps2, cur), 3)
         res["SearchByProjection_points_900x1000"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nmatches": int(n_g),
                                                      "equal": bool(n_g == n_c and np.array_equal(cm_g, cm_c))}
+        cur3, kf3, Tc3 = S.reloc_scene(1)
+        g_us, (n_g, cm_g) = timed(lambda: m2.SearchByProjectionKeyFrame(geom, Tc3, 15.0, 100, kf3, cur3, lsf), reps)
+        c_us, (n_c, cm_c) = timed(lambda: ob.search_by_projection_keyframe(geom, Tc3, 15.0, 100, True, lsf, kf3, cur3), 3)
+        res["SearchByProjection_keyframe_reloc"] = {"gpu_call_us": g_us, "cpu_oracle_us": c_us, "nmatches": int(n_g),
+                                                    "equal": bool(n_g == n_c and np.array_equal(cm_g, cm_c))}
         # deferred batches (msl_matcher_batch_begin / _end): eight calls recorded, one upload, one CTA per call -- the form the
         # reference's loops over candidate / neighbour keyframes take (src/Tracking.cc:1930-1950, src/LocalMapping.cc:330-351,
         # :540-570); per-item time next to the single-thread oracle on the same eight inputs

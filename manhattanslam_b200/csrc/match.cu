@@ -902,16 +902,21 @@ static int matcher_execute(msl_matcher *m);
 static int ensure_scratch(msl_matcher *m, size_t n_a, size_t n_b) {
     const size_t need = (n_a + n_b) * 96 + 4096;
     if (m->batchOff + need <= m->scrCap) return MSL_OK;
-    if (!m->pending.empty()) {  // a deferred batch has filled the arena: run what is recorded, then start over at offset 0
+    size_t want = need + need / 2;
+    if (!m->pending.empty()) {
+        // a deferred batch has filled the arena: run what is recorded, start over at offset 0 -- and quadruple the arena
+        // (up to 256 MB) so that the caller's next batch of this size runs as ONE execution
         const int rc = matcher_execute(m);
         if (rc) return rc;
-    }
-    if (need <= m->scrCap) return MSL_OK;
+        want = std::max(want, std::min(m->scrCap * 4, (size_t)256 << 20));
+    } else if (need <= m->scrCap)
+        return MSL_OK;
+    if (want <= m->scrCap) return MSL_OK;
     MSL_CUDA(cudaStreamSynchronize(m->stream));
     if (m->d_scr) cudaFree(m->d_scr);
     if (m->h_scr) cudaFreeHost(m->h_scr);
     m->d_scr = nullptr, m->h_scr = nullptr, m->scrCap = 0;
-    const size_t cap = need + need / 2;
+    const size_t cap = want;
     MSL_CUDA(cudaMalloc((void **)&m->d_scr, cap));
     MSL_CUDA(cudaMallocHost((void **)&m->h_scr, cap));
     m->scrCap = cap;
