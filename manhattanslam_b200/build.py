@@ -57,6 +57,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = _nvcc()
+    stamp = _source_hash()  # of what is about to be compiled: an edit made while nvcc runs must not be stamped as built
     objs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
@@ -76,7 +77,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart"])
     with open(STAMP, "w") as f:
-        f.write(_source_hash())
+        f.write(stamp)
     return OUT
 
 

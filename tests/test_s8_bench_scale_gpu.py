@@ -21,6 +21,7 @@ REF0 = 100
 # environment knobs of the fuse kernels (read by msl_surfel_create): every launch form the library can be switched to
 VARIANTS = {
     "default": {},                                                  # k_fuse_pipe: TMA-staged segments, scan(s+1) / fuse(s) interleaved per warp
+    "pipe_carry": {"MSL_FUSE_CARRY": "1"},                           # full fuse rounds only, partial rounds carried in registers
     "pipe_64regs_wave4": {"MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "4"},
     "pipe_late_loads_wave2": {"MSL_STREAM_EARLY": "0", "MSL_STREAM_WAVE": "2"},
     "pipe_no_prefetch": {"MSL_STREAM_PF": "0"},
