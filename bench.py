@@ -717,6 +717,8 @@ def per_kernel_pass(torch, step_dev, barrier, steps, alg, peak):
             for _ in range(steps):
                 step_dev()
             barrier()
+        if os.environ.get("MSL_TIMELINE"):  # diagnostic: the launches' start / end times per stream, for tools/timeline.py
+            prof.export_chrome_trace(os.environ["MSL_TIMELINE"])
         agg = {}
         for ev in prof.key_averages():
             us = getattr(ev, "self_device_time_total", None)
@@ -944,9 +946,19 @@ def run_ours(a, rank, world, local_rank):
         sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), (d_memdet[0] if do_detect else d_mem).data_ptr(), poses, B, True)
         state["ref"] += B
         iso_chain, iso_frames = sf.chain_times()
-        sf.set_timing(0)
         st1 = sf.read_stats()
         info = sf.launch_info()
+        # ---- and alone with a full wave of CTAs (three per SM): inside a batch the library launches two per SM so that the
+        # next batch's superpixel kernels find room beside the chain (msl_surfel_set_fuse_ctas_per_sm) -- better for the
+        # step, 6 % worse for the kernel on its own
+        barrier()
+        sf.set_fuse_ctas_per_sm(3, 0)
+        sf.fuse_batch_dev(state["ref"], d_gray.data_ptr(), W, W * H, d_depth.data_ptr(), (d_memdet[0] if do_detect else d_mem).data_ptr(), poses, B, True)
+        state["ref"] += B
+        full_chain, full_frames = sf.chain_times()
+        info_full = sf.launch_info()
+        sf.set_fuse_ctas_per_sm(int(os.environ.get("MSL_STREAM_WAVE_BATCH", os.environ.get("MSL_STREAM_WAVE", "2"))), 0)
+        sf.set_timing(0)
         n_map = st1[3]
         # stats accumulate per fuse_batch call: st1 holds the last call's totals over its B launches
         upd_per_launch = st1[1] / B
@@ -981,6 +993,13 @@ def run_ours(a, rank, world, local_rank):
         roofline["launch"] = info
         roofline["chain_us_per_frame"] = {k: 1e3 * v / max(chain_frames, 1) for k, v in chain.items()}
         roofline["isolated"]["chain_us_per_frame"] = {k: 1e3 * v / max(iso_frames, 1) for k, v in iso_chain.items()}
+        roofline["isolated"]["grid"] = info["grid"]
+        full_ms = (full_chain["scan"] + (full_chain["apply"] if info["kernels"] == 2 else 0.0)) / max(full_frames, 1)
+        ach_full = alg_one / (full_ms * 1e-3) / 1e9 if full_ms > 0 else None
+        roofline["isolated_full_wave"] = {"avg_launch_ms": full_ms, "achieved": ach_full, "frac": ach_full / peak if ach_full else None,
+                                          "grid": info_full["grid"], "note": "same kernel alone with three CTAs per SM (the geometry "
+                                          "of single-frame calls); the step's chain launches two per SM to leave room for the next "
+                                          "batch's superpixel kernels"}
         roofline["fused_per_launch"] = upd_per_launch
         roofline["killed_per_launch"] = del_per_launch
         roofline["note"] = "timed-region launches share the SMs with the next batch's superpixel kernels (stream overlap)"

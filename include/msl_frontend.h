@@ -493,6 +493,11 @@ int msl_surfel_set_count_table(msl_surfel_fusion *, int32_t *d_table);
 /* launch geometry of the last fuseSurfelsKernel launch (test / bench evidence that the persistent multi-draw path ran):
  * out = {kernels, form (MSL_FUSE_ONE), persistent, grid (CTAs), warps per CTA, 128-surfel segments} */
 int msl_surfel_launch_info(const msl_surfel_fusion *, int32_t out[6]);
+/* CTAs per SM of the persistent fuse kernel (k_fuse_pipe; 3 fill an SM's registers).  batch_ctas applies to the per-frame
+ * chain of msl_surfel_fuse_batch(_dev) calls of >= 8 frames, where the NEXT batch's superpixel stage runs beside the chain:
+ * the default 2 leaves a third of every SM to it (measured: 8.50 -> 8.15 ms per 64-frame step; the kernel itself is 6 %
+ * slower alone); single_ctas (default 3) applies to single frames and short batches.  0 keeps a value. */
+int msl_surfel_set_fuse_ctas_per_sm(msl_surfel_fusion *, int batch_ctas, int single_ctas);
 void *msl_surfel_stream(msl_surfel_fusion *);
 /* cudaStream_t on which msl_surfel_fuse_batch_dev / msl_surfel_fuse_dev READ their frame inputs (gray, depth, membership): a
  * producer of device-resident inputs (msl_plane_detect_dev's membership image, src/Tracking.cc:227-229) makes it wait for

@@ -143,6 +143,10 @@ class SurfelFusion:
         """device pointer of a (batch, 2) int32 table filled by every following fuse_batch_dev: {new, updated} per frame"""
         check(self._L.msl_surfel_set_count_table(self._h, ptr(d_table) if d_table else None))
 
+    def set_fuse_ctas_per_sm(self, batch_ctas=0, single_ctas=0):
+        """CTAs per SM of the persistent fuse kernel inside batches of >= 8 frames / for single frames (0: keep)"""
+        check(self._L.msl_surfel_set_fuse_ctas_per_sm(self._h, int(batch_ctas), int(single_ctas)))
+
     def launch_info(self):
         """launch geometry of the last fuseSurfelsKernel launch (msl_surfel_launch_info)"""
         out = np.zeros(6, np.int32)
