@@ -83,9 +83,12 @@ def parse():
     return a
 
 
+NO_GATHER = os.environ.get("MSL_BENCH_NO_GATHER") == "1"  # diagnostic (N > 1): ranks run free, no count-table collective; not a bench value
+
+
 def config_of(a):
     """the SAME dict in both arms (the driver compares them); descriptive extras go to `config_detail`"""
-    name = a.workload + ("_DIAGNOSTIC" if a.diagnostic else "")
+    name = a.workload + ("_DIAGNOSTIC" if a.diagnostic or NO_GATHER else "")
     return {"workload": name, "frame": "%dx%d" % (a.W, a.H), "batch_per_gpu": a.batch, "surfels_per_gpu": a.surfels,
             "stages": list(a.stages)}
 
@@ -411,12 +414,14 @@ class ClockSampler:
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         self.p = None
         self.t0 = self.t1 = None
+        if index is None:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                       "--format=csv,noheader,nounits", "-lms", str(period_ms)], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -758,7 +763,12 @@ def run_ours(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B, W, H, st = a.batch, a.W, a.H, a.stages
     K4 = camera(a)
-    gray, depth, mem, poses, surfels = make_inputs(rank, B, a.surfels, W, H, K4)
+    # Weak scaling: every rank streams the SAME synthetic scene, so that the work per GPU is exactly the N = 1 work (a scene
+    # of its own per rank makes the ranks' steps differ by up to 4 % -- keypoints, superpixel iterations, surfels in view --
+    # and the job, which advances in lock step through the count-table gather, runs at the slowest scene's pace:
+    # profiles/r03l-r03n).  MSL_BENCH_RANK_SCENES=1 gives every rank its own scene again; MSL_BENCH_SCENE=<r> picks one.
+    scene = rank if os.environ.get("MSL_BENCH_RANK_SCENES") == "1" else int(os.environ.get("MSL_BENCH_SCENE", "0"))
+    gray, depth, mem, poses, surfels = make_inputs(scene, B, a.surfels, W, H, K4)
     depth16 = make_inputs.depth16
 
     do_orb, do_match, do_plane, do_surfel = "orb" in st, "hamming_match" in st and "orb" in st, "plane_prestage" in st, "surfel_fuse" in st
@@ -872,7 +882,7 @@ def run_ours(a, rank, world, local_rank):
                 ev.record(s_sfin)
                 ev_mem_free[k] = ev
         state["ref"] += B
-        if world > 1:  # the path's single collective: the per-frame count table to every rank, off the compute streams
+        if world > 1 and not NO_GATHER:  # the path's single collective: the per-frame count table to every rank, off the compute streams
             for s in lib_streams:
                 s_comm.wait_stream(s)
             with torch.cuda.stream(s_comm):
@@ -896,8 +906,10 @@ def run_ours(a, rank, world, local_rank):
         ev0.record(cur)
         for s in lib_streams + [s_comm]:
             s.wait_event(ev0)
+        th0 = time.perf_counter()
         for _ in range(n):
             step_dev()
+        state["host_enqueue_ms"] = 1e3 * (time.perf_counter() - th0) / max(n, 1)  # host time to enqueue one step (no sync inside)
         for s in lib_streams + [s_comm]:
             e = torch.cuda.Event()
             e.record(s)
@@ -906,7 +918,10 @@ def run_ours(a, rank, world, local_rank):
         barrier()
         return ev0.elapsed_time(ev1)
 
-    clk = ClockSampler(local_rank)
+    # MSL_BENCH_CLOCKS (diagnostic): "off" = no sampler, "rank0" = only rank 0 samples (its own GPU); default: every rank its GPU
+    clk_mode = os.environ.get("MSL_BENCH_CLOCKS", "")
+    clk = ClockSampler(None if clk_mode == "off" or (clk_mode == "rank0" and rank != 0) else local_rank,
+                       int(os.environ.get("MSL_BENCH_CLOCKS_MS", "20")))
     for _ in range(a.warmup):
         step_dev()
     barrier()
@@ -914,6 +929,7 @@ def run_ours(a, rank, world, local_rank):
     # ---- the headline: K steps, no timing aid of any kind inside the region
     clk.begin()
     ms_total = timed_steps(a.steps)
+    host_enqueue_ms = state.get("host_enqueue_ms")
     clk.end()
     clocks = clk.stop()
     launches = int(msl.lib().msl_kernel_launch_count() - launches0)
@@ -1004,10 +1020,11 @@ def run_ours(a, rank, world, local_rank):
         roofline["killed_per_launch"] = del_per_launch
         roofline["note"] = "timed-region launches share the SMs with the next batch's superpixel kernels (stream overlap)"
         if world > 1:  # per-rank step and kernel times: is a slow rank or a slow kernel behind the max-over-ranks time?
-            mine = torch.tensor([mine_ms, roofline["avg_launch_ms"] * 1e3], dtype=torch.float64, device=dev)
-            allr = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+            mine = torch.tensor([mine_ms, roofline["avg_launch_ms"] * 1e3, host_enqueue_ms or 0.0], dtype=torch.float64, device=dev)
+            allr = torch.zeros((world, 3), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(allr, mine)
-            per_rank = {"ms_per_step": [float(x) for x in allr[:, 0]], "fuse_kernel_us": [float(x) for x in allr[:, 1]]}
+            per_rank = {"ms_per_step": [float(x) for x in allr[:, 0]], "fuse_kernel_us": [float(x) for x in allr[:, 1]],
+                        "host_enqueue_ms_per_step": [float(x) for x in allr[:, 2]]}
     elif world > 1:
         mine = torch.tensor([mine_ms], dtype=torch.float64, device=dev)
         allr = torch.zeros((world, 1), dtype=torch.float64, device=dev)
@@ -1348,7 +1365,9 @@ def run_ours(a, rank, world, local_rank):
                                      n_map * 56 // 1000000, B * W * H * 5 // 1000000),
                                  "collective": "nccl all_gather_into_tensor of the per-frame {keypoints, new, updated} table on "
                                                "its own stream" if world > 1 else "none (1 GPU)",
-                                 "timing": "CUDA events around K steps, all library streams fenced; no timing aid inside the region"},
+                                 "timing": "CUDA events around K steps, all library streams fenced; no timing aid inside the region",
+                                 "scenes": ("one synthetic scene per rank (MSL_BENCH_RANK_SCENES=1)" if os.environ.get("MSL_BENCH_RANK_SCENES") == "1"
+                                            else "every rank streams the same synthetic scene: per-GPU work is exactly the N = 1 work")},
                "roofline": roofline, "cpu_baseline": cpu,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fh2d), "d2h_bytes_per_step": int(fd2h),
                        "what": "host C ABI, pinned host buffers: the sensor frames (gray CV_8U + depth CV_16U%s) uploaded once per step "
@@ -1364,7 +1383,7 @@ def run_ours(a, rank, world, local_rank):
                                           "three times), which is what a binding that keeps the reference's per-class cv::Mat "
                                           "arguments pays"},
                "e2e_dropin": dropin,
-               "gpu_launches": launches, "clocks": clocks, "parity_check": parity, "per_rank": per_rank, "widened": widened}
+               "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "parity_check": parity, "per_rank": per_rank, "widened": widened}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

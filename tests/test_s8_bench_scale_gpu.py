@@ -21,6 +21,10 @@ REF0 = 100
 # environment knobs of the fuse kernels (read by msl_surfel_create): every launch form the library can be switched to
 VARIANTS = {
     "default": {},                                                  # k_fuse_pipe: TMA-staged segments, scan(s+1) / fuse(s) interleaved per warp
+    "pipe_full_wave": {"MSL_STREAM_WAVE_BATCH": "3"},                # three CTAs per SM inside a batch too (the default there is two)
+    "pipe_grid_259": {"MSL_STREAM_GRID": "259"},                     # an uneven share of CTAs per SM
+    "pipe_pdl": {"MSL_FUSE_PDL": "1"},                               # programmatic dependent launch along the chain
+    "pipe_pixels_1px": {"MSL_SP_PIX4": "0"},                         # updatePixels with one pixel per thread
     "pipe_carry": {"MSL_FUSE_CARRY": "1"},                           # full fuse rounds only, partial rounds carried in registers
     "pipe_64regs_wave4": {"MSL_STREAM_REGS": "4", "MSL_STREAM_WAVE": "4"},
     "pipe_late_loads_wave2": {"MSL_STREAM_EARLY": "0", "MSL_STREAM_WAVE": "2"},
@@ -71,7 +75,7 @@ def _oracle_stream(oracle, entry, batch, n_batches):
     return entry["ref"]
 
 
-def _gpu_stream(msl, entry, batch, n_batches, env):
+def _gpu_stream(msl, entry, batch, n_batches, env, ctas=None):
     import torch
     gray, depth, mem, poses, surfels = entry["in"]
     saved = {k: os.environ.get(k) for k in KNOBS}
@@ -86,6 +90,8 @@ def _gpu_stream(msl, entry, batch, n_batches, env):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+    if ctas:  # msl_surfel_set_fuse_ctas_per_sm: the launch geometry is a performance knob, never a result
+        sf.set_fuse_ctas_per_sm(*ctas)
     sf.upload_map(surfels)
     dev = torch.device("cuda", 0)
     d_gray = torch.from_numpy(gray).to(dev)
@@ -129,11 +135,11 @@ def test_fuse_stream_5M_two_batches(oracle, msl, variant):
         assert draws >= (8 if info["grid"] <= 444 else 5), info  # the persistent multi-draw loop is what is being pinned here
 
 
-@pytest.mark.parametrize("variant", ["default", "two_kernel_chain"])
+@pytest.mark.parametrize("variant", ["default", "two_kernel_chain", "api_ctas"])
 def test_fuse_stream_1M_three_batches(oracle, msl, variant):
     batch, n_batches, n_surfels = 64, 3, 1_000_000
     entry = _inputs(n_surfels, batch)
     ref, _ = _oracle_stream(oracle, entry, batch, n_batches)
-    got, stats, _ = _gpu_stream(msl, entry, batch, n_batches, VARIANTS[variant])
+    got, stats, _ = _gpu_stream(msl, entry, batch, n_batches, VARIANTS.get(variant, {}), ctas=(1, 2) if variant == "api_ctas" else None)
     _check(got, ref, "1M map after %d frames (%s)" % (batch * n_batches, variant))
     assert stats[3] == len(ref)
