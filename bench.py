@@ -931,6 +931,13 @@ def run_ours(a, rank, world, local_rank):
     ms_total = timed_steps(a.steps)
     host_enqueue_ms = state.get("host_enqueue_ms")
     clk.end()
+    # the same with an empty launch queue (one step after a full synchronisation): what the host really spends per step --
+    # inside the timed loop the figure above includes waiting for room in the queue once the host is a few steps ahead
+    barrier()
+    th0 = time.perf_counter()
+    step_dev()
+    host_unloaded_ms = 1e3 * (time.perf_counter() - th0)
+    barrier()
     clocks = clk.stop()
     launches = int(msl.lib().msl_kernel_launch_count() - launches0)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -1209,8 +1216,8 @@ def run_ours(a, rank, world, local_rank):
     # ONCE from pinned host memory into a frame set every stage reads (msl_glue_upload_frames; the CV_32F depth of
     # Tracking::GrabImageRGBD is produced on the device), the stages run through their *_dev entry points on their own
     # streams, and every result comes back to pinned host memory.  Steps are pipelined the way a streaming front-end runs:
-    # the upload and the launches of step k+1 are issued before the host waits for the results of step k (two frame sets,
-    # two sets of result buffers); all K uploads and all K downloads lie inside the timed region, which ends when the last
+    # the upload of step k+2 and the launches of step k+1 are issued before the host waits for the results of step k (three
+    # frame sets, two sets of result buffers); all K uploads and all K downloads lie inside the timed region, which ends when the last
     # step's results are on the host.
     glue_up = glue if glue is not None else msl.FrameGlue(W, H, max_batch=B, device=local_rank)
     wait_streams = [x for x in (orb.stream if orb else None, plane.stream if plane else None,
@@ -1236,9 +1243,11 @@ def run_ours(a, rank, world, local_rank):
     hres.append({k_: (pin_like(v_) if v_ is not None else None) for k_, v_ in hres[0].items()})
     done_ev = [None, None]
 
+    NSETS = 3  # MSL_GLUE_FRAME_SETS
+
     def launch_frames(i, sets):
-        slot = i & 1
-        H_ = hres[slot]
+        slot = i % NSETS
+        H_ = hres[i & 1]
         for st_ in wait_streams:
             glue_up.frames_wait(slot, st_)
         k = state["k"] & 1
@@ -1278,7 +1287,7 @@ def run_ours(a, rank, world, local_rank):
                 e_ = torch.cuda.Event()
                 e_.record(s_sf)
                 evs.append(e_)
-        done_ev[slot] = evs
+        done_ev[i & 1] = evs
 
     def collect_frames(i):
         for e_ in done_ev[i & 1] or []:
@@ -1286,14 +1295,19 @@ def run_ours(a, rank, world, local_rank):
         done_ev[i & 1] = None
 
     def run_frames(n_steps):
-        sets = [None, None]
+        # three frame sets: the frames of step i+2 go up while step i runs, so that step i+1's superpixel stage finds its
+        # input on the device when step i's fuse chain starts and runs beside it, as in the device-resident loop (with two
+        # sets the upload of step i+1 could only start once step i-1 was collected, 1.7 ms into step i's chain)
+        sets = [None] * NSETS
         sets[0] = upload(0)
+        if n_steps > 1:
+            sets[1] = upload(1)
         for i in range(n_steps):
             launch_frames(i, sets)
             if i > 0:
                 collect_frames(i - 1)  # step i-1 is complete on the host: its frame set may be overwritten
-            if i + 1 < n_steps:
-                sets[(i + 1) & 1] = upload((i + 1) & 1)
+            if i + 2 < n_steps:
+                sets[(i + 2) % NSETS] = upload((i + 2) % NSETS)  # the set of step i-1
         collect_frames(n_steps - 1)
 
     barrier()
@@ -1373,7 +1387,7 @@ def run_ours(a, rank, world, local_rank):
                        "what": "host C ABI, pinned host buffers: the sensor frames (gray CV_8U + depth CV_16U%s) uploaded once per step "
                                "into a frame set every stage reads (msl_glue_upload_frames, CV_32F depth produced on the device), "
                                "stages through their *_dev entry points, every result copied back to the host inside the step; "
-                               "the upload and the launches of step k+1 are issued before the results of step k are awaited (two frame sets, two "
+                               "the upload of step k+2 and the launches of step k+1 are issued before the results of step k are awaited (three frame sets, two "
                                "sets of host result buffers), every copy inside the timed region" % (
                                    " + the host-computed membership image" if aux is not None else "")},
                "e2e_host_calls": {"value": e2e_calls_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -1383,7 +1397,7 @@ def run_ours(a, rank, world, local_rank):
                                           "three times), which is what a binding that keeps the reference's per-class cv::Mat "
                                           "arguments pays"},
                "e2e_dropin": dropin,
-               "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "parity_check": parity, "per_rank": per_rank, "widened": widened}
+               "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_unloaded": host_unloaded_ms, "clocks": clocks, "parity_check": parity, "per_rank": per_rank, "widened": widened}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -296,12 +296,14 @@ int msl_glue_depth_to_float_dev(msl_glue *, const uint16_t *d_depth16, int64_t n
  * every consumer -- ExtractORB(imGray), ComputeStereoFromRGBD(imDepth), ExtractPlanes(imDepth as CV_16U) (src/Frame.cc:90-110,
  * :604-610) and later SurfelFusion through the KeyFrame (src/SurfelMapping.cpp:353-364) -- so a binding that goes through the
  * host entry points uploads gray twice and depth three times.  Here gray (CV_8U) and the sensor depth (CV_16U) go up once, on
- * the handle's own copy stream, into frame set `slot` (0 or 1: double-buffered so that the upload of the next batch overlaps the
- * work on the current one), and the CV_32F depth of Tracking::GrabImageRGBD (convertTo(CV_32F, mDepthMapFactor),
+ * the handle's own copy stream, into frame set `slot` (0 .. MSL_GLUE_FRAME_SETS - 1: with three sets the upload of batch k+2 can
+ * be issued while batch k is being worked on, so that batch k+1's frames are on the device before batch k's fuse chain starts
+ * and its superpixel stage can run beside that chain), and the CV_32F depth of Tracking::GrabImageRGBD (convertTo(CV_32F, mDepthMapFactor),
  * src/Tracking.cc:205-207) is produced on the device.  `aux` (optional, aux_ints int32 values) rides along, e.g. a
  * membership image computed on the host.  Returns at once; the device pointers stay valid until the slot's next upload and are
  * meant for the *_dev entry points after msl_glue_frames_wait(glue, slot, <that handle's stream>).  The caller must not upload
  * into a slot whose consumers of the previous upload have not been synchronised. */
+#define MSL_GLUE_FRAME_SETS 3
 int msl_glue_upload_frames(msl_glue *, int slot, const uint8_t *gray, int gray_stride, const uint16_t *depth16,
                            int depth_stride_px, int batch, float factor, const int32_t *aux, size_t aux_ints,
                            const uint8_t **d_gray, const uint16_t **d_depth16, const float **d_depth, const int32_t **d_aux);

@@ -143,7 +143,7 @@ struct msl_glue {
         size_t auxCap = 0;
         cudaEvent_t ready = nullptr;
         bool used = false;
-    } fs[2];
+    } fs[MSL_GLUE_FRAME_SETS];
 };
 
 static int glue_reserve(msl_glue *g, size_t in, size_t out) {
@@ -272,7 +272,7 @@ int msl_glue_depth_to_float(msl_glue *g, const uint16_t *depth16, int batch, flo
 int msl_glue_upload_frames(msl_glue *g, int slot, const uint8_t *gray, int gray_stride, const uint16_t *depth16, int depth_stride_px,
                            int batch, float factor, const int32_t *aux, size_t aux_ints, const uint8_t **d_gray,
                            const uint16_t **d_depth16, const float **d_depth, const int32_t **d_aux) {
-    if (!g || !gray || !depth16 || slot < 0 || slot > 1) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad argument");
+    if (!g || !gray || !depth16 || slot < 0 || slot >= MSL_GLUE_FRAME_SETS) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad argument");
     if (batch < 1 || batch > g->maxBatch) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad batch");
     if (gray_stride < g->w || depth_stride_px < g->w) return fail(MSL_ERR_INVALID, "msl_glue_upload_frames: bad stride");
     MSL_CUDA(cudaSetDevice(g->device));
@@ -310,7 +310,7 @@ int msl_glue_upload_frames(msl_glue *g, int slot, const uint8_t *gray, int gray_
 }
 
 int msl_glue_frames_wait(msl_glue *g, int slot, void *stream) {
-    if (!g || slot < 0 || slot > 1 || !g->fs[slot].used) return fail(MSL_ERR_INVALID, "msl_glue_frames_wait: no upload in this slot");
+    if (!g || slot < 0 || slot >= MSL_GLUE_FRAME_SETS || !g->fs[slot].used) return fail(MSL_ERR_INVALID, "msl_glue_frames_wait: no upload in this slot");
     MSL_CUDA(cudaSetDevice(g->device));
     if (stream) MSL_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g->fs[slot].ready, 0));
     else MSL_CUDA(cudaEventSynchronize(g->fs[slot].ready));
