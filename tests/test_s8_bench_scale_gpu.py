@@ -23,6 +23,7 @@ VARIANTS = {
     "default": {},                                                  # k_fuse_pipe: TMA-staged segments, scan(s+1) / fuse(s) interleaved per warp
     "pipe_full_wave": {"MSL_STREAM_WAVE_BATCH": "3"},                # three CTAs per SM inside a batch too (the default there is two)
     "pipe_grid_259": {"MSL_STREAM_GRID": "259"},                     # an uneven share of CTAs per SM
+    "pipe_nb3": {"MSL_PIPE_NB": "3"},                                # three staged segments per warp (two CTAs per SM)
     "pipe_pdl": {"MSL_FUSE_PDL": "1"},                               # programmatic dependent launch along the chain
     "pipe_pixels_1px": {"MSL_SP_PIX4": "0"},                         # updatePixels with one pixel per thread
     "pipe_carry": {"MSL_FUSE_CARRY": "1"},                           # full fuse rounds only, partial rounds carried in registers
