@@ -669,6 +669,7 @@ def kernel_alg_bytes(W, H, B, n_map, upd, killed, kp_rows):
         "k_peac_frame": B * (npx * 1.0 + w2 * h2 * (4.0 + 4.0)),  # depth in, membership + distance map out; the rest stays on chip
         "k_sp_init": B * (nseeds * (72.0 + 40.0) + nseeds * 8.0),
         "k_sp_pixels": B * (npx * (1 + 4 + 1) + npx * 8.0),           # gray + depth + membership(1/4 res, 4 B) R; target + index W
+        "k_sp_pixels4": B * (npx * (1 + 4 + 1) + npx * 8.0),          # the same, four pixels per thread
         "k_sp_fix": B * npx * 8.0 * 0.25,                                # pending pixels only (a quarter, typically)
         "k_sp_seeds": B * (npx * (4 + 1 + 4) + nseeds * 112.0 * 2),      # index + gray + depth R once; seeds R + W
         "k_sp_seeds2": B * (npx * (4 + 1 + 4) + nseeds * 112.0 * 2),
@@ -700,6 +701,7 @@ BOUND_NOTE = {  # what each kernel is bound by in practice
     "k_track_last": "latency (depth ranks by counting, one CTA per frame)",
     "k_peac_frame": "latency (one CTA per frame: ~600 dependent merge steps with an fp64 eigen-solve each, then a level-synchronous region grow)",
     "k_plane_edges": "latency", "k_sp_pixels": "fp64 issue (the reference's float/double cost)", "k_sp_fix": "latency",
+    "k_sp_pixels4": "float<->double conversion rate (30 per pixel; F2F issues at 15.5 per clock per SM, profiles/r03e)",
     "k_sp_seeds2": "shared-memory latency (sequential float sums per seed)", "k_sp_fit2": "fp64 latency (sequential sums per seed)",
     "k_resize": "L2", "k_blur": "L2", "k_load_level0": "hbm", "k_sp_norms": "hbm", "k_sp_records": "hbm",
 }

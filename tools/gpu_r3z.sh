@@ -43,4 +43,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fu
   python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline --no-extras >> $OUT/${TAG}_ncu_bench.log 2>&1
 python tools/ncu_brief.py $OUT/${TAG}_k_fuse_pipe.ncu-rep > $OUT/${TAG}_k_fuse_pipe_brief.txt 2>&1
 cat $OUT/${TAG}_k_fuse_pipe_brief.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_sp_pixels4 -s 1 -c 1 -f -o $OUT/${TAG}_k_sp_pixels4 \
+  python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline --no-extras >> $OUT/${TAG}_ncu_bench.log 2>&1
+python tools/ncu_brief.py $OUT/${TAG}_k_sp_pixels4.ncu-rep > $OUT/${TAG}_k_sp_pixels4_brief.txt 2>&1
+cat $OUT/${TAG}_k_sp_pixels4_brief.txt
 tail -c 400 $OUT/${TAG}_bench.err
