@@ -1057,6 +1057,15 @@ def run_ours(a, rank, world, local_rank):
                         "in_practice": top["in_practice"] if top else None}
         roofline["kernels"] = kt.get("kernels")
         roofline["kernels_source"] = kt.get("source", kt.get("error"))
+        # the whole step against the HBM roofline: the algorithmic bytes of every launch of a step over the step's time.  The
+        # dominant kernel's own `frac` divides by its launch duration INSIDE the step, where -- by design -- it shares every
+        # SM with the other streams' kernels (two of its CTAs per SM, the rest of the SM theirs)
+        steps_k = min(a.steps, 5)
+        step_bytes = sum((k_["alg_bytes_per_launch"] or 0.0) * k_["launches"] / steps_k for k_ in (kt.get("kernels") or []))
+        if step_bytes and ms_step:
+            ach_step = step_bytes / (ms_step * 1e-3) / 1e9
+            roofline["step"] = {"alg_bytes_per_step": step_bytes, "achieved": ach_step, "unit": "GB/s", "frac": ach_step / peak,
+                                "note": "sum over the step's launches of their algorithmic bytes / ms_per_step"}
 
     # ---- parity replay: the last frames of the run again on the CPU oracle from the downloaded pre-state
     parity = None
