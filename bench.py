@@ -690,6 +690,7 @@ def kernel_alg_bytes(W, H, B, n_map, upd, killed, kp_rows):
     for l in range(1, 8):
         t["k_resize_L%d" % l] = B * (px[l - 1] + px[l]) * 1.0
     t["k_resize"] = sum(t["k_resize_L%d" % l] for l in range(1, 8)) / 7.0  # average launch (7 launches per batch)
+    t["k_resize4"] = t["k_resize"]  # the same bytes, four output pixels per thread (default)
     return t
 
 
@@ -703,7 +704,7 @@ BOUND_NOTE = {  # what each kernel is bound by in practice
     "k_plane_edges": "latency", "k_sp_pixels": "fp64 issue (the reference's float/double cost)", "k_sp_fix": "latency",
     "k_sp_pixels4": "float<->double conversion rate (30 per pixel; F2F issues at 15.5 per clock per SM, profiles/r03e)",
     "k_sp_seeds2": "shared-memory latency (sequential float sums per seed)", "k_sp_fit2": "fp64 latency (sequential sums per seed)",
-    "k_resize": "L2", "k_blur": "L2", "k_load_level0": "hbm", "k_sp_norms": "hbm", "k_sp_records": "hbm",
+    "k_resize": "L2", "k_resize4": "latency (seven dependent launches per batch, two round trips per CTA)", "k_blur": "L2", "k_load_level0": "hbm", "k_sp_norms": "hbm", "k_sp_records": "hbm",
 }
 
 

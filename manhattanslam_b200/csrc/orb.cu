@@ -45,6 +45,8 @@ struct LevelInfo {
     float hX;
     int width, height;   // maxBorder - minBorder
     int tabOff;          // offset (in shorts) of the resize tables of this level
+    int xtOff;           // offset (in int2 entries, even) of this level's packed column table (k_resize4)
+    int xSpan;           // max over groups of four output columns of (last source column + 1) - (first source column & ~3)
     float scale;         // mvScaleFactor[level]
     int kpBase, kpCap;   // slot range of this level in the per-frame level-keypoint array
     int candBase, candCap;  // slot range of this level in the per-frame candidate arrays (nCells*capCell: cannot overflow)
@@ -118,6 +120,49 @@ __global__ void __launch_bounds__(256) k_resize(const LevelInfo *__restrict__ lv
     const int h1 = r1[sx] * a0 + r1[sx1] * a1;
     const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
     pyr[blockIdx.z * frameStride + L.offset + (size_t)y * L.pitch + x] = (uint8_t)v;
+}
+
+// The same, four output pixels of a row per thread (default; MSL_ORB_RESIZE4=0 for the one-pixel form).  k_resize is a
+// few loads per thread behind two dependent round trips, in ~50 k tiny CTAs per level and batch: it runs at the latency of
+// a CTA times the number of waves, not at any throughput.  Here a thread's four columns come from two 16-byte loads of a
+// packed column table {sx | sx1 << 16, a0 | a1 << 16}, and the source bytes of both rows from three aligned words each
+// (four output columns span at most 12 source bytes from the word the first one lies in -- xSpan, checked on the host);
+// the arithmetic per pixel is k_resize's.
+__device__ __forceinline__ unsigned resize_pick(unsigned w0, unsigned w1, unsigned w2, int o) {  // byte o (0..11) of {w0, w1, w2}
+    const unsigned w = o < 8 ? (o < 4 ? w0 : w1) : w2;
+    return (w >> (8 * (o & 3))) & 255u;
+}
+__global__ void __launch_bounds__(256) k_resize4(const LevelInfo *__restrict__ lv, int level, uint8_t *pyr, size_t frameStride,
+                                                 const short *__restrict__ tab, const int4 *__restrict__ xt4) {
+    const LevelInfo L = lv[level], P = lv[level - 1];
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= L.w || y >= L.h) return;
+    const int4 e01 = __ldg(xt4 + (L.xtOff + x0) / 2), e23 = __ldg(xt4 + (L.xtOff + x0) / 2 + 1);  // (the table is padded to four columns)
+    const int ex[4] = {e01.x, e01.z, e23.x, e23.z}, ea[4] = {e01.y, e01.w, e23.y, e23.w};
+    const short *ty = tab + L.tabOff + 3 * L.w;
+    const int sy = ty[y], b0 = ty[L.h + y], b1 = ty[2 * L.h + y];
+    const int sy0 = min(max(sy, 0), P.h - 1), sy1 = min(max(sy + 1, 0), P.h - 1);
+    const uint8_t *src = pyr + blockIdx.z * frameStride + P.offset;
+    const int base = (ex[0] & 0xffff) & ~3;
+    const unsigned *r0 = reinterpret_cast<const unsigned *>(src + (size_t)sy0 * P.pitch + base);
+    const unsigned *r1 = reinterpret_cast<const unsigned *>(src + (size_t)sy1 * P.pitch + base);
+    const unsigned u0 = r0[0], u1 = r0[1], u2 = r0[2], v0 = r1[0], v1 = r1[1], v2 = r1[2];
+    unsigned out = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int o0 = (ex[q] & 0xffff) - base, o1 = (int)((unsigned)ex[q] >> 16) - base;
+        const int a0 = ea[q] & 0xffff, a1 = (int)((unsigned)ea[q] >> 16);
+        const int h0 = (int)resize_pick(u0, u1, u2, o0) * a0 + (int)resize_pick(u0, u1, u2, o1) * a1;
+        const int h1 = (int)resize_pick(v0, v1, v2, o0) * a0 + (int)resize_pick(v0, v1, v2, o1) * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        out |= (unsigned)(v & 255) << (8 * q);
+    }
+    uint8_t *dst = pyr + blockIdx.z * frameStride + L.offset + (size_t)y * L.pitch + x0;
+    if (x0 + 3 < L.w) {
+        *reinterpret_cast<unsigned *>(dst) = out;  // rows are 16-byte aligned and padded: an aligned word inside the row
+    } else {
+        for (int q = 0; x0 + q < L.w; q++) dst[q] = (uint8_t)(out >> (8 * q));
+    }
 }
 
 // ------------------------------------------------------------------------------------------ O2
@@ -862,6 +907,8 @@ struct msl_orb {
     LevelInfo *d_lv = nullptr;
     Cell *d_cells = nullptr;
     short *d_cellLevel = nullptr, *d_tab = nullptr;
+    int4 *d_xt4 = nullptr;   // packed column tables of k_resize4 (two int2 entries per int4)
+    bool resize4 = true;     // MSL_ORB_RESIZE4
     int *d_blurTileBase = nullptr;
     uint8_t *d_pyr = nullptr, *d_blur = nullptr;
     uint32_t *d_staging = nullptr, *d_candRec = nullptr;
@@ -877,7 +924,7 @@ struct msl_orb {
 static void orb_free(msl_orb *o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void *ptrs[] = {o->d_lv, o->d_cells, o->d_cellLevel, o->d_tab, o->d_blurTileBase, o->d_pyr, o->d_blur,
+    void *ptrs[] = {o->d_lv, o->d_cells, o->d_cellLevel, o->d_tab, o->d_xt4, o->d_blurTileBase, o->d_pyr, o->d_blur,
                     o->d_staging, o->d_candRec, o->d_candNode, o->d_cellCount, o->d_candCount, o->d_lvlCount,
                     o->d_err, o->d_lvlKps, o->d_kps, o->d_desc, o->d_counts, o->d_tmaps};
     for (void *p : ptrs)
@@ -945,6 +992,7 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     // ---- level geometry, resize tables, FAST cells
     o->lv.resize(nl);
     std::vector<short> tab;
+    std::vector<int> xtab;  // k_resize4's packed column tables, two ints per column
     std::vector<Cell> cells;
     std::vector<short> cellLevel;
     size_t off = 0;
@@ -1009,6 +1057,7 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
         blurTiles += cdiv(L.w, BLUR_TW) * cdiv(L.h, BLUR_TH);
         // resize tables for level l from level l-1 (cv::resize, imgproc/resize.cpp)
         L.tabOff = (int)tab.size();
+        L.xtOff = 0, L.xSpan = 0;
         if (l > 0) {
             const LevelInfo &P = o->lv[l - 1];
             const double sx_ = 1. / ((double)L.w / P.w), sy_ = 1. / ((double)L.h / P.h);
@@ -1032,6 +1081,25 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
                 b1[dy] = sat_short(fy * 2048);
             }
             for (auto *v : {&xo, &a0, &a1, &yo, &b0, &b1}) tab.insert(tab.end(), v->begin(), v->end());
+            // packed column table of k_resize4: {sx | sx1 << 16, a0 | a1 << 16}, padded to four columns with the last one
+            L.xtOff = (int)(xtab.size() / 2);
+            L.xSpan = 0;
+            const int wPad = (L.w + 3) & ~3;
+            for (int dx = 0; dx < wPad; dx++) {
+                const int c = std::min(dx, L.w - 1);
+                const int sx0_ = xo[c], sx1_ = std::min(sx0_ + 1, P.w - 1);
+                xtab.push_back((sx0_ & 0xffff) | (sx1_ << 16));
+                xtab.push_back(((int)a0[c] & 0xffff) | ((int)a1[c] << 16));
+                if (a0[c] < 0 || a1[c] < 0) L.xSpan = 1 << 20;  // (coefficients are 0..2048: never)
+            }
+            for (int g = 0; g < wPad; g += 4) {
+                const int first = xo[std::min(g, L.w - 1)] & ~3;
+                for (int q = 0; q < 4; q++) {
+                    const int c = std::min(g + q, L.w - 1);
+                    L.xSpan = std::max(L.xSpan, std::min((int)xo[c] + 1, P.w - 1) + 1 - first);
+                    if (xo[c] < xo[std::min(g, L.w - 1)]) L.xSpan = 1 << 20;  // (source columns ascend: never)
+                }
+            }
         }
     }
     o->blurTileBase[nl] = blurTiles;
@@ -1073,6 +1141,7 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     ALLOC(o->d_cells, sizeof(Cell) * cells.size());
     ALLOC(o->d_cellLevel, sizeof(short) * cells.size());
     ALLOC(o->d_tab, sizeof(short) * tab.size());
+    ALLOC(o->d_xt4, sizeof(int) * std::max<size_t>(xtab.size(), 4));
     ALLOC(o->d_blurTileBase, sizeof(int) * (nl + 1));
     ALLOC(o->d_pyr, B * o->pyrBytes);
     ALLOC(o->d_blur, B * o->pyrBytes);
@@ -1093,6 +1162,8 @@ int msl_orb_create(const msl_orb_params *prm, int w, int h, int max_batch, int d
     MSL_CUDA(cudaMemcpy(o->d_cells, cells.data(), sizeof(Cell) * cells.size(), cudaMemcpyHostToDevice));
     MSL_CUDA(cudaMemcpy(o->d_cellLevel, cellLevel.data(), sizeof(short) * cells.size(), cudaMemcpyHostToDevice));
     MSL_CUDA(cudaMemcpy(o->d_tab, tab.data(), sizeof(short) * tab.size(), cudaMemcpyHostToDevice));
+    if (!xtab.empty()) MSL_CUDA(cudaMemcpy(o->d_xt4, xtab.data(), sizeof(int) * xtab.size(), cudaMemcpyHostToDevice));
+    if (const char *e = getenv("MSL_ORB_RESIZE4")) o->resize4 = atoi(e) != 0;
     MSL_CUDA(cudaMemcpy(o->d_blurTileBase, o->blurTileBase.data(), sizeof(int) * (nl + 1), cudaMemcpyHostToDevice));
     {   // one 3-D tensor map (x, y, frame) per pyramid level for the TMA tile loads of k_fast_cells
         typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -1156,8 +1227,13 @@ static int orb_run(msl_orb *o, int batch, msl_keypoint *d_kps, uint8_t *d_desc, 
     cudaStream_t st = o->stream;
     const int nl = o->nlevels;
     for (int l = 1; l < nl; l++) {
-        dim3 g(cdiv(o->lv[l].w, 32), cdiv(o->lv[l].h, 8), batch);
-        k_resize<<<g, dim3(32, 8), 0, st>>>(o->d_lv, l, o->d_pyr, o->pyrBytes, o->d_tab);
+        if (o->resize4 && o->lv[l].xSpan <= 12) {  // four columns per thread: their source bytes lie in three aligned words
+            dim3 g(cdiv(cdiv(o->lv[l].w, 4), 32), cdiv(o->lv[l].h, 8), batch);
+            k_resize4<<<g, dim3(32, 8), 0, st>>>(o->d_lv, l, o->d_pyr, o->pyrBytes, o->d_tab, o->d_xt4);
+        } else {
+            dim3 g(cdiv(o->lv[l].w, 32), cdiv(o->lv[l].h, 8), batch);
+            k_resize<<<g, dim3(32, 8), 0, st>>>(o->d_lv, l, o->d_pyr, o->pyrBytes, o->d_tab);
+        }
         MSL_LAUNCH_CHECK();
     }
     k_fast_cells<<<dim3(o->totalCells, batch), 128, 0, st>>>(o->d_lv, o->d_cells, o->d_cellLevel, o->d_pyr,
