@@ -76,7 +76,10 @@ def test_orb_edge_images(oracle, msl, kind):
 
 
 @pytest.mark.parametrize("w,h,nf,nl,sf", [(752, 480, 1200, 8, 1.2), (320, 240, 500, 6, 1.2), (1280, 960, 2000, 8, 1.2),
-                                           (640, 480, 1000, 4, 1.5)])
+                                           (640, 480, 1000, 4, 1.5),
+                                           # k_resize4's source window: four columns span exactly 12 bytes at 2.3 (the vector
+                                           # form's limit), 13 at 2.6 (the one-pixel form takes over)
+                                           (640, 480, 500, 3, 2.3), (640, 480, 400, 3, 2.6)])
 def test_orb_other_sizes(oracle, msl, w, h, nf, nl, sf):
     img = S.gray_frame(3, w, h)
     gpu = msl.ORBextractor(nfeatures=nf, scaleFactor=sf, nlevels=nl, width=w, height=h, max_batch=1)
